@@ -1,0 +1,190 @@
+/*
+ * nncf_b200.h — C-ABI of libnncf_b200.so: the B200-native (sm_100a) implementation of NNCF's
+ * sampling-and-scoring training loop and whole@k / given@k evaluation.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative NNCF_E* code; nncf_last_error() gives the text
+ *     (thread-local).  The reference aborts with assert() (sampler/nodesampler.cpp:48,65; main.py:57,100);
+ *     the host wrappers turn a non-zero status into a Python exception.
+ *   - pointers named *_dev are device pointers on the current CUDA device, *_host are host pointers.
+ *     All buffers are caller-owned (torch allocates); kernels never allocate except inside the opaque
+ *     handles created by *_create and released by *_destroy.
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).  Calls are asynchronous
+ *     with respect to the host unless stated otherwise.
+ *   - no torch types appear in any signature.
+ *
+ * Paths cited as "ref:" are relative to the reference tree (chentingpc/NNCF).
+ */
+#ifndef NNCF_B200_H
+#define NNCF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NNCF_OK            0
+#define NNCF_EINVAL       -1   /* bad argument */
+#define NNCF_ECUDA        -2   /* CUDA runtime error (text in nncf_last_error) */
+#define NNCF_ENOMEM       -3
+#define NNCF_EUNSUPPORTED -4   /* shape / mode outside what the kernels implement */
+
+/* enums are plain ints in the ABI */
+enum { NNCF_SCHEME_NEG_SHARED = 0, NNCF_SCHEME_GROUP_NEG_SHARED = 1, NNCF_SCHEME_PAIRS = 2 };
+enum { NNCF_LOSS_SKIP_GRAM = 0, NNCF_LOSS_MSE = 1, NNCF_LOSS_LOG_LOSS = 2, NNCF_LOSS_MAX_MARGIN = 3 };
+enum { NNCF_PREC_FP32 = 0,   /* CUDA-core fp32 FMA, exact fp32 accumulate (1e-4 parity mode)            */
+       NNCF_PREC_BF16 = 1 }; /* tcgen05 tensor cores: bf16 operands, fp32 accumulate in TMEM (1e-2 mode) */
+enum { NNCF_OPT_NONE = 0, NNCF_OPT_SGD = 1, NNCF_OPT_LAZY_ADAM = 2 };
+
+const char* nncf_last_error(void);
+int nncf_version(void);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches claim) */
+int64_t nncf_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Negative sampler.   ref: sampler/nodesampler.cpp:55-76 (NodeSampler ctor / sample / sample_batch),
+ *     bound by sampler/sampler.pyx:19-38 (MultinomialSampler).  Same target distribution
+ *     p_i ∝ dist[i]^power for dist[i] > 0 (nodesampler.cpp:29-49); the 1e8-entry lookup table + 64-bit
+ *     LCG become a Walker/Vose alias table in HBM + counter-based Philox4x32-10.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nncf_sampler nncf_sampler_t;
+int nncf_sampler_create(const double* dist_host, int dist_size, double neg_sampling_power, uint64_t rand_seed,
+                        nncf_sampler_t** out);
+int nncf_sampler_destroy(nncf_sampler_t* s);
+/* n draws into a device buffer; consumes Philox counters [c, c + n) of this sampler's stream */
+int nncf_sampler_sample_batch_dev(nncf_sampler_t* s, int64_t n, int32_t* out_dev, void* stream);
+/* n draws into a host buffer (the drop-in for NodeSampler::sample_batch(int n, int* result)); synchronous */
+int nncf_sampler_sample_batch_host(nncf_sampler_t* s, int64_t n, int32_t* out_host);
+/* position the stream explicitly (multi-GPU: same key, disjoint counter ranges per rank) */
+int nncf_sampler_seek(nncf_sampler_t* s, uint64_t counter);
+/* copies the alias table to host for inspection by tests: prob[dist_size] (float), alias[dist_size] (int32) */
+int nncf_sampler_export_table(nncf_sampler_t* s, float* prob_host, int32_t* alias_host);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Batch-index builders.   ref: configs/data_utils.py:218-241 (group_shuffle_train), the per-scheme
+ *     assembly in models/train_original.py:49-56 and models/train_group_sample.py:75-85.
+ *     The three permutations come from the host's shared random stream (same draw order as the
+ *     reference); the device does the gathers, the STABLE sort by key and the chop-block permutation.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[r, :] = train[row_perm[r], :]            (np.random.shuffle(train), train rows are int32[3]) */
+int nncf_permute_rows(const int32_t* train_dev, int64_t n_rows, const int64_t* row_perm_dev, int32_t* out_dev,
+                      void* stream);
+size_t nncf_group_shuffle_workspace_bytes(int64_t n_rows, int64_t n_keys);
+/* Full group_shuffle_train: key[r] = iidx[train[row_perm[r], col]]; stable sort by key; if chop > 0 the
+ * first (n_rows / chop) blocks of `chop` rows are permuted by block_perm (out block b = sorted block
+ * block_perm[b]) and the tail is appended unshuffled.  iidx_dev holds the ALREADY shuffled iidx array. */
+int nncf_group_shuffle(const int32_t* train_dev, int64_t n_rows, int col, const int64_t* iidx_dev, int64_t n_keys,
+                       const int64_t* row_perm_dev, const int64_t* block_perm_dev, int chop, int32_t* out_dev,
+                       void* workspace_dev, size_t workspace_bytes, void* stream);
+/* (1+k)B-row batch of the 'original' / 'group_sample' schemes: rows [0,B) = positives; row B + p*k + n is
+ * positive p with column `neg_col` (1 = item, 0 = user) replaced by negs[p*k + n] and column 2 by neg_sign. */
+int nncf_assemble_pairs_batch(const int32_t* pos_dev, int B, int k, const int32_t* negs_dev, int neg_col,
+                              int neg_sign, int32_t* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (3) Fused training step.   ref: models/model_framework.py:40-65,85-143 (graph), modules/interaction/
+ *     interaction_dot.py:92-107 (scores), utils/objectives.py:35-220 (losses), utils/utilities.py:122-135
+ *     (activity regulariser), utils/optimizer.py:108-147 (lazy Adam); driven like Keras'
+ *     Model.train_on_batch([user_ids, item_ids], [response]) at models/train_neg_shared.py:50.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t scheme;          /* NNCF_SCHEME_*  (PAIRS = row-wise 'mul' view used by original / group_sample) */
+  int32_t loss;            /* NNCF_LOSS_* */
+  int32_t precision;       /* NNCF_PREC_* */
+  int32_t batch_size_p;    /* B: positives per batch */
+  int32_t num_negatives;   /* k (PAIRS scheme only: the batch has (1+k)B rows) */
+  int32_t dim;             /* d = user_dim = item_dim, 1..256 */
+  int32_t norm_u;          /* l2-normalise user rows (emb_normalization, model_framework.py:62-63) */
+  int32_t norm_v;          /* l2-normalise item rows (model_framework.py:109-111; not for 'mf') */
+  int32_t optimizer;       /* NNCF_OPT_* */
+  int32_t replicas;        /* R >= 1 independent batches per call (synchronous data-parallel virtual workers
+                              on one GPU; R = 1 is the reference's sequential loop) */
+  float neg_loss_weight;   /* lambda */
+  float loss_gamma;        /* gamma */
+  float u_reg;             /* activity L2 on the un-normalised user rows */
+  float learn_rate;
+  float beta1, beta2, epsilon;   /* lazy Adam */
+} nncf_step_config;
+
+typedef struct nncf_trainer nncf_trainer_t;
+int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t** out);
+int nncf_trainer_destroy(nncf_trainer_t* t);
+
+/* Embedding-table operands of one step.  Any of the *_m / *_v pointers may be NULL unless optimizer is
+ * LAZY_ADAM.  If item_table is NULL the item side is "dense": item_rows_dev [n_cols, d] holds the item
+ * embeddings produced by a framework tower (mean-pool/CNN/RNN) for the batch's columns and the item
+ * gradient is only returned (grad_item_rows_dev), never applied. */
+typedef struct {
+  float* user_table;  float* user_m;  float* user_v;   int64_t n_users;
+  float* item_table;  float* item_m;  float* item_v;   int64_t n_items;
+} nncf_tables;
+
+/* Runs `n_steps` consecutive steps; step s, replica r reads ids at  ids + (s * R + r) * rows_per_batch,
+ * rows_per_batch = B (matmul schemes) or (1+k)B (PAIRS).  loss_out_dev[n_steps * R] receives each batch's
+ * loss (task loss + regulariser = what Keras' train_on_batch returns).  Lazy Adam's step counter t is kept
+ * in the handle (advanced once per step).
+ * Optional outputs of the LAST step, replica 0 (NULL to skip), used by parity tests and by framework
+ * towers: grad_user_rows_dev [rows, d] and grad_item_rows_dev [n_cols, d] are dLoss/d(raw gathered row),
+ * per batch position (duplicates not merged); n_cols = rows (neg_shared, PAIRS) or n_unique
+ * (group_neg_shared; unique_ids_dev[B], inverse_dev[B], n_unique_dev[1] receive tf.unique's outputs). */
+typedef struct {
+  float* loss_out_dev;
+  float* grad_user_rows_dev;
+  float* grad_item_rows_dev;
+  int32_t* unique_ids_dev;
+  int32_t* inverse_dev;
+  int32_t* n_unique_dev;
+  const float* item_rows_dev;     /* dense item side only: [n_cols, d] */
+} nncf_step_io;
+
+int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,
+                     const int32_t* item_ids_dev, int64_t n_steps, const nncf_step_io* io, void* stream);
+/* tf.unique on device (first-occurrence order), exposed because group_neg_shared towers need it before
+ * they can produce item_rows_dev.   ref: models/model_framework.py:45-48 */
+int nncf_unique_first_occurrence(const int32_t* ids_dev, int n, int32_t* unique_ids_dev, int32_t* inverse_dev,
+                                 int32_t* n_unique_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (4) Mean-of-word-vectors item encoder.   ref: modules/content/mean_pool.py:27-33 (AverageEmbeddings:
+ *     mean over ALL L positions, pad id 0 included) on word rows gathered per models/model_framework.py:51-56.
+ * ---------------------------------------------------------------------------------------------- */
+/* out[n, :] = mean_l word_table[content[item_ids[n], l], :]    (item_ids may be NULL: rows 0..n-1) */
+int nncf_meanpool_fwd(const float* word_table_dev, int word_dim, const int32_t* content_dev, int content_len,
+                      const int32_t* item_ids_dev, int n_items, float* out_dev, void* stream);
+/* grad_word_table[content[item_ids[n], l], :] += grad_out[n, :] / L   (atomic scatter-add) */
+int nncf_meanpool_bwd(float* grad_word_table_dev, int word_dim, const int32_t* content_dev, int content_len,
+                      const int32_t* item_ids_dev, int n_items, const float* grad_out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (5) Evaluation.   ref: utils/objectives.py:296-321 (test_eval_mat: all users x candidate items),
+ *     utils/metrics_ranking.py:6-35 (eval_multiple), utils/objectives.py:333-370 (evaluate_mat),
+ *     utils/objectives.py:231-294 + utils/metrics_ranking.py:38-61 (given@-1).
+ * ---------------------------------------------------------------------------------------------- */
+size_t nncf_eval_topk_workspace_bytes(int64_t n_users, int64_t n_items, int dim, int topk, int precision);
+/* For each of n_users rows of user_rows_dev [n_users, d] score all n_items rows of item_rows_dev
+ * [n_items, d] and return the k best columns: topk_ids_dev [n_users, k] (column index into item_rows),
+ * topk_scores_dev [n_users, k]; order = score descending, ties by LOWEST column index.  The score matrix
+ * is never written to memory. */
+int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const float* item_rows_dev, int64_t n_items, int dim,
+                   int topk, int precision, int32_t* topk_ids_dev, float* topk_scores_dev, void* workspace_dev,
+                   size_t workspace_bytes, void* stream);
+/* Ranking metrics from top-k ids and CSR truth (truth_indptr [n_users+1], truth_cols sorted ascending within a
+ * row, in candidate-column space).  per_user_dev [n_users, 3] = (AP@k, recall@k, precision@k), zeros for users
+ * with no relevant candidate; sums_dev[4] (double) = (sum AP, sum recall, sum precision, #users kept). */
+int nncf_eval_metrics(const int32_t* topk_ids_dev, int64_t n_users, int topk, const int64_t* truth_indptr_dev,
+                      const int32_t* truth_cols_dev, float* per_user_dev, double* sums_dev, void* stream);
+/* given@k: scores of listed (user, item) pairs = row-wise dot (interaction_dot.py:92-99). */
+int nncf_score_pairs(const float* user_table_dev, const float* item_table_dev, int dim, const int32_t* user_ids_dev,
+                     const int32_t* item_ids_dev, int64_t n_pairs, float* scores_dev, void* stream);
+/* given@-1 metrics: pairs grouped by user (seg_indptr [n_groups+1] over the pair list), full descending sort per
+ * group (ties: lowest position first), AP over the whole list and AUC (Mann-Whitney, average ranks).
+ * per_group_dev [n_groups, 2] = (AP, AUC). */
+int nncf_eval_given(const float* scores_dev, const int32_t* truth_dev, const int64_t* seg_indptr_dev, int64_t n_groups,
+                    float* per_group_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NNCF_B200_H */

@@ -1,0 +1,1220 @@
+// train_step.cu — fused training step of the sampling-and-scoring loop.
+//
+// One step on R independent batches (replicas):
+//   [unique_kernel]      group_neg_shared only: tf.unique (first-occurrence order) of the item ids
+//   gather_rows_kernel   ids -> rows: fp32 staging (l2-normalised if asked), bf16 "tile image" for the tensor
+//                        cores, 1/||x||, zeroed gradient accumulators                       (HBM-bound part)
+//   [pos_score_kernel]   pairwise losses: positive score per column / per row
+//   score_grad_*         S = U V^T tile by tile, loss + dL/dS in the epilogue, dU = G V, dV = G^T U; the
+//                        score matrix lives in TMEM / registers only                       (tensor-bound part)
+//   finalize_kernel      positive/diagonal corrections, l2-normalise backward, activity regulariser,
+//                        sparse SGD scatter-add (atomics) or row gradients for lazy Adam    (HBM-bound part)
+//   [adam kernels]       duplicate-summing + lazy Adam on the touched rows
+// The PAIRS scheme ('original' / 'group_sample': row-wise dot on (1+k)B listed pairs) has its own two kernels.
+//
+// ref: models/model_framework.py:40-65,85-143; modules/interaction/interaction_dot.py:92-107;
+//      utils/objectives.py:35-220; utils/utilities.py:122-135; utils/optimizer.py:108-147.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace nncf {
+
+// =================================================================================================
+// tf.unique (first occurrence order), one block per replica.   ref: models/model_framework.py:45-48
+// =================================================================================================
+constexpr int kUniqueThreads = 1024;
+
+__global__ void __launch_bounds__(kUniqueThreads)
+unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, int32_t* __restrict__ uniq_all,
+              int32_t* __restrict__ inv_all, int32_t* __restrict__ nuniq_all, int out_stride) {
+  extern __shared__ int32_t sm[];
+  int32_t* s_ids = sm;            // [n]
+  int32_t* s_first = sm + n;      // [n]
+  int32_t* s_rank = sm + 2 * n;   // [n]
+  __shared__ int s_warp_tot[32];
+  __shared__ int s_carry;
+  const int r = blockIdx.x;
+  const int32_t* ids = ids_all + r * ids_stride;
+  int32_t* uniq = uniq_all + (int64_t)r * out_stride;
+  int32_t* inv = inv_all + (int64_t)r * out_stride;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < n; i += blockDim.x) s_ids[i] = ids[i];
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int32_t me = s_ids[i];
+    int f = i;
+    for (int j = 0; j < i; ++j)
+      if (s_ids[j] == me) { f = j; break; }
+    s_first[i] = f;
+  }
+  __syncthreads();
+  // exclusive scan of is_first flags, chunk by chunk
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int i = base + tid;
+    const int flag = (i < n && s_first[i] == i) ? 1 : 0;
+    int x = flag;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int t = (lane < nwarps) ? s_warp_tot[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xffffffffu, t, o);
+        if (lane >= o) t += y;
+      }
+      s_warp_tot[lane] = t;   // inclusive over warps
+    }
+    __syncthreads();
+    const int warp_off = (warp == 0) ? 0 : s_warp_tot[warp - 1];
+    const int excl = s_carry + warp_off + x - flag;
+    if (i < n) s_rank[i] = excl;
+    __syncthreads();
+    if (tid == 0) s_carry += s_warp_tot[nwarps - 1];
+    __syncthreads();
+  }
+  for (int i = tid; i < n; i += blockDim.x) {
+    const int f = s_first[i];
+    inv[i] = s_rank[f];
+    if (f == i) uniq[s_rank[i]] = s_ids[i];
+  }
+  if (tid == 0) nuniq_all[r] = s_carry;
+}
+
+// =================================================================================================
+// gather rows -> staging.  One warp per (padded) row.
+// =================================================================================================
+struct GatherArgs {
+  const float* table;        // [n_rows_table, d] or NULL
+  const float* dense_rows;   // [count, d] (used when table == NULL)
+  const int32_t* ids;        // [R][ids_stride] (ignored for dense rows)
+  int64_t ids_stride;
+  const int32_t* count_dev;  // optional per-replica valid-row count (group_neg_shared n_unique), else NULL
+  int count;                 // valid rows when count_dev == NULL
+  int rows_pad;              // rows per replica in the staging buffers (multiple of 128)
+  int d, dp;                 // true / padded dim
+  int normalize;
+  int write_img;
+  float* Xf;                 // [R][rows_pad][dp]
+  float* inv;                // [R][rows_pad]
+  uint8_t* img;              // [R][rows_pad/128][dp/64][16 KiB]
+  float* dX;                 // [R][rows_pad][dp]  zeroed here
+  float* corr;               // [R][rows_pad]      zeroed here
+};
+
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(GatherArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int r = blockIdx.y;
+  if (row >= a.rows_pad) return;
+  const int count = a.count_dev ? a.count_dev[r] : a.count;
+  const int nchunk = a.dp / 64;
+  float x[8];   // columns 2*lane + 64*m (+1) for m < nchunk (dp <= 256)
+#pragma unroll
+  for (int m = 0; m < 8; ++m) x[m] = 0.0f;
+  if (row < count) {
+    const float* src;
+    if (a.table) {
+      const int64_t id = a.ids[r * a.ids_stride + row];
+      src = a.table + id * a.d;
+    } else {
+      src = a.dense_rows + (int64_t)row * a.d;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m < nchunk) {
+        const int c = m * 64 + 2 * lane;
+        if (c < a.d) x[2 * m] = __ldg(src + c);
+        if (c + 1 < a.d) x[2 * m + 1] = __ldg(src + c + 1);
+      }
+    }
+  }
+  float inv = 1.0f;
+  if (a.normalize) {
+    float ss = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) ss += x[m] * x[m];
+    ss = warp_sum(ss);
+    inv = rsqrtf(fmaxf(ss, 1e-12f));   // tf.nn.l2_normalize: x * rsqrt(max(sum(x^2), 1e-12))
+    if (row >= count) inv = 1.0f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) x[m] *= inv;
+  }
+  const int64_t rowoff = ((int64_t)r * a.rows_pad + row);
+  float* xf = a.Xf + rowoff * a.dp;
+  float* dx = a.dX + rowoff * a.dp;
+#pragma unroll
+  for (int m = 0; m < 4; ++m) {
+    if (m < nchunk) {
+      const int c = m * 64 + 2 * lane;
+      *reinterpret_cast<float2*>(xf + c) = make_float2(x[2 * m], x[2 * m + 1]);
+      *reinterpret_cast<float2*>(dx + c) = make_float2(0.0f, 0.0f);
+    }
+  }
+  if (lane == 0) {
+    a.inv[rowoff] = inv;
+    a.corr[rowoff] = 0.0f;
+  }
+  if (a.write_img) {
+    uint8_t* blk = a.img + ((int64_t)r * (a.rows_pad / 128) + (row >> 7)) * nchunk * kSubBytes;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      if (m < nchunk) {
+        uint8_t* p = blk + m * kSubBytes + sw128_offset(row & 127, 2 * lane);
+        *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(x[2 * m], x[2 * m + 1]);
+      }
+    }
+  }
+}
+
+// positive score per batch row:  spos[b] = <U_b, V_pos(b)>  (pos(b) = b for neg_shared, inverse[b] for group).
+// In bf16 mode the operands are rounded to bf16 first so the value matches what the tensor cores see.
+__global__ void __launch_bounds__(256)
+pos_score_kernel(const float* __restrict__ Uf, const float* __restrict__ Vf, const int32_t* __restrict__ inverse,
+                 int rows_pad, int dp, int B, int round_bf16, float* __restrict__ spos) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  const int r = blockIdx.y;
+  if (b >= B) return;
+  const int64_t base = (int64_t)r * rows_pad;
+  const int p = inverse ? inverse[base + b] : b;
+  const float* u = Uf + (base + b) * dp;
+  const float* v = Vf + (base + p) * dp;
+  float acc = 0.0f;
+  for (int c = lane; c < dp; c += 32) {
+    float a = u[c], w = v[c];
+    if (round_bf16) { a = __bfloat162float(__float2bfloat16(a)); w = __bfloat162float(__float2bfloat16(w)); }
+    acc += a * w;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) spos[base + b] = acc;
+}
+
+// =================================================================================================
+// score + gradient tiles, CUDA-core fp32 path (precision = fp32).  CTA = 64 x 64 tile of S.
+// =================================================================================================
+struct ScoreArgs {
+  const float* Uf; const float* Vf;      // [R][rows_pad][dp]
+  const uint8_t* Uimg; const uint8_t* Vimg;
+  float* dU; float* dV;                  // [R][rows_pad][dp]
+  float* corrU; float* corrV;            // [R][rows_pad]
+  const float* spos;                     // [R][rows_pad]
+  const int32_t* inverse;                // [R][rows_pad] (group) or NULL
+  const int32_t* ncols_dev;              // [R] (group) or NULL
+  double* loss;                          // [R]
+  int rows_pad, dp, B, scheme, loss_kind;
+  float lambda, gamma;
+};
+
+constexpr int kSimtTile = 64;
+
+__global__ void __launch_bounds__(256)
+score_grad_simt_kernel(ScoreArgs a) {
+  extern __shared__ float smf[];
+  const int dp = a.dp, ld = dp + 1;
+  float* Us = smf;                       // [64][ld]
+  float* Vs = Us + kSimtTile * ld;       // [64][ld]
+  float* Gs = Vs + kSimtTile * ld;       // [64][65]
+  __shared__ float s_colA[kSimtTile];
+  __shared__ float s_rowA[kSimtTile];
+  __shared__ float s_loss[8];
+  const int r = blockIdx.z;
+  const int ncols = a.ncols_dev ? a.ncols_dev[r] : a.B;
+  const int i0 = blockIdx.y * kSimtTile, j0 = blockIdx.x * kSimtTile;
+  if (j0 >= ncols) return;
+  const int tid = threadIdx.x;
+  const int64_t base = (int64_t)r * a.rows_pad;
+  for (int idx = tid; idx < kSimtTile * dp; idx += 256) {
+    const int rr = idx / dp, c = idx - rr * dp;
+    Us[rr * ld + c] = a.Uf[(base + i0 + rr) * dp + c];
+    Vs[rr * ld + c] = a.Vf[(base + j0 + rr) * dp + c];
+  }
+  if (tid < kSimtTile) { s_colA[tid] = 0.0f; s_rowA[tid] = 0.0f; }
+  __syncthreads();
+  const int ty = tid >> 4, tx = tid & 15;
+  float acc[4][4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x)
+#pragma unroll
+    for (int y = 0; y < 4; ++y) acc[x][y] = 0.0f;
+  for (int k = 0; k < dp; ++k) {
+    float u[4], v[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) { u[x] = Us[(ty * 4 + x) * ld + k]; v[x] = Vs[(tx * 4 + x) * ld + k]; }
+#pragma unroll
+    for (int x = 0; x < 4; ++x)
+#pragma unroll
+      for (int y = 0; y < 4; ++y) acc[x][y] = fmaf(u[x], v[y], acc[x][y]);
+  }
+  const EpiParams ep = make_epi(a.scheme, a.loss_kind, a.B, ncols, a.lambda, a.gamma);
+  const bool pairwise = a.loss_kind >= NNCF_LOSS_LOG_LOSS;
+  float lsum = 0.0f;
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int il = ty * 4 + x, i = i0 + il;
+    const int posc = (a.scheme == NNCF_SCHEME_GROUP_NEG_SHARED && i < a.B) ? a.inverse[base + i] : i;
+#pragma unroll
+    for (int y = 0; y < 4; ++y) {
+      const int jl = tx * 4 + y, j = j0 + jl;
+      float g = 0.0f, av = 0.0f, l = 0.0f;
+      if (i < a.B && j < ncols) {
+        float sp = 0.0f;
+        if (pairwise) sp = (a.scheme == NNCF_SCHEME_NEG_SHARED) ? a.spos[base + j] : a.spos[base + i];
+        epi_elem<false>(ep, acc[x][y], j == posc, sp, g, av, l);
+        lsum += l;
+        if (pairwise) {
+          if (a.scheme == NNCF_SCHEME_NEG_SHARED) atomicAdd(&s_colA[jl], av);
+          else atomicAdd(&s_rowA[il], av);
+        }
+      }
+      Gs[il * 65 + jl] = g;
+    }
+  }
+  lsum = warp_sum(lsum);
+  if ((tid & 31) == 0) s_loss[tid >> 5] = lsum;
+  __syncthreads();
+  if (tid == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += s_loss[w];
+    atomicAdd(&a.loss[r], static_cast<double>(t));
+  }
+  if (pairwise && tid < kSimtTile) {
+    if (a.scheme == NNCF_SCHEME_NEG_SHARED) { if (j0 + tid < ncols) atomicAdd(&a.corrV[base + j0 + tid], s_colA[tid]); }
+    else { if (i0 + tid < a.B) atomicAdd(&a.corrU[base + i0 + tid], s_rowA[tid]); }
+  }
+  // dU[i][k] += sum_j G[i][j] V[j][k];  dV[j][k] += sum_i G[i][j] U[i][k]
+  for (int idx = tid; idx < kSimtTile * dp; idx += 256) {
+    const int rr = idx / dp, c = idx - rr * dp;
+    float su = 0.0f, sv = 0.0f;
+    for (int t = 0; t < kSimtTile; ++t) {
+      su = fmaf(Gs[rr * 65 + t], Vs[t * ld + c], su);
+      sv = fmaf(Gs[t * 65 + rr], Us[t * ld + c], sv);
+    }
+    if (i0 + rr < a.B) atomicAdd(&a.dU[(base + i0 + rr) * dp + c], su);
+    if (j0 + rr < ncols) atomicAdd(&a.dV[(base + j0 + rr) * dp + c], sv);
+  }
+}
+
+// =================================================================================================
+// score + gradient tiles, tcgen05 path (precision = bf16).
+//   CTA (ib, r): owns the 128-row block ib of U of replica r and sweeps all 128-column blocks j:
+//     MMA1  S_j   = U_ib V_j^T        (A,B K-major)              -> TMEM S buffer
+//     epi   G_j   = dL/dS_j           (TMEM -> regs -> bf16 -> swizzled smem tile image), loss, corrections
+//     MMA2  dU_ib += G_j  V_j         (A K-major, B MN-major)    -> TMEM accumulator, drained once at the end
+//     MMA3  dV_j   = G_j^T U_ib       (A,B MN-major)             -> TMEM, drained per tile with red.global.add.v4
+//   warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp & 3).
+// =================================================================================================
+constexpr int kTcThreads = 64 + 32 * kEpiWarps;
+
+template <int NSUB>
+struct TcCfg {
+  static constexpr int DP = 64 * NSUB;
+  static constexpr bool kPipelined = (NSUB <= 2);
+  static constexpr int kStages = kPipelined ? 2 : 1;    // V tile stages
+  static constexpr int kSBufs = kPipelined ? 2 : 1;     // S accumulators in TMEM
+  static constexpr int kGBufs = kPipelined ? 2 : 1;     // G tiles in smem
+  static constexpr int kColS = 0;
+  static constexpr int kColDU = kPipelined ? 256 : 128;
+  static constexpr int kColDV = 384;
+  static constexpr int kDvChunks = (DP + 127) / 128;
+  static constexpr size_t kSmemBytes =
+      (size_t)NSUB * kSubBytes * (1 + kStages) + (size_t)kGBufs * 2 * kSubBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int NSUB>
+__global__ void __launch_bounds__(kTcThreads, 1)
+score_grad_tc_kernel(ScoreArgs a) {
+  using C = TcCfg<NSUB>;
+  constexpr int DP = C::DP;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sU = smem;
+  uint8_t* sV = sU + NSUB * kSubBytes;
+  uint8_t* sG = sV + C::kStages * NSUB * kSubBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * 2 * kSubBytes);
+  uint64_t* u_full = bars + 0;
+  uint64_t* v_full = bars + 1;      // [2]
+  uint64_t* v_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_empty = bars + 7;     // [2]
+  uint64_t* g_full = bars + 9;      // [2]
+  uint64_t* g_empty = bars + 11;    // [2]
+  uint64_t* dv_full = bars + 13;
+  uint64_t* dv_empty = bars + 14;
+  uint64_t* du_full = bars + 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ib = blockIdx.x, r = blockIdx.y;
+  const int ncols = a.ncols_dev ? a.ncols_dev[r] : a.B;
+  const int nj = (ncols + 127) >> 7;
+  const int nblk = a.rows_pad >> 7;
+  const int64_t base = (int64_t)r * a.rows_pad;
+  const uint8_t* gU = a.Uimg + ((int64_t)r * nblk + ib) * NSUB * kSubBytes;
+  const uint8_t* gV = a.Vimg + (int64_t)r * nblk * NSUB * kSubBytes;
+
+  if (tid == 0) {
+    mbar_init(u_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kEpiWarps);
+      mbar_init(&g_full[s], kEpiWarps); mbar_init(&g_empty[s], 1);
+    }
+    mbar_init(dv_full, 1); mbar_init(dv_empty, kEpiWarps); mbar_init(du_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      mbar_expect_tx(u_full, NSUB * kSubBytes);
+      for (int s = 0; s < NSUB; ++s) bulk_g2s(sU + s * kSubBytes, gU + (size_t)s * kSubBytes, kSubBytes, u_full);
+      for (int j = 0; j < nj; ++j) {
+        const int st = j % C::kStages;
+        const uint32_t use = j / C::kStages;
+        mbar_wait(&v_empty[st], (use & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
+        for (int s = 0; s < NSUB; ++s)
+          bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + ((size_t)j * NSUB + s) * kSubBytes, kSubBytes, &v_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_du = make_idesc_bf16(128, DP, 0, 1);
+      auto issue_mma1 = [&](int j) {
+        const int st = j % C::kStages, sb = j % C::kSBufs;
+        mbar_wait(&v_full[st], (j / C::kStages) & 1);
+        mbar_wait(&s_empty[sb], ((j / C::kSBufs) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k) {
+          const uint64_t ad = make_smem_desc(smem_u32(sU + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(sV + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem + C::kColS + sb * 128, ad, bd, idesc_s, k > 0);
+        }
+        umma_commit(&s_full[sb]);
+      };
+      mbar_wait(u_full, 0);
+      if (nj > 0) issue_mma1(0);
+      uint32_t dv_use = 0;
+      for (int j = 0; j < nj; ++j) {
+        const int st = j % C::kStages, gb = j % C::kGBufs;
+        if (C::kPipelined && j + 1 < nj) issue_mma1(j + 1);
+        mbar_wait(&g_full[gb], (j / C::kGBufs) & 1);
+        tc_fence_after();
+        const uint8_t* g = sG + gb * 2 * kSubBytes;
+        const uint8_t* v = sV + st * NSUB * kSubBytes;
+        // MMA2: dU += G_j V_j   (K = 128 columns j of this tile)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint64_t ad = make_smem_desc(smem_u32(g + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(v) + k * 2048, kSubBytes, 1024);
+          umma_bf16(tmem + C::kColDU, ad, bd, idesc_du, (j > 0) || (k > 0));
+        }
+        // MMA3: dV_j = G_j^T U   in N-chunks of <= 128 columns
+        for (int c = 0; c < C::kDvChunks; ++c) {
+          const int width = (DP - c * 128) < 128 ? (DP - c * 128) : 128;
+          const uint32_t idesc_dv = make_idesc_bf16(128, width, 1, 1);
+          mbar_wait(dv_empty, (dv_use & 1) ^ 1);
+          tc_fence_after();
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t ad = make_smem_desc(smem_u32(g) + k * 2048, kSubBytes, 1024);
+            const uint64_t bd = make_smem_desc(smem_u32(sU + c * 2 * kSubBytes) + k * 2048, kSubBytes, 1024);
+            umma_bf16(tmem + C::kColDV, ad, bd, idesc_dv, k > 0);
+          }
+          umma_commit(dv_full);
+          ++dv_use;
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&g_empty[gb]);
+        if (!C::kPipelined && j + 1 < nj) issue_mma1(j + 1);
+      }
+      umma_commit(du_full);
+    }
+  } else {
+    // ---------------------------------------------------------------- epilogue warps
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int il = q * 32 + lane;               // row inside the 128-row block
+    const int i = ib * 128 + il;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const EpiParams ep = make_epi(a.scheme, a.loss_kind, a.B, ncols > 1 ? ncols : 2, a.lambda, a.gamma);
+    const bool pairwise = a.loss_kind >= NNCF_LOSS_LOG_LOSS;
+    const bool is_group = a.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
+    const bool row_ok = i < a.B;
+    const int posc = (is_group && row_ok) ? a.inverse[base + i] : i;
+    const float spos_row = (pairwise && is_group && row_ok) ? a.spos[base + i] : 0.0f;
+    float lsum = 0.0f, rowA = 0.0f;
+    uint32_t dv_use = 0;
+
+    auto drain_dv = [&](int j) {
+      for (int c = 0; c < C::kDvChunks; ++c) {
+        const int width = (DP - c * 128) < 128 ? (DP - c * 128) : 128;
+        mbar_wait(dv_full, dv_use & 1);
+        tc_fence_after();
+        const int jrow = j * 128 + il;
+        float* dst = a.dV + (base + jrow) * DP + c * 128;
+        for (int c0 = 0; c0 < width; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem + lane_addr + C::kColDV + c0, v);
+          tmem_ld_wait();
+          if (jrow < ncols) {
+#pragma unroll
+            for (int t = 0; t < 32; t += 4) red_add_v4(dst + c0 + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dv_empty);
+        ++dv_use;
+      }
+    };
+
+    for (int j = 0; j < nj; ++j) {
+      const int sb = j % C::kSBufs, gb = j % C::kGBufs;
+      mbar_wait(&s_full[sb], (j / C::kSBufs) & 1);
+      tc_fence_after();
+      mbar_wait(&g_empty[gb], ((j / C::kGBufs) & 1) ^ 1);
+      uint8_t* g = sG + gb * 2 * kSubBytes;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + lane_addr + C::kColS + sb * 128 + c0, v);
+        tmem_ld_wait();
+        float av[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int jc = j * 128 + c0 + t;
+          float gg = 0.0f, aa = 0.0f, ll = 0.0f;
+          if (row_ok && jc < ncols) {
+            float sp = spos_row;
+            if (pairwise && !is_group) sp = __ldg(a.spos + base + jc);
+            epi_elem<true>(ep, v[t], jc == posc, sp, gg, aa, ll);
+          }
+          lsum += ll;
+          v[t] = gg;
+          av[t] = aa;
+        }
+        // G -> bf16 -> swizzled smem: 32 consecutive columns = four 16-byte chunks of row il
+        {
+          uint8_t* sub = g + (c0 >> 6) * kSubBytes + il * 128;
+          const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            uint4 pk;
+            pk.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+            pk.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+            pk.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+            pk.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+            *reinterpret_cast<uint4*>(sub + (((chunk0 + ch) ^ (il & 7)) << 4)) = pk;
+          }
+        }
+        if (pairwise) {
+          if (is_group) {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) rowA += av[t];
+          } else {
+            // column sums of A over the 32 rows of this warp: recursive-halving transpose-reduce (31 shuffles)
+#pragma unroll
+            for (int h = 16; h >= 1; h >>= 1) {
+              const bool upper = (lane & h) != 0;
+#pragma unroll
+              for (int t = 0; t < h; ++t) {
+                const float mine = upper ? av[t + h] : av[t];
+                const float send = upper ? av[t] : av[t + h];
+                av[t] = mine + __shfl_xor_sync(0xffffffffu, send, h);
+              }
+            }
+            // lane now holds the sum of column (bit-reversal-free mapping): column index = lane's bits pick halves
+            int col = 0;
+#pragma unroll
+            for (int h = 16; h >= 1; h >>= 1) col += (lane & h) ? h : 0;
+            const int jc = j * 128 + c0 + col;
+            if (jc < ncols) atomicAdd(a.corrV + base + jc, av[0]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_full[gb]);
+      if (j > 0) drain_dv(j - 1);
+    }
+    if (nj > 0) drain_dv(nj - 1);
+    // final: dU block
+    mbar_wait(du_full, 0);
+    tc_fence_after();
+    if (nj > 0) {
+      float* dst = a.dU + (base + i) * DP;
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + lane_addr + C::kColDU + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int t = 0; t < 32; t += 4)
+            *reinterpret_cast<float4*>(dst + c0 + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+        }
+      }
+    }
+    if (pairwise && is_group && row_ok) a.corrU[base + i] = rowA;
+    lsum = warp_sum(lsum);
+    if (lane == 0) atomicAdd(&a.loss[r], static_cast<double>(lsum));
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// =================================================================================================
+// finalize: corrections, normalise-backward, regulariser, optimizer.  One warp per batch row.
+// =================================================================================================
+struct FinalizeArgs {
+  int side;                  // 0 = user rows, 1 = item rows
+  int scheme, pairwise;
+  const float* Xf;           // this side's staged rows        [R][rows_pad][dp]
+  const float* Of;           // the other side's staged rows
+  const float* inv;          // this side's 1/||x||
+  float* dX;                 // this side's gradient accumulators (finalised in place)
+  float* dO;                 // other side's accumulators (group pairwise: user side adds into item rows)
+  const float* corr_self;    // group: corrU (side 0).  neg_shared: corrV (both sides use the column sums)
+  const int32_t* inverse;    // group: [R][rows_pad]
+  const int32_t* count_dev;  // per-replica valid rows (group item side) or NULL
+  int count;
+  int rows_pad, d, dp;
+  int normalize;
+  float reg_scale;           // 2 * u_reg / rows  (user side) else 0
+  // optimizer
+  int optimizer;
+  float lr;
+  float* table;
+  const int32_t* ids; int64_t ids_stride;      // table row of each batch row
+  float* grad_out;           // optional [count][d] copy of the final row gradients (replica 0 only)
+};
+
+__global__ void __launch_bounds__(256)
+finalize_kernel(FinalizeArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  const int r = blockIdx.y;
+  const int count = a.count_dev ? a.count_dev[r] : a.count;
+  if (row >= count) return;
+  const int64_t base = (int64_t)r * a.rows_pad;
+  const float* x = a.Xf + (base + row) * a.dp;
+  float* dx = a.dX + (base + row) * a.dp;
+  float g[8], xv[8];
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int c = lane + 32 * m;
+    g[m] = (c < a.dp) ? dx[c] : 0.0f;
+    xv[m] = (c < a.dp) ? x[c] : 0.0f;
+  }
+  if (a.pairwise) {
+    if (a.scheme == NNCF_SCHEME_NEG_SHARED) {
+      // G[j,j] += colsum_j  =>  dU_j += colsum_j V_j ; dV_j += colsum_j U_j
+      const float cs = a.corr_self[base + row];
+      const float* o = a.Of + (base + row) * a.dp;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int c = lane + 32 * m;
+        if (c < a.dp) g[m] = fmaf(cs, o[c], g[m]);
+      }
+    } else if (a.side == 0) {
+      // G[i,pos_i] += rowsum_i  =>  dU_i += rowsum_i V_pos ; dV_pos += rowsum_i U_i (atomic, item side runs later)
+      const float rs = a.corr_self[base + row];
+      const int p = a.inverse[base + row];
+      const float* o = a.Of + (base + p) * a.dp;
+      float* dop = a.dO + (base + p) * a.dp;
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int c = lane + 32 * m;
+        if (c < a.dp) {
+          g[m] = fmaf(rs, o[c], g[m]);
+          atomicAdd(dop + c, rs * xv[m]);
+        }
+      }
+    }
+  }
+  float invn = 1.0f;
+  if (a.normalize) {
+    invn = a.inv[base + row];
+    float dot = 0.0f;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) dot += g[m] * xv[m];
+    dot = warp_sum(dot);
+#pragma unroll
+    for (int m = 0; m < 8; ++m) g[m] = (g[m] - xv[m] * dot) * invn;
+  }
+  if (a.reg_scale != 0.0f) {
+    // regulariser acts on the UN-normalised row: x_raw = xhat / inv
+    const float s = a.reg_scale / invn;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) g[m] = fmaf(s, xv[m], g[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < 8; ++m) {
+    const int c = lane + 32 * m;
+    if (c < a.dp) dx[c] = g[m];
+  }
+  if (a.grad_out && r == 0) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int c = lane + 32 * m;
+      if (c < a.d) a.grad_out[(int64_t)row * a.d + c] = g[m];
+    }
+  }
+  if (a.optimizer == NNCF_OPT_SGD && a.table) {
+    const int64_t id = a.ids[r * a.ids_stride + row];
+    float* t = a.table + id * a.d;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+      const int c = lane + 32 * m;
+      if (c < a.d) atomicAdd(t + c, -a.lr * g[m]);
+    }
+  }
+}
+
+// =================================================================================================
+// lazy Adam on touched rows with duplicate summing.   ref: utils/optimizer.py:108-147
+//   owner[id] (direct-address scratch, INT_MAX when idle) = smallest global batch position holding id.
+// =================================================================================================
+__global__ void adam_owner_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int count,
+                                  const int32_t* __restrict__ count_dev, int rows_pad, int32_t* owner) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  const int cnt = count_dev ? count_dev[r] : count;
+  if (row >= cnt) return;
+  atomicMin(&owner[ids[r * ids_stride + row]], r * rows_pad + row);
+}
+// non-owner rows add their gradient into the owner's row
+__global__ void __launch_bounds__(256)
+adam_combine_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int count, const int32_t* __restrict__ count_dev,
+                    int rows_pad, int dp, const int32_t* __restrict__ owner, float* dX) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  const int cnt = count_dev ? count_dev[r] : count;
+  if (row >= cnt) return;
+  const int me = r * rows_pad + row;
+  const int own = owner[ids[r * ids_stride + row]];
+  if (own == me) return;
+  const float* src = dX + (int64_t)me * dp;
+  float* dst = dX + (int64_t)own * dp;
+  for (int c = lane; c < dp; c += 32) atomicAdd(dst + c, src[c]);
+}
+__global__ void __launch_bounds__(256)
+adam_apply_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int count, const int32_t* __restrict__ count_dev,
+                  int rows_pad, int d, int dp, int32_t* owner, const float* __restrict__ dX, float* table, float* m,
+                  float* v, float lr_t, float beta1, float beta2, float eps) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  const int cnt = count_dev ? count_dev[r] : count;
+  if (row >= cnt) return;
+  const int me = r * rows_pad + row;
+  const int64_t id = ids[r * ids_stride + row];
+  if (owner[id] != me) return;
+  const float* g = dX + (int64_t)me * dp;
+  for (int c = lane; c < d; c += 32) {
+    const int64_t o = id * d + c;
+    const float gg = g[c];
+    const float mm = beta1 * m[o] + (1.0f - beta1) * gg;
+    const float vv = beta2 * v[o] + (1.0f - beta2) * gg * gg;
+    m[o] = mm; v[o] = vv;
+    table[o] -= lr_t * mm / (sqrtf(vv) + eps);
+  }
+}
+__global__ void adam_reset_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int count,
+                                  const int32_t* __restrict__ count_dev, int32_t* owner) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  const int cnt = count_dev ? count_dev[r] : count;
+  if (row >= cnt) return;
+  owner[ids[r * ids_stride + row]] = 0x7fffffff;
+}
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// =================================================================================================
+// PAIRS scheme: row-wise dot on (1+k)B listed pairs.   ref: interaction_dot.py:92-99, objectives.py:35-75
+// =================================================================================================
+struct PairsArgs {
+  const float* EU; const float* EV;
+  const int32_t* uid; const int32_t* cid; int64_t ids_stride;
+  int B, k, d;
+  int norm_u, norm_v, loss_kind;
+  float lambda, gamma, u_reg;
+  float* s;        // [R][n]   scores
+  float* invu;     // [R][n]
+  float* invv;     // [R][n]
+  double* loss;    // [R]
+  // second pass
+  float* dUrows; float* dVrows;   // [R][n][d] final row gradients (optional unless Adam / grad_out)
+  int optimizer; float lr;
+  float* tableU; float* tableV;
+  float* grad_out_u; float* grad_out_v;
+};
+
+__global__ void __launch_bounds__(256)
+pairs_score_kernel(PairsArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = (1 + a.k) * a.B;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  if (row >= n) return;
+  const float* u = a.EU + (int64_t)a.uid[r * a.ids_stride + row] * a.d;
+  const float* v = a.EV + (int64_t)a.cid[r * a.ids_stride + row] * a.d;
+  float su = 0.0f, sv = 0.0f, dot = 0.0f;
+  for (int c = lane; c < a.d; c += 32) {
+    const float x = __ldg(u + c), y = __ldg(v + c);
+    su = fmaf(x, x, su); sv = fmaf(y, y, sv); dot = fmaf(x, y, dot);
+  }
+  su = warp_sum(su); sv = warp_sum(sv); dot = warp_sum(dot);
+  const float iu = a.norm_u ? rsqrtf(fmaxf(su, 1e-12f)) : 1.0f;
+  const float iv = a.norm_v ? rsqrtf(fmaxf(sv, 1e-12f)) : 1.0f;
+  if (lane == 0) {
+    const int64_t o = (int64_t)r * n + row;
+    a.s[o] = dot * iu * iv;
+    a.invu[o] = iu;
+    a.invv[o] = iv;
+    if (a.u_reg != 0.0f) atomicAdd(&a.loss[r], static_cast<double>(a.u_reg * su / n));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pairs_grad_kernel(PairsArgs a) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int B = a.B, k = a.k, n = (1 + k) * B;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  if (row >= n) return;
+  const float* S = a.s + (int64_t)r * n;
+  const float s = S[row];
+  const bool is_pos = row < B;
+  const float invB = 1.0f / B, w = a.lambda / k;
+  float g = 0.0f, l = 0.0f;
+  if (a.loss_kind == NNCF_LOSS_SKIP_GRAM) {
+    if (is_pos) { l = softplus_f<false>(-s) * invB; g = (sigmoid_f<false>(s) - 1.0f) * invB; }
+    else { l = w * softplus_f<false>(s) * invB; g = w * sigmoid_f<false>(s) * invB; }
+  } else if (a.loss_kind == NNCF_LOSS_MSE) {
+    if (is_pos) { l = (1.0f - s) * (1.0f - s) * invB; g = -2.0f * (1.0f - s) * invB; }
+    else { l = w * s * s * invB; g = 2.0f * w * s * invB; }
+  } else {
+    const float inv_cnt = 1.0f / (static_cast<float>(k) * B);
+    if (is_pos) {
+      // g+ = sum over this positive's k negatives of a_n (each lane takes some negatives)
+      float acc = 0.0f;
+      for (int t = lane; t < k; t += 32) {
+        const float dd = s - S[B + row * k + t];
+        if (a.loss_kind == NNCF_LOSS_LOG_LOSS) acc += -a.gamma * sigmoid_f<false>(-a.gamma * dd) * inv_cnt;
+        else acc += (a.gamma - dd > 0.0f) ? -inv_cnt : 0.0f;
+      }
+      g = warp_sum(acc);
+    } else {
+      const int p = (row - B) / k;
+      const float dd = S[p] - s;
+      if (a.loss_kind == NNCF_LOSS_LOG_LOSS) {
+        l = softplus_f<false>(-a.gamma * dd) * inv_cnt;
+        g = a.gamma * sigmoid_f<false>(-a.gamma * dd) * inv_cnt;
+      } else {
+        l = fmaxf(a.gamma - dd, 0.0f) * inv_cnt;
+        g = (a.gamma - dd > 0.0f) ? inv_cnt : 0.0f;
+      }
+    }
+  }
+  if (lane == 0 && l != 0.0f) atomicAdd(&a.loss[r], static_cast<double>(l));
+  const int64_t uidx = a.uid[r * a.ids_stride + row], cidx = a.cid[r * a.ids_stride + row];
+  const float* u = a.EU + uidx * a.d;
+  const float* v = a.EV + cidx * a.d;
+  const int64_t o = (int64_t)r * n + row;
+  const float iu = a.invu[o], iv = a.invv[o];
+  // dU_hat = g * V_hat, dV_hat = g * U_hat; then normalise-backward: dx = (dxhat - xhat (xhat . dxhat)) * inv
+  // with xhat . dxhat = g * s for both sides.
+  const float reg = 2.0f * a.u_reg / n;
+  for (int c = lane; c < a.d; c += 32) {
+    const float x = __ldg(u + c), y = __ldg(v + c);
+    const float xh = x * iu, yh = y * iv;
+    float du = g * yh, dv = g * xh;
+    if (a.norm_u) du = (du - xh * (g * s)) * iu;
+    if (a.norm_v) dv = (dv - yh * (g * s)) * iv;
+    du = fmaf(reg, x, du);
+    if (a.dUrows) { a.dUrows[o * a.d + c] = du; a.dVrows[o * a.d + c] = dv; }
+    if (a.grad_out_u && r == 0) a.grad_out_u[(int64_t)row * a.d + c] = du;
+    if (a.grad_out_v && r == 0) a.grad_out_v[(int64_t)row * a.d + c] = dv;
+  }
+}
+// SGD scatter for the PAIRS scheme runs as a second pass over the stored row gradients so that every
+// gradient of the step is computed from the same snapshot of the tables.
+__global__ void __launch_bounds__(256)
+rows_sgd_kernel(const float* __restrict__ rows, const int32_t* __restrict__ ids, int64_t ids_stride, int n, int d,
+                float lr, float* table) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  if (row >= n) return;
+  const float* g = rows + ((int64_t)r * n + row) * d;
+  float* t = table + (int64_t)ids[r * ids_stride + row] * d;
+  for (int c = lane; c < d; c += 32) atomicAdd(t + c, -lr * g[c]);
+}
+
+__global__ void loss_out_kernel(const double* __restrict__ loss, int R, float* out) {
+  const int r = threadIdx.x;
+  if (r < R) out[r] = static_cast<float>(loss[r]);
+}
+__global__ void reg_loss_kernel(const float* __restrict__ Uf, const float* __restrict__ inv, int rows_pad, int dp,
+                                int rows, float u_reg, double* loss) {
+  // u_reg * sum_d mean_b U_raw[b,d]^2, U_raw = Uf / inv        ref: utils/utilities.py:129-135
+  const int r = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const int64_t base = (int64_t)r * rows_pad + row;
+  const float* x = Uf + base * dp;
+  float ss = 0.0f;
+  for (int c = lane; c < dp; c += 32) ss = fmaf(x[c], x[c], ss);
+  ss = warp_sum(ss);
+  if (lane == 0) {
+    const float iv = inv[base];
+    atomicAdd(&loss[r], static_cast<double>(u_reg * ss / (iv * iv) / rows));
+  }
+}
+
+}  // namespace nncf
+
+// =================================================================================================
+// host side
+// =================================================================================================
+using namespace nncf;
+
+struct nncf_trainer {
+  nncf_step_config cfg;
+  int rows;        // user-side rows per batch: B or (1+k)B
+  int rows_pad;    // padded to 128
+  int dp, nsub;
+  int64_t adam_t = 0;
+  // workspace
+  float *Uf = nullptr, *Vf = nullptr, *invU = nullptr, *invV = nullptr, *dU = nullptr, *dV = nullptr;
+  float *corrU = nullptr, *corrV = nullptr, *spos = nullptr;
+  uint8_t *Uimg = nullptr, *Vimg = nullptr;
+  double* loss = nullptr;
+  int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
+  int32_t *ownerU = nullptr, *ownerV = nullptr;
+  int64_t ownerU_n = 0, ownerV_n = 0;
+  float *ps = nullptr;   // PAIRS scores
+  bool tc_attr_set = false;
+};
+
+template <typename T>
+static int dev_alloc(T** p, size_t n) {
+  NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  NNCF_CUDA(cudaMemset(*p, 0, n * sizeof(T)));
+  return 0;
+}
+
+extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t** out) {
+  NNCF_CHECK_ARG(cfg && out, "nncf_trainer_create: null argument");
+  NNCF_CHECK_ARG(cfg->scheme >= 0 && cfg->scheme <= 2, "unknown scheme");
+  NNCF_CHECK_ARG(cfg->loss >= 0 && cfg->loss <= 3, "[ERROR!] loss not specified.");
+  NNCF_CHECK_ARG(cfg->precision == NNCF_PREC_FP32 || cfg->precision == NNCF_PREC_BF16, "unknown precision");
+  NNCF_CHECK_ARG(cfg->batch_size_p >= 2, "batch_size_p must be >= 2");
+  NNCF_CHECK_ARG(cfg->dim >= 1 && cfg->dim <= 256, "dim must be in [1, 256]");
+  NNCF_CHECK_ARG(cfg->replicas >= 1 && cfg->replicas <= 1024, "replicas must be in [1, 1024]");
+  NNCF_CHECK_ARG(cfg->optimizer >= 0 && cfg->optimizer <= 2, "unknown optimizer");
+  if (cfg->scheme == NNCF_SCHEME_PAIRS) NNCF_CHECK_ARG(cfg->num_negatives >= 1, "num_negatives must be >= 1");
+  if (cfg->scheme == NNCF_SCHEME_GROUP_NEG_SHARED)
+    NNCF_CHECK_ARG(cfg->batch_size_p <= 12288, "group_neg_shared supports batch_size_p <= 12288");
+  auto* t = new nncf_trainer();
+  t->cfg = *cfg;
+  const int R = cfg->replicas;
+  t->rows = cfg->scheme == NNCF_SCHEME_PAIRS ? (1 + cfg->num_negatives) * cfg->batch_size_p : cfg->batch_size_p;
+  t->rows_pad = (t->rows + 127) / 128 * 128;
+  t->dp = (cfg->dim + 63) / 64 * 64;
+  t->nsub = t->dp / 64;
+  const size_t nrow = (size_t)R * t->rows_pad, nel = nrow * t->dp;
+  int rc = 0;
+  rc |= dev_alloc(&t->loss, (size_t)R);
+  if (cfg->scheme == NNCF_SCHEME_PAIRS) {
+    rc |= dev_alloc(&t->ps, (size_t)R * t->rows);
+    rc |= dev_alloc(&t->invU, (size_t)R * t->rows);
+    rc |= dev_alloc(&t->invV, (size_t)R * t->rows);
+    rc |= dev_alloc(&t->dU, (size_t)R * t->rows * cfg->dim);
+    rc |= dev_alloc(&t->dV, (size_t)R * t->rows * cfg->dim);
+  } else {
+    rc |= dev_alloc(&t->Uf, nel); rc |= dev_alloc(&t->Vf, nel);
+    rc |= dev_alloc(&t->dU, nel); rc |= dev_alloc(&t->dV, nel);
+    rc |= dev_alloc(&t->invU, nrow); rc |= dev_alloc(&t->invV, nrow);
+    rc |= dev_alloc(&t->corrU, nrow); rc |= dev_alloc(&t->corrV, nrow); rc |= dev_alloc(&t->spos, nrow);
+    if (cfg->precision == NNCF_PREC_BF16) {
+      rc |= dev_alloc(&t->Uimg, nel * 2); rc |= dev_alloc(&t->Vimg, nel * 2);
+    }
+    if (cfg->scheme == NNCF_SCHEME_GROUP_NEG_SHARED) {
+      rc |= dev_alloc(&t->uniq, nrow); rc |= dev_alloc(&t->inverse, nrow); rc |= dev_alloc(&t->nuniq, (size_t)R);
+    }
+  }
+  if (rc) { nncf_trainer_destroy(t); return NNCF_ECUDA; }
+  *out = t;
+  return NNCF_OK;
+}
+
+extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
+  if (!t) return NNCF_OK;
+  void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
+                  t->loss, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete t;
+  return NNCF_OK;
+}
+
+extern "C" int nncf_unique_first_occurrence(const int32_t* ids_dev, int n, int32_t* unique_ids_dev, int32_t* inverse_dev,
+                                            int32_t* n_unique_dev, void* stream) {
+  NNCF_CHECK_ARG(ids_dev && unique_ids_dev && inverse_dev && n_unique_dev, "nncf_unique_first_occurrence: null argument");
+  NNCF_CHECK_ARG(n >= 1 && n <= 12288, "nncf_unique_first_occurrence: n must be in [1, 12288]");
+  const size_t sm = (size_t)3 * n * sizeof(int32_t);
+  if (sm > 48 * 1024) NNCF_CUDA(cudaFuncSetAttribute(unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+  unique_kernel<<<1, kUniqueThreads, sm, (cudaStream_t)stream>>>(ids_dev, 0, n, unique_ids_dev, inverse_dev, n_unique_dev, 0);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+
+static int ensure_owner(int32_t** owner, int64_t* have, int64_t need, cudaStream_t st) {
+  if (*have >= need) return 0;
+  if (*owner) cudaFree(*owner);
+  NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(owner), need * sizeof(int32_t)));
+  fill_i32_kernel<<<ceil_div(need, 256), 256, 0, st>>>(*owner, need, 0x7fffffff);
+  NNCF_LAUNCH_OK();
+  *have = need;
+  return 0;
+}
+
+static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int count, const int32_t* count_dev,
+                    int rows_stride, int d, int dp, int32_t* owner, float* dX, float* table, float* m, float* v,
+                    float lr_t, cudaStream_t st) {
+  const int R = t->cfg.replicas;
+  dim3 g1(ceil_div(count, 256), R), g8(ceil_div(count, 8), R);
+  adam_owner_kernel<<<g1, 256, 0, st>>>(ids, ids_stride, count, count_dev, rows_stride, owner);
+  NNCF_LAUNCH_OK();
+  adam_combine_kernel<<<g8, 256, 0, st>>>(ids, ids_stride, count, count_dev, rows_stride, dp, owner, dX);
+  NNCF_LAUNCH_OK();
+  adam_apply_kernel<<<g8, 256, 0, st>>>(ids, ids_stride, count, count_dev, rows_stride, d, dp, owner, dX, table, m, v,
+                                        lr_t, t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon);
+  NNCF_LAUNCH_OK();
+  adam_reset_kernel<<<g1, 256, 0, st>>>(ids, ids_stride, count, count_dev, owner);
+  NNCF_LAUNCH_OK();
+  return 0;
+}
+
+template <int NSUB>
+static int launch_tc(nncf_trainer* t, const ScoreArgs& sa, int nib, int R, cudaStream_t st) {
+  using C = TcCfg<NSUB>;
+  if (!t->tc_attr_set) {
+    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)C::kSmemBytes));
+    t->tc_attr_set = true;
+  }
+  score_grad_tc_kernel<NSUB><<<dim3(nib, R), kTcThreads, C::kSmemBytes, st>>>(sa);
+  NNCF_LAUNCH_OK();
+  return 0;
+}
+
+static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
+                       const nncf_step_io* io, bool last, cudaStream_t st) {
+  const nncf_step_config& c = t->cfg;
+  const int R = c.replicas, B = c.batch_size_p, d = c.dim, dp = t->dp, rp = t->rows_pad;
+  const bool group = c.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
+  const bool pairwise = c.loss >= NNCF_LOSS_LOG_LOSS;
+  const bool bf16 = c.precision == NNCF_PREC_BF16;
+  const bool dense_items = tb->item_table == nullptr;
+  NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
+  const int32_t* item_ids = cid;
+  int64_t item_stride = B;
+  if (group) {
+    if (dense_items) {
+      // the framework tower already called nncf_unique_first_occurrence; it hands us inverse + n_unique
+      NNCF_CHECK_ARG(io && io->inverse_dev && io->n_unique_dev, "dense group_neg_shared needs inverse_dev and n_unique_dev");
+      NNCF_CUDA(cudaMemcpyAsync(t->inverse, io->inverse_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+      NNCF_CUDA(cudaMemcpyAsync(t->nuniq, io->n_unique_dev, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    } else {
+      const size_t sm = (size_t)3 * B * sizeof(int32_t);
+      if (sm > 48 * 1024)
+        NNCF_CUDA(cudaFuncSetAttribute(unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      unique_kernel<<<R, kUniqueThreads, sm, st>>>(cid, B, B, t->uniq, t->inverse, t->nuniq, rp);
+      NNCF_LAUNCH_OK();
+      item_ids = t->uniq;
+      item_stride = rp;
+    }
+  }
+  // gather
+  GatherArgs gu{};
+  gu.table = tb->user_table; gu.ids = uid; gu.ids_stride = B; gu.count = B; gu.rows_pad = rp; gu.d = d; gu.dp = dp;
+  gu.normalize = c.norm_u; gu.write_img = bf16; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
+  gu.corr = t->corrU;
+  gather_rows_kernel<<<dim3(rp / 8, R), 256, 0, st>>>(gu);
+  NNCF_LAUNCH_OK();
+  GatherArgs gv = gu;
+  gv.table = tb->item_table; gv.dense_rows = dense_items ? io->item_rows_dev : nullptr;
+  gv.ids = item_ids; gv.ids_stride = item_stride; gv.count_dev = group ? t->nuniq : nullptr;
+  gv.normalize = c.norm_v; gv.Xf = t->Vf; gv.inv = t->invV; gv.img = t->Vimg; gv.dX = t->dV; gv.corr = t->corrV;
+  gather_rows_kernel<<<dim3(rp / 8, R), 256, 0, st>>>(gv);
+  NNCF_LAUNCH_OK();
+  if (pairwise) {
+    pos_score_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->Vf, group ? t->inverse : nullptr, rp, dp, B,
+                                                              bf16 ? 1 : 0, t->spos);
+    NNCF_LAUNCH_OK();
+  }
+  if (c.u_reg != 0.0f) {
+    reg_loss_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss);
+    NNCF_LAUNCH_OK();
+  }
+  // score + grad
+  ScoreArgs sa{};
+  sa.Uf = t->Uf; sa.Vf = t->Vf; sa.Uimg = t->Uimg; sa.Vimg = t->Vimg; sa.dU = t->dU; sa.dV = t->dV;
+  sa.corrU = t->corrU; sa.corrV = t->corrV; sa.spos = t->spos; sa.inverse = group ? t->inverse : nullptr;
+  sa.ncols_dev = group ? t->nuniq : nullptr; sa.loss = t->loss; sa.rows_pad = rp; sa.dp = dp; sa.B = B;
+  sa.scheme = c.scheme; sa.loss_kind = c.loss; sa.lambda = c.neg_loss_weight; sa.gamma = c.loss_gamma;
+  if (bf16) {
+    int rc = 0;
+    switch (t->nsub) {
+      case 1: rc = launch_tc<1>(t, sa, rp / 128, R, st); break;
+      case 2: rc = launch_tc<2>(t, sa, rp / 128, R, st); break;
+      case 3: rc = launch_tc<3>(t, sa, rp / 128, R, st); break;
+      default: rc = launch_tc<4>(t, sa, rp / 128, R, st); break;
+    }
+    if (rc) return rc;
+  } else {
+    const size_t sm = ((size_t)2 * kSimtTile * (dp + 1) + kSimtTile * 65) * sizeof(float);
+    if (!t->tc_attr_set) {
+      NNCF_CUDA(cudaFuncSetAttribute(score_grad_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      t->tc_attr_set = true;
+    }
+    const int nt = ceil_div(B, kSimtTile);
+    score_grad_simt_kernel<<<dim3(nt, nt, R), 256, sm, st>>>(sa);
+    NNCF_LAUNCH_OK();
+  }
+  // finalize (user side first: for group pairwise it adds into the item accumulators)
+  const bool sgd = c.optimizer == NNCF_OPT_SGD;
+  FinalizeArgs fu{};
+  fu.side = 0; fu.scheme = c.scheme; fu.pairwise = pairwise; fu.Xf = t->Uf; fu.Of = t->Vf; fu.inv = t->invU;
+  fu.dX = t->dU; fu.dO = t->dV; fu.corr_self = group ? t->corrU : t->corrV; fu.inverse = group ? t->inverse : nullptr;
+  fu.count = B; fu.rows_pad = rp; fu.d = d; fu.dp = dp; fu.normalize = c.norm_u;
+  fu.reg_scale = 2.0f * c.u_reg / B; fu.optimizer = c.optimizer; fu.lr = c.learn_rate; fu.table = tb->user_table;
+  fu.ids = uid; fu.ids_stride = B; fu.grad_out = (last && io) ? io->grad_user_rows_dev : nullptr;
+  finalize_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(fu);
+  NNCF_LAUNCH_OK();
+  FinalizeArgs fv = fu;
+  fv.side = 1; fv.Xf = t->Vf; fv.Of = t->Uf; fv.inv = t->invV; fv.dX = t->dV; fv.dO = nullptr; fv.corr_self = t->corrV;
+  fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.reg_scale = 0.0f;
+  fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
+  fv.grad_out = (last && io) ? io->grad_item_rows_dev : nullptr;
+  finalize_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(fv);
+  NNCF_LAUNCH_OK();
+  (void)sgd;
+  if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
+    NNCF_CHECK_ARG(tb->user_m && tb->user_v, "lazy Adam needs user_m / user_v");
+    t->adam_t += 1;
+    const double b1t = pow((double)c.beta1, (double)t->adam_t), b2t = pow((double)c.beta2, (double)t->adam_t);
+    const float lr_t = (float)(c.learn_rate * sqrt(1.0 - b2t) / (1.0 - b1t));   // optimizer.py:109-111
+    if (ensure_owner(&t->ownerU, &t->ownerU_n, tb->n_users, st)) return NNCF_ECUDA;
+    if (run_adam(t, uid, B, B, nullptr, rp, d, dp, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v, lr_t, st))
+      return NNCF_ECUDA;
+    if (!dense_items) {
+      NNCF_CHECK_ARG(tb->item_m && tb->item_v, "lazy Adam needs item_m / item_v");
+      if (ensure_owner(&t->ownerV, &t->ownerV_n, tb->n_items, st)) return NNCF_ECUDA;
+      if (run_adam(t, item_ids, item_stride, B, group ? t->nuniq : nullptr, rp, d, dp, t->ownerV, t->dV, tb->item_table,
+                   tb->item_m, tb->item_v, lr_t, st))
+        return NNCF_ECUDA;
+    }
+  }
+  if (last && io && group && !dense_items) {
+    if (io->unique_ids_dev) NNCF_CUDA(cudaMemcpyAsync(io->unique_ids_dev, t->uniq, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    if (io->inverse_dev) NNCF_CUDA(cudaMemcpyAsync(io->inverse_dev, t->inverse, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
+    if (io->n_unique_dev) NNCF_CUDA(cudaMemcpyAsync(io->n_unique_dev, t->nuniq, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  }
+  return NNCF_OK;
+}
+
+static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
+                      const nncf_step_io* io, bool last, cudaStream_t st) {
+  const nncf_step_config& c = t->cfg;
+  NNCF_CHECK_ARG(tb->item_table, "PAIRS scheme needs an item embedding table");
+  const int R = c.replicas, n = t->rows, d = c.dim;
+  NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
+  PairsArgs pa{};
+  pa.EU = tb->user_table; pa.EV = tb->item_table; pa.uid = uid; pa.cid = cid; pa.ids_stride = n;
+  pa.B = c.batch_size_p; pa.k = c.num_negatives; pa.d = d; pa.norm_u = c.norm_u; pa.norm_v = c.norm_v;
+  pa.loss_kind = c.loss; pa.lambda = c.neg_loss_weight; pa.gamma = c.loss_gamma; pa.u_reg = c.u_reg;
+  pa.s = t->ps; pa.invu = t->invU; pa.invv = t->invV; pa.loss = t->loss;
+  pa.dUrows = t->dU; pa.dVrows = t->dV; pa.optimizer = c.optimizer; pa.lr = c.learn_rate;
+  pa.tableU = tb->user_table; pa.tableV = tb->item_table;
+  pa.grad_out_u = (last && io) ? io->grad_user_rows_dev : nullptr;
+  pa.grad_out_v = (last && io) ? io->grad_item_rows_dev : nullptr;
+  dim3 g8(ceil_div(n, 8), R);
+  pairs_score_kernel<<<g8, 256, 0, st>>>(pa);
+  NNCF_LAUNCH_OK();
+  pairs_grad_kernel<<<g8, 256, 0, st>>>(pa);
+  NNCF_LAUNCH_OK();
+  if (c.optimizer == NNCF_OPT_SGD) {
+    rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
+    NNCF_LAUNCH_OK();
+    rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dV, cid, n, n, d, c.learn_rate, tb->item_table);
+    NNCF_LAUNCH_OK();
+  } else if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
+    NNCF_CHECK_ARG(tb->user_m && tb->user_v && tb->item_m && tb->item_v, "lazy Adam needs m / v tables");
+    t->adam_t += 1;
+    const double b1t = pow((double)c.beta1, (double)t->adam_t), b2t = pow((double)c.beta2, (double)t->adam_t);
+    const float lr_t = (float)(c.learn_rate * sqrt(1.0 - b2t) / (1.0 - b1t));
+    if (ensure_owner(&t->ownerU, &t->ownerU_n, tb->n_users, st)) return NNCF_ECUDA;
+    if (ensure_owner(&t->ownerV, &t->ownerV_n, tb->n_items, st)) return NNCF_ECUDA;
+    if (run_adam(t, uid, n, n, nullptr, n, d, d, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v, lr_t, st))
+      return NNCF_ECUDA;
+    if (run_adam(t, cid, n, n, nullptr, n, d, d, t->ownerV, t->dV, tb->item_table, tb->item_m, tb->item_v, lr_t, st))
+      return NNCF_ECUDA;
+  }
+  return NNCF_OK;
+}
+
+extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,
+                                const int32_t* item_ids_dev, int64_t n_steps, const nncf_step_io* io, void* stream) {
+  NNCF_CHECK_ARG(t && tables && user_ids_dev && item_ids_dev, "nncf_train_steps: null argument");
+  NNCF_CHECK_ARG(tables->user_table, "nncf_train_steps: user_table is required");
+  NNCF_CHECK_ARG(n_steps >= 0, "nncf_train_steps: n_steps < 0");
+  const bool dense_items = tables->item_table == nullptr;
+  if (dense_items) {
+    NNCF_CHECK_ARG(io && io->item_rows_dev, "dense item side needs io->item_rows_dev");
+    NNCF_CHECK_ARG(t->cfg.replicas == 1 && n_steps <= 1, "dense item side supports one batch per call");
+    NNCF_CHECK_ARG(t->cfg.scheme != NNCF_SCHEME_PAIRS, "dense item side is not available for the PAIRS scheme");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = t->cfg.replicas;
+  const int64_t per_step = (int64_t)R * t->rows;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const bool last = (s + 1 == n_steps);
+    int rc;
+    if (t->cfg.scheme == NNCF_SCHEME_PAIRS)
+      rc = step_pairs(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
+    else
+      rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
+    if (rc) return rc;
+    if (io && io->loss_out_dev) {
+      loss_out_kernel<<<1, R < 32 ? 32 : ((R + 31) / 32 * 32), 0, st>>>(t->loss, R, io->loss_out_dev + s * R);
+      NNCF_LAUNCH_OK();
+    }
+  }
+  return NNCF_OK;
+}

@@ -1,0 +1,320 @@
+"""Torch-tensor level wrappers over the C-ABI.  torch is used for device memory and streams only; every
+computation below happens in libnncf_b200.so's CUDA kernels.  No CPU fallback: tensors must live on a CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ._lib import (LOSSES, OPTIMIZERS, PRECISIONS, SCHEMES, NNCFError, StepConfig, StepIO, Tables, check, lib)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise NNCFError("nncf_b200 kernels need CUDA tensors (no CPU fallback); got a %s tensor" % t.device)
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    return t.to(dtype=torch.int32).contiguous()
+
+
+def launch_count() -> int:
+    return int(lib.nncf_launch_count())
+
+
+# ------------------------------------------------------------------------------------------------
+# sampler
+# ------------------------------------------------------------------------------------------------
+class DeviceSampler:
+    """Alias-table + Philox sampler handle (nncf_sampler_*)."""
+
+    def __init__(self, dist: np.ndarray, power: float = 0.75, seed: int = 0):
+        dist = np.ascontiguousarray(dist, dtype=np.float64)
+        self.n = int(dist.size)
+        h = C.c_void_p()
+        check(lib.nncf_sampler_create(dist.ctypes.data_as(C.c_void_p), self.n, float(power), int(seed) & (2**64 - 1),
+                                      C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.nncf_sampler_destroy(h)
+            self._h = None
+
+    def seek(self, counter: int) -> None:
+        check(lib.nncf_sampler_seek(self._h, int(counter)))
+
+    def sample_device(self, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(int(n), dtype=torch.int32, device="cuda")
+        _need_cuda(out)
+        check(lib.nncf_sampler_sample_batch_dev(self._h, int(n), _ptr(out), _stream()))
+        return out
+
+    def sample_host(self, n: int) -> np.ndarray:
+        out = np.zeros(int(n), dtype=np.int32)
+        check(lib.nncf_sampler_sample_batch_host(self._h, int(n), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def export_table(self):
+        prob = np.zeros(self.n, dtype=np.float32)
+        alias = np.zeros(self.n, dtype=np.int32)
+        check(lib.nncf_sampler_export_table(self._h, prob.ctypes.data_as(C.c_void_p), alias.ctypes.data_as(C.c_void_p)))
+        return prob, alias
+
+
+# ------------------------------------------------------------------------------------------------
+# batch builders
+# ------------------------------------------------------------------------------------------------
+def permute_rows(train: torch.Tensor, row_perm: torch.Tensor) -> torch.Tensor:
+    _need_cuda(train, row_perm)
+    train = _i32(train)
+    row_perm = row_perm.to(torch.int64).contiguous()
+    out = torch.empty_like(train)
+    check(lib.nncf_permute_rows(_ptr(train), train.shape[0], _ptr(row_perm), _ptr(out), _stream()))
+    return out
+
+
+def group_shuffle(train: torch.Tensor, col: int, iidx: torch.Tensor, row_perm: torch.Tensor,
+                  block_perm: Optional[torch.Tensor], chop: int) -> torch.Tensor:
+    _need_cuda(train, iidx, row_perm, block_perm)
+    train = _i32(train)
+    iidx = iidx.to(torch.int64).contiguous()
+    row_perm = row_perm.to(torch.int64).contiguous()
+    if block_perm is not None:
+        block_perm = block_perm.to(torch.int64).contiguous()
+    n = train.shape[0]
+    out = torch.empty_like(train)
+    wsb = int(lib.nncf_group_shuffle_workspace_bytes(n, iidx.numel()))
+    ws = torch.empty(wsb, dtype=torch.uint8, device=train.device)
+    check(lib.nncf_group_shuffle(_ptr(train), n, int(col), _ptr(iidx), iidx.numel(), _ptr(row_perm), _ptr(block_perm),
+                                 int(chop), _ptr(out), _ptr(ws), wsb, _stream()))
+    return out
+
+
+def assemble_pairs_batch(pos: torch.Tensor, k: int, negs: torch.Tensor, neg_col: int, neg_sign: int) -> torch.Tensor:
+    _need_cuda(pos, negs)
+    pos = _i32(pos)
+    negs = _i32(negs)
+    B = pos.shape[0]
+    out = torch.empty(((1 + k) * B, 3), dtype=torch.int32, device=pos.device)
+    check(lib.nncf_assemble_pairs_batch(_ptr(pos), B, int(k), _ptr(negs), int(neg_col), int(neg_sign), _ptr(out), _stream()))
+    return out
+
+
+def unique_first_occurrence(ids: torch.Tensor):
+    _need_cuda(ids)
+    ids = _i32(ids)
+    n = ids.numel()
+    uniq = torch.empty(n, dtype=torch.int32, device=ids.device)
+    inv = torch.empty(n, dtype=torch.int32, device=ids.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=ids.device)
+    check(lib.nncf_unique_first_occurrence(_ptr(ids), n, _ptr(uniq), _ptr(inv), _ptr(cnt), _stream()))
+    return uniq, inv, cnt
+
+
+# ------------------------------------------------------------------------------------------------
+# fused training step
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class StepSpec:
+    scheme: str = "neg_shared"          # neg_shared | group_neg_shared | pairs
+    loss: str = "skip-gram"
+    precision: str = "bf16"             # fp32 (CUDA cores) | bf16 (tcgen05)
+    batch_size_p: int = 512
+    num_negatives: int = 10
+    dim: int = 50
+    norm_u: bool = False
+    norm_v: bool = False
+    optimizer: str = "sgd"              # none | sgd | lazy_adam
+    replicas: int = 1
+    neg_loss_weight: float = 128.0
+    loss_gamma: float = 10.0
+    u_reg: float = 0.0
+    learn_rate: float = 0.01
+    beta1: float = 0.9
+    beta2: float = 0.999
+    epsilon: float = 1e-8
+
+    def to_c(self) -> StepConfig:
+        if self.loss not in LOSSES:
+            raise AssertionError("[ERROR!] loss %s not specified." % self.loss)
+        return StepConfig(SCHEMES[self.scheme], LOSSES[self.loss], PRECISIONS[self.precision], self.batch_size_p,
+                          self.num_negatives, self.dim, int(self.norm_u), int(self.norm_v), OPTIMIZERS[self.optimizer],
+                          self.replicas, self.neg_loss_weight, self.loss_gamma, self.u_reg, self.learn_rate, self.beta1,
+                          self.beta2, self.epsilon)
+
+
+class FusedStep:
+    """Handle on nncf_trainer_*: owns the staging workspace of one (scheme, loss, B, d, replicas) configuration."""
+
+    def __init__(self, spec: StepSpec):
+        if not torch.cuda.is_available():
+            raise NNCFError("nncf_b200 needs a CUDA device (no CPU fallback)")
+        self.spec = spec
+        cfg = spec.to_c()
+        h = C.c_void_p()
+        check(lib.nncf_trainer_create(C.byref(cfg), C.byref(h)))
+        self._h = h
+        self.rows = (1 + spec.num_negatives) * spec.batch_size_p if spec.scheme == "pairs" else spec.batch_size_p
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.nncf_trainer_destroy(h)
+            self._h = None
+
+    def run(self, user_table: torch.Tensor, item_table: Optional[torch.Tensor], user_ids: torch.Tensor,
+            item_ids: torch.Tensor, n_steps: int = 1, *, adam_state=None, want_grads: bool = False,
+            item_rows: Optional[torch.Tensor] = None, inverse: Optional[torch.Tensor] = None,
+            n_unique: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
+        """Runs n_steps steps (each over `replicas` batches).  Returns dict(loss=[n_steps*R] tensor, and if
+        want_grads: grad_user_rows, grad_item_rows (+ unique_ids, inverse, n_unique for group_neg_shared))."""
+        sp = self.spec
+        _need_cuda(user_table, item_table, user_ids, item_ids, item_rows)
+        assert user_table.dtype == torch.float32 and user_table.is_contiguous()
+        assert user_ids.dtype == torch.int32 and item_ids.dtype == torch.int32
+        need = n_steps * sp.replicas * self.rows
+        assert user_ids.numel() >= need and item_ids.numel() >= need, "not enough ids for n_steps x replicas batches"
+        dev = user_table.device
+        tb = Tables()
+        tb.user_table = user_table.data_ptr()
+        tb.n_users = user_table.shape[0]
+        if item_table is not None:
+            assert item_table.dtype == torch.float32 and item_table.is_contiguous()
+            tb.item_table = item_table.data_ptr()
+            tb.n_items = item_table.shape[0]
+        if adam_state is not None:
+            um, uv, im, iv = adam_state
+            tb.user_m, tb.user_v = um.data_ptr(), uv.data_ptr()
+            if im is not None:
+                tb.item_m, tb.item_v = im.data_ptr(), iv.data_ptr()
+        io = StepIO()
+        if loss_out is None:
+            loss_out = torch.empty(n_steps * sp.replicas, dtype=torch.float32, device=dev)
+        io.loss_out_dev = loss_out.data_ptr()
+        out = {"loss": loss_out}
+        keep = []
+        if want_grads:
+            gu = torch.zeros((self.rows, sp.dim), dtype=torch.float32, device=dev)
+            gv = torch.zeros((self.rows, sp.dim), dtype=torch.float32, device=dev)
+            io.grad_user_rows_dev, io.grad_item_rows_dev = gu.data_ptr(), gv.data_ptr()
+            out["grad_user_rows"], out["grad_item_rows"] = gu, gv
+            if sp.scheme == "group_neg_shared" and item_table is not None:
+                uq = torch.zeros(self.rows, dtype=torch.int32, device=dev)
+                iv_ = torch.zeros(self.rows, dtype=torch.int32, device=dev)
+                nu = torch.zeros(1, dtype=torch.int32, device=dev)
+                io.unique_ids_dev, io.inverse_dev, io.n_unique_dev = uq.data_ptr(), iv_.data_ptr(), nu.data_ptr()
+                out["unique_ids"], out["inverse"], out["n_unique"] = uq, iv_, nu
+        if item_rows is not None:
+            item_rows = item_rows.contiguous()
+            keep.append(item_rows)
+            io.item_rows_dev = item_rows.data_ptr()
+            if inverse is not None:
+                io.inverse_dev = inverse.data_ptr()
+                io.n_unique_dev = n_unique.data_ptr()
+        check(lib.nncf_train_steps(self._h, C.byref(tb), _ptr(user_ids), _ptr(item_ids), int(n_steps), C.byref(io), _stream()))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# mean-pool encoder
+# ------------------------------------------------------------------------------------------------
+def meanpool_fwd(word_table: torch.Tensor, content: torch.Tensor, item_ids: Optional[torch.Tensor], n: int) -> torch.Tensor:
+    _need_cuda(word_table, content, item_ids)
+    out = torch.empty((n, word_table.shape[1]), dtype=torch.float32, device=word_table.device)
+    check(lib.nncf_meanpool_fwd(_ptr(word_table), word_table.shape[1], _ptr(content), content.shape[1], _ptr(item_ids), n,
+                                _ptr(out), _stream()))
+    return out
+
+
+def meanpool_bwd(grad_word_table: torch.Tensor, content: torch.Tensor, item_ids: Optional[torch.Tensor], n: int,
+                 grad_out: torch.Tensor) -> None:
+    _need_cuda(grad_word_table, content, item_ids, grad_out)
+    grad_out = grad_out.contiguous()
+    check(lib.nncf_meanpool_bwd(_ptr(grad_word_table), grad_word_table.shape[1], _ptr(content), content.shape[1],
+                                _ptr(item_ids), n, _ptr(grad_out), _stream()))
+
+
+class MeanPoolFunction(torch.autograd.Function):
+    """Segmented gather-mean over word rows with a dense-gradient backward (scatter-add kernel)."""
+
+    @staticmethod
+    def forward(ctx, word_table, content, item_ids):
+        n = item_ids.numel() if item_ids is not None else content.shape[0]
+        ctx.save_for_backward(content, item_ids)
+        ctx.shape = word_table.shape
+        ctx.n = n
+        return meanpool_fwd(word_table, content, item_ids, n)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        content, item_ids = ctx.saved_tensors
+        dW = torch.zeros(ctx.shape, dtype=torch.float32, device=grad_out.device)
+        meanpool_bwd(dW, content, item_ids, ctx.n, grad_out)
+        return dW, None, None
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation
+# ------------------------------------------------------------------------------------------------
+def eval_topk(user_rows: torch.Tensor, item_rows: torch.Tensor, k: int, precision: str = "bf16"):
+    _need_cuda(user_rows, item_rows)
+    user_rows = user_rows.contiguous().float()
+    item_rows = item_rows.contiguous().float()
+    nu, d = user_rows.shape
+    ni = item_rows.shape[0]
+    prec = PRECISIONS[precision]
+    wsb = int(lib.nncf_eval_topk_workspace_bytes(nu, ni, d, int(k), prec))
+    if wsb == 0:
+        raise NNCFError("eval_topk: %s" % lib.nncf_last_error().decode())
+    ws = torch.empty(wsb, dtype=torch.uint8, device=user_rows.device)
+    ids = torch.empty((nu, k), dtype=torch.int32, device=user_rows.device)
+    sc = torch.empty((nu, k), dtype=torch.float32, device=user_rows.device)
+    check(lib.nncf_eval_topk(_ptr(user_rows), nu, _ptr(item_rows), ni, d, int(k), prec, _ptr(ids), _ptr(sc), _ptr(ws), wsb,
+                             _stream()))
+    return ids, sc
+
+
+def eval_metrics(topk_ids: torch.Tensor, indptr: torch.Tensor, cols: torch.Tensor):
+    """Returns (per_user [n,3] float32, sums [4] float64 = sum AP, sum recall, sum precision, users kept)."""
+    _need_cuda(topk_ids, indptr, cols)
+    nu, k = topk_ids.shape
+    per_user = torch.empty((nu, 3), dtype=torch.float32, device=topk_ids.device)
+    sums = torch.zeros(4, dtype=torch.float64, device=topk_ids.device)
+    indptr = indptr.to(torch.int64).contiguous()
+    cols = _i32(cols)
+    check(lib.nncf_eval_metrics(_ptr(topk_ids.contiguous()), nu, k, _ptr(indptr), _ptr(cols), _ptr(per_user), _ptr(sums),
+                                _stream()))
+    return per_user, sums
+
+
+def score_pairs(user_table: torch.Tensor, item_table: torch.Tensor, uid: torch.Tensor, cid: torch.Tensor) -> torch.Tensor:
+    _need_cuda(user_table, item_table, uid, cid)
+    uid, cid = _i32(uid), _i32(cid)
+    out = torch.empty(uid.numel(), dtype=torch.float32, device=user_table.device)
+    check(lib.nncf_score_pairs(_ptr(user_table), _ptr(item_table), user_table.shape[1], _ptr(uid), _ptr(cid), uid.numel(),
+                               _ptr(out), _stream()))
+    return out
+
+
+def eval_given(scores: torch.Tensor, truth: torch.Tensor, indptr: torch.Tensor) -> torch.Tensor:
+    _need_cuda(scores, truth, indptr)
+    ng = indptr.numel() - 1
+    out = torch.empty((ng, 2), dtype=torch.float32, device=scores.device)
+    check(lib.nncf_eval_given(_ptr(scores.contiguous()), _ptr(_i32(truth)), _ptr(indptr.to(torch.int64).contiguous()), ng,
+                              _ptr(out), _stream()))
+    return out

@@ -1,0 +1,239 @@
+"""GPU parity: the fused training step (CUDA path, through the C-ABI) against the CPU oracle on the same seeded
+inputs.  Tolerances are the north_star's: 1e-4 relative for the fp32 mode, 1e-2 for the bf16 tensor-core mode
+(relative = max-abs error over the max-abs reference value of the same tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nncf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-4, "bf16": 1e-2}
+LOSSES = ["skip-gram", "mse", "log-loss", "max-margin"]
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
+
+
+def _tables(nu, ni, d, seed, scale=0.5):
+    rng = np.random.RandomState(seed)
+    EU = rng.uniform(-scale, scale, size=(nu, d)).astype(np.float32)
+    EV = rng.uniform(-scale, scale, size=(ni, d)).astype(np.float32)
+    return EU, EV
+
+
+def _params(loss):
+    lam = 8.0 if loss == "mse" else 128.0
+    gamma = 0.1 if loss == "max-margin" else 10.0
+    return lam, gamma
+
+
+def _scatter(n, ids, rows):
+    out = np.zeros((n, rows.shape[1]), dtype=np.float64)
+    np.add.at(out, ids, rows.astype(np.float64))
+    return out
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("loss", LOSSES)
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
+@pytest.mark.parametrize("B,d,norm", [(96, 50, False), (200, 64, True), (256, 128, True)])
+def test_matmul_schemes_loss_and_grads(scheme, loss, precision, B, d, norm):
+    from nncf_b200.ops import FusedStep, StepSpec
+    nu, ni = 300, 120          # few items => duplicate items inside a batch (exercises tf.unique + dup columns)
+    EU, EV = _tables(nu, ni, d, seed=B + d)
+    if loss == "max-margin" and precision == "bf16" and not norm:
+        # the max-margin gradient is an indicator (discontinuous in the score): feed bf16-representable tables so
+        # that operand rounding cannot flip indicators that sit within bf16 error of the margin
+        EU = torch.from_numpy(EU).bfloat16().float().numpy()
+        EV = torch.from_numpy(EV).bfloat16().float().numpy()
+    rng = np.random.RandomState(7)
+    uid = rng.randint(0, nu, size=B).astype(np.int32)
+    cid = rng.randint(0, ni, size=B).astype(np.int32)
+    lam, gamma = _params(loss)
+    u_reg = 1e-3
+    ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, scheme, loss, lam, gamma, u_reg=u_reg,
+                        norm_u=norm, norm_v=norm)
+    spec = StepSpec(scheme=scheme, loss=loss, precision=precision, batch_size_p=B, dim=d, norm_u=norm, norm_v=norm,
+                    optimizer="none", neg_loss_weight=lam, loss_gamma=gamma, u_reg=u_reg)
+    step = FusedStep(spec)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    out = step.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1, want_grads=True)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    loss_gpu = float(out["loss"][0].item())
+    assert abs(loss_gpu - ref["loss"]) <= tol * max(abs(ref["loss"]), 1e-6), (loss_gpu, ref["loss"])
+    gu = out["grad_user_rows"].cpu().numpy()
+    gv = out["grad_item_rows"].cpu().numpy()
+    dEU = _scatter(nu, uid, gu)
+    if scheme == "neg_shared":
+        dEV = _scatter(ni, cid, gv)
+    else:
+        n_u = int(out["n_unique"].item())
+        cid_u, cid_x = O.unique_first_occurrence(cid)
+        assert n_u == cid_u.size
+        np.testing.assert_array_equal(out["unique_ids"].cpu().numpy()[:n_u], cid_u)     # integer work: bit-exact
+        np.testing.assert_array_equal(out["inverse"].cpu().numpy(), cid_x)
+        dEV = _scatter(ni, cid_u, gv[:n_u])
+    assert _rel(dEU, ref["dEU"]) <= tol, ("dEU", _rel(dEU, ref["dEU"]))
+    assert _rel(dEV, ref["dEV"]) <= tol, ("dEV", _rel(dEV, ref["dEV"]))
+    # optimizer='none' must leave the tables untouched
+    np.testing.assert_array_equal(tU.cpu().numpy(), EU)
+    np.testing.assert_array_equal(tV.cpu().numpy(), EV)
+
+
+@pytest.mark.parametrize("loss", LOSSES)
+@pytest.mark.parametrize("norm", [False, True])
+def test_pairs_scheme_loss_and_grads(loss, norm):
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, k, d, nu, ni = 64, 5, 50, 200, 90
+    EU, EV = _tables(nu, ni, d, seed=3)
+    rng = np.random.RandomState(11)
+    n = (1 + k) * B
+    uid = np.concatenate([rng.randint(0, nu, size=B), np.zeros(k * B, dtype=np.int64)]).astype(np.int32)
+    uid[B:] = np.repeat(uid[:B], k)                       # 'original': negatives keep the positive's user
+    cid = rng.randint(0, ni, size=n).astype(np.int32)
+    lam, gamma = _params(loss)
+    ref = O.step_mul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, B, k, loss, lam, gamma, u_reg=1e-3,
+                     norm_u=norm, norm_v=norm)
+    spec = StepSpec(scheme="pairs", loss=loss, precision="fp32", batch_size_p=B, num_negatives=k, dim=d, norm_u=norm,
+                    norm_v=norm, optimizer="none", neg_loss_weight=lam, loss_gamma=gamma, u_reg=1e-3)
+    out = FusedStep(spec).run(torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda(), torch.from_numpy(uid).cuda(),
+                              torch.from_numpy(cid).cuda(), 1, want_grads=True)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss"][0]) - ref["loss"]) <= 1e-4 * max(abs(ref["loss"]), 1e-6)
+    assert _rel(_scatter(nu, uid, out["grad_user_rows"].cpu().numpy()), ref["dEU"]) <= 1e-4
+    assert _rel(_scatter(ni, cid, out["grad_item_rows"].cpu().numpy()), ref["dEV"]) <= 1e-4
+
+
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared", "pairs"])
+def test_sgd_update_matches_oracle(scheme):
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, k, d, nu, ni, lr = 128, 3, 64, 150, 60, 0.05
+    EU, EV = _tables(nu, ni, d, seed=5)
+    rng = np.random.RandomState(2)
+    rows = (1 + k) * B if scheme == "pairs" else B
+    uid = rng.randint(0, nu, size=rows).astype(np.int32)
+    cid = rng.randint(0, ni, size=rows).astype(np.int32)
+    if scheme == "pairs":
+        ref = O.step_mul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, B, k, "skip-gram", 128.0, 10.0)
+    else:
+        ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, scheme, "skip-gram", 128.0, 10.0)
+    spec = StepSpec(scheme=scheme, loss="skip-gram", precision="fp32", batch_size_p=B, num_negatives=k, dim=d,
+                    optimizer="sgd", learn_rate=lr)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
+    torch.cuda.synchronize()
+    assert _rel(tU.cpu().numpy() - EU, -lr * ref["dEU"]) <= 1e-3
+    assert _rel(tV.cpu().numpy() - EV, -lr * ref["dEV"]) <= 1e-3
+
+
+def test_lazy_adam_two_steps_match_oracle():
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, d, nu, ni, lr = 128, 64, 100, 40, 0.01
+    EU, EV = _tables(nu, ni, d, seed=9)
+    rng = np.random.RandomState(4)
+    uid = rng.randint(0, nu, size=2 * B).astype(np.int32)
+    cid = rng.randint(0, ni, size=2 * B).astype(np.int32)
+    U, V = EU.astype(np.float64), EV.astype(np.float64)
+    mU, vU, mV, vV = np.zeros_like(U), np.zeros_like(U), np.zeros_like(V), np.zeros_like(V)
+    for t in range(2):
+        u, c = uid[t * B:(t + 1) * B], cid[t * B:(t + 1) * B]
+        ref = O.step_matmul(U, V, u, c, "neg_shared", "skip-gram", 128.0, 10.0)
+        U, mU, vU = O.lazy_adam_sparse(U, mU, vU, u, ref["dEU"], lr, t + 1)
+        V, mV, vV = O.lazy_adam_sparse(V, mV, vV, c, ref["dEV"], lr, t + 1)
+    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="fp32", batch_size_p=B, dim=d,
+                    optimizer="lazy_adam", learn_rate=lr)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    st = [torch.zeros_like(tU), torch.zeros_like(tU), torch.zeros_like(tV), torch.zeros_like(tV)]
+    FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 2, adam_state=st)
+    torch.cuda.synchronize()
+    # Adam's first steps are sign-like (m/sqrt(v)), so compare the updated tables themselves
+    assert np.max(np.abs(tU.cpu().numpy() - U)) <= 2e-4
+    assert np.max(np.abs(tV.cpu().numpy() - V)) <= 2e-4
+    assert _rel(st[0].cpu().numpy(), mU) <= 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_replicas_are_independent_batches_on_one_snapshot(precision):
+    """R replicas in one call == R separate calls on the same table snapshot, updates summed (synchronous DP)."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, d, nu, ni, R, lr = 128, 64, 500, 400, 3, 0.1
+    EU, EV = _tables(nu, ni, d, seed=21)
+    rng = np.random.RandomState(8)
+    uid = rng.randint(0, nu, size=R * B).astype(np.int32)
+    cid = rng.randint(0, ni, size=R * B).astype(np.int32)
+    dU = np.zeros((nu, d)); dV = np.zeros((ni, d)); losses = []
+    for r in range(R):
+        ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B],
+                            "neg_shared", "skip-gram", 128.0, 10.0)
+        dU += ref["dEU"]; dV += ref["dEV"]; losses.append(ref["loss"])
+    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision=precision, batch_size_p=B, dim=d, optimizer="sgd",
+                    learn_rate=lr, replicas=R)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    out = FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    np.testing.assert_allclose(out["loss"].cpu().numpy(), np.array(losses), rtol=tol)
+    assert _rel(tU.cpu().numpy() - EU, -lr * dU) <= max(tol, 1e-3)
+    assert _rel(tV.cpu().numpy() - EV, -lr * dV) <= max(tol, 1e-3)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_reduces_loss_full_size_property(precision):
+    """Size-independent property at the benchmark's batch shape (B=512, d=128): repeated steps on the same batch
+    must monotonically reduce its loss, and fp32/bf16 must agree on the first loss."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, d, nu, ni = 512, 128, 20000, 20000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    tU = (torch.rand((nu, d), device="cuda", generator=g) - 0.5) * 0.1
+    tV = (torch.rand((ni, d), device="cuda", generator=g) - 0.5) * 0.1
+    uid = torch.randint(0, nu, (B,), device="cuda", generator=g, dtype=torch.int32).repeat(8)
+    cid = torch.randint(0, ni, (B,), device="cuda", generator=g, dtype=torch.int32).repeat(8)
+    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision=precision, batch_size_p=B, dim=d, optimizer="sgd",
+                    learn_rate=5.0)
+    out = FusedStep(spec).run(tU, tV, uid, cid, 8)
+    losses = out["loss"].cpu().numpy()
+    assert np.all(np.isfinite(losses))
+    assert np.all(np.diff(losses) < 1e-3) and losses[-1] < losses[0] - 0.05, losses
+    expected0 = 128.0 * np.log(2.0) + np.log(2.0)      # all scores ~ 0 at init: (lambda + 1) * log 2
+    assert abs(losses[0] - expected0) / expected0 < 2e-2
+
+
+def test_dense_item_side_for_framework_towers():
+    """item_table = NULL: item rows come from a tower; gradient w.r.t. those rows is returned, users updated."""
+    from nncf_b200.ops import FusedStep, StepSpec, unique_first_occurrence
+    B, d, nu, ni = 128, 50, 100, 30
+    EU, EV = _tables(nu, ni, d, seed=13)
+    rng = np.random.RandomState(6)
+    uid = rng.randint(0, nu, size=B).astype(np.int32)
+    cid = rng.randint(0, ni, size=B).astype(np.int32)
+    ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, "group_neg_shared", "log-loss", 128.0, 10.0,
+                        norm_u=True, norm_v=True)
+    tU = torch.from_numpy(EU).cuda()
+    tc = torch.from_numpy(cid).cuda()
+    uq, inv, nuq = unique_first_occurrence(tc)
+    n_u = int(nuq.item())
+    rows = torch.from_numpy(EV).cuda()[uq[:n_u].long()]
+    spec = StepSpec(scheme="group_neg_shared", loss="log-loss", precision="fp32", batch_size_p=B, dim=d, norm_u=True,
+                    norm_v=True, optimizer="none", loss_gamma=10.0)
+    out = FusedStep(spec).run(tU, None, torch.from_numpy(uid).cuda(), tc, 1, want_grads=True, item_rows=rows, inverse=inv,
+                              n_unique=nuq)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss"][0]) - ref["loss"]) <= 1e-4 * abs(ref["loss"])
+    cid_u, _ = O.unique_first_occurrence(cid)
+    dEV = _scatter(ni, cid_u, out["grad_item_rows"].cpu().numpy()[:n_u])
+    assert _rel(dEV, ref["dEV"]) <= 1e-4
+    assert _rel(_scatter(nu, uid, out["grad_user_rows"].cpu().numpy()), ref["dEU"]) <= 1e-4
+
+
+def test_bad_arguments_raise():
+    from nncf_b200.ops import FusedStep, StepSpec
+    from nncf_b200._lib import NNCFError
+    with pytest.raises(NNCFError):
+        FusedStep(StepSpec(dim=1000))
+    with pytest.raises(AssertionError):
+        FusedStep(StepSpec(loss="hinge"))
