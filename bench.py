@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — positive links/sec of the neg_shared training loop on the C3 workload (synthetic 1M users x 1M items,
+100M power-law links, dim 128, skip-gram, batch_size_p 512), plus whole@k users/sec as an extra.
+
+  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path through the C-ABI)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (NumPy transcription)
+
+One "step" = one pass of the hot path over one device batch = R replicas x batch_size_p positive links
+(R independent neg_shared batches computed against one table snapshot: synchronous data-parallel virtual workers;
+R = 1 is the reference's strictly sequential loop and is reported alongside as `sequential`).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3: synthetic 1M users x 1M items, 100M power-law links, dim 128, neg_shared skip-gram, batch_size_p 512"
+N_USERS = N_ITEMS = 1_000_000
+N_LINKS = 100_000_000
+DIM = 128
+BATCH = 512
+LAMBDA = 128.0
+LR = 0.01
+
+
+def _peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return {"hbm": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "src": "measured"}
+    except Exception:
+        return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# synthetic data
+# ----------------------------------------------------------------------------------------------------------------
+def synth_links_device(n_links, n_users, n_items, seed, torch):
+    """int32 [n_links, 3] rows (user, item, 1) on the device: items ~ (rank+10)^-1.0, users ~ (rank+10)^-0.8 over
+    seeded permutations of the id spaces; duplicates kept (the reference never dedupes)."""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+
+    def draw(n_ids, expo, perm_seed, n):
+        p = torch.pow(torch.arange(n_ids, device="cuda", dtype=torch.float64) + 10.0, -expo)
+        cdf = torch.cumsum(p, 0)
+        cdf = cdf / cdf[-1]
+        r = torch.searchsorted(cdf, torch.rand(n, device="cuda", generator=g, dtype=torch.float64), right=True)
+        r.clamp_(max=n_ids - 1)
+        perm = torch.randperm(n_ids, device="cuda", generator=torch.Generator(device="cuda").manual_seed(perm_seed))
+        return perm[r].to(torch.int32)
+
+    out = torch.empty((n_links, 3), dtype=torch.int32, device="cuda")
+    chunk = 20_000_000
+    for s in range(0, n_links, chunk):
+        n = min(chunk, n_links - s)
+        out[s:s + n, 0] = draw(n_users, 0.8, 124, n)
+        out[s:s + n, 1] = draw(n_items, 1.0, 123, n)
+    out[:, 2] = 1
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in self.rows if len(r) >= 7)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's path, NumPy transcription (oracle/), all host threads BLAS can use
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_links_per_sec(n_steps, warmup, n_rows=N_USERS):
+    from oracle import nncf_oracle as O
+    rng = np.random.RandomState(7)
+    EU = rng.uniform(-0.05, 0.05, size=(n_rows, DIM)).astype(np.float32)
+    EV = rng.uniform(-0.05, 0.05, size=(n_rows, DIM)).astype(np.float32)
+    from nncf_b200.data_utils import powerlaw_ids
+    n = (n_steps + warmup) * BATCH
+    uid = powerlaw_ids(n_rows, n, 0.8, 124, rng).astype(np.int64)
+    cid = powerlaw_ids(n_rows, n, 1.0, 123, rng).astype(np.int64)
+    for s in range(warmup):
+        O.baseline_neg_shared_sgd_step(EU, EV, uid[s * BATCH:(s + 1) * BATCH], cid[s * BATCH:(s + 1) * BATCH], LAMBDA, LR)
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + n_steps):
+        O.baseline_neg_shared_sgd_step(EU, EV, uid[s * BATCH:(s + 1) * BATCH], cid[s * BATCH:(s + 1) * BATCH], LAMBDA, LR)
+    dt = time.perf_counter() - t0
+    return n_steps * BATCH / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 20000))
+    v, dt = cpu_links_per_sec(steps, max(3, min(args.warmup, 50)))
+    cores = os.cpu_count()
+    line = {
+        "impl": "reference", "metric": "positive links/sec train (neg_shared)", "value": v, "unit": "links/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_size_p": BATCH, "dim": DIM, "optimizer": "sparse SGD",
+                   "note": "reference CPU path: Keras 1.2.2 / TF 1.0 / py2 cannot be installed offline -> NumPy "
+                           "transcription of the same step (oracle/nncf_oracle.py baseline_neg_shared_sgd_step), one "
+                           "batch of 512 links per step, strictly sequential"},
+        "cpu_baseline": {"value": v, "unit": "links/s", "cores": cores, "kind": "port",
+                         "sample": "%d sequential neg_shared steps of 512 links on 1M x 128 fp32 tables" % steps},
+        "e2e": {"value": v, "unit": "links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from nncf_b200 import ops
+    from nncf_b200.ops import FusedStep, StepSpec
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    peaks = _peaks()
+    R, B, d = args.replicas, BATCH, DIM
+    links_per_step = R * B
+
+    # ---- resident state: tables + this rank's links, shuffled once on the device (np.random.shuffle semantics are
+    #      exercised by the parity tests; the order itself is not part of the timed hot path)
+    g = torch.Generator(device="cuda").manual_seed(7 + rank)
+    EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
+    EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
+    n_links = args.links
+    train = synth_links_device(n_links, N_USERS, N_ITEMS, 2017 + rank, torch)
+    perm = torch.randperm(n_links, device="cuda", generator=g)
+    train = ops.permute_rows(train, perm)
+    uid_all = train[:, 0].contiguous()
+    cid_all = train[:, 1].contiguous()
+    del train, perm
+    steps_per_pass = n_links // links_per_step
+    assert steps_per_pass >= 1
+
+    step = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
+                              optimizer="sgd", learn_rate=LR, replicas=R, neg_loss_weight=LAMBDA))
+    loss_buf = torch.empty(max(args.steps, args.warmup, 1) * R, dtype=torch.float32, device="cuda")
+
+    def run_steps(k, start_step):
+        """k consecutive steps starting at step index start_step (wraps around the link array between passes)"""
+        done = 0
+        while done < k:
+            s0 = (start_step + done) % steps_per_pass
+            n = min(k - done, steps_per_pass - s0)
+            off = s0 * links_per_step
+            step.run(EU, EV, uid_all[off:], cid_all[off:], n, loss_out=loss_buf[done * R:])
+            done += n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident throughput ------------------------------------------------------------------
+    run_steps(args.warmup, 0)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_steps(args.steps, args.warmup)
+    e1.record()
+    barrier()
+    launches = ops.launch_count() - launches0
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.join(timeout=2)
+    final_loss = float(loss_buf[(args.steps - 1) * R:(args.steps) * R].mean().item())
+    assert np.isfinite(final_loss), "training diverged"
+    value = world * args.steps * links_per_step / (ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- sequential reference semantics (R = 1) --------------------------------------------------------------
+    seq = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
+                             optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA))
+    nseq = min(2000, n_links // B)
+    seq.run(EU, EV, uid_all, cid_all, 50)
+    torch.cuda.synchronize()
+    e0.record()
+    seq.run(EU, EV, uid_all, cid_all, nseq)
+    e1.record()
+    torch.cuda.synchronize()
+    seq_value = nseq * B / (e0.elapsed_time(e1) * 1e-3)
+
+    # ---- roofline of the dominant kernel: CUDA events around the score+gradient kernel, on its stream ---------
+    step.set_profile(True)
+    nprof = min(200, steps_per_pass)
+    step.run(EU, EV, uid_all, cid_all, nprof)
+    torch.cuda.synchronize()
+    phase_ms, psteps = step.get_profile()
+    step.set_profile(False)
+    gather_ms, score_ms, final_ms = [x / max(psteps, 1) for x in phase_ms]
+    flops = 6.0 * B * B * d * R
+    achieved_tf = flops / (score_ms * 1e-3) / 1e12
+    step_bytes = links_per_step * (8 + 16 * d)
+    roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<2>", "achieved": achieved_tf, "peak": peaks["bf16_burst"],
+                "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["src"],
+                "ms_per_launch": score_ms, "flops_per_launch": flops,
+                "phases_ms": {"gather_prepare": gather_ms, "score_grad": score_ms, "finalize_update": final_ms},
+                "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+                             "peak_gbs": peaks["hbm"], "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"]}}
+
+    # ---- e2e: the public train_on_batch-style call with HOST buffers, H2D of the ids and D2H of the loss each step
+    e2e_steps = min(args.steps, 300)
+    h_uid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
+    h_cid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
+    h_uid.copy_(uid_all[:h_uid.numel()].view(h_uid.shape).cpu())
+    h_cid.copy_(cid_all[:h_cid.numel()].view(h_cid.shape).cpu())
+    d_uid = torch.empty(links_per_step, dtype=torch.int32, device="cuda")
+    d_cid = torch.empty(links_per_step, dtype=torch.int32, device="cuda")
+
+    def e2e_step(i):
+        d_uid.copy_(h_uid[i], non_blocking=True)
+        d_cid.copy_(h_cid[i], non_blocking=True)
+        out = step.run(EU, EV, d_uid, d_cid, 1)
+        return out["loss"].cpu()            # D2H + sync: the python-float loss Keras' train_on_batch returns
+
+    for i in range(5):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(5, 5 + e2e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_value = e2e_steps * links_per_step / (time.perf_counter() - t0)
+
+    # ---- extra: whole@k users/sec on a C4-shaped shard (all 2M items, k = 50) ---------------------------------
+    extra = {}
+    if not args.no_eval:
+        n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
+        Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5
+        Ve = torch.randn((n_eval_items, d), device="cuda", generator=g) / d ** 0.5
+        ops.eval_topk(Ue[:1024], Ve, k, "bf16")
+        torch.cuda.synchronize()
+        e0.record()
+        ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
+        e1.record()
+        torch.cuda.synchronize()
+        ems = e0.elapsed_time(e1)
+        etf = 2.0 * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
+        extra = {"whole_at_k": {"users_per_sec": n_eval_users / (ems * 1e-3), "k": k, "users": n_eval_users,
+                                "items": n_eval_items, "dim": d, "ms": ems,
+                                "roofline": {"bound": "tensor", "achieved": etf, "peak": peaks["bf16_burst"],
+                                             "unit": "TFLOP/s", "frac": etf / peaks["bf16_burst"]}}}
+        del Ue, Ve, ids
+
+    # ---- cpu baseline: bounded sample on the box's host cores -------------------------------------------------
+    cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
+    line = {
+        "metric": "positive links/sec train (neg_shared)", "value": value, "unit": "links/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_size_p": B, "dim": d, "replicas_per_gpu": R, "links_per_step": links_per_step,
+                   "links_resident": n_links, "optimizer": "sparse SGD (atomic scatter-add)", "precision": "bf16 operands, fp32 accumulate (tcgen05)",
+                   "semantics": "each step = R independent neg_shared batches against one table snapshot (synchronous "
+                                "data-parallel virtual workers); R=1 (the reference's sequential loop) is reported in `sequential`",
+                   "l2": "inputs larger than L2: 1.02 GB of embedding tables, random rows, batches never repeat within a pass"},
+        "sequential": {"value": seq_value, "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq},
+        "final_loss": final_loss,
+        "roofline": roofline,
+        "cpu_baseline": {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": "%d sequential neg_shared steps of 512 links (%.1f s) on 1M x 128 fp32 tables, NumPy/BLAS" % (args.cpu_steps, cpu_dt)},
+        "e2e": {"value": e2e_value * world, "unit": "links/s", "h2d_bytes_per_step": 2 * 4 * links_per_step,
+                "d2h_bytes_per_step": 4 * R, "steps": e2e_steps,
+                "note": "per step: pinned-host ids -> device, one super-step through the C-ABI, loss read back (sync)"},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "extra": extra,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas", type=int, default=32)
+    ap.add_argument("--links", type=int, default=N_LINKS)
+    ap.add_argument("--cpu-steps", type=int, default=3000)
+    ap.add_argument("--eval-users", type=int, default=65536)
+    ap.add_argument("--no-eval", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -141,10 +141,30 @@ typedef struct {
 
 int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,
                      const int32_t* item_ids_dev, int64_t n_steps, const nncf_step_io* io, void* stream);
+/* Optional per-phase device timing with CUDA events on the launching stream (used by bench.py's roofline leg; it
+ * synchronises after every step, so never enable it inside a throughput measurement).
+ * phase_ms_out[3] = accumulated ms of { gather/prepare, score+gradient kernel, finalize/optimizer }. */
+int nncf_trainer_set_profile(nncf_trainer_t* t, int enable);
+int nncf_trainer_get_profile(nncf_trainer_t* t, double* phase_ms_out, int64_t* steps_out);
 /* tf.unique on device (first-occurrence order), exposed because group_neg_shared towers need it before
  * they can produce item_rows_dev.   ref: models/model_framework.py:45-48 */
 int nncf_unique_first_occurrence(const int32_t* ids_dev, int n, int32_t* unique_ids_dev, int32_t* inverse_dev,
                                  int32_t* n_unique_dev, void* stream);
+
+/* Stand-alone row gather and sparse row update: the two halves of the step that framework towers and the
+ * row-sharded multi-GPU path run on their own (owners gather rows for peers / apply the gradients they get back).
+ *   nncf_gather_rows:    out[r, :] = table[ids[r], :]
+ *   nncf_updater_apply:  per-position row gradients grads[n, dim] (clobbered) applied to table rows ids[n]:
+ *                        SGD = atomic scatter-add, duplicates sum; lazy Adam = duplicates summed, then the
+ *                        _apply_sparse rule of ref utils/optimizer.py:108-147 with step count t
+ *                        (advance t once per training step with nncf_updater_begin_step). */
+int nncf_gather_rows(const float* table_dev, int dim, const int32_t* ids_dev, int64_t n, float* out_dev, void* stream);
+typedef struct nncf_updater nncf_updater_t;
+int nncf_updater_create(int optimizer, float learn_rate, float beta1, float beta2, float epsilon, nncf_updater_t** out);
+int nncf_updater_destroy(nncf_updater_t* u);
+int nncf_updater_begin_step(nncf_updater_t* u);
+int nncf_updater_apply(nncf_updater_t* u, float* table_dev, float* m_dev, float* v_dev, int64_t n_table_rows, int dim,
+                       const int32_t* ids_dev, int64_t n, float* grads_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (4) Mean-of-word-vectors item encoder.   ref: modules/content/mean_pool.py:27-33 (AverageEmbeddings:

@@ -52,8 +52,8 @@ struct TopkShared {
   uint64_t* scratch;  // [4 warps][256]
 };
 
-// Merge row `il`'s pending candidates into its sorted list in global memory; returns the new threshold score.
-__device__ __forceinline__ float flush_row(uint64_t* list, int KP, int k, int sortn, const uint64_t* pend_row, int cnt,
+// Merge row `il`'s pending candidates into its sorted list in global memory; returns the new threshold key.
+__device__ __forceinline__ uint64_t flush_row(uint64_t* list, int KP, int k, int sortn, const uint64_t* pend_row, int cnt,
                                            uint64_t* scratch, int lane) {
   for (int t = lane; t < sortn; t += 32) {
     uint64_t v = 0;
@@ -66,12 +66,13 @@ __device__ __forceinline__ float flush_row(uint64_t* list, int KP, int k, int so
   for (int t = lane; t < KP; t += 32) list[t] = (t < k) ? scratch[t] : 0ull;
   const uint64_t kth = scratch[k - 1];
   __syncwarp();
-  return kth ? key_score(kth) : -INFINITY;
+  return kth;
 }
 
 // One epilogue step: thread (= row) looks at 32 consecutive scores of its row.
 struct RowState {
-  float thr;
+  float thr;          // score of the current k-th best (-inf until k candidates are known)
+  uint64_t thr_key;   // its full ordering key (0 = none): ties are decided on keys, so tiles may arrive in any order
   int cnt;
 };
 
@@ -79,16 +80,27 @@ __device__ __forceinline__ void consider32(const float* v, uint32_t col0, uint32
                                            uint64_t* pend_row, bool row_ok) {
   float m = -INFINITY;
   if (col0 + 32 <= col_end) {
+    // four independent chains (the compiler folds pairs into 3-input FMNMX3) instead of one 32-deep dependency
+    float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
 #pragma unroll
-    for (int t = 0; t < 32; ++t) m = fmaxf(m, v[t]);
+    for (int t = 8; t < 32; t += 8) {
+      m0 = fmaxf(m0, fmaxf(v[t], v[t + 1]));
+      m1 = fmaxf(m1, fmaxf(v[t + 2], v[t + 3]));
+      m2 = fmaxf(m2, fmaxf(v[t + 4], v[t + 5]));
+      m3 = fmaxf(m3, fmaxf(v[t + 6], v[t + 7]));
+    }
+    m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
   } else {
 #pragma unroll
     for (int t = 0; t < 32; ++t) m = (col0 + t < col_end) ? fmaxf(m, v[t]) : m;
   }
-  if (row_ok && m > st.thr) {
+  if (row_ok && m >= st.thr) {
 #pragma unroll
     for (int t = 0; t < 32; ++t) {
-      if (v[t] > st.thr && col0 + t < col_end) { pend_row[st.cnt] = make_key(v[t], col0 + t); ++st.cnt; }
+      if (v[t] >= st.thr && col0 + t < col_end) {
+        const uint64_t key = make_key(v[t], col0 + t);
+        if (key > st.thr_key) { pend_row[st.cnt] = key; ++st.cnt; }
+      }
     }
   }
 }
@@ -101,9 +113,9 @@ __device__ __forceinline__ void flush_if_needed(RowState& st, uint64_t* list_bas
     const int rl = __ffs(need) - 1;
     need &= need - 1;
     const int cnt = __shfl_sync(0xffffffffu, st.cnt, rl);
-    const float nt = flush_row(list_base + rl * list_row_stride, KP, k, sortn, sh.pend + (q * 32 + rl) * kPend, cnt,
-                               sh.scratch + q * 256, lane);
-    if (lane == rl) { st.thr = nt; st.cnt = 0; }
+    const uint64_t kth = flush_row(list_base + rl * list_row_stride, KP, k, sortn, sh.pend + (q * 32 + rl) * kPend, cnt,
+                                   sh.scratch + q * 256, lane);
+    if (lane == rl) { st.thr_key = kth; st.thr = kth ? key_score(kth) : -INFINITY; st.cnt = 0; }
   }
 }
 
@@ -175,6 +187,9 @@ eval_topk_tc_kernel(EvalArgs a) {
   const int t0 = sp * a.tiles_per_split;
   const int t1 = min(n_tiles, t0 + a.tiles_per_split);
   const int nj = max(0, t1 - t0);
+  // CTAs sweep the item tiles in rotated order so that at any moment they read DIFFERENT tiles (no L2 hot spot on
+  // one tile); the top-k logic is order independent (ties are decided on full keys)
+  const int rot = nj > 0 ? static_cast<int>((static_cast<unsigned>(ub) * 37u + static_cast<unsigned>(sp) * 11u) % static_cast<unsigned>(nj)) : 0;
 
   if (tid == 0) {
     mbar_init(u_full, 1);
@@ -197,7 +212,8 @@ eval_topk_tc_kernel(EvalArgs a) {
         const int st = j % C::kStages;
         mbar_wait(&v_empty[st], ((j / C::kStages) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
-        const uint8_t* gV = a.Vimg + (size_t)(t0 + j) * NSUB * kSubBytes;
+        const int jj = (j + rot) % nj;
+        const uint8_t* gV = a.Vimg + (size_t)(t0 + jj) * NSUB * kSubBytes;
         for (int s = 0; s < NSUB; ++s)
           bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + (size_t)s * kSubBytes, kSubBytes, &v_full[st]);
       }
@@ -227,7 +243,7 @@ eval_topk_tc_kernel(EvalArgs a) {
     const int64_t urow = (int64_t)ub * 128 + il;
     const bool row_ok = urow < a.n_users;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    RowState rs; rs.thr = -INFINITY; rs.cnt = 0;
+    RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.cnt = 0;
     uint64_t* pend_row = sh.pend + il * kPend;
     const int64_t lstride = (int64_t)a.nsplit * a.KP;
     uint64_t* list_base = a.lists + ((int64_t)ub * 128 + q * 32) * lstride + (int64_t)sp * a.KP;
@@ -236,17 +252,20 @@ eval_topk_tc_kernel(EvalArgs a) {
       const int sb = j % C::kSBufs;
       mbar_wait(&s_full[sb], (j / C::kSBufs) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + lane_addr + sb * 128 + c0, v);
-        tmem_ld_wait();
-        consider32(v, static_cast<uint32_t>((t0 + j) * 128 + c0), col_end, rs, pend_row, row_ok);
-        flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, false);
-      }
+      // pull the whole 128-column row of the tile into registers with four back-to-back TMEM loads, hand the
+      // accumulator back to the MMA warp immediately, then filter from registers
+      float v[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        consider32(v[c], static_cast<uint32_t>((t0 + (j + rot) % nj) * 128 + c * 32), col_end, rs, pend_row, row_ok);
+        flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, false);
+      }
     }
     flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, true);
   }
@@ -277,7 +296,7 @@ eval_topk_simt_kernel(EvalArgs a) {
   const int il = tid, q = warp;
   const int64_t urow = (int64_t)ub * 128 + il;
   const bool row_ok = urow < a.n_users;
-  RowState rs; rs.thr = -INFINITY; rs.cnt = 0;
+  RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.cnt = 0;
   uint64_t* pend_row = sh.pend + il * kPend;
   const int64_t lstride = (int64_t)a.nsplit * a.KP;
   uint64_t* list_base = a.lists + ((int64_t)ub * 128 + q * 32) * lstride + (int64_t)sp * a.KP;

@@ -1,0 +1,378 @@
+// score_tc.cuh — score + gradient on the 5th-gen tensor cores (precision = bf16), one-sided formulation.
+//
+// Every CTA owns ONE 128-row block of one side X (X = U rows i when side = 0, X = V rows j when side = 1) and sweeps
+// the 128-row blocks Y_t of the other side:
+//     MMA1  S'_t  = X_ob Y_t^T       A, B K-major             -> TMEM, double buffered (2 x 128 columns)
+//     epi   G'_t  = dL/dS'_t         TMEM -> registers -> bf16 -> swizzled smem tile image
+//                                    (+ loss / positive-score corrections, see below)
+//     MMA2  dX_ob += G'_t Y_t        A K-major, B MN-major    -> TMEM accumulator (DP columns), drained ONCE
+// so the gradient of the owned rows is complete inside the CTA: no atomics, no second drain, and the score matrix
+// exists only in TMEM.  The two sides recompute S (side 1 sees its transpose), which costs a second pass of the
+// cheap K = d contraction but removes the B^2 d / 128 float atomics of a one-pass scheme (measured: 21k cycles per
+// tile on B200).  side 0 also produces the loss and, for group pairwise losses, the per-row sums of dL/dD; side 1
+// produces the per-column sums for neg_shared pairwise losses (both are per-thread running sums here).
+//
+// The kernel is specialised at compile time on <NSUB (= dp/64), LOSS, GROUP>: the epilogue is straight-line,
+// branch-free code (a first version that switched on the loss per element ran 24k cycles per tile: the unrolled
+// 4-way switch blew the instruction cache).
+//
+// Warp roles: warp 0 = bulk-copy (TMA engine) producer, warp 1 = MMA issuer, warps 2..9 = epilogue; epilogue warp w
+// reads TMEM lanes 32*(w&3).. and the 64-column half (w-2)>>2 of every S tile, i.e. exactly one G sub-tile.
+#pragma once
+#include "common.cuh"
+#include "sm100.cuh"
+
+namespace nncf {
+
+constexpr int kScoreEpiWarps = 8;
+constexpr int kScoreThreads = 64 + 32 * kScoreEpiWarps;
+
+struct ScoreTcArgs {
+  const uint8_t* Uimg; const uint8_t* Vimg;   // [R][rows_pad/128][NSUB][16 KiB]
+  float* dU; float* dV;                       // [R][rows_pad][dp]   plain stores (each row has one owner)
+  float* corrU; float* corrV;                 // [R][rows_pad]
+  const float* spos;                          // [R][rows_pad] positive score of batch row b
+  const int32_t* inverse;                     // group: [R][rows_pad] compact column of batch row i, else NULL
+  const int32_t* ncols_dev;                   // group: [R] number of unique items, else NULL
+  double* loss;                               // [R]
+  int rows_pad, B, scheme, loss_kind;
+  float lambda, gamma;
+  long long* dbg;                             // optional [grid][64] clock64 stamps (developer tool)
+};
+
+// declared here, defined in score_tc_nsub{1,2,4}.cu (one translation unit per NSUB so they compile in parallel)
+int launch_score_tc_nsub1(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st);
+int launch_score_tc_nsub2(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st);
+int launch_score_tc_nsub4(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st);
+
+template <int NSUB>
+struct ScoreTcCfg {
+  static constexpr int DP = 64 * NSUB;
+  static constexpr int kStages = 2;
+  static constexpr int kGBufs = NSUB <= 3 ? 2 : 1;
+  static constexpr int kColDX = 256;
+  static constexpr size_t kSmemBytes =
+      (size_t)NSUB * kSubBytes * (1 + kStages) + (size_t)kGBufs * 2 * kSubBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct EpiConst {
+  float w_neg, gamma, inv_b, inv_cnt, ns_margin;   // ns_margin = gamma for neg_shared (zero margin at the positive), else 0
+};
+
+// One element, straight-line.  w = loss weight of the element, posf = 1 for the row's positive else 0,
+// sp = positive score it is compared with (pairwise losses).
+template <int LOSS, bool NEED_LOSS>
+__device__ __forceinline__ void epi_val(const EpiConst& c, float s, float w, float posf, float sp, float& g, float& a,
+                                        float& l) {
+  a = 0.0f; l = 0.0f;
+  if (LOSS == NNCF_LOSS_SKIP_GRAM) {
+    const float e = __expf(-fabsf(s));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    const float sg = (s >= 0.0f) ? r : e * r;                                   // sigmoid(s)
+    if (NEED_LOSS) l = w * (fmaxf(s, 0.0f) + __logf(1.0f + e) - posf * s) * c.inv_b;   // softplus(s) [- s for the positive]
+    g = w * (sg - posf) * c.inv_b;
+  } else if (LOSS == NNCF_LOSS_MSE) {
+    const float t = s - posf;
+    if (NEED_LOSS) l = w * t * t * c.inv_b;
+    g = 2.0f * w * t * c.inv_b;
+  } else if (LOSS == NNCF_LOSS_LOG_LOSS) {
+    const float x = -c.gamma * (sp - s);                                        // -gamma * D
+    const float e = __expf(-fabsf(x));
+    const float r = __fdividef(1.0f, 1.0f + e);
+    const float sg = (x >= 0.0f) ? r : e * r;                                   // sigmoid(-gamma D)
+    if (NEED_LOSS) l = (fmaxf(x, 0.0f) + __logf(1.0f + e)) * c.inv_cnt;
+    a = -c.gamma * sg * c.inv_cnt;
+    g = -a;
+  } else {
+    const float t = (c.gamma - posf * c.ns_margin) - (sp - s);                  // M - D
+    if (NEED_LOSS) l = fmaxf(t, 0.0f) * c.inv_cnt;
+    a = (t > 0.0f) ? -c.inv_cnt : 0.0f;
+    g = -a;
+  }
+}
+
+// 32 consecutive swept columns of my row.  GENERAL = false: the tile is full and holds no positive (fast path).
+template <int LOSS, bool SIDE1, bool GROUP, bool GENERAL>
+__device__ __forceinline__ void epi_chunk(const EpiConst& c, float (&v)[32], int x0, int n_other, bool row_ok, int o,
+                                          int my_posc, float my_sp, const int32_t* __restrict__ inv_row,
+                                          const float* __restrict__ spos_row, float& lsum, float& asum) {
+  constexpr bool kPairwise = LOSS >= NNCF_LOSS_LOG_LOSS;
+  constexpr bool kSpMine = kPairwise && (SIDE1 != GROUP);       // positive score constant along my row
+  constexpr bool kPosByInverse = SIDE1 && GROUP;                // positive test needs inverse[x] of the swept row
+#pragma unroll
+  for (int u4 = 0; u4 < 32; u4 += 4) {
+    int4 iv = make_int4(0, 0, 0, 0);
+    float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (GENERAL && kPosByInverse) iv = __ldg(reinterpret_cast<const int4*>(inv_row + x0 + u4));
+    if (kPairwise && !kSpMine) sv = __ldg(reinterpret_cast<const float4*>(spos_row + x0 + u4));
+    const int ivs[4] = {iv.x, iv.y, iv.z, iv.w};
+    const float svs[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int u = u4 + k;
+      const int x = x0 + u;
+      float w = c.w_neg, posf = 0.0f;
+      if (GENERAL) {
+        const bool pos = kPosByInverse ? (ivs[k] == o) : (x == my_posc);
+        w = pos ? 1.0f : c.w_neg;
+        posf = pos ? 1.0f : 0.0f;
+      }
+      const float sp = kSpMine ? my_sp : svs[k];
+      float g, aa, ll;
+      epi_val<LOSS, !SIDE1>(c, v[u], w, posf, sp, g, aa, ll);
+      const bool valid = GENERAL ? (row_ok && x < n_other) : row_ok;
+      v[u] = valid ? g : 0.0f;
+      if (!SIDE1) lsum += valid ? ll : 0.0f;
+      if (kPairwise) asum += valid ? aa : 0.0f;
+    }
+  }
+}
+
+template <int NSUB, int LOSS, bool GROUP>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+score_grad_tc_kernel(ScoreTcArgs a) {
+  using C = ScoreTcCfg<NSUB>;
+  constexpr int DP = C::DP;
+  constexpr bool kPairwise = LOSS >= NNCF_LOSS_LOG_LOSS;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sX = smem;
+  uint8_t* sY = sX + NSUB * kSubBytes;
+  uint8_t* sG = sY + C::kStages * NSUB * kSubBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * 2 * kSubBytes);
+  uint64_t* x_full = bars + 0;
+  uint64_t* y_full = bars + 1;      // [2]
+  uint64_t* y_empty = bars + 3;     // [2]
+  uint64_t* s_full = bars + 5;      // [2]
+  uint64_t* s_empty = bars + 7;     // [2]
+  uint64_t* g_full = bars + 9;      // [2]
+  uint64_t* g_empty = bars + 11;    // [2]
+  uint64_t* dx_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
+  const int ncols = GROUP ? a.ncols_dev[r] : a.B;
+  const int n_owner = side == 0 ? a.B : ncols;     // valid rows on the owner side
+  const int n_other = side == 0 ? ncols : a.B;     // valid rows on the swept side
+  if (ob * 128 >= n_owner) return;                 // whole CTA exits together (no barrier touched yet)
+  const int nt = (n_other + 127) >> 7;
+  const int nblk = a.rows_pad >> 7;
+  const int64_t base = (int64_t)r * a.rows_pad;
+  const uint8_t* gX = (side == 0 ? a.Uimg : a.Vimg) + ((int64_t)r * nblk + ob) * NSUB * kSubBytes;
+  const uint8_t* gY = (side == 0 ? a.Vimg : a.Uimg) + (int64_t)r * nblk * NSUB * kSubBytes;
+
+  if (tid == 0) {
+    mbar_init(x_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kScoreEpiWarps);
+      mbar_init(&g_full[s], kScoreEpiWarps); mbar_init(&g_empty[s], 1);
+    }
+    mbar_init(dx_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  long long* dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
+#define NNCF_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
+  if (tid == 0) NNCF_STAMP(0);
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------ producer
+    if (lane == 0) {
+      mbar_expect_tx(x_full, NSUB * kSubBytes);
+      for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t % C::kStages;
+        mbar_wait(&y_empty[st], ((t / C::kStages) & 1) ^ 1);
+        mbar_expect_tx(&y_full[st], NSUB * kSubBytes);
+        for (int s = 0; s < NSUB; ++s)
+          bulk_g2s(sY + (st * NSUB + s) * kSubBytes, gY + ((size_t)t * NSUB + s) * kSubBytes, kSubBytes, &y_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_dx = make_idesc_bf16(128, DP, 0, 1);
+      auto issue_mma1 = [&](int t) {
+        const int st = t % C::kStages, sb = t & 1;
+        mbar_wait(&y_full[st], (t / C::kStages) & 1);
+        mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k) {
+          const uint64_t ad = make_smem_desc(smem_u32(sX + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(sY + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem + sb * 128, ad, bd, idesc_s, k > 0);
+        }
+        umma_commit(&s_full[sb]);
+      };
+      mbar_wait(x_full, 0);
+      NNCF_STAMP(1);
+      issue_mma1(0);
+      NNCF_STAMP(2);
+      for (int t = 0; t < nt; ++t) {
+        const int st = t % C::kStages, gb = t % C::kGBufs;
+        if (t + 1 < nt) issue_mma1(t + 1);
+        mbar_wait(&g_full[gb], (t / C::kGBufs) & 1);
+        if (t < 8) NNCF_STAMP(8 + t);
+        tc_fence_after();
+        const uint8_t* g = sG + gb * 2 * kSubBytes;
+        const uint8_t* y = sY + st * NSUB * kSubBytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {   // K = the 128 swept rows of this tile, 16 per MMA
+          const uint64_t ad = make_smem_desc(smem_u32(g + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(y) + k * 2048, kSubBytes, 1024);
+          umma_bf16(tmem + C::kColDX, ad, bd, idesc_dx, (t > 0) || (k > 0));
+        }
+        umma_commit(&y_empty[st]);
+        umma_commit(&g_empty[gb]);
+      }
+      umma_commit(dx_full);
+      NNCF_STAMP(3);
+    }
+  } else {
+    // ------------------------------------------------------------------------------ epilogue warps
+    const int ew = warp - 2;
+    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
+    const int h = ew >> 2;                      // 64-column half of each S tile = G sub-tile index
+    const int ol = q * 32 + lane;               // row inside the owned block
+    const int o = ob * 128 + ol;                // owner-side index (i on side 0, j on side 1)
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int nc = ncols > 1 ? ncols : 2;
+    EpiConst ec;
+    ec.w_neg = a.lambda / static_cast<float>(nc - 1);
+    ec.gamma = a.gamma;
+    ec.inv_b = 1.0f / static_cast<float>(a.B);
+    ec.inv_cnt = 1.0f / (static_cast<float>(a.B) * static_cast<float>(nc));
+    ec.ns_margin = GROUP ? 0.0f : a.gamma;
+    const bool row_ok = o < n_owner;
+    // side 0: the positive column of my row.  side 1 (neg_shared): my own index (the diagonal).
+    const int my_posc = (side == 0 && GROUP) ? (row_ok ? a.inverse[base + o] : -1) : o;
+    const bool sp_mine = kPairwise && ((side == 0) == GROUP);
+    const float my_sp = (sp_mine && row_ok) ? a.spos[base + o] : 0.0f;
+    const int32_t* inv_row = GROUP ? a.inverse + base : nullptr;
+    const float* spos_row = a.spos + base;
+    float lsum = 0.0f, asum = 0.0f;
+
+    for (int t = 0; t < nt; ++t) {
+      const int sb = t & 1, gb = t % C::kGBufs;
+      mbar_wait(&s_full[sb], (t >> 1) & 1);
+      if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(16 + t);
+      tc_fence_after();
+      float v0[32], v1[32];
+      tmem_ld32(tmem + lane_addr + sb * 128 + h * 64, v0);
+      tmem_ld32(tmem + lane_addr + sb * 128 + h * 64 + 32, v1);
+      tmem_ld_wait();
+      // the S buffer is in registers now: hand it back to the MMA warp before doing the math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      const int x0 = t * 128 + h * 64;
+      // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tile has them)
+      const bool general = GROUP || (t == ob) || (t * 128 + 128 > n_other);
+      if (side == 0) {
+        if (general) {
+          epi_chunk<LOSS, false, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, false, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+        } else {
+          epi_chunk<LOSS, false, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, false, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+        }
+      } else {
+        if (general) {
+          epi_chunk<LOSS, true, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, true, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+        } else {
+          epi_chunk<LOSS, true, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, true, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+        }
+      }
+      mbar_wait(&g_empty[gb], ((t / C::kGBufs) & 1) ^ 1);
+      uint8_t* grow = sG + gb * 2 * kSubBytes + h * kSubBytes + ol * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const float* src = (ch < 4) ? (v0 + ch * 8) : (v1 + (ch - 4) * 8);
+        uint4 pk;
+        pk.x = pack_bf16x2(src[0], src[1]);
+        pk.y = pack_bf16x2(src[2], src[3]);
+        pk.z = pack_bf16x2(src[4], src[5]);
+        pk.w = pack_bf16x2(src[6], src[7]);
+        *reinterpret_cast<uint4*>(grow + ((ch ^ (ol & 7)) << 4)) = pk;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&g_full[gb]);
+      if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(24 + t);
+    }
+    // drain the accumulated gradient of the owned rows: this warp takes columns [h*DP/2, (h+1)*DP/2)
+    mbar_wait(dx_full, 0);
+    if (warp == 2 && lane == 0) NNCF_STAMP(4);
+    tc_fence_after();
+    {
+      float* dst = (side == 0 ? a.dU : a.dV) + (base + o) * DP;
+#pragma unroll 1
+      for (int c0 = h * (DP / 2); c0 < (h + 1) * (DP / 2); c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem + lane_addr + C::kColDX + c0, v);
+        tmem_ld_wait();
+        if (row_ok) {
+#pragma unroll
+          for (int u = 0; u < 32; u += 4)
+            *reinterpret_cast<float4*>(dst + c0 + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
+        }
+      }
+    }
+    // per-row sums of dL/dD: the two column halves of a row live in two warps -> atomics on two addends only
+    if (kPairwise && row_ok) {
+      if (side == 0 && GROUP) atomicAdd(a.corrU + base + o, asum);
+      if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
+    }
+    if (side == 0) {
+      lsum = warp_sum(lsum);
+      if (lane == 0) atomicAdd(&a.loss[r], static_cast<double>(lsum));
+    }
+    if (warp == 2 && lane == 0) NNCF_STAMP(5);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+  if (tid == 0) NNCF_STAMP(6);
+#undef NNCF_STAMP
+}
+
+// host-side dispatch over <LOSS, GROUP> for one NSUB (instantiated by score_tc_nsub*.cu)
+template <int NSUB, int LOSS, bool GROUP>
+int launch_score_tc_one(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) {
+  using C = ScoreTcCfg<NSUB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)C::kSmemBytes));
+    attr_set = true;
+  }
+  score_grad_tc_kernel<NSUB, LOSS, GROUP><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes, st>>>(a);
+  NNCF_LAUNCH_OK();
+  return 0;
+}
+
+template <int NSUB>
+int launch_score_tc_all(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) {
+  const bool g = a.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
+  switch (a.loss_kind) {
+    case NNCF_LOSS_SKIP_GRAM: return g ? launch_score_tc_one<NSUB, 0, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 0, false>(a, nblk, R, st);
+    case NNCF_LOSS_MSE: return g ? launch_score_tc_one<NSUB, 1, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 1, false>(a, nblk, R, st);
+    case NNCF_LOSS_LOG_LOSS: return g ? launch_score_tc_one<NSUB, 2, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 2, false>(a, nblk, R, st);
+    default: return g ? launch_score_tc_one<NSUB, 3, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 3, false>(a, nblk, R, st);
+  }
+}
+
+}  // namespace nncf

@@ -19,6 +19,7 @@
 #include <vector>
 #include "common.cuh"
 #include "sm100.cuh"
+#include "score_tc.cuh"
 
 namespace nncf {
 
@@ -104,6 +105,7 @@ struct GatherArgs {
   int d, dp;                 // true / padded dim
   int normalize;
   int write_img;
+  int zero_grad;             // zero dX (needed by the atomically-accumulating fp32 path only)
   float* Xf;                 // [R][rows_pad][dp]
   float* inv;                // [R][rows_pad]
   uint8_t* img;              // [R][rows_pad/128][dp/64][16 KiB]
@@ -158,7 +160,7 @@ gather_rows_kernel(GatherArgs a) {
     if (m < nchunk) {
       const int c = m * 64 + 2 * lane;
       *reinterpret_cast<float2*>(xf + c) = make_float2(x[2 * m], x[2 * m + 1]);
-      *reinterpret_cast<float2*>(dx + c) = make_float2(0.0f, 0.0f);
+      if (a.zero_grad) *reinterpret_cast<float2*>(dx + c) = make_float2(0.0f, 0.0f);
     }
   }
   if (lane == 0) {
@@ -305,288 +307,7 @@ score_grad_simt_kernel(ScoreArgs a) {
   }
 }
 
-// =================================================================================================
-// score + gradient tiles, tcgen05 path (precision = bf16).
-//   CTA (ib, r): owns the 128-row block ib of U of replica r and sweeps all 128-column blocks j:
-//     MMA1  S_j   = U_ib V_j^T        (A,B K-major)              -> TMEM S buffer
-//     epi   G_j   = dL/dS_j           (TMEM -> regs -> bf16 -> swizzled smem tile image), loss, corrections
-//     MMA2  dU_ib += G_j  V_j         (A K-major, B MN-major)    -> TMEM accumulator, drained once at the end
-//     MMA3  dV_j   = G_j^T U_ib       (A,B MN-major)             -> TMEM, drained per tile with red.global.add.v4
-//   warp 0 = bulk-copy producer, warp 1 = MMA issuer, warps 2..5 = epilogue (TMEM lane quadrant = warp & 3).
-// =================================================================================================
-constexpr int kTcThreads = 64 + 32 * kEpiWarps;
-
-template <int NSUB>
-struct TcCfg {
-  static constexpr int DP = 64 * NSUB;
-  static constexpr bool kPipelined = (NSUB <= 2);
-  static constexpr int kStages = kPipelined ? 2 : 1;    // V tile stages
-  static constexpr int kSBufs = kPipelined ? 2 : 1;     // S accumulators in TMEM
-  static constexpr int kGBufs = kPipelined ? 2 : 1;     // G tiles in smem
-  static constexpr int kColS = 0;
-  static constexpr int kColDU = kPipelined ? 256 : 128;
-  static constexpr int kColDV = 384;
-  static constexpr int kDvChunks = (DP + 127) / 128;
-  static constexpr size_t kSmemBytes =
-      (size_t)NSUB * kSubBytes * (1 + kStages) + (size_t)kGBufs * 2 * kSubBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-};
-
-template <int NSUB>
-__global__ void __launch_bounds__(kTcThreads, 1)
-score_grad_tc_kernel(ScoreArgs a) {
-  using C = TcCfg<NSUB>;
-  constexpr int DP = C::DP;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sU = smem;
-  uint8_t* sV = sU + NSUB * kSubBytes;
-  uint8_t* sG = sV + C::kStages * NSUB * kSubBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * 2 * kSubBytes);
-  uint64_t* u_full = bars + 0;
-  uint64_t* v_full = bars + 1;      // [2]
-  uint64_t* v_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2]
-  uint64_t* g_full = bars + 9;      // [2]
-  uint64_t* g_empty = bars + 11;    // [2]
-  uint64_t* dv_full = bars + 13;
-  uint64_t* dv_empty = bars + 14;
-  uint64_t* du_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ib = blockIdx.x, r = blockIdx.y;
-  const int ncols = a.ncols_dev ? a.ncols_dev[r] : a.B;
-  const int nj = (ncols + 127) >> 7;
-  const int nblk = a.rows_pad >> 7;
-  const int64_t base = (int64_t)r * a.rows_pad;
-  const uint8_t* gU = a.Uimg + ((int64_t)r * nblk + ib) * NSUB * kSubBytes;
-  const uint8_t* gV = a.Vimg + (int64_t)r * nblk * NSUB * kSubBytes;
-
-  if (tid == 0) {
-    mbar_init(u_full, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kEpiWarps);
-      mbar_init(&g_full[s], kEpiWarps); mbar_init(&g_empty[s], 1);
-    }
-    mbar_init(dv_full, 1); mbar_init(dv_empty, kEpiWarps); mbar_init(du_full, 1);
-    mbar_fence_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 0) {
-    // ---------------------------------------------------------------- producer
-    if (lane == 0) {
-      mbar_expect_tx(u_full, NSUB * kSubBytes);
-      for (int s = 0; s < NSUB; ++s) bulk_g2s(sU + s * kSubBytes, gU + (size_t)s * kSubBytes, kSubBytes, u_full);
-      for (int j = 0; j < nj; ++j) {
-        const int st = j % C::kStages;
-        const uint32_t use = j / C::kStages;
-        mbar_wait(&v_empty[st], (use & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
-        for (int s = 0; s < NSUB; ++s)
-          bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + ((size_t)j * NSUB + s) * kSubBytes, kSubBytes, &v_full[st]);
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-      const uint32_t idesc_du = make_idesc_bf16(128, DP, 0, 1);
-      auto issue_mma1 = [&](int j) {
-        const int st = j % C::kStages, sb = j % C::kSBufs;
-        mbar_wait(&v_full[st], (j / C::kStages) & 1);
-        mbar_wait(&s_empty[sb], ((j / C::kSBufs) & 1) ^ 1);
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < DP / 16; ++k) {
-          const uint64_t ad = make_smem_desc(smem_u32(sU + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(smem_u32(sV + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem + C::kColS + sb * 128, ad, bd, idesc_s, k > 0);
-        }
-        umma_commit(&s_full[sb]);
-      };
-      mbar_wait(u_full, 0);
-      if (nj > 0) issue_mma1(0);
-      uint32_t dv_use = 0;
-      for (int j = 0; j < nj; ++j) {
-        const int st = j % C::kStages, gb = j % C::kGBufs;
-        if (C::kPipelined && j + 1 < nj) issue_mma1(j + 1);
-        mbar_wait(&g_full[gb], (j / C::kGBufs) & 1);
-        tc_fence_after();
-        const uint8_t* g = sG + gb * 2 * kSubBytes;
-        const uint8_t* v = sV + st * NSUB * kSubBytes;
-        // MMA2: dU += G_j V_j   (K = 128 columns j of this tile)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint64_t ad = make_smem_desc(smem_u32(g + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(smem_u32(v) + k * 2048, kSubBytes, 1024);
-          umma_bf16(tmem + C::kColDU, ad, bd, idesc_du, (j > 0) || (k > 0));
-        }
-        // MMA3: dV_j = G_j^T U   in N-chunks of <= 128 columns
-        for (int c = 0; c < C::kDvChunks; ++c) {
-          const int width = (DP - c * 128) < 128 ? (DP - c * 128) : 128;
-          const uint32_t idesc_dv = make_idesc_bf16(128, width, 1, 1);
-          mbar_wait(dv_empty, (dv_use & 1) ^ 1);
-          tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t ad = make_smem_desc(smem_u32(g) + k * 2048, kSubBytes, 1024);
-            const uint64_t bd = make_smem_desc(smem_u32(sU + c * 2 * kSubBytes) + k * 2048, kSubBytes, 1024);
-            umma_bf16(tmem + C::kColDV, ad, bd, idesc_dv, k > 0);
-          }
-          umma_commit(dv_full);
-          ++dv_use;
-        }
-        umma_commit(&v_empty[st]);
-        umma_commit(&g_empty[gb]);
-        if (!C::kPipelined && j + 1 < nj) issue_mma1(j + 1);
-      }
-      umma_commit(du_full);
-    }
-  } else {
-    // ---------------------------------------------------------------- epilogue warps
-    const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int il = q * 32 + lane;               // row inside the 128-row block
-    const int i = ib * 128 + il;
-    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const EpiParams ep = make_epi(a.scheme, a.loss_kind, a.B, ncols > 1 ? ncols : 2, a.lambda, a.gamma);
-    const bool pairwise = a.loss_kind >= NNCF_LOSS_LOG_LOSS;
-    const bool is_group = a.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
-    const bool row_ok = i < a.B;
-    const int posc = (is_group && row_ok) ? a.inverse[base + i] : i;
-    const float spos_row = (pairwise && is_group && row_ok) ? a.spos[base + i] : 0.0f;
-    float lsum = 0.0f, rowA = 0.0f;
-    uint32_t dv_use = 0;
-
-    auto drain_dv = [&](int j) {
-      for (int c = 0; c < C::kDvChunks; ++c) {
-        const int width = (DP - c * 128) < 128 ? (DP - c * 128) : 128;
-        mbar_wait(dv_full, dv_use & 1);
-        tc_fence_after();
-        const int jrow = j * 128 + il;
-        float* dst = a.dV + (base + jrow) * DP + c * 128;
-        for (int c0 = 0; c0 < width; c0 += 32) {
-          float v[32];
-          tmem_ld32(tmem + lane_addr + C::kColDV + c0, v);
-          tmem_ld_wait();
-          if (jrow < ncols) {
-#pragma unroll
-            for (int t = 0; t < 32; t += 4) red_add_v4(dst + c0 + t, v[t], v[t + 1], v[t + 2], v[t + 3]);
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(dv_empty);
-        ++dv_use;
-      }
-    };
-
-    for (int j = 0; j < nj; ++j) {
-      const int sb = j % C::kSBufs, gb = j % C::kGBufs;
-      mbar_wait(&s_full[sb], (j / C::kSBufs) & 1);
-      tc_fence_after();
-      mbar_wait(&g_empty[gb], ((j / C::kGBufs) & 1) ^ 1);
-      uint8_t* g = sG + gb * 2 * kSubBytes;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + lane_addr + C::kColS + sb * 128 + c0, v);
-        tmem_ld_wait();
-        float av[32];
-#pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int jc = j * 128 + c0 + t;
-          float gg = 0.0f, aa = 0.0f, ll = 0.0f;
-          if (row_ok && jc < ncols) {
-            float sp = spos_row;
-            if (pairwise && !is_group) sp = __ldg(a.spos + base + jc);
-            epi_elem<true>(ep, v[t], jc == posc, sp, gg, aa, ll);
-          }
-          lsum += ll;
-          v[t] = gg;
-          av[t] = aa;
-        }
-        // G -> bf16 -> swizzled smem: 32 consecutive columns = four 16-byte chunks of row il
-        {
-          uint8_t* sub = g + (c0 >> 6) * kSubBytes + il * 128;
-          const int chunk0 = (c0 & 63) >> 3;
-#pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
-            uint4 pk;
-            pk.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
-            pk.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
-            pk.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
-            pk.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
-            *reinterpret_cast<uint4*>(sub + (((chunk0 + ch) ^ (il & 7)) << 4)) = pk;
-          }
-        }
-        if (pairwise) {
-          if (is_group) {
-#pragma unroll
-            for (int t = 0; t < 32; ++t) rowA += av[t];
-          } else {
-            // column sums of A over the 32 rows of this warp: recursive-halving transpose-reduce (31 shuffles)
-#pragma unroll
-            for (int h = 16; h >= 1; h >>= 1) {
-              const bool upper = (lane & h) != 0;
-#pragma unroll
-              for (int t = 0; t < h; ++t) {
-                const float mine = upper ? av[t + h] : av[t];
-                const float send = upper ? av[t] : av[t + h];
-                av[t] = mine + __shfl_xor_sync(0xffffffffu, send, h);
-              }
-            }
-            // lane now holds the sum of column (bit-reversal-free mapping): column index = lane's bits pick halves
-            int col = 0;
-#pragma unroll
-            for (int h = 16; h >= 1; h >>= 1) col += (lane & h) ? h : 0;
-            const int jc = j * 128 + c0 + col;
-            if (jc < ncols) atomicAdd(a.corrV + base + jc, av[0]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&g_full[gb]);
-      if (j > 0) drain_dv(j - 1);
-    }
-    if (nj > 0) drain_dv(nj - 1);
-    // final: dU block
-    mbar_wait(du_full, 0);
-    tc_fence_after();
-    if (nj > 0) {
-      float* dst = a.dU + (base + i) * DP;
-      for (int c0 = 0; c0 < DP; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem + lane_addr + C::kColDU + c0, v);
-        tmem_ld_wait();
-        if (row_ok) {
-#pragma unroll
-          for (int t = 0; t < 32; t += 4)
-            *reinterpret_cast<float4*>(dst + c0 + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
-        }
-      }
-    }
-    if (pairwise && is_group && row_ok) a.corrU[base + i] = rowA;
-    lsum = warp_sum(lsum);
-    if (lane == 0) atomicAdd(&a.loss[r], static_cast<double>(lsum));
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
-  }
-}
+// (the tcgen05 score + gradient kernel lives in score_tc.cuh)
 
 // =================================================================================================
 // finalize: corrections, normalise-backward, regulariser, optimizer.  One warp per batch row.
@@ -919,7 +640,13 @@ struct nncf_trainer {
   int64_t ownerU_n = 0, ownerV_n = 0;
   float *ps = nullptr;   // PAIRS scores
   bool tc_attr_set = false;
+  // optional per-phase device timing (CUDA events on the launching stream)
+  bool profile = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  double phase_ms[3] = {0.0, 0.0, 0.0};
+  int64_t phase_steps = 0;
 };
+#define NNCF_PROFILE_MARK(t, i, st) do { if ((t)->profile) NNCF_CUDA(cudaEventRecord((t)->ev[i], st)); } while (0)
 
 template <typename T>
 static int dev_alloc(T** p, size_t n) {
@@ -945,7 +672,7 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
   const int R = cfg->replicas;
   t->rows = cfg->scheme == NNCF_SCHEME_PAIRS ? (1 + cfg->num_negatives) * cfg->batch_size_p : cfg->batch_size_p;
   t->rows_pad = (t->rows + 127) / 128 * 128;
-  t->dp = (cfg->dim + 63) / 64 * 64;
+  t->dp = cfg->dim <= 64 ? 64 : (cfg->dim <= 128 ? 128 : 256);   // tensor-core kernels exist for dp = 64 / 128 / 256
   t->nsub = t->dp / 64;
   const size_t nrow = (size_t)R * t->rows_pad, nel = nrow * t->dp;
   int rc = 0;
@@ -978,7 +705,24 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
                   t->loss, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
   for (void* p : ptrs) if (p) cudaFree(p);
+  for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   delete t;
+  return NNCF_OK;
+}
+
+extern "C" int nncf_trainer_set_profile(nncf_trainer_t* t, int enable) {
+  NNCF_CHECK_ARG(t, "nncf_trainer_set_profile: null trainer");
+  if (enable && !t->ev[0])
+    for (int i = 0; i < 4; ++i) NNCF_CUDA(cudaEventCreate(&t->ev[i]));
+  t->profile = enable != 0;
+  t->phase_ms[0] = t->phase_ms[1] = t->phase_ms[2] = 0.0;
+  t->phase_steps = 0;
+  return NNCF_OK;
+}
+extern "C" int nncf_trainer_get_profile(nncf_trainer_t* t, double* phase_ms_out, int64_t* steps_out) {
+  NNCF_CHECK_ARG(t && phase_ms_out && steps_out, "nncf_trainer_get_profile: null argument");
+  for (int p = 0; p < 3; ++p) phase_ms_out[p] = t->phase_ms[p];
+  *steps_out = t->phase_steps;
   return NNCF_OK;
 }
 
@@ -1020,19 +764,6 @@ static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int
   return 0;
 }
 
-template <int NSUB>
-static int launch_tc(nncf_trainer* t, const ScoreArgs& sa, int nib, int R, cudaStream_t st) {
-  using C = TcCfg<NSUB>;
-  if (!t->tc_attr_set) {
-    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)C::kSmemBytes));
-    t->tc_attr_set = true;
-  }
-  score_grad_tc_kernel<NSUB><<<dim3(nib, R), kTcThreads, C::kSmemBytes, st>>>(sa);
-  NNCF_LAUNCH_OK();
-  return 0;
-}
-
 static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
                        const nncf_step_io* io, bool last, cudaStream_t st) {
   const nncf_step_config& c = t->cfg;
@@ -1041,6 +772,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool pairwise = c.loss >= NNCF_LOSS_LOG_LOSS;
   const bool bf16 = c.precision == NNCF_PREC_BF16;
   const bool dense_items = tb->item_table == nullptr;
+  NNCF_PROFILE_MARK(t, 0, st);
   NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
   const int32_t* item_ids = cid;
   int64_t item_stride = B;
@@ -1063,7 +795,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // gather
   GatherArgs gu{};
   gu.table = tb->user_table; gu.ids = uid; gu.ids_stride = B; gu.count = B; gu.rows_pad = rp; gu.d = d; gu.dp = dp;
-  gu.normalize = c.norm_u; gu.write_img = bf16; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
+  gu.normalize = c.norm_u; gu.write_img = bf16; gu.zero_grad = bf16 ? 0 : 1; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
   gu.corr = t->corrU;
   gather_rows_kernel<<<dim3(rp / 8, R), 256, 0, st>>>(gu);
   NNCF_LAUNCH_OK();
@@ -1082,6 +814,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     reg_loss_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss);
     NNCF_LAUNCH_OK();
   }
+  NNCF_PROFILE_MARK(t, 1, st);
   // score + grad
   ScoreArgs sa{};
   sa.Uf = t->Uf; sa.Vf = t->Vf; sa.Uimg = t->Uimg; sa.Vimg = t->Vimg; sa.dU = t->dU; sa.dV = t->dV;
@@ -1089,12 +822,15 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   sa.ncols_dev = group ? t->nuniq : nullptr; sa.loss = t->loss; sa.rows_pad = rp; sa.dp = dp; sa.B = B;
   sa.scheme = c.scheme; sa.loss_kind = c.loss; sa.lambda = c.neg_loss_weight; sa.gamma = c.loss_gamma;
   if (bf16) {
+    ScoreTcArgs ta{};
+    ta.Uimg = t->Uimg; ta.Vimg = t->Vimg; ta.dU = t->dU; ta.dV = t->dV; ta.corrU = t->corrU; ta.corrV = t->corrV;
+    ta.spos = t->spos; ta.inverse = sa.inverse; ta.ncols_dev = sa.ncols_dev; ta.loss = t->loss; ta.rows_pad = rp;
+    ta.B = B; ta.scheme = c.scheme; ta.loss_kind = c.loss; ta.lambda = c.neg_loss_weight; ta.gamma = c.loss_gamma;
     int rc = 0;
     switch (t->nsub) {
-      case 1: rc = launch_tc<1>(t, sa, rp / 128, R, st); break;
-      case 2: rc = launch_tc<2>(t, sa, rp / 128, R, st); break;
-      case 3: rc = launch_tc<3>(t, sa, rp / 128, R, st); break;
-      default: rc = launch_tc<4>(t, sa, rp / 128, R, st); break;
+      case 1: rc = launch_score_tc_nsub1(ta, rp / 128, R, st); break;
+      case 2: rc = launch_score_tc_nsub2(ta, rp / 128, R, st); break;
+      default: rc = launch_score_tc_nsub4(ta, rp / 128, R, st); break;
     }
     if (rc) return rc;
   } else {
@@ -1107,6 +843,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     score_grad_simt_kernel<<<dim3(nt, nt, R), 256, sm, st>>>(sa);
     NNCF_LAUNCH_OK();
   }
+  NNCF_PROFILE_MARK(t, 2, st);
   // finalize (user side first: for group pairwise it adds into the item accumulators)
   const bool sgd = c.optimizer == NNCF_OPT_SGD;
   FinalizeArgs fu{};
@@ -1141,6 +878,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
         return NNCF_ECUDA;
     }
   }
+  NNCF_PROFILE_MARK(t, 3, st);
   if (last && io && group && !dense_items) {
     if (io->unique_ids_dev) NNCF_CUDA(cudaMemcpyAsync(io->unique_ids_dev, t->uniq, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
     if (io->inverse_dev) NNCF_CUDA(cudaMemcpyAsync(io->inverse_dev, t->inverse, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
@@ -1165,10 +903,13 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
   pa.grad_out_u = (last && io) ? io->grad_user_rows_dev : nullptr;
   pa.grad_out_v = (last && io) ? io->grad_item_rows_dev : nullptr;
   dim3 g8(ceil_div(n, 8), R);
+  NNCF_PROFILE_MARK(t, 0, st);
   pairs_score_kernel<<<g8, 256, 0, st>>>(pa);
   NNCF_LAUNCH_OK();
+  NNCF_PROFILE_MARK(t, 1, st);
   pairs_grad_kernel<<<g8, 256, 0, st>>>(pa);
   NNCF_LAUNCH_OK();
+  NNCF_PROFILE_MARK(t, 2, st);
   if (c.optimizer == NNCF_OPT_SGD) {
     rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
     NNCF_LAUNCH_OK();
@@ -1186,6 +927,7 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
     if (run_adam(t, cid, n, n, nullptr, n, d, d, t->ownerV, t->dV, tb->item_table, tb->item_m, tb->item_v, lr_t, st))
       return NNCF_ECUDA;
   }
+  NNCF_PROFILE_MARK(t, 3, st);
   return NNCF_OK;
 }
 
@@ -1211,10 +953,104 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
     else
       rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
     if (rc) return rc;
+    if (t->profile) {
+      NNCF_CUDA(cudaEventSynchronize(t->ev[3]));
+      for (int p = 0; p < 3; ++p) {
+        float ms = 0.0f;
+        NNCF_CUDA(cudaEventElapsedTime(&ms, t->ev[p], t->ev[p + 1]));
+        t->phase_ms[p] += ms;
+      }
+      t->phase_steps += 1;
+    }
     if (io && io->loss_out_dev) {
       loss_out_kernel<<<1, R < 32 ? 32 : ((R + 31) / 32 * 32), 0, st>>>(t->loss, R, io->loss_out_dev + s * R);
       NNCF_LAUNCH_OK();
     }
   }
+  return NNCF_OK;
+}
+
+// =================================================================================================
+// stand-alone row gather / sparse row update (used by framework towers and by the row-sharded multi-GPU path:
+// owners gather rows for their peers and apply the gradients they receive back)
+// =================================================================================================
+namespace nncf {
+__global__ void __launch_bounds__(256)
+gather_plain_kernel(const float* __restrict__ table, int d, const int32_t* __restrict__ ids, int64_t n, float* __restrict__ out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= n) return;
+  const float* src = table + (int64_t)ids[row] * d;
+  float* dst = out + row * d;
+  for (int c = lane; c < d; c += 32) dst[c] = __ldg(src + c);
+}
+}  // namespace nncf
+
+struct nncf_updater {
+  int optimizer;
+  float lr, beta1, beta2, eps;
+  int64_t t = 0;
+  int32_t* owner = nullptr;
+  int64_t owner_n = 0;
+};
+
+extern "C" int nncf_gather_rows(const float* table_dev, int dim, const int32_t* ids_dev, int64_t n, float* out_dev,
+                                void* stream) {
+  NNCF_CHECK_ARG(n >= 0 && dim >= 1, "nncf_gather_rows: bad sizes");
+  if (n == 0) return NNCF_OK;
+  NNCF_CHECK_ARG(table_dev && ids_dev && out_dev, "nncf_gather_rows: null argument");
+  gather_plain_kernel<<<ceil_div(n, 8), 256, 0, (cudaStream_t)stream>>>(table_dev, dim, ids_dev, n, out_dev);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+
+extern "C" int nncf_updater_create(int optimizer, float learn_rate, float beta1, float beta2, float epsilon,
+                                   nncf_updater_t** out) {
+  NNCF_CHECK_ARG(out, "nncf_updater_create: null argument");
+  NNCF_CHECK_ARG(optimizer == NNCF_OPT_SGD || optimizer == NNCF_OPT_LAZY_ADAM, "nncf_updater_create: optimizer must be SGD or LAZY_ADAM");
+  auto* u = new nncf_updater();
+  u->optimizer = optimizer; u->lr = learn_rate; u->beta1 = beta1; u->beta2 = beta2; u->eps = epsilon;
+  *out = u;
+  return NNCF_OK;
+}
+extern "C" int nncf_updater_destroy(nncf_updater_t* u) {
+  if (!u) return NNCF_OK;
+  if (u->owner) cudaFree(u->owner);
+  delete u;
+  return NNCF_OK;
+}
+extern "C" int nncf_updater_begin_step(nncf_updater_t* u) {
+  NNCF_CHECK_ARG(u, "nncf_updater_begin_step: null updater");
+  u->t += 1;
+  return NNCF_OK;
+}
+extern "C" int nncf_updater_apply(nncf_updater_t* u, float* table_dev, float* m_dev, float* v_dev, int64_t n_table_rows,
+                                  int dim, const int32_t* ids_dev, int64_t n, float* grads_dev, void* stream) {
+  NNCF_CHECK_ARG(u && table_dev, "nncf_updater_apply: null argument");
+  NNCF_CHECK_ARG(n >= 0 && n < (int64_t)0x7fffffff && dim >= 1, "nncf_updater_apply: bad sizes");
+  if (n == 0) return NNCF_OK;
+  NNCF_CHECK_ARG(ids_dev && grads_dev, "nncf_updater_apply: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cnt = static_cast<int>(n);
+  if (u->optimizer == NNCF_OPT_SGD) {
+    rows_sgd_kernel<<<dim3(ceil_div(n, 8), 1), 256, 0, st>>>(grads_dev, ids_dev, 0, cnt, dim, u->lr, table_dev);
+    NNCF_LAUNCH_OK();
+    return NNCF_OK;
+  }
+  NNCF_CHECK_ARG(m_dev && v_dev, "nncf_updater_apply: lazy Adam needs m / v");
+  NNCF_CHECK_ARG(u->t >= 1, "nncf_updater_apply: call nncf_updater_begin_step first");
+  if (ensure_owner(&u->owner, &u->owner_n, n_table_rows, st)) return NNCF_ECUDA;
+  const double b1t = pow((double)u->beta1, (double)u->t), b2t = pow((double)u->beta2, (double)u->t);
+  const float lr_t = (float)(u->lr * sqrt(1.0 - b2t) / (1.0 - b1t));
+  dim3 g1(ceil_div(n, 256), 1), g8(ceil_div(n, 8), 1);
+  adam_owner_kernel<<<g1, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, 0, u->owner);
+  NNCF_LAUNCH_OK();
+  adam_combine_kernel<<<g8, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, 0, dim, u->owner, grads_dev);
+  NNCF_LAUNCH_OK();
+  adam_apply_kernel<<<g8, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, 0, dim, dim, u->owner, grads_dev, table_dev, m_dev, v_dev,
+                                        lr_t, u->beta1, u->beta2, u->eps);
+  NNCF_LAUNCH_OK();
+  adam_reset_kernel<<<g1, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, u->owner);
+  NNCF_LAUNCH_OK();
   return NNCF_OK;
 }

@@ -1,0 +1,186 @@
+"""Data layer: the reference's array contract, the sampler factory and the batch-index builders.
+
+ref: configs/data_utils.py:15-70 (get_data, DataSpec, the four samplers), :193-215 (get_sampler),
+     :218-241 (group_shuffle_train); data/readme.txt:1-9 (pickle keys and array layouts).
+Array contract kept: train/test/test_seen = int [N,3] rows (user, item, label); C = int [items, L] left-zero-padded.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+
+import numpy as np
+
+from .sampler import MultinomialSampler
+
+data_root = './data'
+
+
+class DataHelper(object):
+    """Plain attribute holder, as used on the reference's run path (configs/data_utils.py:74,103)."""
+
+    def __init__(self):
+        self.data = None
+        self.data_spec = None
+        self.sampler_dict = None
+
+
+class DataSpec(object):
+    def __init__(self, user_count, word_count, item_count, max_content_len):
+        self.user_count = user_count
+        self.word_count = word_count
+        self.item_count = item_count
+        self.max_content_len = max_content_len
+        self.W_pretrain = None
+        self.C_pretrain = None
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic power-law interaction data of the named shapes
+# ------------------------------------------------------------------------------------------------
+def powerlaw_ids(n_ids, n_draws, exponent, perm_seed, draw_rng, offset=10.0):
+    """ids ~ p(rank) ∝ (rank + offset)^-exponent over a seeded random permutation of the id space."""
+    p = np.power(np.arange(n_ids, dtype=np.float64) + offset, -exponent)
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    ranks = np.searchsorted(cdf, draw_rng.random_sample(n_draws), side='right')
+    ranks = np.minimum(ranks, n_ids - 1)
+    perm = np.random.RandomState(perm_seed).permutation(n_ids)
+    return perm[ranks]
+
+
+def make_synthetic(user_count=5551, item_count=16980, n_links=204986, content_len=300, vocab=8000,
+                   cold_fraction=0.2, seed=2017, n_test_negatives=4):
+    """CiteULike-shaped stand-in (the data blob is absent from the reference tree, .MISSING_LARGE_BLOBS):
+    power-law links, 20% of the items held out as cold-start test items, 0-left-padded content matrix."""
+    rng = np.random.RandomState(seed)
+    users = powerlaw_ids(user_count, n_links, 0.8, 124, rng)
+    items = powerlaw_ids(item_count, n_links, 1.0, 123, rng)
+    links = np.stack([users, items, np.ones(n_links, dtype=np.int64)], 1)
+    cold = np.random.RandomState(5).uniform(size=item_count) < cold_fraction
+    is_test = cold[links[:, 1]]
+    train = links[~is_test]
+    test_pos = links[is_test]
+    test_items = np.nonzero(cold)[0]
+    neg_u = np.repeat(test_pos[:, 0], n_test_negatives)
+    neg_i = test_items[rng.randint(0, test_items.size, size=neg_u.size)]
+    test = np.vstack([test_pos, np.stack([neg_u, neg_i, np.zeros(neg_u.size, dtype=np.int64)], 1)])
+    sub = rng.choice(train.shape[0], size=min(train.shape[0], 20000), replace=False)
+    seen_pos = train[sub]
+    train_items = np.unique(train[:, 1])
+    neg_u = np.repeat(seen_pos[:, 0], n_test_negatives)
+    neg_i = train_items[rng.randint(0, train_items.size, size=neg_u.size)]
+    test_seen = np.vstack([seen_pos, np.stack([neg_u, neg_i, np.zeros(neg_u.size, dtype=np.int64)], 1)])
+    # content: random length in [5, L], words ~ Zipf over the vocabulary, zero padding in the beginning
+    C = np.zeros((item_count, content_len), dtype=np.int32)
+    lens = rng.randint(5, content_len + 1, size=item_count)
+    words = 1 + powerlaw_ids(vocab - 1, int(lens.sum()), 1.0, 77, rng, offset=2.0)
+    pos = 0
+    for i in range(item_count):
+        C[i, content_len - lens[i]:] = words[pos:pos + lens[i]]
+        pos += lens[i]
+    return {'C': C, 'train': train.astype(np.int32), 'test': test.astype(np.int32),
+            'test_seen': test_seen.astype(np.int32), 'train_items': train_items.tolist(), 'test_items': test_items.tolist()}
+
+
+def _get_data(data_name):
+    """Loads the reference's `data_split_cold_item.pkl` (a Python-2 pickle of NumPy arrays, keys per
+    data/readme.txt:3-9) when present under ./data, else builds the synthetic stand-in of the same shape."""
+    data_helper = DataHelper()
+    import re
+    sub_folder = ''
+    fold = re.findall(r'fold(\d+)', data_name)
+    if len(fold) == 1:
+        sub_folder = 'fold%d' % int(fold[0])
+    split_file = None
+    for family, prefix in (('citeulike', 'citeulike_'), ('news', 'news_')):
+        for kind in ('title_only', 'title_and_abstract'):
+            if data_name.startswith(prefix + kind):
+                split_file = '%s/%s/%s/%s/data_split_cold_item.pkl' % (data_root, family, kind, sub_folder)
+    if split_file is not None and os.path.exists(split_file):
+        with open(split_file, 'rb') as fp:
+            data_helper.data = pickle.load(fp, encoding='latin1')
+    elif data_name.startswith('synthetic_small'):
+        data_helper.data = make_synthetic(600, 1500, 20000, content_len=40, vocab=500, seed=11)
+    elif split_file is not None or data_name.startswith('synthetic'):
+        print('[INFO] %s: data blob not found, using the synthetic CiteULike-shaped stand-in' % data_name)
+        data_helper.data = make_synthetic()
+    else:
+        assert False, '[ERROR] unseen data_name %s' % data_name
+    return data_helper
+
+
+def get_data(data_name, conf, reverse_samping=False):
+    """configs/data_utils.py:15-70 (the misspelt keyword `reverse_samping` is the reference's, main.py:67)."""
+    data_helper = _get_data(data_name)
+    train = data_helper.data['train']
+    test = data_helper.data['test']
+    C = data_helper.data['C']
+    user_count = int(max(np.max(train[:, 0]), np.max(test[:, 0])) + 1)
+    word_count = int(np.max(C) + 1)
+    item_count = C.shape[0]
+    max_content_len = C.shape[1]
+    data_spec = DataSpec(user_count, word_count, item_count, max_content_len)
+    if conf is not None:
+        neg_dist = conf.neg_dist
+        try:
+            neg_sampling_power = conf.neg_sampling_power
+        except AttributeError:
+            neg_sampling_power = 0.75
+        seed = getattr(conf, 'seed', 0)
+        sampler_dict = {}
+        if reverse_samping:
+            train_r = train[:, [1, 0, 2]]
+            sampler_dict['sample_u'] = get_sampler(train_r, neg_dist, neg_sampling_power, rand_seed=seed + 1,
+                                                   batch_mode=False)
+            sampler_dict['sample_batch_u'] = get_sampler(train_r, neg_dist, neg_sampling_power, rand_seed=seed + 2,
+                                                         batch_mode=True)
+        sampler_dict['sample'] = get_sampler(train, neg_dist, neg_sampling_power, rand_seed=seed + 3, batch_mode=False)
+        sampler_dict['sample_batch'] = get_sampler(train, neg_dist, neg_sampling_power, rand_seed=seed + 4,
+                                                   batch_mode=True)
+        data_helper.sampler_dict = sampler_dict
+    data_helper.data_spec = data_spec
+    return data_helper
+
+
+def get_sampler(ratings, neg_dist='unigram', neg_sampling_power=0.75, column=1, rand_seed=0, batch_mode=True):
+    """configs/data_utils.py:193-215: degree histogram of `column` -> MultinomialSampler; returns the bound
+    sample_batch / sample method.  'uniform' => dist[dist > 0] = 1; a suffix after '_' in neg_dist is ignored."""
+    neg_dist = neg_dist.split('_')[0]
+    assert neg_dist == 'uniform' or neg_dist == 'unigram', [neg_dist]
+    dist = np.bincount(ratings[:, column], minlength=int(np.max(ratings[:, column])) + 1).astype(float)
+    if neg_dist == 'uniform':
+        dist[dist > 0] = 1
+    s = MultinomialSampler(dist, dist.size, neg_sampling_power, rand_seed)
+    return s.sample_batch if batch_mode else s.sample
+
+
+def group_shuffle_train(train, by='item', chop=0, iidx=None, rng=None):
+    """group_shuffle_train (configs/data_utils.py:218-241) with the work on the device: the host draws the three
+    permutations from the shared legacy stream in the reference's order (np.random by default, as the reference),
+    the device applies them with a stable radix sort.  `train` may be a NumPy array (returned as NumPy) or a CUDA
+    int32 tensor (returned as a CUDA tensor).  iidx is shuffled IN PLACE and persists across epochs."""
+    import torch
+    from . import ops
+    rng = np.random if rng is None else rng
+    col = 0 if by == 'user' else 1
+    is_np = isinstance(train, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(train, dtype=np.int32)).cuda() if is_np else train
+    n = t.shape[0]
+    if iidx is None:
+        iidx = np.arange(int(t[:, col].max().item()) + 1)
+    rng.shuffle(iidx)
+    row_perm = np.arange(n)
+    rng.shuffle(row_perm)
+    block_perm = None
+    if chop > 0:
+        block_perm = np.arange(n // chop)
+        rng.shuffle(block_perm)
+    dev = t.device
+    out = ops.group_shuffle(t, col, torch.from_numpy(iidx).to(dev), torch.from_numpy(row_perm).to(dev),
+                            None if block_perm is None else torch.from_numpy(block_perm).to(dev), chop)
+    if is_np:
+        # the reference also shuffles its input rows in place (np.random.shuffle(train))
+        train[:] = train[row_perm]
+        return out.cpu().numpy().astype(train.dtype)
+    return out

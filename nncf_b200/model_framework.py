@@ -1,0 +1,264 @@
+"""get_model(conf, data_helper, model_name) -> model_dict, the reference's model surface.
+
+ref: models/model_framework.py:18-206.  The reference builds ONE shared Keras graph and nine compiled views of it;
+here one `SharedState` (embedding tables + optional content tower, all torch CUDA tensors) is shared by view objects
+that expose the Keras methods the trainers and the Evaluator call:
+
+  model_dict['model']                   .train_on_batch([uid, cid], [resp])      'mul' view, (1+k)B listed pairs
+  model_dict['model_neg_shared']        .train_on_batch / .predict_on_batch([users, items]) -> [U, M]
+  model_dict['model_group_neg_shared']  .train_on_batch
+  model_dict['model_user_emb'] / ['model_item_emb']   .predict_on_batch([ids]) -> embeddings
+  model_dict['model_pred_pairs']        .predict([Uemb, Vemb, uid, cid], batch_size) -> [n, 1]
+
+All arithmetic is done by libnncf_b200.so kernels; the Dense/BatchNorm/ReLU of the mean-pool tower (and the CNN/RNN
+towers) stay torch modules feeding the fused score kernel, as the north_star prescribes.  Keys absent here
+(`model_sampled_neg_shared`, the two monitor dicts) belong to trainers outside the scoped train_scheme list.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import FusedStep, SparseUpdater, StepSpec
+
+
+def _dev_i32(x, device):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.int32).reshape(-1).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1), dtype=np.int32)).to(device)
+
+
+class MeanPoolTower(torch.nn.Module):
+    """word Embedding -> mean over all L positions -> Dense -> BatchNorm -> relu   (modules/content/mean_pool.py:46-110).
+    The gather-mean is the nncf_meanpool kernel; BN uses Keras-1 defaults (epsilon 1e-3, momentum 0.99)."""
+
+    def __init__(self, data_spec, conf, content, generator):
+        super().__init__()
+        dw, d = conf.word_dim, conf.item_dense_transform['dense_hidden_dim']
+        w = (torch.rand((data_spec.word_count, dw), generator=generator, device='cuda') - 0.5) * 0.1   # Keras-1 'uniform'
+        self.word_embedding = torch.nn.Parameter(w)
+        self.dense = torch.nn.Linear(dw, d)
+        self.use_bn = not getattr(conf, 'no_BN', False)
+        self.bn = torch.nn.BatchNorm1d(d, eps=1e-3, momentum=0.01) if self.use_bn else None
+        self.dropout_rate = float(conf.word_emb_dropout_rate)
+        self.content = content            # int32 [items, L] on device
+        self.actv = conf.item_dense_transform['dense_hidden_actv']
+
+    def forward(self, item_ids):
+        W = self.word_embedding
+        if self.training and self.dropout_rate > 0:
+            # Keras-1 Embedding(dropout=p): whole word rows are dropped and the rest rescaled by 1/(1-p)
+            keep = (torch.rand((W.shape[0], 1), device=W.device) >= self.dropout_rate).float() / (1.0 - self.dropout_rate)
+            W = W * keep
+        h = ops.MeanPoolFunction.apply(W, self.content, item_ids)
+        h = self.dense(h)
+        if self.bn is not None:
+            h = self.bn(h)
+        if self.actv == 'relu':
+            h = torch.relu(h)
+        elif self.actv == 'tanh':
+            h = torch.tanh(h)
+        return h
+
+
+class SharedState(object):
+    """Parameters shared by every view (the reference's single Keras graph)."""
+
+    def __init__(self, conf, data_helper, model_name):
+        assert torch.cuda.is_available(), '[ERROR] nncf_b200 needs a CUDA device (there is no CPU fallback)'
+        self.conf = conf
+        self.model_name = model_name
+        spec = data_helper.data_spec
+        self.data_spec = spec
+        dev = torch.device('cuda')
+        self.device = dev
+        g = torch.Generator(device='cuda').manual_seed(int(getattr(conf, 'seed', 0)) + 7)
+        d = conf.user_dim
+        assert conf.user_dim == conf.item_dim, 'dot-product interaction needs user_dim == item_dim'
+        assert conf.interaction_bias is None, 'interaction_bias is outside the scoped path (SURVEY.md §8f)'
+        self.dim = d
+        # Keras-1 Embedding init 'uniform' = U(-0.05, 0.05)
+        self.user_table = (torch.rand((spec.user_count, d), generator=g, device=dev) - 0.5) * 0.1
+        self.opt_kind, self.lr = conf.optimizer
+        self.tower = None
+        self.item_table = None
+        if model_name == 'mf':
+            self.item_table = (torch.rand((spec.item_count, d), generator=g, device=dev) - 0.5) * 0.1
+        elif model_name == 'basic_embedding':
+            content = torch.from_numpy(np.ascontiguousarray(data_helper.data['C'], dtype=np.int32)).to(dev)
+            self.tower = MeanPoolTower(spec, conf, content, g).to(dev)
+            self.tower_opt = torch.optim.Adam(self.tower.parameters(), lr=self.lr, eps=1e-8)   # Keras Adam(lr)
+        else:
+            assert False, '[ERROR] Model name {} unknown (cnn/rnn towers: plug a torch module with the MeanPoolTower ' \
+                          'contract into SharedState.tower)'.format(model_name)
+        self.norm_u = bool(conf.emb_normalization)
+        # reference quirk: the 'mf' branch never l2-normalises the item embedding (models/model_framework.py:85-88)
+        self.norm_v = bool(conf.emb_normalization) and model_name != 'mf'
+        self.adam = None
+        if self.opt_kind == 'lazy_adam':
+            z = torch.zeros_like
+            self.adam = [z(self.user_table), z(self.user_table),
+                         z(self.item_table) if self.item_table is not None else None,
+                         z(self.item_table) if self.item_table is not None else None]
+        self._steps = {}
+        self._user_updater = None
+
+    def step(self, scheme):
+        if scheme not in self._steps:
+            c = self.conf
+            self._steps[scheme] = FusedStep(StepSpec(
+                scheme=scheme, loss=c.loss, precision=c.precision, batch_size_p=c.batch_size_p,
+                num_negatives=c.num_negatives, dim=self.dim, norm_u=self.norm_u, norm_v=self.norm_v,
+                optimizer=self.opt_kind, replicas=(c.replicas if self.item_table is not None else 1),
+                neg_loss_weight=float(c.neg_loss_weight), loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg),
+                learn_rate=float(self.lr)))
+        return self._steps[scheme]
+
+    # ---- embeddings as the views see them (test phase: dropout off, BN running statistics)
+    def user_emb(self, ids):
+        rows = ops.gather_rows(self.user_table, ids)
+        return torch.nn.functional.normalize(rows, dim=-1, eps=1e-6) if self.norm_u else rows
+
+    def item_emb(self, ids):
+        if self.item_table is not None:
+            rows = ops.gather_rows(self.item_table, ids)
+        else:
+            self.tower.eval()
+            with torch.no_grad():
+                rows = self.tower(ids)
+        return torch.nn.functional.normalize(rows, dim=-1, eps=1e-6) if self.norm_v else rows
+
+
+class _View(object):
+    def __init__(self, state):
+        self.state = state
+
+
+class MatmulView(_View):
+    """model_neg_shared / model_group_neg_shared  (models/model_framework.py:126-136,151-161)."""
+
+    def __init__(self, state, scheme):
+        super().__init__(state)
+        self.scheme = scheme
+
+    def train_on_batches(self, user_ids, item_ids, n_steps, loss_out=None):
+        """Device-resident fast path: `n_steps` consecutive steps over ids already in HBM (embedding-table models)."""
+        st = self.state
+        assert st.item_table is not None
+        return st.step(self.scheme).run(st.user_table, st.item_table, user_ids, item_ids, n_steps, adam_state=st.adam,
+                                        loss_out=loss_out)['loss']
+
+    def train_on_batch(self, x, y=None):
+        """Keras signature: x = [user_batch, item_batch] (host or device int arrays), y = [response] (ignored: the
+        matmul views define positives by position).  Returns the python float loss, like Keras."""
+        st = self.state
+        uid, cid = _dev_i32(x[0], st.device), _dev_i32(x[1], st.device)
+        if st.item_table is not None:
+            loss = self.train_on_batches(uid, cid, 1)
+            return float(loss.mean().item())
+        return self._train_with_tower(uid, cid)
+
+    def _train_with_tower(self, uid, cid):
+        st = self.state
+        step = st.step(self.scheme)
+        st.tower.train()
+        uq, inv, nuq = ops.unique_first_occurrence(cid)
+        n_u = int(nuq.item())
+        compact = st.tower(uq[:n_u])                                   # item tower runs once per UNIQUE item
+        if self.scheme == 'group_neg_shared':
+            rows = compact
+            out = step.run(st.user_table, None, uid, cid, 1, adam_state=st.adam, want_grads=True,
+                           item_rows=rows.detach(), inverse=inv, n_unique=nuq)
+            g = out['grad_item_rows'][:n_u]
+        else:
+            rows = compact[inv.long()]                                 # C_emb = C_emb_compact[cid_x]
+            out = step.run(st.user_table, None, uid, cid, 1, adam_state=st.adam, want_grads=True, item_rows=rows.detach())
+            g = out['grad_item_rows']
+        st.tower_opt.zero_grad(set_to_none=True)
+        rows.backward(g)
+        st.tower_opt.step()
+        return float(out['loss'][0].item())
+
+    def predict_on_batch(self, x):
+        """[users, items] -> float32 [len(users), len(items)] score matrix (host), for API compatibility with
+        utils/objectives.py:310.  The evaluator's fast path never materialises this (see Evaluator)."""
+        st = self.state
+        U = st.user_emb(_dev_i32(x[0], st.device))
+        V = st.item_emb(_dev_i32(x[1], st.device))
+        nu, ni = U.shape[0], V.shape[0]
+        # all (user, item) pairs of the block through the pair-scoring kernel in one launch
+        uidx = torch.arange(nu, device=st.device, dtype=torch.int32).repeat_interleave(ni)
+        cidx = torch.arange(ni, device=st.device, dtype=torch.int32).repeat(nu)
+        return ops.score_pairs(U, V, uidx, cidx).reshape(nu, ni).cpu().numpy()
+
+
+class PairsView(_View):
+    """model: the row-wise 'mul' view used by train_original / train_group_sample (model_framework.py:123,147-149)."""
+
+    def train_on_batches(self, user_ids, item_ids, n_steps, loss_out=None):
+        st = self.state
+        assert st.item_table is not None
+        return st.step('pairs').run(st.user_table, st.item_table, user_ids, item_ids, n_steps, adam_state=st.adam,
+                                    loss_out=loss_out)['loss']
+
+    def train_on_batch(self, x, y=None):
+        st = self.state
+        uid, cid = _dev_i32(x[0], st.device), _dev_i32(x[1], st.device)
+        if st.item_table is not None:
+            return float(self.train_on_batches(uid, cid, 1).mean().item())
+        # content tower: the unique items' embeddings act as a temporary item table indexed by tf.unique's inverse
+        c = st.conf
+        st.tower.train()
+        uq, inv, nuq = ops.unique_first_occurrence(cid)
+        n_u = int(nuq.item())
+        compact = st.tower(uq[:n_u])
+        key = ('pairs_tower',)
+        if key not in st._steps:
+            st._steps[key] = FusedStep(StepSpec(
+                scheme='pairs', loss=c.loss, precision='fp32', batch_size_p=c.batch_size_p, num_negatives=c.num_negatives,
+                dim=st.dim, norm_u=st.norm_u, norm_v=st.norm_v, optimizer='none', neg_loss_weight=float(c.neg_loss_weight),
+                loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg)))
+            st._user_updater = SparseUpdater(st.opt_kind, st.lr)
+        out = st._steps[key].run(st.user_table, compact.detach().contiguous(), uid, inv, 1, want_grads=True)
+        st._user_updater.begin_step()
+        st._user_updater.apply(st.user_table, uid, out['grad_user_rows'], *(st.adam[:2] if st.adam else (None, None)))
+        g = torch.zeros_like(compact)
+        g.index_add_(0, inv.long(), out['grad_item_rows'])
+        st.tower_opt.zero_grad(set_to_none=True)
+        compact.backward(g)
+        st.tower_opt.step()
+        return float(out['loss'][0].item())
+
+
+class UserEmbView(_View):
+    def predict_on_batch(self, x):
+        return self.state.user_emb(_dev_i32(x[0], self.state.device)).cpu().numpy()
+
+
+class ItemEmbView(_View):
+    def predict_on_batch(self, x):
+        return self.state.item_emb(_dev_i32(x[0], self.state.device)).cpu().numpy()
+
+
+class PredPairsView(_View):
+    def predict(self, x, batch_size=4096):
+        """[U_emb_given, C_emb_given, uid, cid] -> [n, 1]: row-wise dot of the given embeddings
+        (model_framework.py:125,174-176; utils/objectives.py:245-247)."""
+        dev = self.state.device
+        U = torch.as_tensor(np.asarray(x[0], dtype=np.float32)).to(dev)
+        V = torch.as_tensor(np.asarray(x[1], dtype=np.float32)).to(dev)
+        idx = torch.arange(U.shape[0], device=dev, dtype=torch.int32)
+        return ops.score_pairs(U, V, idx, idx).cpu().numpy().reshape(-1, 1)
+
+
+def get_model(conf, data_helper, model_name):
+    state = SharedState(conf, data_helper, model_name)
+    model_dict = {'model': PairsView(state),
+                  'model_neg_shared': MatmulView(state, 'neg_shared'),
+                  'model_group_neg_shared': MatmulView(state, 'group_neg_shared'),
+                  'model_user_emb': UserEmbView(state),
+                  'model_item_emb': ItemEmbView(state),
+                  'model_pred_pairs': PredPairsView(state),
+                  '_state': state}
+    return model_dict

@@ -177,6 +177,16 @@ class FusedStep:
             lib.nncf_trainer_destroy(h)
             self._h = None
 
+    def set_profile(self, enable: bool) -> None:
+        check(lib.nncf_trainer_set_profile(self._h, int(bool(enable))))
+
+    def get_profile(self):
+        """(ms_gather, ms_score, ms_finalize) accumulated over `steps` profiled steps."""
+        ms = (C.c_double * 3)()
+        steps = C.c_int64()
+        check(lib.nncf_trainer_get_profile(self._h, ms, C.byref(steps)))
+        return [ms[0], ms[1], ms[2]], int(steps.value)
+
     def run(self, user_table: torch.Tensor, item_table: Optional[torch.Tensor], user_ids: torch.Tensor,
             item_ids: torch.Tensor, n_steps: int = 1, *, adam_state=None, want_grads: bool = False,
             item_rows: Optional[torch.Tensor] = None, inverse: Optional[torch.Tensor] = None,
@@ -318,3 +328,42 @@ def eval_given(scores: torch.Tensor, truth: torch.Tensor, indptr: torch.Tensor) 
     check(lib.nncf_eval_given(_ptr(scores.contiguous()), _ptr(_i32(truth)), _ptr(indptr.to(torch.int64).contiguous()), ng,
                               _ptr(out), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# stand-alone gather / sparse update
+# ------------------------------------------------------------------------------------------------
+def gather_rows(table: torch.Tensor, ids: torch.Tensor) -> torch.Tensor:
+    _need_cuda(table, ids)
+    ids = _i32(ids)
+    out = torch.empty((ids.numel(), table.shape[1]), dtype=torch.float32, device=table.device)
+    check(lib.nncf_gather_rows(_ptr(table), table.shape[1], _ptr(ids), ids.numel(), _ptr(out), _stream()))
+    return out
+
+
+class SparseUpdater:
+    """nncf_updater_*: applies per-position row gradients to an embedding table (SGD or lazy Adam)."""
+
+    def __init__(self, optimizer: str, learn_rate: float, beta1: float = 0.9, beta2: float = 0.999, epsilon: float = 1e-8):
+        h = C.c_void_p()
+        check(lib.nncf_updater_create(OPTIMIZERS[optimizer], learn_rate, beta1, beta2, epsilon, C.byref(h)))
+        self._h = h
+        self.optimizer = optimizer
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.nncf_updater_destroy(h)
+            self._h = None
+
+    def begin_step(self) -> None:
+        check(lib.nncf_updater_begin_step(self._h))
+
+    def apply(self, table: torch.Tensor, ids: torch.Tensor, grads: torch.Tensor, m: Optional[torch.Tensor] = None,
+              v: Optional[torch.Tensor] = None) -> None:
+        """grads [n, d] is clobbered (lazy Adam sums duplicates in place)."""
+        _need_cuda(table, ids, grads, m, v)
+        ids = _i32(ids)
+        assert grads.dtype == torch.float32 and grads.is_contiguous()
+        check(lib.nncf_updater_apply(self._h, _ptr(table), _ptr(m), _ptr(v), table.shape[0], table.shape[1], _ptr(ids),
+                                     ids.numel(), _ptr(grads), _stream()))

@@ -518,3 +518,43 @@ def given_eval(user_emb, item_emb, pairs, topk=-1):
         a, _, _ = f(pairs[sel, 2], pred[sel], topk)
         ap.append(a); auc.append(auc_score(pairs[sel, 2], pred[sel]))
     return {"map": round(float(np.mean(ap)), 16), "auc": round(float(np.mean(auc)), 16)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline (bench.py's cpu_baseline / --impl reference legs): the same neg_shared step as step_matmul,
+# written the way the reference's CPU path executes it — gather, one sgemm for S, element-wise loss and
+# gradient, two sgemms for dU/dV, sparse update in place — without the dense [table] gradient buffers that
+# the checker above returns.  float32 throughout (Keras floatx).  BASELINE.md §2.
+# ---------------------------------------------------------------------------------------------
+def baseline_neg_shared_sgd_step(EU, EV, uid, cid, neg_loss_weight, lr):
+    """One neg_shared skip-gram step with sparse SGD, in place on EU / EV (float32).  Returns the loss.
+    ref: models/train_neg_shared.py:46-50 -> models/model_framework.py:59-61,86-87,126 ->
+    modules/interaction/interaction_dot.py:100-103 -> utils/objectives.py:99-105."""
+    B = uid.shape[0]
+    U = EU[uid]
+    V = EV[cid]
+    S = U @ V.T
+    w = np.float32(neg_loss_weight / (B - 1.0))
+    sg = 1.0 / (1.0 + np.exp(-S))
+    diag = np.arange(B)
+    # loss = -sum(W * log(sigmoid(Y * S))) / B
+    ls = np.log1p(np.exp(-np.abs(S))) + np.maximum(S, 0)          # softplus(S) = -log sigmoid(-S)
+    loss = w * (ls.sum() - ls[diag, diag].sum()) + (ls[diag, diag] - S[diag, diag]).sum()
+    G = sg * w
+    G[diag, diag] = sg[diag, diag] - 1.0
+    G /= np.float32(B)
+    dU = G @ V
+    dV = G.T @ U
+    np.add.at(EU, uid, -lr * dU)
+    np.add.at(EV, cid, -lr * dV)
+    return float(loss) / B
+
+
+def baseline_whole_eval_block(U, V, k):
+    """Reference-style whole@k on a block of users: blocked U @ V.T (1024 items per block, utils/objectives.py:308-313),
+    np.argpartition top-k per user (metrics_ranking.py:7) and the k-element sort.  Returns top-k column ids."""
+    pred = np.hstack([U @ V[b:b + 1024].T for b in range(0, V.shape[0], 1024)])
+    idx = np.argpartition(-pred, k, axis=1)[:, :k]
+    part = np.take_along_axis(pred, idx, axis=1)
+    order = np.argsort(-part, axis=1, kind="stable")
+    return np.take_along_axis(idx, order, axis=1)
