@@ -335,7 +335,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=32)
+    ap.add_argument("--replicas", type=int, default=37)  # 37 x 8 CTAs = 2 full waves of 148 SMs
     ap.add_argument("--links", type=int, default=N_LINKS)
     ap.add_argument("--cpu-steps", type=int, default=3000)
     ap.add_argument("--eval-users", type=int, default=65536)

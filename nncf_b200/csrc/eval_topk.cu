@@ -78,28 +78,27 @@ struct RowState {
 
 __device__ __forceinline__ void consider32(const float* v, uint32_t col0, uint32_t col_end, RowState& st,
                                            uint64_t* pend_row, bool row_ok) {
-  float m = -INFINITY;
-  if (col0 + 32 <= col_end) {
-    // four independent chains (the compiler folds pairs into 3-input FMNMX3) instead of one 32-deep dependency
-    float m0 = fmaxf(v[0], v[1]), m1 = fmaxf(v[2], v[3]), m2 = fmaxf(v[4], v[5]), m3 = fmaxf(v[6], v[7]);
+  // maxima of the four contiguous groups of 8 (independent chains; pairs fold into 3-input FMNMX3).  Almost every
+  // chunk has a candidate in SOME lane of the warp, so the slow path must be cheap: it only walks the groups whose
+  // maximum reaches the threshold instead of all 32 elements.
+  float gm[4];
 #pragma unroll
-    for (int t = 8; t < 32; t += 8) {
-      m0 = fmaxf(m0, fmaxf(v[t], v[t + 1]));
-      m1 = fmaxf(m1, fmaxf(v[t + 2], v[t + 3]));
-      m2 = fmaxf(m2, fmaxf(v[t + 4], v[t + 5]));
-      m3 = fmaxf(m3, fmaxf(v[t + 6], v[t + 7]));
-    }
-    m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-  } else {
-#pragma unroll
-    for (int t = 0; t < 32; ++t) m = (col0 + t < col_end) ? fmaxf(m, v[t]) : m;
+  for (int g = 0; g < 4; ++g) {
+    const float* w = v + g * 8;
+    gm[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
   }
+  const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
   if (row_ok && m >= st.thr) {
 #pragma unroll
-    for (int t = 0; t < 32; ++t) {
-      if (v[t] >= st.thr && col0 + t < col_end) {
-        const uint64_t key = make_key(v[t], col0 + t);
-        if (key > st.thr_key) { pend_row[st.cnt] = key; ++st.cnt; }
+    for (int g = 0; g < 4; ++g) {
+      if (gm[g] >= st.thr) {
+#pragma unroll
+        for (int t = g * 8; t < g * 8 + 8; ++t) {
+          if (v[t] >= st.thr && col0 + t < col_end) {
+            const uint64_t key = make_key(v[t], col0 + t);
+            if (key > st.thr_key) { pend_row[st.cnt] = key; ++st.cnt; }
+          }
+        }
       }
     }
   }

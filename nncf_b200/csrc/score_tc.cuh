@@ -48,16 +48,58 @@ int launch_score_tc_nsub4(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st
 template <int NSUB>
 struct ScoreTcCfg {
   static constexpr int DP = 64 * NSUB;
-  static constexpr int kStages = 2;
+  static constexpr int kStages = NSUB <= 2 ? 4 : 2;   // Y tiles in flight: the bulk-copy latency (~2k cycles) must hide
+                                                      // behind >= 2 tile times (measured: 2 stages exposed it every tile)
   static constexpr int kGBufs = NSUB <= 3 ? 2 : 1;
   static constexpr int kColDX = 256;
   static constexpr size_t kSmemBytes =
       (size_t)NSUB * kSubBytes * (1 + kStages) + (size_t)kGBufs * 2 * kSubBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// packed bf16x2 arithmetic (two elements per instruction, and per MUFU op)
+__device__ __forceinline__ uint32_t bf2_mul(uint32_t a, uint32_t b) {
+  uint32_t d; asm("mul.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+__device__ __forceinline__ uint32_t bf2_fma(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t bf2_tanh(uint32_t a) {
+  uint32_t d; asm("tanh.approx.bf16x2 %0, %1;" : "=r"(d) : "r"(a)); return d;
+}
+constexpr uint32_t kBf2Half = 0x3F003F00u;   // (0.5, 0.5)
+
 struct EpiConst {
   float w_neg, gamma, inv_b, inv_cnt, ns_margin;   // ns_margin = gamma for neg_shared (zero margin at the positive), else 0
+  float inv_wneg;   // 1 / w_neg
+  float g_scale;    // skip-gram stores G' = (w / w_neg) (sigmoid - pos) in bf16 and applies w_neg / B to the fp32
+                    // accumulator at the drain (keeps sigmoid's full bf16 precision, no constant rounded to bf16)
 };
+
+// skip-gram fast path: 32 scores of a full tile without positives.  G' = sigmoid(s) through packed bf16x2 math
+// (1 MUFU.TANH per PAIR); the loss uses sum softplus(s) = sum max(s,0) - ln(prod sigmoid(|s|)): ONE MUFU.LG2 per chunk.
+template <bool NEED_LOSS>
+__device__ __forceinline__ void epi_chunk_sg_fast(const float (&v)[32], uint32_t (&pk)[16], float& lraw) {
+  float summax = 0.0f, prod0 = 1.0f, prod1 = 1.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t xb = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    const uint32_t t = bf2_tanh(bf2_mul(xb, kBf2Half));                 // tanh(s / 2)
+    pk[i] = bf2_fma(t, kBf2Half, kBf2Half);                             // sigmoid(s)
+    if (NEED_LOSS) {
+      const uint32_t sa = bf2_fma(t & 0x7FFF7FFFu, kBf2Half, kBf2Half); // sigmoid(|s|) in [0.5, 1]
+      prod0 *= __uint_as_float(sa << 16);
+      prod1 *= __uint_as_float(sa & 0xFFFF0000u);
+      summax += fmaxf(v[2 * i], 0.0f) + fmaxf(v[2 * i + 1], 0.0f);
+    }
+  }
+  if (NEED_LOSS) lraw += summax - __logf(prod0 * prod1);                // product of 32 values >= 2^-32: safe in fp32
+}
 
 // One element, straight-line.  w = loss weight of the element, posf = 1 for the row's positive else 0,
 // sp = positive score it is compared with (pairwise losses).
@@ -65,22 +107,23 @@ template <int LOSS, bool NEED_LOSS>
 __device__ __forceinline__ void epi_val(const EpiConst& c, float s, float w, float posf, float sp, float& g, float& a,
                                         float& l) {
   a = 0.0f; l = 0.0f;
+  // The epilogue is MUFU-bound on B200 (16 special-function lanes per SM), so every transcendental counts:
+  //   sigmoid(|x|) = 0.5 * tanh(|x| / 2) + 0.5                      one MUFU.TANH instead of EX2 + RCP
+  //   softplus(x)  = max(x, 0) - ln(sigmoid(|x|))                    one MUFU.LG2, argument in [0.5, 1)
   if (LOSS == NNCF_LOSS_SKIP_GRAM) {
-    const float e = __expf(-fabsf(s));
-    const float r = __fdividef(1.0f, 1.0f + e);
-    const float sg = (s >= 0.0f) ? r : e * r;                                   // sigmoid(s)
-    if (NEED_LOSS) l = w * (fmaxf(s, 0.0f) + __logf(1.0f + e) - posf * s) * c.inv_b;   // softplus(s) [- s for the positive]
-    g = w * (sg - posf) * c.inv_b;
+    const float sa = fmaf(0.5f, tanh_approx(0.5f * fabsf(s)), 0.5f);            // sigmoid(|s|)
+    const float sg = (s >= 0.0f) ? sa : 1.0f - sa;                              // sigmoid(s)
+    if (NEED_LOSS) l = w * (fmaxf(s, 0.0f) - __logf(sa) - posf * s) * c.inv_b;  // softplus(s) [- s for the positive]
+    g = w * c.inv_wneg * (sg - posf);                                           // G' (scaled by w_neg / B at the drain)
   } else if (LOSS == NNCF_LOSS_MSE) {
     const float t = s - posf;
     if (NEED_LOSS) l = w * t * t * c.inv_b;
     g = 2.0f * w * t * c.inv_b;
   } else if (LOSS == NNCF_LOSS_LOG_LOSS) {
     const float x = -c.gamma * (sp - s);                                        // -gamma * D
-    const float e = __expf(-fabsf(x));
-    const float r = __fdividef(1.0f, 1.0f + e);
-    const float sg = (x >= 0.0f) ? r : e * r;                                   // sigmoid(-gamma D)
-    if (NEED_LOSS) l = (fmaxf(x, 0.0f) + __logf(1.0f + e)) * c.inv_cnt;
+    const float sa = fmaf(0.5f, tanh_approx(0.5f * fabsf(x)), 0.5f);
+    const float sg = (x >= 0.0f) ? sa : 1.0f - sa;                              // sigmoid(-gamma D)
+    if (NEED_LOSS) l = (fmaxf(x, 0.0f) - __logf(sa)) * c.inv_cnt;
     a = -c.gamma * sg * c.inv_cnt;
     g = -a;
   } else {
@@ -95,7 +138,8 @@ __device__ __forceinline__ void epi_val(const EpiConst& c, float s, float w, flo
 template <int LOSS, bool SIDE1, bool GROUP, bool GENERAL>
 __device__ __forceinline__ void epi_chunk(const EpiConst& c, float (&v)[32], int x0, int n_other, bool row_ok, int o,
                                           int my_posc, float my_sp, const int32_t* __restrict__ inv_row,
-                                          const float* __restrict__ spos_row, float& lsum, float& asum) {
+                                          const float* __restrict__ spos_row, float& lsum, float& asum,
+                                          uint32_t (&pk)[16]) {
   constexpr bool kPairwise = LOSS >= NNCF_LOSS_LOG_LOSS;
   constexpr bool kSpMine = kPairwise && (SIDE1 != GROUP);       // positive score constant along my row
   constexpr bool kPosByInverse = SIDE1 && GROUP;                // positive test needs inverse[x] of the swept row
@@ -126,6 +170,8 @@ __device__ __forceinline__ void epi_chunk(const EpiConst& c, float (&v)[32], int
       if (kPairwise) asum += valid ? aa : 0.0f;
     }
   }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 }
 
 template <int NSUB, int LOSS, bool GROUP>
@@ -141,14 +187,14 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   uint8_t* sG = sY + C::kStages * NSUB * kSubBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * 2 * kSubBytes);
   uint64_t* x_full = bars + 0;
-  uint64_t* y_full = bars + 1;      // [2]
-  uint64_t* y_empty = bars + 3;     // [2]
-  uint64_t* s_full = bars + 5;      // [2]
-  uint64_t* s_empty = bars + 7;     // [2]
-  uint64_t* g_full = bars + 9;      // [2]
-  uint64_t* g_empty = bars + 11;    // [2]
-  uint64_t* dx_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* y_full = bars + 1;      // [4]
+  uint64_t* y_empty = bars + 5;     // [4]
+  uint64_t* s_full = bars + 9;      // [2]
+  uint64_t* s_empty = bars + 11;    // [2]
+  uint64_t* g_full = bars + 13;     // [2]
+  uint64_t* g_empty = bars + 15;    // [2]
+  uint64_t* dx_full = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
@@ -164,8 +210,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 
   if (tid == 0) {
     mbar_init(x_full, 1);
+    for (int s = 0; s < 4; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kScoreEpiWarps);
       mbar_init(&g_full[s], kScoreEpiWarps); mbar_init(&g_empty[s], 1);
     }
@@ -251,6 +297,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     ec.inv_b = 1.0f / static_cast<float>(a.B);
     ec.inv_cnt = 1.0f / (static_cast<float>(a.B) * static_cast<float>(nc));
     ec.ns_margin = GROUP ? 0.0f : a.gamma;
+    ec.inv_wneg = 1.0f / ec.w_neg;
+    ec.g_scale = (LOSS == NNCF_LOSS_SKIP_GRAM) ? ec.w_neg * ec.inv_b : 1.0f;
     const bool row_ok = o < n_owner;
     // side 0: the positive column of my row.  side 1 (neg_shared): my own index (the diagonal).
     const int my_posc = (side == 0 && GROUP) ? (row_ok ? a.inverse[base + o] : -1) : o;
@@ -258,7 +306,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     const float my_sp = (sp_mine && row_ok) ? a.spos[base + o] : 0.0f;
     const int32_t* inv_row = GROUP ? a.inverse + base : nullptr;
     const float* spos_row = a.spos + base;
-    float lsum = 0.0f, asum = 0.0f;
+    float lsum = 0.0f, asum = 0.0f, lraw = 0.0f;
 
     for (int t = 0; t < nt; ++t) {
       const int sb = t & 1, gb = t % C::kGBufs;
@@ -276,34 +324,37 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       const int x0 = t * 128 + h * 64;
       // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tile has them)
       const bool general = GROUP || (t == ob) || (t * 128 + 128 > n_other);
+      uint32_t p0[16], p1[16];
+      constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
       if (side == 0) {
         if (general) {
-          epi_chunk<LOSS, false, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
-          epi_chunk<LOSS, false, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, false, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
+          epi_chunk<LOSS, false, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
+        } else if (kFastSg) {
+          epi_chunk_sg_fast<true>(v0, p0, lraw);
+          epi_chunk_sg_fast<true>(v1, p1, lraw);
         } else {
-          epi_chunk<LOSS, false, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
-          epi_chunk<LOSS, false, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, false, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
+          epi_chunk<LOSS, false, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
         }
       } else {
         if (general) {
-          epi_chunk<LOSS, true, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
-          epi_chunk<LOSS, true, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, true, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
+          epi_chunk<LOSS, true, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
+        } else if (kFastSg) {
+          epi_chunk_sg_fast<false>(v0, p0, lraw);
+          epi_chunk_sg_fast<false>(v1, p1, lraw);
         } else {
-          epi_chunk<LOSS, true, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
-          epi_chunk<LOSS, true, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum);
+          epi_chunk<LOSS, true, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
+          epi_chunk<LOSS, true, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
         }
       }
       mbar_wait(&g_empty[gb], ((t / C::kGBufs) & 1) ^ 1);
       uint8_t* grow = sG + gb * 2 * kSubBytes + h * kSubBytes + ol * 128;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        const float* src = (ch < 4) ? (v0 + ch * 8) : (v1 + (ch - 4) * 8);
-        uint4 pk;
-        pk.x = pack_bf16x2(src[0], src[1]);
-        pk.y = pack_bf16x2(src[2], src[3]);
-        pk.z = pack_bf16x2(src[4], src[5]);
-        pk.w = pack_bf16x2(src[6], src[7]);
-        *reinterpret_cast<uint4*>(grow + ((ch ^ (ol & 7)) << 4)) = pk;
+        const uint32_t* src = (ch < 4) ? (p0 + ch * 4) : (p1 + (ch - 4) * 4);
+        *reinterpret_cast<uint4*>(grow + ((ch ^ (ol & 7)) << 4)) = make_uint4(src[0], src[1], src[2], src[3]);
       }
       fence_proxy_async();
       __syncwarp();
@@ -315,17 +366,26 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     if (warp == 2 && lane == 0) NNCF_STAMP(4);
     tc_fence_after();
     {
-      float* dst = (side == 0 ? a.dU : a.dV) + (base + o) * DP;
+      // TMEM rows live in lanes, so a direct store would scatter 32 rows per instruction (measured: 4.4k cycles).
+      // Transpose through shared memory (the Y/G buffers are idle now) and write whole rows, coalesced.
+      constexpr int LD = DP + 4;                                  // padded row: STS.128 at the 4-wavefront minimum
+      float* stage = reinterpret_cast<float*>(sY);
 #pragma unroll 1
       for (int c0 = h * (DP / 2); c0 < (h + 1) * (DP / 2); c0 += 32) {
         float v[32];
         tmem_ld32(tmem + lane_addr + C::kColDX + c0, v);
         tmem_ld_wait();
-        if (row_ok) {
 #pragma unroll
-          for (int u = 0; u < 32; u += 4)
-            *reinterpret_cast<float4*>(dst + c0 + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
-        }
+        for (int u = 0; u < 32; u += 4)
+          *reinterpret_cast<float4*>(stage + ol * LD + c0 + u) =
+              make_float4(v[u] * ec.g_scale, v[u + 1] * ec.g_scale, v[u + 2] * ec.g_scale, v[u + 3] * ec.g_scale);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");   // epilogue warps only
+      float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
+      for (int row = ew; row < 128; row += kScoreEpiWarps) {
+        if (ob * 128 + row >= n_owner) break;
+        const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
+        for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
       }
     }
     // per-row sums of dL/dD: the two column halves of a row live in two warps -> atomics on two addends only
@@ -334,6 +394,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
     }
     if (side == 0) {
+      if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
       lsum = warp_sum(lsum);
       if (lane == 0) atomicAdd(&a.loss[r], static_cast<double>(lsum));
     }

@@ -105,6 +105,7 @@ struct GatherArgs {
   int d, dp;                 // true / padded dim
   int normalize;
   int write_img;
+  int write_xf;              // write the fp32 staging rows (skipped when nothing downstream reads them)
   int zero_grad;             // zero dX (needed by the atomically-accumulating fp32 path only)
   float* Xf;                 // [R][rows_pad][dp]
   float* inv;                // [R][rows_pad]
@@ -114,7 +115,8 @@ struct GatherArgs {
 };
 
 __global__ void __launch_bounds__(256)
-gather_rows_kernel(GatherArgs a) {
+gather_rows_kernel(GatherArgs a0, GatherArgs a1) {
+  const GatherArgs& a = blockIdx.z ? a1 : a0;     // z = 0 user side, z = 1 item side: one launch for both
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   const int r = blockIdx.y;
@@ -159,7 +161,7 @@ gather_rows_kernel(GatherArgs a) {
   for (int m = 0; m < 4; ++m) {
     if (m < nchunk) {
       const int c = m * 64 + 2 * lane;
-      *reinterpret_cast<float2*>(xf + c) = make_float2(x[2 * m], x[2 * m + 1]);
+      if (a.write_xf) *reinterpret_cast<float2*>(xf + c) = make_float2(x[2 * m], x[2 * m + 1]);
       if (a.zero_grad) *reinterpret_cast<float2*>(dx + c) = make_float2(0.0f, 0.0f);
     }
   }
@@ -326,6 +328,8 @@ struct FinalizeArgs {
   int count;
   int rows_pad, d, dp;
   int normalize;
+  int write_back;            // store the finalised row gradient back to dX (lazy Adam reads it)
+  int need_x;                // rows of Xf are read (normalise-backward, corrections or regulariser)
   float reg_scale;           // 2 * u_reg / rows  (user side) else 0
   // optimizer
   int optimizer;
@@ -336,7 +340,8 @@ struct FinalizeArgs {
 };
 
 __global__ void __launch_bounds__(256)
-finalize_kernel(FinalizeArgs a) {
+finalize_kernel(FinalizeArgs a0, FinalizeArgs a1) {
+  const FinalizeArgs& a = blockIdx.z ? a1 : a0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   const int r = blockIdx.y;
@@ -350,7 +355,7 @@ finalize_kernel(FinalizeArgs a) {
   for (int m = 0; m < 8; ++m) {
     const int c = lane + 32 * m;
     g[m] = (c < a.dp) ? dx[c] : 0.0f;
-    xv[m] = (c < a.dp) ? x[c] : 0.0f;
+    xv[m] = (a.need_x && c < a.dp) ? x[c] : 0.0f;
   }
   if (a.pairwise) {
     if (a.scheme == NNCF_SCHEME_NEG_SHARED) {
@@ -416,6 +421,10 @@ finalize_kernel(FinalizeArgs a) {
     }
   }
 }
+
+}  // namespace nncf
+#include "row_kernels.cuh"
+namespace nncf {
 
 // =================================================================================================
 // lazy Adam on touched rows with duplicate summing.   ref: utils/optimizer.py:108-147
@@ -795,15 +804,17 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // gather
   GatherArgs gu{};
   gu.table = tb->user_table; gu.ids = uid; gu.ids_stride = B; gu.count = B; gu.rows_pad = rp; gu.d = d; gu.dp = dp;
-  gu.normalize = c.norm_u; gu.write_img = bf16; gu.zero_grad = bf16 ? 0 : 1; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
+  gu.normalize = c.norm_u; gu.write_img = bf16; gu.zero_grad = bf16 ? 0 : 1;
+  gu.write_xf = (!bf16 || c.norm_u || c.norm_v || pairwise || c.u_reg != 0.0f) ? 1 : 0; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
   gu.corr = t->corrU;
-  gather_rows_kernel<<<dim3(rp / 8, R), 256, 0, st>>>(gu);
-  NNCF_LAUNCH_OK();
   GatherArgs gv = gu;
   gv.table = tb->item_table; gv.dense_rows = dense_items ? io->item_rows_dev : nullptr;
   gv.ids = item_ids; gv.ids_stride = item_stride; gv.count_dev = group ? t->nuniq : nullptr;
   gv.normalize = c.norm_v; gv.Xf = t->Vf; gv.inv = t->invV; gv.img = t->Vimg; gv.dX = t->dV; gv.corr = t->corrV;
-  gather_rows_kernel<<<dim3(rp / 8, R), 256, 0, st>>>(gv);
+  const bool vec = (d % 4 == 0);   // 16-byte aligned rows: 128-bit loads / vector reductions
+  if (vec && dp <= 128) gather_rows_vec_kernel<1><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
+  else if (vec) gather_rows_vec_kernel<2><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
+  else gather_rows_kernel<<<dim3(rp / 8, R, 2), 256, 0, st>>>(gu, gv);
   NNCF_LAUNCH_OK();
   if (pairwise) {
     pos_score_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->Vf, group ? t->inverse : nullptr, rp, dp, B,
@@ -849,18 +860,30 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   FinalizeArgs fu{};
   fu.side = 0; fu.scheme = c.scheme; fu.pairwise = pairwise; fu.Xf = t->Uf; fu.Of = t->Vf; fu.inv = t->invU;
   fu.dX = t->dU; fu.dO = t->dV; fu.corr_self = group ? t->corrU : t->corrV; fu.inverse = group ? t->inverse : nullptr;
-  fu.count = B; fu.rows_pad = rp; fu.d = d; fu.dp = dp; fu.normalize = c.norm_u;
+  fu.count = B; fu.rows_pad = rp; fu.d = d; fu.dp = dp; fu.normalize = c.norm_u; fu.need_x = (c.norm_u || pairwise || c.u_reg != 0.0f) ? 1 : 0;
+  fu.write_back = (c.optimizer == NNCF_OPT_LAZY_ADAM) ? 1 : 0;
   fu.reg_scale = 2.0f * c.u_reg / B; fu.optimizer = c.optimizer; fu.lr = c.learn_rate; fu.table = tb->user_table;
   fu.ids = uid; fu.ids_stride = B; fu.grad_out = (last && io) ? io->grad_user_rows_dev : nullptr;
-  finalize_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(fu);
-  NNCF_LAUNCH_OK();
   FinalizeArgs fv = fu;
   fv.side = 1; fv.Xf = t->Vf; fv.Of = t->Uf; fv.inv = t->invV; fv.dX = t->dV; fv.dO = nullptr; fv.corr_self = t->corrV;
-  fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.reg_scale = 0.0f;
+  fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.need_x = (c.norm_v || pairwise) ? 1 : 0; fv.reg_scale = 0.0f;
   fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
   fv.grad_out = (last && io) ? io->grad_item_rows_dev : nullptr;
-  finalize_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(fv);
-  NNCF_LAUNCH_OK();
+  auto launch_finalize = [&](const FinalizeArgs& x, const FinalizeArgs& y, int nz) {
+    if (vec && dp <= 128) finalize_vec_kernel<1><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
+    else if (vec) finalize_vec_kernel<2><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
+    else finalize_kernel<<<dim3(ceil_div(B, 8), R, nz), 256, 0, st>>>(x, y);
+  };
+  if (group && pairwise) {
+    // the user side adds the positive-column corrections into the item accumulators: strictly before the item side
+    launch_finalize(fu, fu, 1);
+    NNCF_LAUNCH_OK();
+    launch_finalize(fv, fv, 1);
+    NNCF_LAUNCH_OK();
+  } else {
+    launch_finalize(fu, fv, 2);
+    NNCF_LAUNCH_OK();
+  }
   (void)sgd;
   if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
     NNCF_CHECK_ARG(tb->user_m && tb->user_v, "lazy Adam needs user_m / user_v");
