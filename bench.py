@@ -163,11 +163,22 @@ def run_ours(args):
     R, B, d = args.replicas, BATCH, DIM
     links_per_step = R * B
 
-    # ---- resident state: tables + this rank's links, shuffled once on the device (np.random.shuffle semantics are
-    #      exercised by the parity tests; the order itself is not part of the timed hot path)
+    # ---- resident state.  N = 1: the two 1M x 128 tables live on the GPU.  N > 1: the SAME global tables are sharded by
+    #      row over the ranks (owner = id mod N, peer memory over NVLink) and every rank trains on its own links (weak
+    #      scaling: per-GPU work fixed).  Links are shuffled once on the device; np.random.shuffle semantics are
+    #      exercised by the parity tests, the order itself is not part of the timed hot path.
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
-    EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
-    EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
+    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="sgd",
+                    learn_rate=LR, replicas=R, neg_loss_weight=LAMBDA)
+    sharded = None
+    if world > 1:
+        from nncf_b200.parallel import ShardedTrainer
+        sharded = ShardedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
+        step, EU, EV = sharded.step, sharded.users.local, sharded.items.local
+    else:
+        EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
+        EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
+        step = FusedStep(spec)
     n_links = args.links
     train = synth_links_device(n_links, N_USERS, N_ITEMS, 2017 + rank, torch)
     perm = torch.randperm(n_links, device="cuda", generator=g)
@@ -177,9 +188,6 @@ def run_ours(args):
     del train, perm
     steps_per_pass = n_links // links_per_step
     assert steps_per_pass >= 1
-
-    step = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
-                              optimizer="sgd", learn_rate=LR, replicas=R, neg_loss_weight=LAMBDA))
     loss_buf = torch.empty(max(args.steps, args.warmup, 1) * R, dtype=torch.float32, device="cuda")
 
     def run_steps(k, start_step):
@@ -197,6 +205,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     # ---- value: device-resident throughput ------------------------------------------------------------------
     run_steps(args.warmup, 0)
     barrier()
@@ -210,35 +225,14 @@ def run_ours(args):
     barrier()
     launches = ops.launch_count() - launches0
     sampler.stop_flag = True
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(e0.elapsed_time(e1))
     sampler.join(timeout=2)
     final_loss = float(loss_buf[(args.steps - 1) * R:(args.steps) * R].mean().item())
     assert np.isfinite(final_loss), "training diverged"
     value = world * args.steps * links_per_step / (ms * 1e-3)
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
-
-    # ---- sequential reference semantics (R = 1) --------------------------------------------------------------
-    seq = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
-                             optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA))
-    nseq = min(2000, n_links // B)
-    seq.run(EU, EV, uid_all, cid_all, 50)
-    torch.cuda.synchronize()
-    e0.record()
-    seq.run(EU, EV, uid_all, cid_all, nseq)
-    e1.record()
-    torch.cuda.synchronize()
-    seq_value = nseq * B / (e0.elapsed_time(e1) * 1e-3)
-
-    # ---- roofline of the dominant kernel: CUDA events around the score+gradient kernel, on its stream ---------
+    # ---- roofline of the dominant kernel: CUDA events around the score+gradient kernel, on its stream (every rank
+    #      runs the same number of profiled steps so that the device barriers of the sharded mode pair up)
     step.set_profile(True)
     nprof = min(200, steps_per_pass)
     step.run(EU, EV, uid_all, cid_all, nprof)
@@ -246,15 +240,6 @@ def run_ours(args):
     phase_ms, psteps = step.get_profile()
     step.set_profile(False)
     gather_ms, score_ms, final_ms = [x / max(psteps, 1) for x in phase_ms]
-    flops = 6.0 * B * B * d * R
-    achieved_tf = flops / (score_ms * 1e-3) / 1e12
-    step_bytes = links_per_step * (8 + 16 * d)
-    roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<2>", "achieved": achieved_tf, "peak": peaks["bf16_burst"],
-                "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": None, "peak_source": peaks["src"],
-                "ms_per_launch": score_ms, "flops_per_launch": flops,
-                "phases_ms": {"gather_prepare": gather_ms, "score_grad": score_ms, "finalize_update": final_ms},
-                "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / (ms / args.steps * 1e-3) / 1e9,
-                             "peak_gbs": peaks["hbm"], "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"]}}
 
     # ---- e2e: the public train_on_batch-style call with HOST buffers, H2D of the ids and D2H of the loss each step
     e2e_steps = min(args.steps, 300)
@@ -273,59 +258,100 @@ def run_ours(args):
 
     for i in range(5):
         e2e_step(i)
-    torch.cuda.synchronize()
+    barrier()
     t0 = time.perf_counter()
     for i in range(5, 5 + e2e_steps):
         e2e_step(i)
     torch.cuda.synchronize()
-    e2e_value = e2e_steps * links_per_step / (time.perf_counter() - t0)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * e2e_steps * links_per_step / e2e_s
+    barrier()
 
-    # ---- extra: whole@k users/sec on a C4-shaped shard (all 2M items, k = 50) ---------------------------------
-    extra = {}
-    if not args.no_eval:
-        n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
-        Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5
-        Ve = torch.randn((n_eval_items, d), device="cuda", generator=g) / d ** 0.5
-        ops.eval_topk(Ue[:1024], Ve, k, "bf16")
+    if rank != 0:
+        if sharded is not None:
+            dist.barrier()
+            sharded.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    flops = 6.0 * B * B * d * R
+    achieved_tf = flops / (score_ms * 1e-3) / 1e12
+    step_bytes = links_per_step * (8 + 16 * d)
+    step_s = ms / args.steps * 1e-3
+    roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<2,skip-gram,neg_shared>", "achieved": achieved_tf,
+                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": None,
+                "peak_source": peaks["src"], "ms_per_launch": score_ms, "flops_per_launch": flops,
+                "note": "algorithmic 6*B^2*d*R flops per launch; the one-sided kernel executes 8*B^2*dp*R (S is recomputed "
+                        "by the item side); its epilogue is MUFU-bound (DESIGN.md 3.1)",
+                "phases_ms": {"gather_prepare": gather_ms, "score_grad": score_ms, "finalize_update": final_ms},
+                "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / step_s / 1e9,
+                             "peak_gbs": peaks["hbm"], "frac": step_bytes / step_s / 1e9 / peaks["hbm"]}}
+
+    seq_info, extra, cpu = None, {}, None
+    if world == 1:
+        # ---- sequential reference semantics (R = 1) ----------------------------------------------------------
+        seq = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
+                                 optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA))
+        nseq = min(2000, n_links // B)
+        seq.run(EU, EV, uid_all, cid_all, 50)
         torch.cuda.synchronize()
         e0.record()
-        ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
+        seq.run(EU, EV, uid_all, cid_all, nseq)
         e1.record()
         torch.cuda.synchronize()
-        ems = e0.elapsed_time(e1)
-        etf = 2.0 * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
-        extra = {"whole_at_k": {"users_per_sec": n_eval_users / (ems * 1e-3), "k": k, "users": n_eval_users,
-                                "items": n_eval_items, "dim": d, "ms": ems,
-                                "roofline": {"bound": "tensor", "achieved": etf, "peak": peaks["bf16_burst"],
-                                             "unit": "TFLOP/s", "frac": etf / peaks["bf16_burst"]}}}
-        del Ue, Ve, ids
+        seq_info = {"value": nseq * B / (e0.elapsed_time(e1) * 1e-3), "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq}
+        # ---- extra: whole@k users/sec on a C4-shaped shard (all 2M items, k = 50) -----------------------------
+        if not args.no_eval:
+            n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
+            Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5
+            Ve = torch.randn((n_eval_items, d), device="cuda", generator=g) / d ** 0.5
+            ops.eval_topk(Ue[:1024], Ve, k, "bf16")
+            torch.cuda.synchronize()
+            e0.record()
+            ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
+            e1.record()
+            torch.cuda.synchronize()
+            ems = e0.elapsed_time(e1)
+            etf = 2.0 * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
+            extra = {"whole_at_k": {"users_per_sec": n_eval_users / (ems * 1e-3), "k": k, "users": n_eval_users,
+                                    "items": n_eval_items, "dim": d, "ms": ems,
+                                    "roofline": {"bound": "tensor", "achieved": etf, "peak": peaks["bf16_burst"],
+                                                 "unit": "TFLOP/s", "frac": etf / peaks["bf16_burst"]}}}
+            del Ue, Ve, ids
+        # ---- cpu baseline: bounded sample on the box's host cores (rank 0, N = 1 only) ------------------------
+        cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
+        cpu = {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "%d sequential neg_shared steps of 512 links (%.1f s) on 1M x 128 fp32 tables, NumPy/BLAS" % (args.cpu_steps, cpu_dt)}
 
-    # ---- cpu baseline: bounded sample on the box's host cores -------------------------------------------------
-    cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
     line = {
         "metric": "positive links/sec train (neg_shared)", "value": value, "unit": "links/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_size_p": B, "dim": d, "replicas_per_gpu": R, "links_per_step": links_per_step,
-                   "links_resident": n_links, "optimizer": "sparse SGD (atomic scatter-add)", "precision": "bf16 operands, fp32 accumulate (tcgen05)",
-                   "semantics": "each step = R independent neg_shared batches against one table snapshot (synchronous "
+        "config": {"workload": WORKLOAD, "batch_size_p": B, "dim": d, "replicas_per_gpu": R, "links_per_step_per_gpu": links_per_step,
+                   "links_resident_per_gpu": n_links, "optimizer": "sparse SGD (atomic scatter-add)",
+                   "precision": "bf16 operands, fp32 accumulate (tcgen05)",
+                   "parallelism": "1 GPU" if world == 1 else "tables row-sharded over %d GPUs (owner = id mod N), rows read and "
+                                  "updated over NVLink peer memory inside the step kernels, 2 device barriers per step" % world,
+                   "semantics": "each step = R independent neg_shared batches per GPU against one table snapshot (synchronous "
                                 "data-parallel virtual workers); R=1 (the reference's sequential loop) is reported in `sequential`",
                    "l2": "inputs larger than L2: 1.02 GB of embedding tables, random rows, batches never repeat within a pass"},
-        "sequential": {"value": seq_value, "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq},
+        "sequential": seq_info,
         "final_loss": final_loss,
         "roofline": roofline,
-        "cpu_baseline": {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
-                         "sample": "%d sequential neg_shared steps of 512 links (%.1f s) on 1M x 128 fp32 tables, NumPy/BLAS" % (args.cpu_steps, cpu_dt)},
-        "e2e": {"value": e2e_value * world, "unit": "links/s", "h2d_bytes_per_step": 2 * 4 * links_per_step,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "links/s", "h2d_bytes_per_step": 2 * 4 * links_per_step,
                 "d2h_bytes_per_step": 4 * R, "steps": e2e_steps,
-                "note": "per step: pinned-host ids -> device, one super-step through the C-ABI, loss read back (sync)"},
+                "note": "per step and per GPU: pinned-host ids -> device, one super-step through the C-ABI, loss read back (sync)"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "extra": extra,
     }
     print(json.dumps(line))
-    if world > 1:
+    if sharded is not None:
         dist.barrier()
+        sharded.close()
+    if world > 1:
         dist.destroy_process_group()
 
 

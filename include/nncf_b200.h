@@ -151,6 +151,27 @@ int nncf_trainer_get_profile(nncf_trainer_t* t, double* phase_ms_out, int64_t* s
 int nncf_unique_first_occurrence(const int32_t* ids_dev, int n, int32_t* unique_ids_dev, int32_t* inverse_dev,
                                  int32_t* n_unique_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * (3b) Multi-GPU: row-sharded embedding tables addressed directly over NVLink / NVSwitch peer memory.
+ *      The reference is single-device; this is the extension the north_star prescribes (tables sharded by
+ *      row, rows and gradients exchanged over NVLink).  Row `id` of a table lives on rank (id mod N) at local
+ *      row (id div N).  Each rank allocates its shards with nncf_peer_alloc, exchanges the 64-byte handles
+ *      (e.g. torch.distributed.all_gather_object), opens the others with nncf_peer_open and registers the N
+ *      pointers with nncf_trainer_set_shards.  The gather kernel then LOADS remote rows and the update kernel
+ *      issues red.global.add.v4 to remote rows inside the same kernels that do the local work; two
+ *      device-side barriers per step (nncf_peer_barrier, flag words in peer memory) keep the step synchronous:
+ *      nobody updates before everybody has gathered, nobody gathers before every update has landed.
+ *      Sparse SGD only (optimizer state is not sharded yet); matmul schemes; dim % 4 == 0.
+ * ---------------------------------------------------------------------------------------------- */
+int nncf_peer_alloc(size_t bytes, void** ptr_out, unsigned char* handle_out /* [64] */);
+int nncf_peer_open(const unsigned char* handle /* [64] */, void** ptr_out);
+int nncf_peer_close(void* ptr);
+int nncf_peer_free(void* ptr);
+int nncf_peer_barrier(void* const* flag_ptrs /* [n_ranks] 64-byte flag arrays */, int n_ranks, int rank, unsigned int epoch,
+                      void* stream);
+int nncf_trainer_set_shards(nncf_trainer_t* t, int n_shards, int rank, void* const* user_shards, void* const* item_shards,
+                            void* const* barrier_flags);
+
 /* Stand-alone row gather and sparse row update: the two halves of the step that framework towers and the
  * row-sharded multi-GPU path run on their own (owners gather rows for peers / apply the gradients they get back).
  *   nncf_gather_rows:    out[r, :] = table[ids[r], :]

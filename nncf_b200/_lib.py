@@ -21,6 +21,7 @@ EXPORTS = [
     "nncf_trainer_get_profile", "nncf_unique_first_occurrence", "nncf_gather_rows", "nncf_updater_create",
     "nncf_updater_destroy", "nncf_updater_begin_step", "nncf_updater_apply",
     "nncf_meanpool_fwd", "nncf_meanpool_bwd",
+    "nncf_peer_alloc", "nncf_peer_open", "nncf_peer_close", "nncf_peer_free", "nncf_peer_barrier", "nncf_trainer_set_shards",
     "nncf_eval_topk_workspace_bytes", "nncf_eval_topk", "nncf_eval_metrics", "nncf_score_pairs", "nncf_eval_given",
 ]
 
@@ -86,6 +87,12 @@ def _load():
         "nncf_updater_destroy": (i32, [vp]),
         "nncf_updater_begin_step": (i32, [vp]),
         "nncf_updater_apply": (i32, [vp, vp, vp, vp, i64, i32, vp, i64, vp, vp]),
+        "nncf_peer_alloc": (i32, [sz, C.POINTER(vp), vp]),
+        "nncf_peer_open": (i32, [vp, C.POINTER(vp)]),
+        "nncf_peer_close": (i32, [vp]),
+        "nncf_peer_free": (i32, [vp]),
+        "nncf_peer_barrier": (i32, [vp, i32, i32, C.c_uint, vp]),
+        "nncf_trainer_set_shards": (i32, [vp, i32, i32, vp, vp, vp]),
         "nncf_meanpool_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
         "nncf_meanpool_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
         "nncf_eval_topk_workspace_bytes": (sz, [i64, i64, i32, i32, i32]),

@@ -30,7 +30,8 @@ gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
   for (int k = 0; k < kRowsPerWarp; ++k) {
     const int row = row0 + k;
     const int64_t id = __shfl_sync(0xffffffffu, myid, k);
-    const float* src = a.table ? a.table + id * a.d : a.dense_rows + (int64_t)row * a.d;
+    const float* src = a.shards.n > 1 ? a.shards.p[id % a.shards.n] + (id / a.shards.n) * a.d
+                                      : (a.table ? a.table + id * a.d : a.dense_rows + (int64_t)row * a.d);
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int c = 4 * (lane + 32 * v);
@@ -165,7 +166,7 @@ finalize_vec_kernel(FinalizeArgs a0, FinalizeArgs a1) {
       if (c < a.d) {
         if (a.grad_out && r == 0) *reinterpret_cast<float4*>(a.grad_out + (int64_t)row * a.d + c) = g[k][v];
         if (a.optimizer == NNCF_OPT_SGD && a.table)
-          red_add_v4(a.table + id * a.d + c, -a.lr * g[k][v].x, -a.lr * g[k][v].y, -a.lr * g[k][v].z, -a.lr * g[k][v].w);
+          red_add_v4((a.shards.n > 1 ? a.shards.p[id % a.shards.n] + (id / a.shards.n) * a.d : a.table + id * a.d) + c, -a.lr * g[k][v].x, -a.lr * g[k][v].y, -a.lr * g[k][v].z, -a.lr * g[k][v].w);
       }
     }
   }

@@ -94,7 +94,14 @@ unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, in
 // =================================================================================================
 // gather rows -> staging.  One warp per (padded) row.
 // =================================================================================================
+// row-sharded tables (multi-GPU): row `id` lives on rank id % n at local row id / n; p[] are peer-mapped pointers
+struct ShardPtrs {
+  float* p[16];
+  int n;                     // <= 1: not sharded
+};
+
 struct GatherArgs {
+  ShardPtrs shards;
   const float* table;        // [n_rows_table, d] or NULL
   const float* dense_rows;   // [count, d] (used when table == NULL)
   const int32_t* ids;        // [R][ids_stride] (ignored for dense rows)
@@ -315,6 +322,7 @@ score_grad_simt_kernel(ScoreArgs a) {
 // finalize: corrections, normalise-backward, regulariser, optimizer.  One warp per batch row.
 // =================================================================================================
 struct FinalizeArgs {
+  ShardPtrs shards;
   int side;                  // 0 = user rows, 1 = item rows
   int scheme, pairwise;
   const float* Xf;           // this side's staged rows        [R][rows_pad][dp]
@@ -649,6 +657,12 @@ struct nncf_trainer {
   int64_t ownerU_n = 0, ownerV_n = 0;
   float *ps = nullptr;   // PAIRS scores
   bool tc_attr_set = false;
+  // row-sharded multi-GPU mode (nncf_trainer_set_shards)
+  int n_shards = 1, rank = 0;
+  float* ushards[16] = {nullptr};
+  float* ishards[16] = {nullptr};
+  void* flags[16] = {nullptr};
+  unsigned int epoch = 0;
   // optional per-phase device timing (CUDA events on the launching stream)
   bool profile = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -716,6 +730,29 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   delete t;
+  return NNCF_OK;
+}
+
+extern "C" int nncf_peer_barrier(void* const* flag_ptrs, int n_ranks, int rank, unsigned int epoch, void* stream);
+
+extern "C" int nncf_trainer_set_shards(nncf_trainer_t* t, int n_shards, int rank, void* const* user_shards,
+                                       void* const* item_shards, void* const* barrier_flags) {
+  NNCF_CHECK_ARG(t, "nncf_trainer_set_shards: null trainer");
+  NNCF_CHECK_ARG(n_shards >= 1 && n_shards <= 16 && rank >= 0 && rank < n_shards, "nncf_trainer_set_shards: bad rank / n_shards");
+  if (n_shards > 1) {
+    NNCF_CHECK_ARG(user_shards && item_shards && barrier_flags, "nncf_trainer_set_shards: null pointer arrays");
+    NNCF_CHECK_ARG(t->cfg.scheme != NNCF_SCHEME_PAIRS, "sharded tables: matmul schemes only");
+    NNCF_CHECK_ARG(t->cfg.optimizer != NNCF_OPT_LAZY_ADAM, "sharded tables: sparse SGD only (optimizer state is not sharded yet)");
+    NNCF_CHECK_ARG(t->cfg.dim % 4 == 0, "sharded tables need dim % 4 == 0");
+    for (int i = 0; i < n_shards; ++i) {
+      t->ushards[i] = static_cast<float*>(user_shards[i]);
+      t->ishards[i] = static_cast<float*>(item_shards[i]);
+      t->flags[i] = barrier_flags[i];
+    }
+  }
+  t->n_shards = n_shards;
+  t->rank = rank;
+  t->epoch = 0;
   return NNCF_OK;
 }
 
@@ -811,6 +848,12 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   gv.table = tb->item_table; gv.dense_rows = dense_items ? io->item_rows_dev : nullptr;
   gv.ids = item_ids; gv.ids_stride = item_stride; gv.count_dev = group ? t->nuniq : nullptr;
   gv.normalize = c.norm_v; gv.Xf = t->Vf; gv.inv = t->invV; gv.img = t->Vimg; gv.dX = t->dV; gv.corr = t->corrV;
+  const bool sharded = t->n_shards > 1;
+  if (sharded) {
+    NNCF_CHECK_ARG(!dense_items, "sharded tables: embedding-table models only");
+    gu.shards.n = gv.shards.n = t->n_shards;
+    for (int i = 0; i < t->n_shards; ++i) { gu.shards.p[i] = t->ushards[i]; gv.shards.p[i] = t->ishards[i]; }
+  }
   const bool vec = (d % 4 == 0);   // 16-byte aligned rows: 128-bit loads / vector reductions
   if (vec && dp <= 128) gather_rows_vec_kernel<1><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
   else if (vec) gather_rows_vec_kernel<2><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
@@ -869,6 +912,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.need_x = (c.norm_v || pairwise) ? 1 : 0; fv.reg_scale = 0.0f;
   fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
   fv.grad_out = (last && io) ? io->grad_item_rows_dev : nullptr;
+  if (sharded) {
+    fu.shards = gu.shards; fv.shards = gv.shards;
+    // every rank has finished READING its peers' rows (gather) before anybody starts updating them
+    if (int rc = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc;
+  }
   auto launch_finalize = [&](const FinalizeArgs& x, const FinalizeArgs& y, int nz) {
     if (vec && dp <= 128) finalize_vec_kernel<1><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
     else if (vec) finalize_vec_kernel<2><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
@@ -883,6 +931,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   } else {
     launch_finalize(fu, fv, 2);
     NNCF_LAUNCH_OK();
+  }
+  if (sharded) {
+    // all updates of this step have landed before the next step's gathers read the tables
+    if (int rc = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc;
   }
   (void)sgd;
   if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
