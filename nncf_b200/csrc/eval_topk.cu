@@ -6,6 +6,7 @@
 //      utils/metrics_ranking.py:6-35 (eval_multiple), :38-61 (eval_multiple_original).
 // Tie rule (declared realisation of the reference's random tie-break): score descending, then lowest column.
 #include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 #include "sm100.cuh"
 
@@ -26,6 +27,16 @@ __device__ __forceinline__ float key_score(uint64_t k) {
   return __uint_as_float(b);
 }
 __device__ __forceinline__ uint32_t key_col(uint64_t k) { return 0xFFFFFFFFu - static_cast<uint32_t>(k); }
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+  const uint32_t hi = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), src);
+  const uint32_t lo = __shfl_sync(0xffffffffu, static_cast<uint32_t>(v), src);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+  const uint32_t hi = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v >> 32), m);
+  const uint32_t lo = __shfl_xor_sync(0xffffffffu, static_cast<uint32_t>(v), m);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
 
 // warp-cooperative bitonic sort, descending, n a power of two (<= 256), data in shared memory
 __device__ __forceinline__ void warp_bitonic_desc(uint64_t* a, int n, int lane) {
@@ -44,78 +55,124 @@ __device__ __forceinline__ void warp_bitonic_desc(uint64_t* a, int n, int lane) 
   }
 }
 
-constexpr int kPend = 64;          // pending candidates per row (smem)
 constexpr int kMaxKP = 128;        // largest padded k
 
-struct TopkShared {
-  uint64_t* pend;     // [128][kPend]
-  uint64_t* scratch;  // [4 warps][256]
+// ------------------------------------------------------------------------------------------------
+// Streaming exact top-k, one row per thread of the epilogue warp (row = TMEM lane).
+//   Every row keeps an UNSORTED set of its k best keys in shared memory plus, in registers, the smallest of them
+//   (thr_key, at position minpos) — the exact running threshold, so the number of candidates is the minimum a
+//   streaming scan can have (~k ln(I/k) per row).
+//   Fast path per 128-column tile: the row maximum (tree of FMNMX3) against the threshold, ONE ballot per warp.
+//   Hit path (some lane's maximum reaches its threshold — most tiles, because a warp covers 32 rows): warp-
+//   COOPERATIVE, no per-lane divergent loops: the hitting lane parks a 32-score chunk in shared memory, lane t tests
+//   column t, a ballot yields the candidates, and each candidate replaces the row's current minimum followed by a
+//   warp arg-min over the k keys.  (Measured on B200: per-lane divergent candidate handling cost ~500 cycles per
+//   candidate and a sort-based pending-buffer merge ~6k cycles per flush — together 3x the tensor-core pipeline.)
+// ------------------------------------------------------------------------------------------------
+struct RowState {
+  float thr;          // score of thr_key (-inf while the set is not full)
+  uint64_t thr_key;   // smallest key of the row's set (0 = an empty slot exists)
+  int minpos;         // its position in the set
 };
 
-// Merge row `il`'s pending candidates into its sorted list in global memory; returns the new threshold key.
-__device__ __forceinline__ uint64_t flush_row(uint64_t* list, int KP, int k, int sortn, const uint64_t* pend_row, int cnt,
-                                           uint64_t* scratch, int lane) {
-  for (int t = lane; t < sortn; t += 32) {
-    uint64_t v = 0;
-    if (t < KP) v = list[t];
-    else if (t - KP < cnt) v = pend_row[t - KP];
-    scratch[t] = v;
+// chunk = 32 scores of lane L (already staged in `stage`), columns col0 .. col0+31
+__device__ __forceinline__ void coop_chunk(int L, const float* stage, uint32_t col0, uint32_t col_end, RowState& st,
+                                           uint64_t* list_L, int k, int lane) {
+  const float x = stage[lane];
+  const uint32_t col = col0 + lane;
+  const uint64_t key = make_key(x, col);
+  uint64_t tk = shfl_u64(st.thr_key, L);
+  unsigned cm = __ballot_sync(0xffffffffu, (col < col_end) && (key > tk));
+  while (cm) {
+    const int t = __ffs(cm) - 1;
+    cm &= cm - 1;
+    const uint64_t kc = shfl_u64(key, t);
+    if (kc > tk) {                                      // warp-uniform (tk may have risen since the ballot)
+      const int mp = __shfl_sync(0xffffffffu, st.minpos, L);
+      if (lane == 0) list_L[mp] = kc;
+      __syncwarp();
+      uint64_t best = ~0ull;
+      int bpos = 0;
+      for (int i = lane; i < k; i += 32) {
+        const uint64_t kk = list_L[i];
+        if (kk < best) { best = kk; bpos = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const uint64_t ob = shfl_xor_u64(best, o);
+        const int op = __shfl_xor_sync(0xffffffffu, bpos, o);
+        if (ob < best || (ob == best && op < bpos)) { best = ob; bpos = op; }
+      }
+      tk = best;
+      if (lane == L) { st.thr_key = best; st.minpos = bpos; st.thr = best ? key_score(best) : -INFINITY; }
+    }
   }
-  __syncwarp();
-  warp_bitonic_desc(scratch, sortn, lane);
-  for (int t = lane; t < KP; t += 32) list[t] = (t < k) ? scratch[t] : 0ull;
-  const uint64_t kth = scratch[k - 1];
-  __syncwarp();
-  return kth;
 }
 
-// One epilogue step: thread (= row) looks at 32 consecutive scores of its row.
-struct RowState {
-  float thr;          // score of the current k-th best (-inf until k candidates are known)
-  uint64_t thr_key;   // its full ordering key (0 = none): ties are decided on keys, so tiles may arrive in any order
-  int cnt;
-};
-
-__device__ __forceinline__ void consider32(const float* v, uint32_t col0, uint32_t col_end, RowState& st,
-                                           uint64_t* pend_row, bool row_ok) {
-  // maxima of the four contiguous groups of 8 (independent chains; pairs fold into 3-input FMNMX3).  Almost every
-  // chunk has a candidate in SOME lane of the warp, so the slow path must be cheap: it only walks the groups whose
-  // maximum reaches the threshold instead of all 32 elements.
+// one 128-column tile held in registers as v[4][32]; lists = this warp's 32 rows x KP keys in shared memory
+__device__ __forceinline__ void filter_tile(const float (&v)[4][32], uint32_t col0, uint32_t col_end, RowState& st, bool row_ok,
+                                            uint64_t* lists_warp, int KP, int k, float* stage, int lane, unsigned own_mask) {
   float gm[4];
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
-    const float* w = v + g * 8;
-    gm[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
-  }
-  const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
-  if (row_ok && m >= st.thr) {
+  for (int c = 0; c < 4; ++c) {
+    float m8[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-      if (gm[g] >= st.thr) {
+      const float* w = v[c] + g * 8;
+      m8[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
+    }
+    gm[c] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  }
+  const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  // several warps read the same 32 TMEM lanes; each handles only the rows it owns (own_mask), so the serial
+  // candidate work of a quadrant is split between them while every row still has exactly one owner
+  unsigned hits = __ballot_sync(0xffffffffu, row_ok && m >= st.thr) & own_mask;
+  while (hits) {
+    const int L = __ffs(hits) - 1;
+    hits &= hits - 1;
+    const float thr_l = __shfl_sync(0xffffffffu, st.thr, L);
 #pragma unroll
-        for (int t = g * 8; t < g * 8 + 8; ++t) {
-          if (v[t] >= st.thr && col0 + t < col_end) {
-            const uint64_t key = make_key(v[t], col0 + t);
-            if (key > st.thr_key) { pend_row[st.cnt] = key; ++st.cnt; }
-          }
+    for (int c = 0; c < 4; ++c) {
+      const float gmc = __shfl_sync(0xffffffffu, gm[c], L);
+      if (gmc >= thr_l && col0 + c * 32 < col_end) {    // warp-uniform
+        if (lane == L) {
+#pragma unroll
+          for (int t = 0; t < 32; t += 4)
+            *reinterpret_cast<float4*>(stage + t) = make_float4(v[c][t], v[c][t + 1], v[c][t + 2], v[c][t + 3]);
         }
+        __syncwarp();
+        coop_chunk(L, stage, col0 + c * 32, col_end, st, lists_warp + L * KP, k, lane);
+        __syncwarp();
       }
     }
   }
 }
 
-__device__ __forceinline__ void flush_if_needed(RowState& st, uint64_t* list_base /*row 0 of this warp's quadrant*/,
-                                                int64_t list_row_stride, int KP, int k, int sortn, TopkShared sh, int q,
-                                                int lane, bool force) {
-  unsigned need = __ballot_sync(0xffffffffu, force ? (st.cnt > 0) : (st.cnt > kPend - 32));
-  while (need) {
-    const int rl = __ffs(need) - 1;
-    need &= need - 1;
-    const int cnt = __shfl_sync(0xffffffffu, st.cnt, rl);
-    const uint64_t kth = flush_row(list_base + rl * list_row_stride, KP, k, sortn, sh.pend + (q * 32 + rl) * kPend, cnt,
-                                   sh.scratch + q * 256, lane);
-    if (lane == rl) { st.thr_key = kth; st.thr = kth ? key_score(kth) : -INFINITY; st.cnt = 0; }
+// same for ONE 32-column chunk (CUDA-core kernel)
+__device__ __forceinline__ void filter_chunk(const float (&v)[32], uint32_t col0, uint32_t col_end, RowState& st, bool row_ok,
+                                             uint64_t* lists_warp, int KP, int k, float* stage, int lane) {
+  float m = v[0];
+#pragma unroll
+  for (int t = 1; t < 32; ++t) m = fmaxf(m, v[t]);
+  unsigned hits = __ballot_sync(0xffffffffu, row_ok && m >= st.thr);
+  while (hits) {
+    const int L = __ffs(hits) - 1;
+    hits &= hits - 1;
+    if (lane == L) {
+#pragma unroll
+      for (int t = 0; t < 32; t += 4) *reinterpret_cast<float4*>(stage + t) = make_float4(v[t], v[t + 1], v[t + 2], v[t + 3]);
+    }
+    __syncwarp();
+    coop_chunk(L, stage, col0, col_end, st, lists_warp + L * KP, k, lane);
+    __syncwarp();
   }
+}
+
+// copy this warp's 32 unsorted sets to the global per-(user, slot) lists (sorted later by topk_merge_kernel)
+__device__ __forceinline__ void store_lists(const uint64_t* lists_warp, int KP, uint64_t* glists_row0, int64_t gstride, int lane,
+                                            int nrows = 32) {
+  for (int r = 0; r < nrows; ++r)
+    for (int i = lane; i < KP; i += 32) glists_row0[r * gstride + i] = lists_warp[r * KP + i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,46 +196,51 @@ rows_to_img_kernel(const float* __restrict__ rows, int64_t n, int d, int nsub, u
 }
 
 // ------------------------------------------------------------------------------------------------
-// tcgen05 eval kernel.  CTA (ub, sp): 128 users x item tiles [tile_begin, tile_end) of split sp.
-//   warp 0 producer, warp 1 MMA issuer, warps 2..5 epilogue.  4 S accumulators of 128 columns in TMEM.
+// tcgen05 eval kernel.  CTA (ub, sp): 128 users x the item tiles of split sp.
+//   warp 0 bulk-copy producer, warp 1 MMA issuer, warps 2..5 epilogue (TMEM lane quadrant = warp & 3);
+//   4 S accumulators of 128 columns in TMEM so the MMA runs up to four tiles ahead of the filter.
+//   CL > 1: thread-block cluster of CL CTAs (CL consecutive user blocks) sweeping the SAME item tiles: every CTA loads
+//   1/CL of each V tile and multicasts it into all CL shared memories, so a tile crosses L2 -> SM once per CL*128 users.
 // ------------------------------------------------------------------------------------------------
 struct EvalArgs {
   const uint8_t* Uimg; const uint8_t* Vimg;   // tile images
-  const float* Uf; const float* Vf;           // fp32 rows (SIMT path)
+  const float* Uf; const float* Vf;           // fp32 rows (CUDA-core path)
   int64_t n_users, n_items;
   int d, dp;
-  int k, KP, sortn;
+  int k, KP;
   int nsplit, tiles_per_split;
-  uint64_t* lists;                            // [n_user_blocks*128][nsplit][KP]
+  int nstages;                                // V stages in flight (shared memory left after the top-k sets)
+  uint64_t* lists;                            // [n_user_blocks*128][nsplit][KP]  unsorted k-best sets per split
+  int dbg_mode;                               // developer switch (env NNCF_EVAL_DBG): 1 = skip the filter, 2 = also the TMEM loads
 };
 
-template <int NSUB>
-struct EvalCfg {
-  static constexpr int kStages = NSUB <= 2 ? 3 : (NSUB == 3 ? 2 : 1);
-  static constexpr int kSBufs = 4;
-  static constexpr size_t kSmemBytes = (size_t)NSUB * kSubBytes * (1 + kStages) + 128 * kPend * 8 + 4 * 256 * 8 +
-                                       1024 + 256;
-};
+constexpr int kEvalRowGroups = 2;                 // epilogue warps per TMEM lane quadrant; each owns 32 / kEvalRowGroups rows
+constexpr int kEvalEpiWarps = 4 * kEvalRowGroups;
+constexpr int kEvalThreads = 64 + 32 * kEvalEpiWarps;
+constexpr int kEvalCluster = 4;
 
-template <int NSUB>
-__global__ void __launch_bounds__(192, 1)
+__host__ __device__ inline size_t eval_smem_bytes(int nsub, int nstages, int KP) {
+  return (size_t)nsub * kSubBytes * (1 + nstages) + (size_t)128 * KP * 8 + 8 * 32 * 4 + 1024 + 256;
+}
+
+template <int NSUB, int CL>
+__global__ void __launch_bounds__(kEvalThreads, 1)
 eval_topk_tc_kernel(EvalArgs a) {
-  using C = EvalCfg<NSUB>;
   constexpr int DP = 64 * NSUB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nst = a.nstages;
   uint8_t* sU = smem;
   uint8_t* sV = sU + NSUB * kSubBytes;
-  TopkShared sh;
-  sh.pend = reinterpret_cast<uint64_t*>(sV + C::kStages * NSUB * kSubBytes);
-  sh.scratch = sh.pend + 128 * kPend;
-  uint64_t* bars = sh.scratch + 4 * 256;
+  uint64_t* lists_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);   // [128][KP]
+  float* stage_all = reinterpret_cast<float*>(lists_sm + 128 * a.KP);              // [4 warps][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 8 * 32);
   uint64_t* u_full = bars;
-  uint64_t* v_full = bars + 1;    // [3]
-  uint64_t* v_empty = bars + 4;   // [3]
-  uint64_t* s_full = bars + 7;    // [4]
-  uint64_t* s_empty = bars + 11;  // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* v_full = bars + 1;    // [4]
+  uint64_t* v_empty = bars + 5;   // [4]
+  uint64_t* s_full = bars + 9;    // [4]
+  uint64_t* s_empty = bars + 13;  // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ub = blockIdx.x, sp = blockIdx.y;
@@ -186,19 +248,23 @@ eval_topk_tc_kernel(EvalArgs a) {
   const int t0 = sp * a.tiles_per_split;
   const int t1 = min(n_tiles, t0 + a.tiles_per_split);
   const int nj = max(0, t1 - t0);
-  // CTAs sweep the item tiles in rotated order so that at any moment they read DIFFERENT tiles (no L2 hot spot on
-  // one tile); the top-k logic is order independent (ties are decided on full keys)
-  const int rot = nj > 0 ? static_cast<int>((static_cast<unsigned>(ub) * 37u + static_cast<unsigned>(sp) * 11u) % static_cast<unsigned>(nj)) : 0;
+  // clusters sweep the item tiles in rotated order so that at any moment different clusters read DIFFERENT tiles; the
+  // top-k logic is order independent (ties are decided on full keys)
+  const int rot = nj > 0 ? static_cast<int>((static_cast<unsigned>(ub / CL) * 37u + static_cast<unsigned>(sp) * 11u) % static_cast<unsigned>(nj)) : 0;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
+  for (int i = tid; i < 128 * a.KP; i += kEvalThreads) lists_sm[i] = 0ull;
   if (tid == 0) {
     mbar_init(u_full, 1);
-    for (int s = 0; s < 3; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kEpiWarps); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], CL); }
+    for (int s = 0; s < 4; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kEvalEpiWarps); }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();     // peers' barriers are initialised before anybody multicasts into this CTA
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -208,13 +274,18 @@ eval_topk_tc_kernel(EvalArgs a) {
       mbar_expect_tx(u_full, NSUB * kSubBytes);
       for (int s = 0; s < NSUB; ++s) bulk_g2s(sU + s * kSubBytes, gU + (size_t)s * kSubBytes, kSubBytes, u_full);
       for (int j = 0; j < nj; ++j) {
-        const int st = j % C::kStages;
-        mbar_wait(&v_empty[st], ((j / C::kStages) & 1) ^ 1);
+        const int st = j % nst;
+        mbar_wait(&v_empty[st], ((j / nst) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
         const int jj = (j + rot) % nj;
         const uint8_t* gV = a.Vimg + (size_t)(t0 + jj) * NSUB * kSubBytes;
-        for (int s = 0; s < NSUB; ++s)
-          bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + (size_t)s * kSubBytes, kSubBytes, &v_full[st]);
+        if (CL > 1) {
+          constexpr uint32_t kSlice = NSUB * kSubBytes / CL;      // my share of the tile, delivered to every CTA
+          bulk_g2s_multicast(sV + st * NSUB * kSubBytes + crank * kSlice, gV + (size_t)crank * kSlice, kSlice, &v_full[st], kMask);
+        } else {
+          for (int s = 0; s < NSUB; ++s)
+            bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + (size_t)s * kSubBytes, kSubBytes, &v_full[st]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -222,9 +293,9 @@ eval_topk_tc_kernel(EvalArgs a) {
       const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
       mbar_wait(u_full, 0);
       for (int j = 0; j < nj; ++j) {
-        const int st = j % C::kStages, sb = j % C::kSBufs;
-        mbar_wait(&v_full[st], (j / C::kStages) & 1);
-        mbar_wait(&s_empty[sb], ((j / C::kSBufs) & 1) ^ 1);
+        const int st = j % nst, sb = j & 3;
+        mbar_wait(&v_full[st], (j / nst) & 1);
+        mbar_wait(&s_empty[sb], ((j >> 2) & 1) ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k) {
@@ -233,7 +304,8 @@ eval_topk_tc_kernel(EvalArgs a) {
           umma_bf16(tmem + sb * 128, ad, bd, idesc, k > 0);
         }
         umma_commit(&s_full[sb]);
-        umma_commit(&v_empty[st]);
+        if (CL > 1) umma_commit_multicast(&v_empty[st], kMask);   // the stage is rewritten by all CL producers
+        else umma_commit(&v_empty[st]);
       }
     }
   } else {
@@ -242,34 +314,39 @@ eval_topk_tc_kernel(EvalArgs a) {
     const int64_t urow = (int64_t)ub * 128 + il;
     const bool row_ok = urow < a.n_users;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.cnt = 0;
-    uint64_t* pend_row = sh.pend + il * kPend;
-    const int64_t lstride = (int64_t)a.nsplit * a.KP;
-    uint64_t* list_base = a.lists + ((int64_t)ub * 128 + q * 32) * lstride + (int64_t)sp * a.KP;
+    RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.minpos = 0;
+    uint64_t* lists_warp = lists_sm + (size_t)q * 32 * a.KP;
+    float* stage = stage_all + (warp - 2) * 32;
+    const int rg = (warp - 2) >> 2;
+    constexpr int kOwn = 32 / kEvalRowGroups;
+    const unsigned own_mask = (kOwn == 32 ? 0xffffffffu : ((1u << kOwn) - 1u)) << (rg * kOwn);
     const uint32_t col_end = static_cast<uint32_t>(a.n_items);
     for (int j = 0; j < nj; ++j) {
-      const int sb = j % C::kSBufs;
-      mbar_wait(&s_full[sb], (j / C::kSBufs) & 1);
+      const int sb = j & 3;
+      mbar_wait(&s_full[sb], (j >> 2) & 1);
       tc_fence_after();
       // pull the whole 128-column row of the tile into registers with four back-to-back TMEM loads, hand the
       // accumulator back to the MMA warp immediately, then filter from registers
       float v[4][32];
+      if (a.dbg_mode < 2) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
-      tmem_ld_wait();
+        for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
+        tmem_ld_wait();
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        consider32(v[c], static_cast<uint32_t>((t0 + (j + rot) % nj) * 128 + c * 32), col_end, rs, pend_row, row_ok);
-        flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, false);
-      }
+      if (a.dbg_mode >= 1) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) rs.minpos = 1; continue; }
+      filter_tile(v, static_cast<uint32_t>((t0 + (j + rot) % nj) * 128), col_end, rs, row_ok, lists_warp, a.KP, a.k, stage, lane, own_mask);
     }
-    flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, true);
+    __syncwarp();
+    const int64_t gstride = (int64_t)a.nsplit * a.KP;
+    store_lists(lists_warp + rg * kOwn * a.KP, a.KP,
+                a.lists + ((int64_t)ub * 128 + q * 32 + rg * kOwn) * gstride + (int64_t)sp * a.KP, gstride, lane, kOwn);
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();     // nobody exits while a peer may still multicast into it or signal its barriers
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -283,22 +360,21 @@ __global__ void __launch_bounds__(128)
 eval_topk_simt_kernel(EvalArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw2[];
   const int dp = a.dp;
-  float* Vs = reinterpret_cast<float*>(smem_raw2);           // [32][dp]
-  TopkShared sh;
-  sh.pend = reinterpret_cast<uint64_t*>(Vs + 32 * dp);
-  sh.scratch = sh.pend + 128 * kPend;
+  float* Vs = reinterpret_cast<float*>(smem_raw2);                      // [32][dp]
+  uint64_t* lists_sm = reinterpret_cast<uint64_t*>(Vs + 32 * dp);       // [128][KP]
+  float* stage_all = reinterpret_cast<float*>(lists_sm + 128 * a.KP);   // [4 warps][32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ub = blockIdx.x, sp = blockIdx.y;
   const int n_tiles = static_cast<int>((a.n_items + 127) >> 7);
   const int t0 = sp * a.tiles_per_split;
   const int t1 = min(n_tiles, t0 + a.tiles_per_split);
+  for (int i = tid; i < 128 * a.KP; i += 128) lists_sm[i] = 0ull;
   const int il = tid, q = warp;
   const int64_t urow = (int64_t)ub * 128 + il;
   const bool row_ok = urow < a.n_users;
-  RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.cnt = 0;
-  uint64_t* pend_row = sh.pend + il * kPend;
-  const int64_t lstride = (int64_t)a.nsplit * a.KP;
-  uint64_t* list_base = a.lists + ((int64_t)ub * 128 + q * 32) * lstride + (int64_t)sp * a.KP;
+  RowState rs; rs.thr = -INFINITY; rs.thr_key = 0; rs.minpos = 0;
+  uint64_t* lists_warp = lists_sm + (size_t)q * 32 * a.KP;
+  float* stage = stage_all + q * 32;
   const uint32_t col_end = static_cast<uint32_t>(a.n_items);
   for (int64_t c0 = (int64_t)t0 * 128; c0 < (int64_t)t1 * 128 && c0 < a.n_items; c0 += 32) {
     __syncthreads();
@@ -325,13 +401,14 @@ eval_topk_simt_kernel(EvalArgs a) {
         acc[t] = fmaf(u3, vv.w, acc[t]);
       }
     }
-    consider32(acc, static_cast<uint32_t>(c0), col_end, rs, pend_row, row_ok);
-    flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, false);
+    filter_chunk(acc, static_cast<uint32_t>(c0), col_end, rs, row_ok, lists_warp, a.KP, a.k, stage, lane);
   }
-  flush_if_needed(rs, list_base, lstride, a.KP, a.k, a.sortn, sh, q, lane, true);
+  __syncwarp();
+  const int64_t gstride = (int64_t)a.nsplit * a.KP;
+  store_lists(lists_warp, a.KP, a.lists + ((int64_t)ub * 128 + q * 32) * gstride + (int64_t)sp * a.KP, gstride, lane);
 }
 
-// merge the per-split sorted lists of each user and decode: one warp per user
+// sort + merge the per-split k-best sets of each user and decode: one warp per user
 __global__ void __launch_bounds__(128)
 topk_merge_kernel(const uint64_t* __restrict__ lists, int64_t n_users, int nsplit, int KP, int k, int sortn2,
                   int32_t* __restrict__ ids, float* __restrict__ scores) {
@@ -341,15 +418,13 @@ topk_merge_kernel(const uint64_t* __restrict__ lists, int64_t n_users, int nspli
   if (u >= n_users) return;
   uint64_t* sc = scratch_all[warp];
   const uint64_t* base = lists + u * nsplit * KP;
-  for (int t = lane; t < KP; t += 32) sc[t] = base[t];
-  for (int t = KP + lane; t < sortn2; t += 32) sc[t] = 0;
+  for (int t = lane; t < sortn2; t += 32) sc[t] = (t < KP) ? base[t] : 0ull;
   __syncwarp();
+  warp_bitonic_desc(sc, sortn2, lane);
   for (int s = 1; s < nsplit; ++s) {
-    for (int t = lane; t < KP; t += 32) sc[KP + t] = base[(int64_t)s * KP + t];
+    for (int t = KP + lane; t < sortn2; t += 32) sc[t] = (t - KP < KP) ? base[(int64_t)s * KP + (t - KP)] : 0ull;
     __syncwarp();
     warp_bitonic_desc(sc, sortn2, lane);
-    for (int t = KP + lane; t < sortn2; t += 32) sc[t] = 0;
-    __syncwarp();
   }
   for (int t = lane; t < k; t += 32) {
     const uint64_t key = sc[t];
@@ -477,7 +552,8 @@ static int kpad_of(int k) { return (k + 31) / 32 * 32; }
 static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct EvalPlan {
-  int dp, nsub, KP, sortn, nsplit, tiles_per_split, n_tiles;
+  int dp, nsub, KP, nsplit, nstages, tiles_per_split, n_tiles, cl;
+  int64_t n_ub_grid;
   int64_t n_ub, users_pad, items_pad;
   size_t off_uimg, off_vimg, off_lists, off_end;
 };
@@ -490,9 +566,10 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->dp = (dim + 63) / 64 * 64;
   p->nsub = p->dp / 64;
   p->KP = kpad_of(topk);
-  p->sortn = pow2_ge(p->KP + kPend);
   p->n_ub = (n_users + 127) / 128;
-  p->users_pad = p->n_ub * 128;
+  p->cl = (precision == NNCF_PREC_BF16 && p->n_ub >= kEvalCluster) ? kEvalCluster : 1;
+  p->n_ub_grid = (p->n_ub + p->cl - 1) / p->cl * p->cl;
+  p->users_pad = p->n_ub_grid * 128;
   p->n_tiles = static_cast<int>((n_items + 127) / 128);
   p->items_pad = (int64_t)p->n_tiles * 128;
   // enough CTAs to fill 148 SMs twice when the user dimension alone cannot
@@ -508,6 +585,15 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->off_vimg = take(precision == NNCF_PREC_BF16 ? (size_t)p->items_pad * p->dp * 2 : 0);
   p->off_lists = take((size_t)p->users_pad * p->nsplit * p->KP * 8);
   p->off_end = off + 1024;
+  p->nstages = 0;
+  if (precision == NNCF_PREC_BF16) {
+    for (int st = 4; st >= 1; --st)
+      if (eval_smem_bytes(p->nsub, st, p->KP) <= 232448) { p->nstages = st; break; }
+    if (p->nstages == 0) {
+      set_error("eval (bf16): top-k sets of k > 64 do not fit next to dim > 128 operands; use k <= 64 or precision fp32");
+      return NNCF_EUNSUPPORTED;
+    }
+  }
   return 0;
 }
 
@@ -517,14 +603,27 @@ extern "C" size_t nncf_eval_topk_workspace_bytes(int64_t n_users, int64_t n_item
   return p.off_end;
 }
 
-template <int NSUB>
-static int launch_eval_tc(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
-  using C = EvalCfg<NSUB>;
-  NNCF_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C::kSmemBytes));
-  eval_topk_tc_kernel<NSUB><<<dim3((unsigned)p.n_ub, p.nsplit), 192, C::kSmemBytes, st>>>(ea);
+template <int NSUB, int CL>
+static int launch_eval_tc_cl(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  const size_t smem = eval_smem_bytes(NSUB, p.nstages, p.KP);
+  NNCF_CUDA(cudaFuncSetAttribute(eval_topk_tc_kernel<NSUB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.n_ub_grid, p.nsplit, 1);
+  cfg.blockDim = dim3(kEvalThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNCF_CUDA(cudaLaunchKernelEx(&cfg, eval_topk_tc_kernel<NSUB, CL>, ea));
   NNCF_LAUNCH_OK();
   return 0;
+}
+template <int NSUB>
+static int launch_eval_tc(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  return p.cl > 1 ? launch_eval_tc_cl<NSUB, kEvalCluster>(ea, p, st) : launch_eval_tc_cl<NSUB, 1>(ea, p, st);
 }
 
 extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const float* item_rows_dev, int64_t n_items,
@@ -541,9 +640,9 @@ extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const
   uint8_t* ws = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(workspace_dev) + 1023) & ~uintptr_t(1023));
   EvalArgs ea{};
   ea.Uf = user_rows_dev; ea.Vf = item_rows_dev; ea.n_users = n_users; ea.n_items = n_items; ea.d = dim; ea.dp = p.dp;
-  ea.k = topk; ea.KP = p.KP; ea.sortn = p.sortn; ea.nsplit = p.nsplit; ea.tiles_per_split = p.tiles_per_split;
+  ea.k = topk; ea.KP = p.KP; ea.nsplit = p.nsplit; ea.nstages = p.nstages; ea.tiles_per_split = p.tiles_per_split;
+  { const char* e = getenv("NNCF_EVAL_DBG"); ea.dbg_mode = e ? atoi(e) : 0; }
   ea.lists = reinterpret_cast<uint64_t*>(ws + p.off_lists);
-  NNCF_CUDA(cudaMemsetAsync(ea.lists, 0, (size_t)p.users_pad * p.nsplit * p.KP * 8, st));
   if (precision == NNCF_PREC_BF16) {
     ea.Uimg = ws + p.off_uimg; ea.Vimg = ws + p.off_vimg;
     rows_to_img_kernel<<<ceil_div(p.users_pad, 8), 256, 0, st>>>(user_rows_dev, n_users, dim, p.nsub,
@@ -561,7 +660,7 @@ extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const
     }
     if (rc) return rc;
   } else {
-    const size_t sm = ((size_t)32 * p.dp) * 4 + 128 * kPend * 8 + 4 * 256 * 8;
+    const size_t sm = ((size_t)32 * p.dp) * 4 + (size_t)128 * p.KP * 8 + 4 * 32 * 4;
     NNCF_CUDA(cudaFuncSetAttribute(eval_topk_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     eval_topk_simt_kernel<<<dim3((unsigned)p.n_ub, p.nsplit), 128, sm, st>>>(ea);
     NNCF_LAUNCH_OK();

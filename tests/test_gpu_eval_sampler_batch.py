@@ -19,7 +19,14 @@ def _int_embeddings(n, d, seed):
                                        (5, 129, 200, 128)])
 def test_topk_ids_bit_exact_on_integer_embeddings(precision, nu, ni, d, k):
     from nncf_b200.ops import eval_topk
+    from nncf_b200._lib import NNCFError
     U, V = _int_embeddings(nu, d, 1), _int_embeddings(ni, d, 2)
+    if precision == "bf16" and d > 128 and k > 64:
+        # declared limit of the tensor-core kernel: the per-row top-k sets (128 rows x k keys) share the SM's shared
+        # memory with the operand tiles; k > 64 next to dim > 128 operands does not fit and fails loudly
+        with pytest.raises(NNCFError):
+            eval_topk(torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda(), k, precision)
+        return
     ids, sc = eval_topk(torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda(), k, precision)
     ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
     S = U.astype(np.float64) @ V.astype(np.float64).T
