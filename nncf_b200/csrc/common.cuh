@@ -38,6 +38,12 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
     NNCF_CUDA(cudaGetLastError());            \
   } while (0)
 
+// row-sharded tables (multi-GPU): row `id` lives on rank id % n at local row id / n; p[] are peer-mapped pointers
+struct ShardPtrs {
+  float* p[16];
+  int n;                     // <= 1: not sharded
+};
+
 constexpr int kEpiWarps = 4;   // epilogue warps of the tcgen05 kernels (one per TMEM lane quadrant)
 
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }

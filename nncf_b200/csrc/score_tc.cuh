@@ -38,6 +38,16 @@ struct ScoreTcArgs {
   int rows_pad, B, scheme, loss_kind;
   float lambda, gamma;
   long long* dbg;                             // optional [grid][64] clock64 stamps (developer tool)
+  // fused sparse SGD: the drain adds -lr * dX straight into the embedding rows (red.global.add.v4, duplicates sum in
+  // L2) instead of writing dX for a separate update kernel.  Legal because every row of this step was gathered by the
+  // PREVIOUS kernel, so nothing in this kernel reads the tables.
+  int fuse_sgd;
+  int d;                                      // true embedding dim (table row stride), d % 4 == 0 when fused
+  float neg_lr;
+  float* table_u; float* table_v;
+  const int32_t* ids_u; const int32_t* ids_v; // table row of each owner row: ids_x[r * stride_x + row]
+  int64_t ids_stride_u, ids_stride_v;
+  ShardPtrs shards_u, shards_v;
 };
 
 // declared here, defined in score_tc_nsub{1,2,4}.cu (one translation unit per NSUB so they compile in parallel)
@@ -381,11 +391,27 @@ score_grad_tc_kernel(ScoreTcArgs a) {
               make_float4(v[u] * ec.g_scale, v[u + 1] * ec.g_scale, v[u + 2] * ec.g_scale, v[u + 3] * ec.g_scale);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");   // epilogue warps only
-      float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
-      for (int row = ew; row < 128; row += kScoreEpiWarps) {
-        if (ob * 128 + row >= n_owner) break;
-        const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
-        for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
+      if (a.fuse_sgd) {
+        float* table = side == 0 ? a.table_u : a.table_v;
+        const ShardPtrs& sh = side == 0 ? a.shards_u : a.shards_v;
+        const int32_t* ids = (side == 0 ? a.ids_u + r * a.ids_stride_u : a.ids_v + r * a.ids_stride_v) + ob * 128;
+        for (int row = ew; row < 128; row += kScoreEpiWarps) {
+          if (ob * 128 + row >= n_owner) break;
+          const int64_t id = ids[row];
+          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
+          const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
+          for (int c = lane; c < a.d / 4; c += 32) {
+            const float4 g4 = src[c];
+            red_add_v4(trow + 4 * c, a.neg_lr * g4.x, a.neg_lr * g4.y, a.neg_lr * g4.z, a.neg_lr * g4.w);
+          }
+        }
+      } else {
+        float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
+        for (int row = ew; row < 128; row += kScoreEpiWarps) {
+          if (ob * 128 + row >= n_owner) break;
+          const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
+          for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
+        }
       }
     }
     // per-row sums of dL/dD: the two column halves of a row live in two warps -> atomics on two addends only

@@ -15,6 +15,7 @@
 // ref: models/model_framework.py:40-65,85-143; modules/interaction/interaction_dot.py:92-107;
 //      utils/objectives.py:35-220; utils/utilities.py:122-135; utils/optimizer.py:108-147.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "common.cuh"
@@ -94,12 +95,6 @@ unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, in
 // =================================================================================================
 // gather rows -> staging.  One warp per (padded) row.
 // =================================================================================================
-// row-sharded tables (multi-GPU): row `id` lives on rank id % n at local row id / n; p[] are peer-mapped pointers
-struct ShardPtrs {
-  float* p[16];
-  int n;                     // <= 1: not sharded
-};
-
 struct GatherArgs {
   ShardPtrs shards;
   const float* table;        // [n_rows_table, d] or NULL
@@ -820,6 +815,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool dense_items = tb->item_table == nullptr;
   NNCF_PROFILE_MARK(t, 0, st);
   NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
+  const bool want_row_grads = last && io && (io->grad_user_rows_dev || io->grad_item_rows_dev);
+  // plain sparse SGD with nothing to post-process: the score kernel's drain applies the update itself
+  // (measured on B200 at R=37: the drain's reductions cost +9.7 us inside the 8-warp CTAs and save the 11 us update
+  //  kernel that uses the whole grid: no gain, so the fused variant is opt-in: NNCF_FUSE_SGD=1)
+  static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return e && atoi(e) != 0; }();
+  const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
+                        (d % 4 == 0) && !dense_items && !want_row_grads;
   const int32_t* item_ids = cid;
   int64_t item_stride = B;
   if (group) {
@@ -880,6 +882,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.Uimg = t->Uimg; ta.Vimg = t->Vimg; ta.dU = t->dU; ta.dV = t->dV; ta.corrU = t->corrU; ta.corrV = t->corrV;
     ta.spos = t->spos; ta.inverse = sa.inverse; ta.ncols_dev = sa.ncols_dev; ta.loss = t->loss; ta.rows_pad = rp;
     ta.B = B; ta.scheme = c.scheme; ta.loss_kind = c.loss; ta.lambda = c.neg_loss_weight; ta.gamma = c.loss_gamma;
+    ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
+    ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
+    ta.shards_u = gu.shards; ta.shards_v = gv.shards;
+    if (sharded && fuse_sgd) {
+      // every rank has finished READING its peers' rows (gather) before any drain starts updating them
+      if (int rc2 = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc2;
+    }
     int rc = 0;
     switch (t->nsub) {
       case 1: rc = launch_score_tc_nsub1(ta, rp / 128, R, st); break;
@@ -912,7 +921,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.need_x = (c.norm_v || pairwise) ? 1 : 0; fv.reg_scale = 0.0f;
   fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
   fv.grad_out = (last && io) ? io->grad_item_rows_dev : nullptr;
-  if (sharded) {
+  if (sharded && !fuse_sgd) {
     fu.shards = gu.shards; fv.shards = gv.shards;
     // every rank has finished READING its peers' rows (gather) before anybody starts updating them
     if (int rc = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc;
@@ -922,7 +931,9 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     else if (vec) finalize_vec_kernel<2><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
     else finalize_kernel<<<dim3(ceil_div(B, 8), R, nz), 256, 0, st>>>(x, y);
   };
-  if (group && pairwise) {
+  if (fuse_sgd) {
+    // nothing left to do: the update was applied by the score kernel's drain
+  } else if (group && pairwise) {
     // the user side adds the positive-column corrections into the item accumulators: strictly before the item side
     launch_finalize(fu, fu, 1);
     NNCF_LAUNCH_OK();
