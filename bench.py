@@ -275,12 +275,19 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same R, B, d)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if R == 37:
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     flops = 6.0 * B * B * d * R
     achieved_tf = flops / (score_ms * 1e-3) / 1e12
     step_bytes = links_per_step * (8 + 16 * d)
     step_s = ms / args.steps * 1e-3
     roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<2,skip-gram,neg_shared>", "achieved": achieved_tf,
-                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": None,
+                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": traffic,
                 "peak_source": peaks["src"], "ms_per_launch": score_ms, "flops_per_launch": flops,
                 "note": "algorithmic 6*B^2*d*R flops per launch; the one-sided kernel executes 8*B^2*dp*R (S is recomputed "
                         "by the item side); its epilogue is MUFU-bound (DESIGN.md 3.1)",

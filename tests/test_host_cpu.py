@@ -1,0 +1,122 @@
+"""CPU tests of the host-side mirror of the reference interface (no GPU, no compute calls): config surface, data
+contract, CSR truth construction, CLI parser, and that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import nncf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    import ctypes
+    from nncf_b200 import _lib as L
+    hdr = open(os.path.join(ROOT, "include", "nncf_b200.h")).read()
+    declared = set(re.findall(r"\b(nncf_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(L.EXPORTS), (declared - set(L.EXPORTS), set(L.EXPORTS) - declared)
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), name
+    assert L.lib.nncf_version() >= 100
+    assert L.lib.nncf_launch_count() == 0          # nothing launched: no compute without a GPU
+
+
+def test_product_never_imports_the_oracle():
+    pat = re.compile(r"^\s*(from\s+oracle|import\s+oracle|from\s+\.+oracle)|oracle/", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nncf_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not pat.search(src), (dirpath, f)
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    from nncf_b200._lib import NNCFError
+    from nncf_b200 import ops
+    if torch.cuda.is_available():
+        pytest.skip("this is the CPU-box check")
+    with pytest.raises(NNCFError):
+        ops.FusedStep(ops.StepSpec())
+    with pytest.raises(NNCFError):
+        ops.eval_topk(torch.zeros(4, 8), torch.zeros(16, 8), 2)
+
+
+def test_conf_defaults_and_reference_quirks():
+    from nncf_b200.conf import Conf, get_conf
+    c = Conf("citeulike_title_only_fold1")
+    assert (c.max_epoch, c.batch_size_p, c.num_negatives, c.loss) == (40, 512, 10, "skip-gram")
+    assert (c.learn_rate, c.loss_gamma, c.neg_loss_weight) == (0.01, 10, 128)
+    assert (c.neg_dist, c.neg_sampling_power, c.shuffle_st, c.chop_size, c.group_shuffling_trick) == ("unigram", 1, "by_item_chop", 2, True)
+    assert (c.user_dim, c.item_dim, c.word_dim, c.u_reg, c.eval_topk) == (50, 50, 50, 1e-6, 50)
+    assert c.emb_normalization is False
+    # quirk kept: overriding `loss` alone does not switch lr / gamma / neg weight (they are evaluated before param_dict)
+    c = Conf("x", {"loss": "max-margin"})
+    assert (c.learn_rate, c.loss_gamma, c.neg_loss_weight) == (0.01, 10, 128)
+    assert c.emb_normalization is True                      # but normalisation follows the loss (basic_embedding_conf.py:53-56)
+    # get_conf_best applies its tuned values, then re-applies param_dict only when it carries reset_after_getconf
+    pd = {"max_epoch": 3, "word_emb_dropout_rate": 0.1}
+    assert get_conf("citeulike_title_only_fold1", "best", pd).max_epoch == 30
+    pd["reset_after_getconf"] = True
+    best = get_conf("citeulike_title_only_fold1", "best", pd)
+    assert best.max_epoch == 3 and best.word_emb_dropout_rate == 0.1
+    assert get_conf("news_title_only_fold1", "best", None).max_epoch == 20
+    with pytest.raises(AssertionError):
+        get_conf("x", "nonsense")
+
+
+def test_cli_surface_matches_reference():
+    from nncf_b200.main import build_parser
+    p = build_parser()
+    a = p.parse_args(["--data_name", "d", "--model_choice", "mf", "--conf_choice", "best"])
+    assert (a.train_scheme, a.eval_scheme, a.param_dict, a.pred_name, a.gpu) == ("original", "given", None, None, None)
+    with pytest.raises(SystemExit):
+        p.parse_args(["--data_name", "d"])
+
+
+def test_synthetic_data_contract():
+    from nncf_b200.data_utils import make_synthetic
+    d = make_synthetic(300, 700, 5000, content_len=20, vocab=100, seed=1)
+    assert set(d) == {"C", "train", "test", "test_seen", "train_items", "test_items"}          # data/readme.txt:3
+    assert d["train"].shape[1] == 3 and np.all(d["train"][:, 2] == 1)
+    assert d["C"].shape == (700, 20)
+    assert not set(d["train_items"]) & set(d["test_items"])                                    # cold-start split
+    for row in d["C"][:50]:                                                                     # zero padding in the beginning
+        nz = np.nonzero(row)[0]
+        assert nz.size > 0 and np.all(row[nz[0]:] != 0)
+
+
+def test_csr_truth_equals_reference_dense_truth():
+    from nncf_b200.data_utils import make_synthetic
+    from nncf_b200.objectives import _csr_truth
+    d = make_synthetic(120, 260, 3000, content_len=8, vocab=50, seed=2)
+    user_count = int(max(d["train"][:, 0].max(), d["test"][:, 0].max()) + 1)
+    tr_items, te_items, tr_true, te_true = O.prepare_whole_eval(d["train"], d["test"], user_count)
+    n_items = 260
+    for links, items, dense in ((d["train"], tr_items, tr_true), (d["test"][d["test"][:, 2] == 1], te_items, te_true)):
+        pos = np.full(n_items, -1, dtype=np.int64)
+        pos[items] = np.arange(items.size)
+        indptr, cols = _csr_truth(links, user_count, pos)
+        rebuilt = np.zeros_like(dense)
+        for u in range(user_count):
+            rebuilt[u, cols[indptr[u]:indptr[u + 1]]] = 1
+            assert np.all(np.diff(cols[indptr[u]:indptr[u + 1]]) > 0)       # sorted, unique (binary search in the kernel)
+        np.testing.assert_array_equal(rebuilt, dense)
+
+
+def test_golden_original_and_metric_cases():
+    g = np.load(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"))
+    import json
+    meta = json.loads(str(g["meta"]))
+    for j, case in enumerate(meta["original_cases"]):
+        L, _ = O.original_loss_grad(g["os_%d" % j], case["B"], case["k"], case["loss"], case["lam"], case["gamma"])
+        assert L == pytest.approx(float(g["oL_%d" % j]), rel=1e-12)
+    truth, pred = g["ev_truth"], g["ev_pred"]
+    kept = [u for u in range(truth.shape[0]) if truth[u].sum() > 0]
+    got = np.array([O.eval_multiple(truth[u], pred[u], 10) for u in kept])
+    np.testing.assert_allclose(got, g["ev_per_user"], rtol=1e-12)
+    goto = np.array([O.eval_multiple_original(truth[u], pred[u], -1) for u in kept])
+    np.testing.assert_allclose(goto, g["evo_per_user"], rtol=1e-12)
