@@ -40,7 +40,7 @@ def _scatter(n, ids, rows):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("loss", LOSSES)
 @pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
-@pytest.mark.parametrize("B,d,norm", [(96, 50, False), (200, 64, True), (256, 128, True)])
+@pytest.mark.parametrize("B,d,norm", [(96, 50, False), (200, 64, True), (256, 128, True), (130, 256, True), (384, 192, False)])
 def test_matmul_schemes_loss_and_grads(scheme, loss, precision, B, d, norm):
     from nncf_b200.ops import FusedStep, StepSpec
     nu, ni = 300, 120          # few items => duplicate items inside a batch (exercises tf.unique + dup columns)
@@ -66,6 +66,10 @@ def test_matmul_schemes_loss_and_grads(scheme, loss, precision, B, d, norm):
     tol = TOL[precision]
     loss_gpu = float(out["loss"][0].item())
     assert abs(loss_gpu - ref["loss"]) <= tol * max(abs(ref["loss"]), 1e-6), (loss_gpu, ref["loss"])
+    if loss == "max-margin" and precision == "bf16" and norm:
+        # indicator gradient + l2-normalised operands (not bf16-representable): a score within bf16 rounding of the margin
+        # flips its indicator, which moves the gradient by a whole 1/(B*n) unit; the loss (continuous) keeps 1e-2
+        tol = 3e-2
     gu = out["grad_user_rows"].cpu().numpy()
     gv = out["grad_item_rows"].cpu().numpy()
     dEU = _scatter(nu, uid, gu)
