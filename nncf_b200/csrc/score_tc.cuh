@@ -333,9 +333,29 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (lane == 0) mbar_arrive(&s_empty[sb]);
       const int x0 = t * 128 + h * 64;
       // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tile has them)
-      const bool general = GROUP || (t == ob) || (t * 128 + 128 > n_other);
-      uint32_t p0[16], p1[16];
       constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
+      // neg_shared skip-gram, full diagonal tile: it holds exactly ONE positive per row (column == row).  Run the packed
+      // fast path on all 64 scores and patch that single element afterwards instead of the per-element general path.
+      const bool diag_fast = kFastSg && !GROUP && (t == ob) && (t * 128 + 128 <= n_other);
+      const bool general = (GROUP || (t == ob) || (t * 128 + 128 > n_other)) && !diag_fast;
+      uint32_t p0[16], p1[16];
+      bool do_patch = false;
+      uint16_t patch_bits = 0;
+      if (diag_fast && (ol >> 6) == h) {
+        const int idx = ol & 63;                          // my positive inside this warp's 64 columns
+        float sp = 0.0f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { sp = (idx == u) ? v0[u] : sp; sp = (idx == 32 + u) ? v1[u] : sp; }
+        const float sa = fmaf(0.5f, tanh_approx(0.5f * fabsf(sp)), 0.5f);
+        const float sg = (sp >= 0.0f) ? sa : 1.0f - sa;
+        const __nv_bfloat16 pb = __float2bfloat16(ec.inv_wneg * (sg - 1.0f));      // G' of the positive
+        patch_bits = *reinterpret_cast<const uint16_t*>(&pb);
+        do_patch = row_ok;
+        if (side == 0 && row_ok) {
+          const float sps = fmaxf(sp, 0.0f) - __logf(sa);                           // softplus(s)
+          lsum += ec.inv_b * (sps - sp) - ec.w_neg * ec.inv_b * sps;                // positive's own term minus what the fast path adds
+        }
+      }
       if (side == 0) {
         if (general) {
           epi_chunk<LOSS, false, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
@@ -365,6 +385,10 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       for (int ch = 0; ch < 8; ++ch) {
         const uint32_t* src = (ch < 4) ? (p0 + ch * 4) : (p1 + (ch - 4) * 4);
         *reinterpret_cast<uint4*>(grow + ((ch ^ (ol & 7)) << 4)) = make_uint4(src[0], src[1], src[2], src[3]);
+      }
+      if (do_patch) {
+        const int idx = ol & 63;
+        *reinterpret_cast<uint16_t*>(grow + ((((idx >> 3) ^ (ol & 7))) << 4) + (idx & 7) * 2) = patch_bits;
       }
       fence_proxy_async();
       __syncwarp();
