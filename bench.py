@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--replicas", type=int, default=37)  # 37 x 8 CTAs = 2 full waves of 148 SMs
     ap.add_argument("--links", type=int, default=N_LINKS)
     ap.add_argument("--cpu-steps", type=int, default=3000)
-    ap.add_argument("--eval-users", type=int, default=65536)
+    ap.add_argument("--eval-users", type=int, default=75776)   # 4 full waves of 148 CTAs x 128 users
     ap.add_argument("--no-eval", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -217,7 +217,8 @@ struct EvalArgs {
 constexpr int kEvalRowGroups = 2;                 // epilogue warps per TMEM lane quadrant; each owns 32 / kEvalRowGroups rows
 constexpr int kEvalEpiWarps = 4 * kEvalRowGroups;
 constexpr int kEvalThreads = 64 + 32 * kEvalEpiWarps;
-constexpr int kEvalCluster = 4;
+constexpr int kEvalCluster = 2;     // measured (37,888 users x 1M items, k = 50): CL=1 26.9 ms, CL=2 26.8 ms (pipeline alone 10.6 ms =
+                                    // 914 TFLOP/s), CL=4 40.0 ms — a bigger cluster couples more CTAs to the slowest filter
 
 __host__ __device__ inline size_t eval_smem_bytes(int nsub, int nstages, int KP) {
   return (size_t)nsub * kSubBytes * (1 + nstages) + (size_t)128 * KP * 8 + 8 * 32 * 4 + 1024 + 256;
@@ -568,6 +569,7 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->KP = kpad_of(topk);
   p->n_ub = (n_users + 127) / 128;
   p->cl = (precision == NNCF_PREC_BF16 && p->n_ub >= kEvalCluster) ? kEvalCluster : 1;
+  { const char* e = getenv("NNCF_EVAL_CL"); if (e && precision == NNCF_PREC_BF16) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) p->cl = v; } }   // developer override
   p->n_ub_grid = (p->n_ub + p->cl - 1) / p->cl * p->cl;
   p->users_pad = p->n_ub_grid * 128;
   p->n_tiles = static_cast<int>((n_items + 127) / 128);
@@ -623,7 +625,9 @@ static int launch_eval_tc_cl(const EvalArgs& ea, const EvalPlan& p, cudaStream_t
 }
 template <int NSUB>
 static int launch_eval_tc(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
-  return p.cl > 1 ? launch_eval_tc_cl<NSUB, kEvalCluster>(ea, p, st) : launch_eval_tc_cl<NSUB, 1>(ea, p, st);
+  if (p.cl == 4) return launch_eval_tc_cl<NSUB, 4>(ea, p, st);
+  if (p.cl == 2) return launch_eval_tc_cl<NSUB, 2>(ea, p, st);
+  return launch_eval_tc_cl<NSUB, 1>(ea, p, st);
 }
 
 extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const float* item_rows_dev, int64_t n_items,
