@@ -79,6 +79,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 finalize_vec_kernel(FinalizeArgs a0, FinalizeArgs a1) {
   const FinalizeArgs& a = blockIdx.z ? a1 : a0;
+  finalize_publish_loss(a0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * kRowsPerWarp;
   const int r = blockIdx.y;

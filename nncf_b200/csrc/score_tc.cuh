@@ -16,8 +16,14 @@
 // branch-free code (a first version that switched on the loss per element ran 24k cycles per tile: the unrolled
 // 4-way switch blew the instruction cache).
 //
+// Tile width TN (swept rows per tile): 64 for dp <= 128, 128 for dp = 256.  With TN = 64 a CTA needs 112 KiB of shared
+// memory and 256 TMEM columns, so TWO CTAs are resident per SM: one CTA's prologue (barrier init, TMEM alloc, X load)
+// and drain overlap the other's tile loop, and 16 epilogue warps per SM hide the MUFU / TMEM-load latencies (measured at
+// B = 512: the 1-CTA/SM version spent ~8k of its ~21k cycles per CTA outside the tile loop).  dp = 256 keeps TN = 128 and
+// one CTA per SM (its operand tiles alone are 160 KiB; an N = 64 MMA1 would read 192 B/clk of shared memory).
+//
 // Warp roles: warp 0 = bulk-copy (TMA engine) producer, warp 1 = MMA issuer, warps 2..9 = epilogue; epilogue warp w
-// reads TMEM lanes 32*(w&3).. and the 64-column half (w-2)>>2 of every S tile, i.e. exactly one G sub-tile.
+// reads TMEM lanes 32*(w&3).. and the column half (w-2)>>2 (TN/2 columns) of every S tile.
 #pragma once
 #include "common.cuh"
 #include "sm100.cuh"
@@ -25,7 +31,7 @@
 namespace nncf {
 
 constexpr int kScoreEpiWarps = 8;
-constexpr int kScoreThreads = 64 + 32 * kScoreEpiWarps;
+constexpr int kScoreThreads = 64 + 32 * kScoreEpiWarps + 64;   // 12 warps: registers are allocated in groups of 4 warps
 
 struct ScoreTcArgs {
   const uint8_t* Uimg; const uint8_t* Vimg;   // [R][rows_pad/128][NSUB][16 KiB]
@@ -58,12 +64,27 @@ int launch_score_tc_nsub4(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st
 template <int NSUB>
 struct ScoreTcCfg {
   static constexpr int DP = 64 * NSUB;
-  static constexpr int kStages = NSUB <= 2 ? 4 : 2;   // Y tiles in flight: the bulk-copy latency (~2k cycles) must hide
-                                                      // behind >= 2 tile times (measured: 2 stages exposed it every tile)
-  static constexpr int kGBufs = NSUB <= 3 ? 2 : 1;
-  static constexpr int kColDX = 256;
+  static constexpr int TN = NSUB <= 2 ? 64 : 128;     // swept rows per tile = columns of one S' tile
+  static constexpr int CW = TN / 2;                   // S' columns per epilogue warp
+  static constexpr int kYBytes = TN * 128;            // one [TN rows x 64 bf16] piece of a Y tile (8 or 16 KiB)
+  static constexpr int kGSub = TN / 64;               // [128 x 64] sub-tiles of one G' tile
+#ifndef NNCF_SCORE_STAGES
+#define NNCF_SCORE_STAGES 2
+#endif
+#ifndef NNCF_SCORE_GBUFS
+#define NNCF_SCORE_GBUFS 2
+#endif
+  // Two resident CTAs of a tcgen05 kernel have (228 KiB - 2 x (1 KiB reserved + 1 KiB tcgen05 block)) / 2 = 112 KiB of
+  // dynamic shared memory each (measured with tools/occ_probe.cu), barriers included.
+  static constexpr int kStages = NSUB <= 2 ? NNCF_SCORE_STAGES : 2;   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
+  static constexpr int kGBufs = NSUB <= 2 ? NNCF_SCORE_GBUFS : 1;
+  static constexpr int kColDX = 2 * TN;               // S' is double buffered in TMEM columns [0, 2 TN)
+  static constexpr int kTmemCols = (kColDX + DP) <= 256 ? 256 : 512;
+  static constexpr int kMinBlocks = NSUB <= 2 ? 2 : 1;   // resident CTAs per SM
+  // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry); two CTAs of
+  // dp = 128 need 2 x (112 KiB + 256 B + 1 KiB reserved) <= 228 KiB
   static constexpr size_t kSmemBytes =
-      (size_t)NSUB * kSubBytes * (1 + kStages) + (size_t)kGBufs * 2 * kSubBytes + 1024 /*align*/ + 256 /*barriers*/;
+      (size_t)NSUB * kSubBytes + (size_t)kStages * NSUB * kYBytes + (size_t)kGBufs * kGSub * kSubBytes + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -185,17 +206,20 @@ __device__ __forceinline__ void epi_chunk(const EpiConst& c, float (&v)[32], int
 }
 
 template <int NSUB, int LOSS, bool GROUP>
-__global__ void __launch_bounds__(kScoreThreads, 1)
+__global__ void __launch_bounds__(kScoreThreads, ScoreTcCfg<NSUB>::kMinBlocks)
 score_grad_tc_kernel(ScoreTcArgs a) {
   using C = ScoreTcCfg<NSUB>;
   constexpr int DP = C::DP;
+  constexpr int TN = C::TN;
+  constexpr int CW = C::CW;
+  constexpr int NV = CW / 32;                     // 32-column TMEM loads per epilogue warp per tile
   constexpr bool kPairwise = LOSS >= NNCF_LOSS_LOG_LOSS;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (smem_u32(smem) & 1023u) __trap();           // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* sX = smem;
   uint8_t* sY = sX + NSUB * kSubBytes;
-  uint8_t* sG = sY + C::kStages * NSUB * kSubBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * 2 * kSubBytes);
+  uint8_t* sG = sY + C::kStages * NSUB * C::kYBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * C::kGSub * kSubBytes);
   uint64_t* x_full = bars + 0;
   uint64_t* y_full = bars + 1;      // [4]
   uint64_t* y_empty = bars + 5;     // [4]
@@ -212,7 +236,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   const int n_owner = side == 0 ? a.B : ncols;     // valid rows on the owner side
   const int n_other = side == 0 ? ncols : a.B;     // valid rows on the swept side
   if (ob * 128 >= n_owner) return;                 // whole CTA exits together (no barrier touched yet)
-  const int nt = (n_other + 127) >> 7;
+  const int nt = (n_other + TN - 1) / TN;
   const int nblk = a.rows_pad >> 7;
   const int64_t base = (int64_t)r * a.rows_pad;
   const uint8_t* gX = (side == 0 ? a.Uimg : a.Vimg) + ((int64_t)r * nblk + ob) * NSUB * kSubBytes;
@@ -228,7 +252,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     mbar_init(dx_full, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -245,15 +269,17 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       for (int t = 0; t < nt; ++t) {
         const int st = t % C::kStages;
         mbar_wait(&y_empty[st], ((t / C::kStages) & 1) ^ 1);
-        mbar_expect_tx(&y_full[st], NSUB * kSubBytes);
+        mbar_expect_tx(&y_full[st], NSUB * C::kYBytes);
+        // rows [t TN, (t+1) TN) of the swept side: a contiguous piece of each [128 x 64] sub-tile of block (t TN) / 128
+        const uint8_t* src = gY + (size_t)((t * TN) >> 7) * NSUB * kSubBytes + (size_t)((t * TN) & 127) * 128;
         for (int s = 0; s < NSUB; ++s)
-          bulk_g2s(sY + (st * NSUB + s) * kSubBytes, gY + ((size_t)t * NSUB + s) * kSubBytes, kSubBytes, &y_full[st]);
+          bulk_g2s(sY + (st * NSUB + s) * C::kYBytes, src + (size_t)s * kSubBytes, C::kYBytes, &y_full[st]);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc_s = make_idesc_bf16(128, TN, 0, 0);
       const uint32_t idesc_dx = make_idesc_bf16(128, DP, 0, 1);
       auto issue_mma1 = [&](int t) {
         const int st = t % C::kStages, sb = t & 1;
@@ -263,8 +289,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k) {
           const uint64_t ad = make_smem_desc(smem_u32(sX + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(smem_u32(sY + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem + sb * 128, ad, bd, idesc_s, k > 0);
+          const uint64_t bd = make_smem_desc(smem_u32(sY + (st * NSUB + (k >> 2)) * C::kYBytes) + (k & 3) * 32, 16, 1024);
+          umma_bf16(tmem + sb * TN, ad, bd, idesc_s, k > 0);
         }
         umma_commit(&s_full[sb]);
       };
@@ -278,12 +304,12 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         mbar_wait(&g_full[gb], (t / C::kGBufs) & 1);
         if (t < 8) NNCF_STAMP(8 + t);
         tc_fence_after();
-        const uint8_t* g = sG + gb * 2 * kSubBytes;
-        const uint8_t* y = sY + st * NSUB * kSubBytes;
+        const uint8_t* g = sG + gb * C::kGSub * kSubBytes;
+        const uint8_t* y = sY + st * NSUB * C::kYBytes;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {   // K = the 128 swept rows of this tile, 16 per MMA
+        for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA
           const uint64_t ad = make_smem_desc(smem_u32(g + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(smem_u32(y) + k * 2048, kSubBytes, 1024);
+          const uint64_t bd = make_smem_desc(smem_u32(y) + k * 2048, C::kYBytes, 1024);
           umma_bf16(tmem + C::kColDX, ad, bd, idesc_dx, (t > 0) || (k > 0));
         }
         umma_commit(&y_empty[st]);
@@ -292,11 +318,11 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       umma_commit(dx_full);
       NNCF_STAMP(3);
     }
-  } else {
+  } else if (warp < 2 + kScoreEpiWarps) {
     // ------------------------------------------------------------------------------ epilogue warps
     const int ew = warp - 2;
     const int q = warp & 3;                     // TMEM lane quadrant this warp may access
-    const int h = ew >> 2;                      // 64-column half of each S tile = G sub-tile index
+    const int h = ew >> 2;                      // column half of each S' tile (CW columns)
     const int ol = q * 32 + lane;               // row inside the owned block
     const int o = ob * 128 + ol;                // owner-side index (i on side 0, j on side 1)
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
@@ -323,29 +349,33 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       mbar_wait(&s_full[sb], (t >> 1) & 1);
       if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(16 + t);
       tc_fence_after();
-      float v0[32], v1[32];
-      tmem_ld32(tmem + lane_addr + sb * 128 + h * 64, v0);
-      tmem_ld32(tmem + lane_addr + sb * 128 + h * 64 + 32, v1);
+      float v[NV][32];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) tmem_ld32(tmem + lane_addr + sb * TN + h * CW + 32 * j, v[j]);
       tmem_ld_wait();
       // the S buffer is in registers now: hand it back to the MMA warp before doing the math
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      const int x0 = t * 128 + h * 64;
-      // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tile has them)
+      const int x0 = t * TN + h * CW;                   // swept index of my first column
+      // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tiles have them)
       constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
-      // neg_shared skip-gram, full diagonal tile: it holds exactly ONE positive per row (column == row).  Run the packed
-      // fast path on all 64 scores and patch that single element afterwards instead of the per-element general path.
-      const bool diag_fast = kFastSg && !GROUP && (t == ob) && (t * 128 + 128 <= n_other);
-      const bool general = (GROUP || (t == ob) || (t * 128 + 128 > n_other)) && !diag_fast;
-      uint32_t p0[16], p1[16];
+      const bool on_diag = ((t * TN) >> 7) == ob;       // this tile crosses the diagonal of my 128-row block
+      const bool full = (t * TN + TN <= n_other);
+      // neg_shared skip-gram, full diagonal tile: it holds at most ONE positive per row (column == row).  Run the packed
+      // fast path on all scores and patch that single element afterwards instead of the per-element general path.
+      const bool diag_fast = kFastSg && !GROUP && on_diag && full;
+      const bool general = (GROUP || on_diag || !full) && !diag_fast;
+      uint32_t pk[NV][16];
       bool do_patch = false;
       uint16_t patch_bits = 0;
-      if (diag_fast && (ol >> 6) == h) {
-        const int idx = ol & 63;                          // my positive inside this warp's 64 columns
+      const int pidx = o - x0;                          // my positive's column inside this warp's CW columns (if any)
+      if (diag_fast && pidx >= 0 && pidx < CW) {
         float sp = 0.0f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) { sp = (idx == u) ? v0[u] : sp; sp = (idx == 32 + u) ? v1[u] : sp; }
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int u = 0; u < 32; ++u) sp = (pidx == 32 * j + u) ? v[j][u] : sp;
         const float sa = fmaf(0.5f, tanh_approx(0.5f * fabsf(sp)), 0.5f);
         const float sg = (sp >= 0.0f) ? sa : 1.0f - sa;
         const __nv_bfloat16 pb = __float2bfloat16(ec.inv_wneg * (sg - 1.0f));      // G' of the positive
@@ -356,40 +386,30 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           lsum += ec.inv_b * (sps - sp) - ec.w_neg * ec.inv_b * sps;                // positive's own term minus what the fast path adds
         }
       }
-      if (side == 0) {
-        if (general) {
-          epi_chunk<LOSS, false, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
-          epi_chunk<LOSS, false, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
-        } else if (kFastSg) {
-          epi_chunk_sg_fast<true>(v0, p0, lraw);
-          epi_chunk_sg_fast<true>(v1, p1, lraw);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        if (side == 0) {
+          if (general) epi_chunk<LOSS, false, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+          else if (kFastSg) epi_chunk_sg_fast<true>(v[j], pk[j], lraw);
+          else epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         } else {
-          epi_chunk<LOSS, false, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
-          epi_chunk<LOSS, false, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
-        }
-      } else {
-        if (general) {
-          epi_chunk<LOSS, true, GROUP, true>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
-          epi_chunk<LOSS, true, GROUP, true>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
-        } else if (kFastSg) {
-          epi_chunk_sg_fast<false>(v0, p0, lraw);
-          epi_chunk_sg_fast<false>(v1, p1, lraw);
-        } else {
-          epi_chunk<LOSS, true, GROUP, false>(ec, v0, x0, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p0);
-          epi_chunk<LOSS, true, GROUP, false>(ec, v1, x0 + 32, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, p1);
+          if (general) epi_chunk<LOSS, true, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+          else if (kFastSg) epi_chunk_sg_fast<false>(v[j], pk[j], lraw);
+          else epi_chunk<LOSS, true, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         }
       }
       mbar_wait(&g_empty[gb], ((t / C::kGBufs) & 1) ^ 1);
-      uint8_t* grow = sG + gb * 2 * kSubBytes + h * kSubBytes + ol * 128;
+      // my CW columns = 16-byte chunks [cb, cb + CW/8) of row ol in G' sub-tile gs
+      constexpr int kChunks = CW / 8;
+      const int gs = (h * CW) >> 6, cb = ((h * CW) & 63) >> 3;
+      uint8_t* grow = sG + (gb * C::kGSub + gs) * kSubBytes + ol * 128;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t* src = (ch < 4) ? (p0 + ch * 4) : (p1 + (ch - 4) * 4);
-        *reinterpret_cast<uint4*>(grow + ((ch ^ (ol & 7)) << 4)) = make_uint4(src[0], src[1], src[2], src[3]);
+      for (int ch = 0; ch < kChunks; ++ch) {
+        const uint32_t* src = pk[ch >> 2] + (ch & 3) * 4;
+        *reinterpret_cast<uint4*>(grow + (((cb + ch) ^ (ol & 7)) << 4)) = make_uint4(src[0], src[1], src[2], src[3]);
       }
-      if (do_patch) {
-        const int idx = ol & 63;
-        *reinterpret_cast<uint16_t*>(grow + ((((idx >> 3) ^ (ol & 7))) << 4) + (idx & 7) * 2) = patch_bits;
-      }
+      if (do_patch)
+        *reinterpret_cast<uint16_t*>(grow + (((cb + (pidx >> 3)) ^ (ol & 7)) << 4) + (pidx & 7) * 2) = patch_bits;
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&g_full[gb]);
@@ -403,7 +423,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // TMEM rows live in lanes, so a direct store would scatter 32 rows per instruction (measured: 4.4k cycles).
       // Transpose through shared memory (the Y/G buffers are idle now) and write whole rows, coalesced.
       constexpr int LD = DP + 4;                                  // padded row: STS.128 at the 4-wavefront minimum
-      float* stage = reinterpret_cast<float*>(sY);
+      float* stage = reinterpret_cast<float*>(smem);             // X / Y / G are all idle once dx_full has fired
 #pragma unroll 1
       for (int c0 = h * (DP / 2); c0 < (h + 1) * (DP / 2); c0 += 32) {
         float v[32];
@@ -454,7 +474,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, C::kTmemCols);
   }
   if (tid == 0) NNCF_STAMP(6);
 #undef NNCF_STAMP
@@ -468,6 +488,9 @@ int launch_score_tc_one(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) 
   if (!attr_set) {
     NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)C::kSmemBytes));
+    // two resident CTAs per SM need the full shared-memory carve-out
+    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
   score_grad_tc_kernel<NSUB, LOSS, GROUP><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes, st>>>(a);

@@ -340,11 +340,26 @@ struct FinalizeArgs {
   float* table;
   const int32_t* ids; int64_t ids_stride;      // table row of each batch row
   float* grad_out;           // optional [count][d] copy of the final row gradients (replica 0 only)
+  // loss hand-off, folded into the step's LAST finalize launch (saves a memset node and a one-block kernel per step):
+  // block (0,0,0) publishes the R accumulated losses as fp32 and re-zeroes the accumulators for the next step
+  double* loss_acc;          // [R] or NULL
+  float* loss_out;           // [R] or NULL
+  int n_replicas;
 };
+
+__device__ __forceinline__ void finalize_publish_loss(const FinalizeArgs& a) {
+  if (a.loss_acc && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) {
+    for (int r = threadIdx.x; r < a.n_replicas; r += blockDim.x) {
+      if (a.loss_out) a.loss_out[r] = static_cast<float>(a.loss_acc[r]);
+      a.loss_acc[r] = 0.0;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(FinalizeArgs a0, FinalizeArgs a1) {
   const FinalizeArgs& a = blockIdx.z ? a1 : a0;
+  finalize_publish_loss(a0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
   const int r = blockIdx.y;
@@ -652,6 +667,7 @@ struct nncf_trainer {
   int64_t ownerU_n = 0, ownerV_n = 0;
   float *ps = nullptr;   // PAIRS scores
   bool tc_attr_set = false;
+  bool loss_published = false;   // the step's finalize launch already wrote loss_out and re-zeroed the accumulators
   // row-sharded multi-GPU mode (nncf_trainer_set_shards)
   int n_shards = 1, rank = 0;
   float* ushards[16] = {nullptr};
@@ -806,7 +822,7 @@ static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int
 }
 
 static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
-                       const nncf_step_io* io, bool last, cudaStream_t st) {
+                       const nncf_step_io* io, bool last, float* loss_out_step, cudaStream_t st) {
   const nncf_step_config& c = t->cfg;
   const int R = c.replicas, B = c.batch_size_p, d = c.dim, dp = t->dp, rp = t->rows_pad;
   const bool group = c.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
@@ -814,7 +830,6 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool bf16 = c.precision == NNCF_PREC_BF16;
   const bool dense_items = tb->item_table == nullptr;
   NNCF_PROFILE_MARK(t, 0, st);
-  NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
   const bool want_row_grads = last && io && (io->grad_user_rows_dev || io->grad_item_rows_dev);
   // plain sparse SGD with nothing to post-process: the score kernel's drain applies the update itself
   // (measured on B200 at R=37: the drain's reductions cost +9.7 us inside the 8-warp CTAs and save the 11 us update
@@ -822,6 +837,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return e && atoi(e) != 0; }();
   const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
                         (d % 4 == 0) && !dense_items && !want_row_grads;
+  // t->loss is zero on entry: zeroed at creation and re-zeroed by the last finalize launch of every step; the
+  // fused-SGD path has no finalize launch and keeps the explicit memset + loss_out kernel
+  if (fuse_sgd) NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
+  t->loss_published = !fuse_sgd;
   const int32_t* item_ids = cid;
   int64_t item_stride = B;
   if (group) {
@@ -937,9 +956,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     // the user side adds the positive-column corrections into the item accumulators: strictly before the item side
     launch_finalize(fu, fu, 1);
     NNCF_LAUNCH_OK();
+    fv.loss_acc = t->loss; fv.loss_out = loss_out_step; fv.n_replicas = R;
     launch_finalize(fv, fv, 1);
     NNCF_LAUNCH_OK();
   } else {
+    fu.loss_acc = t->loss; fu.loss_out = loss_out_step; fu.n_replicas = R;
     launch_finalize(fu, fv, 2);
     NNCF_LAUNCH_OK();
   }
@@ -1034,10 +1055,12 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
   for (int64_t s = 0; s < n_steps; ++s) {
     const bool last = (s + 1 == n_steps);
     int rc;
+    float* loss_out_step = (io && io->loss_out_dev) ? io->loss_out_dev + s * R : nullptr;
+    t->loss_published = false;
     if (t->cfg.scheme == NNCF_SCHEME_PAIRS)
       rc = step_pairs(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
     else
-      rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
+      rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, loss_out_step, st);
     if (rc) return rc;
     if (t->profile) {
       NNCF_CUDA(cudaEventSynchronize(t->ev[3]));
@@ -1048,7 +1071,7 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
       }
       t->phase_steps += 1;
     }
-    if (io && io->loss_out_dev) {
+    if (loss_out_step && !t->loss_published) {
       loss_out_kernel<<<1, R < 32 ? 32 : ((R + 31) / 32 * 32), 0, st>>>(t->loss, R, io->loss_out_dev + s * R);
       NNCF_LAUNCH_OK();
     }

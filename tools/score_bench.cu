@@ -28,6 +28,10 @@ int main(int argc, char** argv) {
   a.dbg = dbg;
   using C = ScoreTcCfg<NSUB>;
   CK(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+  CK(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, 0, false>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+  { int nb = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, score_grad_tc_kernel<NSUB, 0, false>, kScoreThreads, C::kSmemBytes)); cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, score_grad_tc_kernel<NSUB, 0, false>));
+    printf("resident CTAs per SM: %d (dyn smem %zu B, static %zu B, regs %d, maxdyn %d, carveout %d)\n", nb, (size_t)C::kSmemBytes, fa.sharedSizeBytes, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
+    for (size_t sz = 100 * 1024; sz <= C::kSmemBytes; sz += 1024) { int q = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, score_grad_tc_kernel<NSUB, 0, false>, kScoreThreads, sz); if (q < 2) { printf("  occupancy drops to %d at dyn smem %zu\n", q, sz); break; } } }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   for (int it = 0; it < 3; ++it) score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
   CK(cudaDeviceSynchronize());
