@@ -141,6 +141,14 @@ typedef struct {
 
 int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,
                      const int32_t* item_ids_dev, int64_t n_steps, const nncf_step_io* io, void* stream);
+/* Host-fed variant of nncf_train_steps: the ids of all n_steps x R batches live in HOST memory (pinned memory lets the
+ * copies overlap the kernels), as the reference's `train` array does (ref: models/train_neg_shared.py:46-50 slices it per
+ * batch and feeds it through feed_dict), and loss_out_host[n_steps * R] receives every batch's loss (what Keras'
+ * train_on_batch returns, ref: models/train_neg_shared.py:50).  Per step: H2D copy of that step's ids on an internal
+ * copy stream (overlapping the previous step's kernels), the step on `stream`, D2H copy of its losses.  Returns when
+ * all steps and copies have completed.  Embedding-table models only. */
+int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
+                          const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream);
 /* Optional per-phase device timing with CUDA events on the launching stream (used by bench.py's roofline leg; it
  * synchronises after every step, so never enable it inside a throughput measurement).
  * phase_ms_out[3] = accumulated ms of { gather/prepare, score+gradient kernel, finalize/optimizer }. */

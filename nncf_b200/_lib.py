@@ -17,7 +17,7 @@ EXPORTS = [
     "nncf_sampler_create", "nncf_sampler_destroy", "nncf_sampler_sample_batch_dev", "nncf_sampler_sample_batch_host",
     "nncf_sampler_seek", "nncf_sampler_export_table",
     "nncf_permute_rows", "nncf_group_shuffle_workspace_bytes", "nncf_group_shuffle", "nncf_assemble_pairs_batch",
-    "nncf_trainer_create", "nncf_trainer_destroy", "nncf_train_steps", "nncf_trainer_set_profile",
+    "nncf_trainer_create", "nncf_trainer_destroy", "nncf_train_steps", "nncf_train_steps_host", "nncf_trainer_set_profile",
     "nncf_trainer_get_profile", "nncf_unique_first_occurrence", "nncf_gather_rows", "nncf_updater_create",
     "nncf_updater_destroy", "nncf_updater_begin_step", "nncf_updater_apply",
     "nncf_meanpool_fwd", "nncf_meanpool_bwd",
@@ -79,6 +79,7 @@ def _load():
         "nncf_trainer_create": (i32, [C.POINTER(StepConfig), C.POINTER(vp)]),
         "nncf_trainer_destroy": (i32, [vp]),
         "nncf_train_steps": (i32, [vp, C.POINTER(Tables), vp, vp, i64, C.POINTER(StepIO), vp]),
+        "nncf_train_steps_host": (i32, [vp, C.POINTER(Tables), vp, vp, i64, vp, vp]),
         "nncf_trainer_set_profile": (i32, [vp, i32]),
         "nncf_trainer_get_profile": (i32, [vp, vp, vp]),
         "nncf_unique_first_occurrence": (i32, [vp, i32, vp, vp, vp, vp]),

@@ -674,6 +674,12 @@ struct nncf_trainer {
   float* ishards[16] = {nullptr};
   void* flags[16] = {nullptr};
   unsigned int epoch = 0;
+  // host-fed mode (nncf_train_steps_host): staging ring for ids / losses, copy streams, hand-off events
+  static constexpr int kHostBufs = 4;
+  int32_t* h_ids[kHostBufs] = {nullptr, nullptr, nullptr, nullptr};   // [2][R * rows] device staging (uid then cid)
+  float* h_loss[kHostBufs] = {nullptr, nullptr, nullptr, nullptr};    // [R] device
+  cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+  cudaEvent_t ev_ready[kHostBufs] = {}, ev_done[kHostBufs] = {}, ev_read[kHostBufs] = {};
   // optional per-phase device timing (CUDA events on the launching stream)
   bool profile = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -740,6 +746,15 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
                   t->loss, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+  for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
+    if (t->h_ids[i]) cudaFree(t->h_ids[i]);
+    if (t->h_loss[i]) cudaFree(t->h_loss[i]);
+    if (t->ev_ready[i]) cudaEventDestroy(t->ev_ready[i]);
+    if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
+    if (t->ev_read[i]) cudaEventDestroy(t->ev_read[i]);
+  }
+  if (t->s_h2d) cudaStreamDestroy(t->s_h2d);
+  if (t->s_d2h) cudaStreamDestroy(t->s_d2h);
   delete t;
   return NNCF_OK;
 }
@@ -1076,6 +1091,57 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
       NNCF_LAUNCH_OK();
     }
   }
+  return NNCF_OK;
+}
+
+// Host-fed training loop: the link ids of every batch live in HOST memory, as the reference's `train` array does (it
+// slices a NumPy array per batch and feeds it through feed_dict, ref: models/train_neg_shared.py:46-50), and every
+// batch's loss goes back to the host (what train_on_batch returns).  Step s's ids travel on a copy stream into a ring of
+// device staging buffers while step s-1's kernels run; the losses return on a second copy stream.  Nothing is skipped:
+// every step does its H2D and D2H; the host is only synchronised once, at the end.
+extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
+                                     const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream) {
+  NNCF_CHECK_ARG(t && tables && user_ids_host && item_ids_host, "nncf_train_steps_host: null argument");
+  NNCF_CHECK_ARG(tables->user_table && tables->item_table, "nncf_train_steps_host: embedding-table models only");
+  NNCF_CHECK_ARG(n_steps >= 0, "nncf_train_steps_host: n_steps < 0");
+  constexpr int NB = nncf_trainer::kHostBufs;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = t->cfg.replicas;
+  const int64_t per_step = (int64_t)R * t->rows;
+  if (!t->s_h2d) {
+    NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
+    NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < NB; ++i) {
+      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_ids[i]), 2 * per_step * sizeof(int32_t)));
+      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_loss[i]), R * sizeof(float)));
+      NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_ready[i], cudaEventDisableTiming));
+      NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
+      NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_read[i], cudaEventDisableTiming));
+    }
+  }
+  nncf_step_io io{};
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int b = static_cast<int>(s % NB);
+    // ids of step s -> staging buffer b (free once step s - NB has finished with it)
+    if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_done[b], 0));
+    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b], user_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
+    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b] + per_step, item_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
+    NNCF_CUDA(cudaEventRecord(t->ev_ready[b], t->s_h2d));
+    // the step itself
+    NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_ready[b], 0));
+    if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_read[b], 0));       // loss slot b has been read back
+    io.loss_out_dev = t->h_loss[b];
+    if (int rc = nncf_train_steps(t, tables, t->h_ids[b], t->h_ids[b] + per_step, 1, &io, st)) return rc;
+    NNCF_CUDA(cudaEventRecord(t->ev_done[b], st));
+    // loss of step s -> host
+    if (loss_out_host) {
+      NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, t->ev_done[b], 0));
+      NNCF_CUDA(cudaMemcpyAsync(loss_out_host + s * R, t->h_loss[b], R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));
+    }
+    NNCF_CUDA(cudaEventRecord(t->ev_read[b], t->s_d2h));
+  }
+  NNCF_CUDA(cudaStreamSynchronize(st));
+  NNCF_CUDA(cudaStreamSynchronize(t->s_d2h));
   return NNCF_OK;
 }
 

@@ -240,6 +240,30 @@ class FusedStep:
         return out
 
 
+    def run_host(self, user_table: torch.Tensor, item_table: torch.Tensor, user_ids_host: torch.Tensor,
+                 item_ids_host: torch.Tensor, n_steps: int, loss_out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host-fed loop (nncf_train_steps_host): ids are HOST int32 tensors (pinned memory lets the copies overlap the
+        kernels), one H2D copy of its ids and one D2H copy of its losses per step; returns the host loss tensor
+        [n_steps * R] after everything has completed.   ref: models/train_neg_shared.py:46-50"""
+        sp = self.spec
+        _need_cuda(user_table, item_table)
+        assert not user_ids_host.is_cuda and not item_ids_host.is_cuda, "run_host takes HOST id tensors"
+        assert user_ids_host.dtype == torch.int32 and item_ids_host.dtype == torch.int32
+        assert user_ids_host.is_contiguous() and item_ids_host.is_contiguous()
+        need = n_steps * sp.replicas * self.rows
+        assert user_ids_host.numel() >= need and item_ids_host.numel() >= need, "not enough ids for n_steps x replicas batches"
+        if loss_out_host is None:
+            loss_out_host = torch.empty(n_steps * sp.replicas, dtype=torch.float32).pin_memory()
+        assert loss_out_host.numel() >= n_steps * sp.replicas and loss_out_host.dtype == torch.float32
+        tb = Tables()
+        tb.user_table, tb.n_users = user_table.data_ptr(), user_table.shape[0]
+        tb.item_table, tb.n_items = item_table.data_ptr(), item_table.shape[0]
+        check(lib.nncf_train_steps_host(self._h, C.byref(tb), C.c_void_p(user_ids_host.data_ptr()),
+                                        C.c_void_p(item_ids_host.data_ptr()), int(n_steps),
+                                        C.c_void_p(loss_out_host.data_ptr()), _stream()))
+        return loss_out_host
+
+
 # ------------------------------------------------------------------------------------------------
 # mean-pool encoder
 # ------------------------------------------------------------------------------------------------

@@ -241,3 +241,35 @@ def test_bad_arguments_raise():
         FusedStep(StepSpec(dim=1000))
     with pytest.raises(AssertionError):
         FusedStep(StepSpec(loss="hinge"))
+
+
+@pytest.mark.parametrize("replicas,n_steps", [(1, 9), (3, 6)])
+def test_host_fed_steps_match_device_fed(replicas, n_steps):
+    """nncf_train_steps_host (ids in host memory, one H2D + one D2H per step on copy streams, staging ring of 4) must
+    produce exactly what the device-fed loop produces on the same ids: same losses, same tables (fp32 path: the update
+    is order-independent only up to atomic ordering, so tables are compared at 1e-6)."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    nu, ni, B, d = 500, 400, 128, 64
+    EU, EV = _tables(nu, ni, d, seed=11)
+    rng = np.random.RandomState(5)
+    n = n_steps * replicas * B
+    uid = rng.randint(0, nu, size=n).astype(np.int32)
+    cid = rng.randint(0, ni, size=n).astype(np.int32)
+    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="sgd",
+                    learn_rate=0.05, replicas=replicas)
+    a = FusedStep(spec)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    out = a.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), n_steps)
+    torch.cuda.synchronize()
+    b = FusedStep(spec)
+    hU, hV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    h_uid, h_cid = torch.from_numpy(uid).pin_memory(), torch.from_numpy(cid).pin_memory()
+    loss_h = b.run_host(hU, hV, h_uid, h_cid, n_steps)
+    assert not loss_h.is_cuda and loss_h.numel() == n_steps * replicas
+    assert np.allclose(loss_h.numpy(), out["loss"].cpu().numpy(), rtol=1e-5, atol=1e-6)
+    assert _rel(hU.cpu().numpy(), tU.cpu().numpy()) < 1e-6 and _rel(hV.cpu().numpy(), tV.cpu().numpy()) < 1e-6
+    # a second call reuses the staging ring; pageable host memory is accepted too
+    loss_h2 = b.run_host(hU, hV, torch.from_numpy(uid), torch.from_numpy(cid), 2)
+    assert np.all(np.isfinite(loss_h2.numpy()[:2 * replicas]))
+    with pytest.raises(AssertionError):
+        b.run_host(hU, hV, h_uid.cuda(), h_cid.cuda(), 1)

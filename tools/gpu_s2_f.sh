@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -6
+timeout 600 python bench.py --steps 2000 --warmup 100 --no-eval --cpu-steps 20 > gpurun_out/s2f_bench.json 2> gpurun_out/s2f_bench.err; echo "rc=$?"; tail -3 gpurun_out/s2f_bench.err
+python - <<PY
+import json
+j=json.load(open("gpurun_out/s2f_bench.json")); print("value=%.3e"%j["value"], "ms/step=%.4f"%j["ms_per_step"], "phases", {k:round(v,4) for k,v in j["roofline"]["phases_ms"].items()}, "e2e=%.3e"%j["e2e"]["value"], "per_call=%.3e"%j["e2e"]["per_call"]["value"], "seq=%.3e"%j["sequential"]["value"])
+PY
