@@ -44,10 +44,15 @@ struct ScoreTcArgs {
   int rows_pad, B, scheme, loss_kind;
   float lambda, gamma;
   long long* dbg;                             // optional [grid][64] clock64 stamps (developer tool)
-  // fused sparse SGD: the drain adds -lr * dX straight into the embedding rows (red.global.add.v4, duplicates sum in
-  // L2) instead of writing dX for a separate update kernel.  Legal because every row of this step was gathered by the
-  // PREVIOUS kernel, so nothing in this kernel reads the tables.
+  // fused sparse SGD: the drain adds -lr * dX straight into the embedding rows instead of writing dX for a separate
+  // update kernel: one bulk async reduction (cp.reduce.async.bulk .add.f32, TMA engine, performed at the L2; duplicates
+  // sum there) per owned row, issued from the staged fp32 block in shared memory.  Legal because every row of this step
+  // was gathered by the PREVIOUS kernel, so nothing in this kernel reads the tables.
   int fuse_sgd;
+  // fused mode has no finalize launch: the last side-0 CTA of a replica publishes the replica's loss and re-arms the
+  // accumulators (loss_count[R] arrival counters, zero between steps)
+  unsigned int* loss_count;
+  float* loss_out;                            // [R] or NULL
   int d;                                      // true embedding dim (table row stride), d % 4 == 0 when fused
   float neg_lr;
   float* table_u; float* table_v;
@@ -335,6 +340,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     ec.ns_margin = GROUP ? 0.0f : a.gamma;
     ec.inv_wneg = 1.0f / ec.w_neg;
     ec.g_scale = (LOSS == NNCF_LOSS_SKIP_GRAM) ? ec.w_neg * ec.inv_b : 1.0f;
+    if (a.fuse_sgd) ec.g_scale *= a.neg_lr;     // the drain adds -lr * dX straight into the table rows
     const bool row_ok = o < n_owner;
     // side 0: the positive column of my row.  side 1 (neg_shared): my own index (the diagonal).
     const int my_posc = (side == 0 && GROUP) ? (row_ok ? a.inverse[base + o] : -1) : o;
@@ -434,20 +440,20 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           *reinterpret_cast<float4*>(stage + ol * LD + c0 + u) =
               make_float4(v[u] * ec.g_scale, v[u + 1] * ec.g_scale, v[u + 2] * ec.g_scale, v[u + 3] * ec.g_scale);
       }
+      if (a.fuse_sgd) fence_proxy_async();                                     // staged rows are read by the TMA engine
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");   // epilogue warps only
       if (a.fuse_sgd) {
-        float* table = side == 0 ? a.table_u : a.table_v;
+        // (the staged rows already carry the factor -lr, see g_scale) one bulk reduction per owned row
         const ShardPtrs& sh = side == 0 ? a.shards_u : a.shards_v;
+        float* table = side == 0 ? a.table_u : a.table_v;
         const int32_t* ids = (side == 0 ? a.ids_u + r * a.ids_stride_u : a.ids_v + r * a.ids_stride_v) + ob * 128;
-        for (int row = ew; row < 128; row += kScoreEpiWarps) {
-          if (ob * 128 + row >= n_owner) break;
+        const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
+        if (row < 128 && ob * 128 + row < n_owner) {
           const int64_t id = ids[row];
           float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
-          const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
-          for (int c = lane; c < a.d / 4; c += 32) {
-            const float4 g4 = src[c];
-            red_add_v4(trow + 4 * c, a.neg_lr * g4.x, a.neg_lr * g4.y, a.neg_lr * g4.z, a.neg_lr * g4.w);
-          }
+          bulk_reduce_add_f32_s2g(trow, stage + row * LD, static_cast<uint32_t>(a.d) * 4u);
+          bulk_commit_group();
+          bulk_wait_group_read0();                                 // shared memory must outlive the engine's reads
         }
       } else {
         float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
@@ -466,7 +472,21 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     if (side == 0) {
       if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
       lsum = warp_sum(lsum);
-      if (lane == 0) atomicAdd(&a.loss[r], static_cast<double>(lsum));
+      if (lane == 0) {
+        atomicAdd(&a.loss[r], static_cast<double>(lsum));
+        if (a.loss_count) {
+          // last arriving warp of the replica (side-0 CTAs x epilogue warps) publishes the loss and re-arms the accumulators
+          __threadfence();
+          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps;
+          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
+            __threadfence();
+            const double total = atomicAdd(&a.loss[r], 0.0);
+            if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
+            a.loss[r] = 0.0;
+            a.loss_count[r] = 0u;
+          }
+        }
+      }
     }
     if (warp == 2 && lane == 0) NNCF_STAMP(5);
     tc_fence_before();

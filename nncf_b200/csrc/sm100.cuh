@@ -90,6 +90,20 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// bulk async REDUCTION shared -> global (TMA engine): global[i] += smem[i] for `bytes` / 4 floats, performed at the L2.
+// bytes % 16 == 0, both addresses 16-byte aligned.  Completion is tracked with bulk groups.
+__device__ __forceinline__ void bulk_reduce_add_f32_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gdst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// waits until the bulk groups of this thread have finished READING their shared-memory sources
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// programmatic dependent launch: wait for the preceding kernel of the stream (no-op unless launched with the
+// programmatic-stream-serialization attribute) / allow the next kernel's CTAs to start their prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 // generic-proxy writes to smem must be fenced before the async proxy (MMA / bulk copy) reads them
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -662,6 +662,7 @@ struct nncf_trainer {
   float *corrU = nullptr, *corrV = nullptr, *spos = nullptr;
   uint8_t *Uimg = nullptr, *Vimg = nullptr;
   double* loss = nullptr;
+  unsigned int* loss_count = nullptr;   // fused mode: per-replica arrival counters of the in-kernel loss hand-off
   int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
   int32_t *ownerU = nullptr, *ownerV = nullptr;
   int64_t ownerU_n = 0, ownerV_n = 0;
@@ -717,6 +718,7 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
   const size_t nrow = (size_t)R * t->rows_pad, nel = nrow * t->dp;
   int rc = 0;
   rc |= dev_alloc(&t->loss, (size_t)R);
+  rc |= dev_alloc(&t->loss_count, (size_t)R);
   if (cfg->scheme == NNCF_SCHEME_PAIRS) {
     rc |= dev_alloc(&t->ps, (size_t)R * t->rows);
     rc |= dev_alloc(&t->invU, (size_t)R * t->rows);
@@ -743,7 +745,7 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
 extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   if (!t) return NNCF_OK;
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
-                  t->loss, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
+                  t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
@@ -846,16 +848,15 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool dense_items = tb->item_table == nullptr;
   NNCF_PROFILE_MARK(t, 0, st);
   const bool want_row_grads = last && io && (io->grad_user_rows_dev || io->grad_item_rows_dev);
-  // plain sparse SGD with nothing to post-process: the score kernel's drain applies the update itself
-  // (measured on B200 at R=37: the drain's reductions cost +9.7 us inside the 8-warp CTAs and save the 11 us update
-  //  kernel that uses the whole grid: no gain, so the fused variant is opt-in: NNCF_FUSE_SGD=1)
-  static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return e && atoi(e) != 0; }();
+  // plain sparse SGD with nothing to post-process: the score kernel's drain applies the update itself, one bulk async
+  // reduction (TMA engine) per row, and publishes the loss, so the step is two launches (NNCF_FUSE_SGD=0 disables it).
+  // (A first version issued red.global.add.v4 from the epilogue warps: +9.7 us in the kernel for the 11 us it saved.)
+  static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return !e || atoi(e) != 0; }();
   const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
                         (d % 4 == 0) && !dense_items && !want_row_grads;
-  // t->loss is zero on entry: zeroed at creation and re-zeroed by the last finalize launch of every step; the
-  // fused-SGD path has no finalize launch and keeps the explicit memset + loss_out kernel
-  if (fuse_sgd) NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
-  t->loss_published = !fuse_sgd;
+  // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
+  // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
+  t->loss_published = true;   // by the last finalize launch, or by the score kernel itself in fused mode
   const int32_t* item_ids = cid;
   int64_t item_stride = B;
   if (group) {
@@ -916,6 +917,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.Uimg = t->Uimg; ta.Vimg = t->Vimg; ta.dU = t->dU; ta.dV = t->dV; ta.corrU = t->corrU; ta.corrV = t->corrV;
     ta.spos = t->spos; ta.inverse = sa.inverse; ta.ncols_dev = sa.ncols_dev; ta.loss = t->loss; ta.rows_pad = rp;
     ta.B = B; ta.scheme = c.scheme; ta.loss_kind = c.loss; ta.lambda = c.neg_loss_weight; ta.gamma = c.loss_gamma;
+    ta.loss_count = fuse_sgd ? t->loss_count : nullptr; ta.loss_out = fuse_sgd ? loss_out_step : nullptr;
     ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;

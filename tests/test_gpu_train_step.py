@@ -273,3 +273,38 @@ def test_host_fed_steps_match_device_fed(replicas, n_steps):
     assert np.all(np.isfinite(loss_h2.numpy()[:2 * replicas]))
     with pytest.raises(AssertionError):
         b.run_host(hU, hV, h_uid.cuda(), h_cid.cuda(), 1)
+
+
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
+@pytest.mark.parametrize("loss", ["skip-gram", "mse"])
+@pytest.mark.parametrize("B,d,replicas", [(128, 64, 1), (200, 128, 2), (512, 128, 3), (130, 256, 1), (96, 52, 1)])
+def test_fused_sgd_drain_matches_oracle(scheme, loss, B, d, replicas):
+    """bf16 + sparse SGD + pointwise loss is the fused mode: the score kernel's drain applies -lr * dX to the table rows
+    with one bulk async reduction per row (duplicates, also across replicas, must sum) and publishes the loss itself.
+    Checked against the oracle's table delta summed over the replicas, for three consecutive steps' worth of re-use."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    nu, ni, lr = 300, 90, 0.05           # few items => many duplicate rows
+    EU, EV = _tables(nu, ni, d, seed=B + d + replicas)
+    rng = np.random.RandomState(B)
+    uid = rng.randint(0, nu, size=B * replicas).astype(np.int32)
+    cid = rng.randint(0, ni, size=B * replicas).astype(np.int32)
+    lam, gamma = _params(loss)
+    dU = np.zeros_like(EU, dtype=np.float64); dV = np.zeros_like(EV, dtype=np.float64); losses = []
+    for r in range(replicas):
+        ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B],
+                            scheme, loss, lam, gamma)
+        dU += ref["dEU"]; dV += ref["dEV"]; losses.append(ref["loss"])
+    spec = StepSpec(scheme=scheme, loss=loss, precision="bf16", batch_size_p=B, dim=d, optimizer="sgd", learn_rate=lr,
+                    replicas=replicas, neg_loss_weight=lam, loss_gamma=gamma)
+    step = FusedStep(spec)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    out = step.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
+    torch.cuda.synchronize()
+    got = out["loss"].cpu().numpy()
+    assert np.allclose(got, losses, rtol=1e-2), (got, losses)
+    assert _rel(tU.cpu().numpy() - EU, -lr * dU) <= 1e-2
+    assert _rel(tV.cpu().numpy() - EV, -lr * dV) <= 1e-2
+    # the in-kernel loss hand-off re-arms itself: a second step on the same handle reports a fresh loss, not a sum
+    out2 = step.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
+    torch.cuda.synchronize()
+    assert np.all(out2["loss"].cpu().numpy() < 1.5 * got + 1.0) and np.all(np.isfinite(out2["loss"].cpu().numpy()))
