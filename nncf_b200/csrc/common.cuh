@@ -46,6 +46,20 @@ struct ShardPtrs {
 
 constexpr int kEpiWarps = 4;   // epilogue warps of the tcgen05 kernels (one per TMEM lane quadrant)
 
+// Launch with programmatic dependent launch allowed: the kernel's CTAs may be scheduled while the preceding kernel of
+// the stream is still running; the kernel itself calls pdl_wait() (griddepcontrol.wait) before it touches anything the
+// predecessor wrote.  Only kernels that contain that wait may be launched this way.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int ceil_div(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }
 
 // ------------------------------------------------------------------------------------------------

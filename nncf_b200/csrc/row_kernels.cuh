@@ -15,6 +15,8 @@ constexpr int kRowsPerWarp = 4;
 template <int NV>   // float4 chunks per lane: 1 for dp <= 128, 2 for dp = 256
 __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
+  pdl_launch_dependents();      // the score kernel may set up its barriers / TMEM while the rows are gathered
+  pdl_wait();                   // the previous step's update (and this step's tf.unique) must have landed
   const GatherArgs& a = blockIdx.z ? a1 : a0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * kRowsPerWarp;
@@ -78,6 +80,8 @@ gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
 template <int NV>
 __global__ void __launch_bounds__(256)
 finalize_vec_kernel(FinalizeArgs a0, FinalizeArgs a1) {
+  pdl_launch_dependents();
+  pdl_wait();                   // the score kernel's gradient blocks
   const FinalizeArgs& a = blockIdx.z ? a1 : a0;
   finalize_publish_loss(a0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

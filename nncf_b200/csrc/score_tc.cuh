@@ -53,6 +53,11 @@ struct ScoreTcArgs {
   // accumulators (loss_count[R] arrival counters, zero between steps)
   unsigned int* loss_count;
   float* loss_out;                            // [R] or NULL
+  // L2 prefetch of the NEXT step's rows (ids known in advance; the two spare warps of every CTA issue one bulk L2
+  // prefetch per row while the tensor pipe works, so the next gather finds its rows in L2).  NULL = no next step.
+  const int32_t* next_ids_u; const int32_t* next_ids_v;
+  int next_count;                             // ids per side (R * B)
+  int64_t n_rows_u, n_rows_v;                 // table sizes (ids are clamped: a hint must never fault)
   int d;                                      // true embedding dim (table row stride), d % 4 == 0 when fused
   float neg_lr;
   float* table_u; float* table_v;
@@ -237,6 +242,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
+  pdl_launch_dependents();                         // the next kernel may start its prologue (it waits for us before reading)
+  if (GROUP) pdl_wait();                           // n_unique comes from a preceding kernel
   const int ncols = GROUP ? a.ncols_dev[r] : a.B;
   const int n_owner = side == 0 ? a.B : ncols;     // valid rows on the owner side
   const int n_other = side == 0 ? ncols : a.B;     // valid rows on the swept side
@@ -262,6 +269,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (!GROUP) pdl_wait();                          // barriers, TMEM and descriptors are set up; now wait for the gather
   long long* dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
 #define NNCF_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (tid == 0) NNCF_STAMP(0);
@@ -491,6 +499,21 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     if (warp == 2 && lane == 0) NNCF_STAMP(5);
     tc_fence_before();
   }
+  else if (a.next_ids_u) {
+    // ------------------------------------------------------------------------------ spare warps: L2 prefetch
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int ncta = gridDim.x * gridDim.y * gridDim.z;
+    const bool vside = warp == 2 + kScoreEpiWarps + 1;
+    const int32_t* ids = vside ? a.next_ids_v : a.next_ids_u;
+    const float* table = vside ? a.table_v : a.table_u;
+    const int64_t nrows = vside ? a.n_rows_v : a.n_rows_u;
+    const uint32_t row_bytes = static_cast<uint32_t>(a.d) * 4u;
+    for (int i = cta * 32 + lane; i < a.next_count; i += ncta * 32) {
+      int64_t id = ids[i];
+      id = id < 0 ? 0 : (id >= nrows ? nrows - 1 : id);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(table + id * a.d), "r"(row_bytes) : "memory");
+    }
+  }
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -513,8 +536,8 @@ int launch_score_tc_one(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) 
                                    (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  score_grad_tc_kernel<NSUB, LOSS, GROUP><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes, st>>>(a);
-  NNCF_LAUNCH_OK();
+  NNCF_CUDA(launch_pdl(score_grad_tc_kernel<NSUB, LOSS, GROUP>, dim3(nblk, 2, R), dim3(kScoreThreads), C::kSmemBytes, st, a));
+  count_launch();
   return 0;
 }
 

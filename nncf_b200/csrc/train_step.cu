@@ -118,6 +118,8 @@ struct GatherArgs {
 
 __global__ void __launch_bounds__(256)
 gather_rows_kernel(GatherArgs a0, GatherArgs a1) {
+  pdl_launch_dependents();
+  pdl_wait();
   const GatherArgs& a = blockIdx.z ? a1 : a0;     // z = 0 user side, z = 1 item side: one launch for both
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp;
@@ -358,6 +360,8 @@ __device__ __forceinline__ void finalize_publish_loss(const FinalizeArgs& a) {
 
 __global__ void __launch_bounds__(256)
 finalize_kernel(FinalizeArgs a0, FinalizeArgs a1) {
+  pdl_launch_dependents();
+  pdl_wait();
   const FinalizeArgs& a = blockIdx.z ? a1 : a0;
   finalize_publish_loss(a0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -668,6 +672,7 @@ struct nncf_trainer {
   int64_t ownerU_n = 0, ownerV_n = 0;
   float *ps = nullptr;   // PAIRS scores
   bool tc_attr_set = false;
+  const int32_t *hint_next_uid = nullptr, *hint_next_cid = nullptr;   // ids of the step after this call's last one (L2 prefetch hint)
   bool loss_published = false;   // the step's finalize launch already wrote loss_out and re-zeroed the accumulators
   // row-sharded multi-GPU mode (nncf_trainer_set_shards)
   int n_shards = 1, rank = 0;
@@ -839,7 +844,8 @@ static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int
 }
 
 static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
-                       const nncf_step_io* io, bool last, float* loss_out_step, cudaStream_t st) {
+                       const nncf_step_io* io, bool last, float* loss_out_step, const int32_t* next_uid,
+                       const int32_t* next_cid, cudaStream_t st) {
   const nncf_step_config& c = t->cfg;
   const int R = c.replicas, B = c.batch_size_p, d = c.dim, dp = t->dp, rp = t->rows_pad;
   const bool group = c.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
@@ -892,10 +898,12 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     for (int i = 0; i < t->n_shards; ++i) { gu.shards.p[i] = t->ushards[i]; gv.shards.p[i] = t->ishards[i]; }
   }
   const bool vec = (d % 4 == 0);   // 16-byte aligned rows: 128-bit loads / vector reductions
-  if (vec && dp <= 128) gather_rows_vec_kernel<1><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
-  else if (vec) gather_rows_vec_kernel<2><<<dim3(rp / 32, R, 2), 256, 0, st>>>(gu, gv);
-  else gather_rows_kernel<<<dim3(rp / 8, R, 2), 256, 0, st>>>(gu, gv);
-  NNCF_LAUNCH_OK();
+  // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
+  // reads what its predecessor wrote, so only launch latency and prologues overlap
+  if (vec && dp <= 128) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<1>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
+  else if (vec) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<2>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
+  else NNCF_CUDA(launch_pdl(gather_rows_kernel, dim3(rp / 8, R, 2), dim3(256), 0, st, gu, gv));
+  count_launch();
   if (pairwise) {
     pos_score_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->Vf, group ? t->inverse : nullptr, rp, dp, B,
                                                               bf16 ? 1 : 0, t->spos);
@@ -921,6 +929,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
+    if (next_uid && next_cid && !sharded && !dense_items && (d % 4 == 0)) {
+      ta.next_ids_u = next_uid; ta.next_ids_v = next_cid; ta.next_count = R * B;
+      ta.n_rows_u = tb->n_users; ta.n_rows_v = tb->n_items;
+    }
     if (sharded && fuse_sgd) {
       // every rank has finished READING its peers' rows (gather) before any drain starts updating them
       if (int rc2 = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc2;
@@ -963,9 +975,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     if (int rc = nncf_peer_barrier(t->flags, t->n_shards, t->rank, ++t->epoch, st)) return rc;
   }
   auto launch_finalize = [&](const FinalizeArgs& x, const FinalizeArgs& y, int nz) {
-    if (vec && dp <= 128) finalize_vec_kernel<1><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
-    else if (vec) finalize_vec_kernel<2><<<dim3(ceil_div(B, 32), R, nz), 256, 0, st>>>(x, y);
-    else finalize_kernel<<<dim3(ceil_div(B, 8), R, nz), 256, 0, st>>>(x, y);
+    cudaError_t e;
+    if (vec && dp <= 128) e = launch_pdl(finalize_vec_kernel<1>, dim3(ceil_div(B, 32), R, nz), dim3(256), 0, st, x, y);
+    else if (vec) e = launch_pdl(finalize_vec_kernel<2>, dim3(ceil_div(B, 32), R, nz), dim3(256), 0, st, x, y);
+    else e = launch_pdl(finalize_kernel, dim3(ceil_div(B, 8), R, nz), dim3(256), 0, st, x, y);
+    if (e != cudaSuccess) ::nncf::set_error(std::string("finalize launch: ") + cudaGetErrorString(e));
   };
   if (fuse_sgd) {
     // nothing left to do: the update was applied by the score kernel's drain
@@ -1077,7 +1091,9 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
     if (t->cfg.scheme == NNCF_SCHEME_PAIRS)
       rc = step_pairs(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
     else
-      rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, loss_out_step, st);
+      rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, loss_out_step,
+                       last ? t->hint_next_uid : user_ids_dev + (s + 1) * per_step,
+                       last ? t->hint_next_cid : item_ids_dev + (s + 1) * per_step, st);
     if (rc) return rc;
     if (t->profile) {
       NNCF_CUDA(cudaEventSynchronize(t->ev[3]));
@@ -1122,18 +1138,29 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
     }
   }
   nncf_step_io io{};
-  for (int64_t s = 0; s < n_steps; ++s) {
+  auto enqueue_ids = [&](int64_t s) -> int {
     const int b = static_cast<int>(s % NB);
     // ids of step s -> staging buffer b (free once step s - NB has finished with it)
     if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_done[b], 0));
     NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b], user_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
     NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b] + per_step, item_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
     NNCF_CUDA(cudaEventRecord(t->ev_ready[b], t->s_h2d));
-    // the step itself
+    return NNCF_OK;
+  };
+  if (n_steps > 0) if (int rc = enqueue_ids(0)) return rc;
+  for (int64_t s = 0; s < n_steps; ++s) {
+    const int b = static_cast<int>(s % NB), bn = static_cast<int>((s + 1) % NB);
+    // the copy of step s + 1's ids is in flight while step s computes; its staging buffer doubles as the L2 prefetch
+    // hint of step s (a hint: if the copy has not landed yet the kernel prefetches stale rows, never faults)
+    if (s + 1 < n_steps) if (int rc = enqueue_ids(s + 1)) return rc;
     NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_ready[b], 0));
     if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_read[b], 0));       // loss slot b has been read back
     io.loss_out_dev = t->h_loss[b];
-    if (int rc = nncf_train_steps(t, tables, t->h_ids[b], t->h_ids[b] + per_step, 1, &io, st)) return rc;
+    t->hint_next_uid = (s + 1 < n_steps) ? t->h_ids[bn] : nullptr;
+    t->hint_next_cid = (s + 1 < n_steps) ? t->h_ids[bn] + per_step : nullptr;
+    const int rc = nncf_train_steps(t, tables, t->h_ids[b], t->h_ids[b] + per_step, 1, &io, st);
+    t->hint_next_uid = t->hint_next_cid = nullptr;
+    if (rc) return rc;
     NNCF_CUDA(cudaEventRecord(t->ev_done[b], st));
     // loss of step s -> host
     if (loss_out_host) {
