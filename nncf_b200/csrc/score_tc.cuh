@@ -2,10 +2,14 @@
 //
 // Every CTA owns ONE 128-row block of one side X (X = U rows i when side = 0, X = V rows j when side = 1) and sweeps
 // the 128-row blocks Y_t of the other side:
-//     MMA1  S'_t  = X_ob Y_t^T       A, B K-major             -> TMEM, double buffered (2 x 128 columns)
-//     epi   G'_t  = dL/dS'_t         TMEM -> registers -> bf16 -> swizzled smem tile image
+//     MMA1  S'_t  = X_ob Y_t^T       A, B K-major (smem)      -> TMEM, double buffered
+//     epi   G'_t  = dL/dS'_t         TMEM -> registers -> bf16 -> back into TMEM, IN PLACE over the S' buffer
 //                                    (+ loss / positive-score corrections, see below)
-//     MMA2  dX_ob += G'_t Y_t        A K-major, B MN-major    -> TMEM accumulator (DP columns), drained ONCE
+//     MMA2  dX_ob += G'_t Y_t        A from TMEM, B MN-major  -> TMEM accumulator (DP columns), drained ONCE
+// G' never touches shared memory: the tile loop is bound by the 128 B/clk shared-memory port (MMA operand fetches, Y tile
+// fills), and routing G' through TMEM takes its 16 KiB write, 16 KiB operand read, the proxy fence and the swizzled
+// stores out of every tile.  tcgen05.mma instructions execute in issue order, so MMA1(t+2) overwriting the buffer that
+// MMA2(t) reads needs no barrier.
 // so the gradient of the owned rows is complete inside the CTA: no atomics, no second drain, and the score matrix
 // exists only in TMEM.  The two sides recompute S (side 1 sees its transpose), which costs a second pass of the
 // cheap K = d contraction but removes the B^2 d / 128 float atomics of a one-pass scheme (measured: 21k cycles per
@@ -77,24 +81,19 @@ struct ScoreTcCfg {
   static constexpr int TN = NSUB <= 2 ? 64 : 128;     // swept rows per tile = columns of one S' tile
   static constexpr int CW = TN / 2;                   // S' columns per epilogue warp
   static constexpr int kYBytes = TN * 128;            // one [TN rows x 64 bf16] piece of a Y tile (8 or 16 KiB)
-  static constexpr int kGSub = TN / 64;               // [128 x 64] sub-tiles of one G' tile
 #ifndef NNCF_SCORE_STAGES
-#define NNCF_SCORE_STAGES 2
-#endif
-#ifndef NNCF_SCORE_GBUFS
-#define NNCF_SCORE_GBUFS 2
+#define NNCF_SCORE_STAGES 4
 #endif
   // Two resident CTAs of a tcgen05 kernel have (228 KiB - 2 x (1 KiB reserved + 1 KiB tcgen05 block)) / 2 = 112 KiB of
   // dynamic shared memory each (measured with tools/occ_probe.cu), barriers included.
   static constexpr int kStages = NSUB <= 2 ? NNCF_SCORE_STAGES : 2;   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
-  static constexpr int kGBufs = NSUB <= 2 ? NNCF_SCORE_GBUFS : 1;
   static constexpr int kColDX = 2 * TN;               // S' is double buffered in TMEM columns [0, 2 TN)
   static constexpr int kTmemCols = (kColDX + DP) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = NSUB <= 2 ? 2 : 1;   // resident CTAs per SM
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry); two CTAs of
   // dp = 128 need 2 x (112 KiB + 256 B + 1 KiB reserved) <= 228 KiB
   static constexpr size_t kSmemBytes =
-      (size_t)NSUB * kSubBytes + (size_t)kStages * NSUB * kYBytes + (size_t)kGBufs * kGSub * kSubBytes + 256 /*barriers*/;
+      (size_t)NSUB * kSubBytes + (size_t)kStages * NSUB * kYBytes + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -228,17 +227,14 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   if (smem_u32(smem) & 1023u) __trap();           // SWIZZLE_128B operands need 1024-byte aligned tiles
   uint8_t* sX = smem;
   uint8_t* sY = sX + NSUB * kSubBytes;
-  uint8_t* sG = sY + C::kStages * NSUB * C::kYBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sG + C::kGBufs * C::kGSub * kSubBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + C::kStages * NSUB * C::kYBytes);
   uint64_t* x_full = bars + 0;
   uint64_t* y_full = bars + 1;      // [4]
   uint64_t* y_empty = bars + 5;     // [4]
-  uint64_t* s_full = bars + 9;      // [2]
-  uint64_t* s_empty = bars + 11;    // [2]
-  uint64_t* g_full = bars + 13;     // [2]
-  uint64_t* g_empty = bars + 15;    // [2]
-  uint64_t* dx_full = bars + 17;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* s_full = bars + 9;      // [2]  S'(t) is in TMEM buffer t & 1
+  uint64_t* g_full = bars + 11;     // [2]  G'(t) has replaced it
+  uint64_t* dx_full = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
@@ -257,10 +253,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   if (tid == 0) {
     mbar_init(x_full, 1);
     for (int s = 0; s < 4; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kScoreEpiWarps);
-      mbar_init(&g_full[s], kScoreEpiWarps); mbar_init(&g_empty[s], 1);
-    }
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&g_full[s], kScoreEpiWarps); }
     mbar_init(dx_full, 1);
     mbar_fence_init();
   }
@@ -297,8 +290,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       auto issue_mma1 = [&](int t) {
         const int st = t % C::kStages, sb = t & 1;
         mbar_wait(&y_full[st], (t / C::kStages) & 1);
-        mbar_wait(&s_empty[sb], ((t >> 1) & 1) ^ 1);
-        tc_fence_after();
+        // buffer sb was last read by MMA2(t - 2), issued earlier by this thread: the tensor pipe runs in issue order
 #pragma unroll
         for (int k = 0; k < DP / 16; ++k) {
           const uint64_t ad = make_smem_desc(smem_u32(sX + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
@@ -312,21 +304,20 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       issue_mma1(0);
       NNCF_STAMP(2);
       for (int t = 0; t < nt; ++t) {
-        const int st = t % C::kStages, gb = t % C::kGBufs;
+        const int st = t % C::kStages, sb = t & 1;
         if (t + 1 < nt) issue_mma1(t + 1);
-        mbar_wait(&g_full[gb], (t / C::kGBufs) & 1);
+        mbar_wait(&g_full[sb], (t >> 1) & 1);
         if (t < 8) NNCF_STAMP(8 + t);
         tc_fence_after();
-        const uint8_t* g = sG + gb * C::kGSub * kSubBytes;
         const uint8_t* y = sY + st * NSUB * C::kYBytes;
 #pragma unroll
-        for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA
-          const uint64_t ad = make_smem_desc(smem_u32(g + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
+        for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA = 8 TMEM columns of G'
+          // K rows 16k.. were written by epilogue column-half (16k) / CW at column offset ((16k) % CW) / 2 of its own range
+          const uint32_t acol = sb * TN + ((16 * k) / CW) * CW + ((16 * k) % CW) / 2;
           const uint64_t bd = make_smem_desc(smem_u32(y) + k * 2048, C::kYBytes, 1024);
-          umma_bf16(tmem + C::kColDX, ad, bd, idesc_dx, (t > 0) || (k > 0));
+          umma_bf16_ts(tmem + C::kColDX, tmem + acol, bd, idesc_dx, (t > 0) || (k > 0));
         }
         umma_commit(&y_empty[st]);
-        umma_commit(&g_empty[gb]);
       }
       umma_commit(dx_full);
       NNCF_STAMP(3);
@@ -359,7 +350,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     float lsum = 0.0f, asum = 0.0f, lraw = 0.0f;
 
     for (int t = 0; t < nt; ++t) {
-      const int sb = t & 1, gb = t % C::kGBufs;
+      const int sb = t & 1;
       mbar_wait(&s_full[sb], (t >> 1) & 1);
       if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(16 + t);
       tc_fence_after();
@@ -367,10 +358,6 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) tmem_ld32(tmem + lane_addr + sb * TN + h * CW + 32 * j, v[j]);
       tmem_ld_wait();
-      // the S buffer is in registers now: hand it back to the MMA warp before doing the math
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[sb]);
       const int x0 = t * TN + h * CW;                   // swept index of my first column
       // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tiles have them)
       constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
@@ -412,21 +399,22 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           else epi_chunk<LOSS, true, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         }
       }
-      mbar_wait(&g_empty[gb], ((t / C::kGBufs) & 1) ^ 1);
-      // my CW columns = 16-byte chunks [cb, cb + CW/8) of row ol in G' sub-tile gs
-      constexpr int kChunks = CW / 8;
-      const int gs = (h * CW) >> 6, cb = ((h * CW) & 63) >> 3;
-      uint8_t* grow = sG + (gb * C::kGSub + gs) * kSubBytes + ol * 128;
+      if (do_patch) {
+        const uint32_t bits = patch_bits;
 #pragma unroll
-      for (int ch = 0; ch < kChunks; ++ch) {
-        const uint32_t* src = pk[ch >> 2] + (ch & 3) * 4;
-        *reinterpret_cast<uint4*>(grow + (((cb + ch) ^ (ol & 7)) << 4)) = make_uint4(src[0], src[1], src[2], src[3]);
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (pidx == 32 * j + 2 * i) pk[j][i] = (pk[j][i] & 0xFFFF0000u) | bits;
+            else if (pidx == 32 * j + 2 * i + 1) pk[j][i] = (pk[j][i] & 0x0000FFFFu) | (bits << 16);
       }
-      if (do_patch)
-        *reinterpret_cast<uint16_t*>(grow + (((cb + (pidx >> 3)) ^ (ol & 7)) << 4) + (pidx & 7) * 2) = patch_bits;
-      fence_proxy_async();
+      // G' goes back into TMEM over the first half of my own S' columns (two bf16 per column): the A operand of MMA2
+#pragma unroll
+      for (int j = 0; j < NV; ++j) tmem_st16(tmem + lane_addr + sb * TN + h * CW + 16 * j, pk[j]);
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&g_full[gb]);
+      if (lane == 0) mbar_arrive(&g_full[sb]);
       if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(24 + t);
     }
     // drain the accumulated gradient of the owned rows: this warp takes columns [h*DP/2, (h+1)*DP/2)
