@@ -16,7 +16,9 @@ template <int NV>   // float4 chunks per lane: 1 for dp <= 128, 2 for dp = 256
 __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
   pdl_launch_dependents();      // the score kernel may set up its barriers / TMEM while the rows are gathered
+  if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[0], global_timer_ns());
   pdl_wait();                   // the previous step's update (and this step's tf.unique) must have landed
+  if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[1], global_timer_ns());
   const GatherArgs& a = blockIdx.z ? a1 : a0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * kRowsPerWarp;
@@ -75,6 +77,7 @@ gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
       a.corr[rowoff] = 0.0f;
     }
   }
+  if (a0.tl && threadIdx.x == 0) atomicMax(&a0.tl[2], global_timer_ns());
 }
 
 template <int NV>

@@ -48,6 +48,7 @@ struct ScoreTcArgs {
   int rows_pad, B, scheme, loss_kind;
   float lambda, gamma;
   long long* dbg;                             // optional [grid][64] clock64 stamps (developer tool)
+  unsigned long long* tl;                     // optional step timeline: [3] first CTA start, [4] first CTA past the wait, [5] last end
   // fused sparse SGD: the drain adds -lr * dX straight into the embedding rows instead of writing dX for a separate
   // update kernel: one bulk async reduction (cp.reduce.async.bulk .add.f32, TMA engine, performed at the L2; duplicates
   // sum there) per owned row, issued from the staged fp32 block in shared memory.  Legal because every row of this step
@@ -239,6 +240,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
   pdl_launch_dependents();                         // the next kernel may start its prologue (it waits for us before reading)
+  if (a.tl && tid == 0) atomicMin(&a.tl[3], global_timer_ns());
   if (GROUP) pdl_wait();                           // n_unique comes from a preceding kernel
   const int ncols = GROUP ? a.ncols_dev[r] : a.B;
   const int n_owner = side == 0 ? a.B : ncols;     // valid rows on the owner side
@@ -263,9 +265,15 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (!GROUP) pdl_wait();                          // barriers, TMEM and descriptors are set up; now wait for the gather
+  long long tl_c0 = 0; unsigned long long tl_g0 = 0;
+  if (a.tl && tid == 0) {
+    tl_g0 = global_timer_ns(); tl_c0 = clock64();
+    atomicMin(&a.tl[4], tl_g0); atomicMax(&a.tl[8], tl_g0);
+  }
   long long* dbg = a.dbg ? a.dbg + ((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 64 : nullptr;
 #define NNCF_STAMP(slot) do { if (dbg) dbg[slot] = clock64(); } while (0)
   if (tid == 0) NNCF_STAMP(0);
+  if (tid == 0 && dbg) { dbg[40] = static_cast<long long>(global_timer_ns()); dbg[42] = static_cast<long long>(sm_id()); }
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ producer
@@ -361,6 +369,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       const int x0 = t * TN + h * CW;                   // swept index of my first column
       // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tiles have them)
       constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
+      constexpr bool kBalanceLoss = kFastSg && !GROUP;
       const bool on_diag = ((t * TN) >> 7) == ob;       // this tile crosses the diagonal of my 128-row block
       const bool full = (t * TN + TN <= n_other);
       // neg_shared skip-gram, full diagonal tile: it holds at most ONE positive per row (column == row).  Run the packed
@@ -387,26 +396,41 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           lsum += ec.inv_b * (sps - sp) - ec.w_neg * ec.inv_b * sps;                // positive's own term minus what the fast path adds
         }
       }
+      // who adds the loss of a fast-path tile: the loss code triples the fast path (279 vs 98 instructions per 32 scores), so
+      // for neg_shared skip-gram the two sides share it by the parity of the TN x TN block the scores sit in (every block is
+      // seen once by each side); blocks that touch a ragged edge stay with side 0, whose general path handles them
+      bool loss_here = (side == 0);
+      if (kBalanceLoss) {
+        const bool take1 = (((o / TN) + t) & 1) && ((o / TN) * TN + TN <= n_owner);   // parity-1 block, my row block is full
+        loss_here = (side == 0) ? !take1 : take1;
+      }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        if (side == 0) {
-          if (general) epi_chunk<LOSS, false, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
-          else if (kFastSg) epi_chunk_sg_fast<true>(v[j], pk[j], lraw);
-          else epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+        if (general) {
+          if (side == 0) epi_chunk<LOSS, false, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+          else epi_chunk<LOSS, true, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+        } else if (kFastSg) {
+          if (loss_here) epi_chunk_sg_fast<true>(v[j], pk[j], lraw);
+          else epi_chunk_sg_fast<false>(v[j], pk[j], lraw);
         } else {
-          if (general) epi_chunk<LOSS, true, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
-          else if (kFastSg) epi_chunk_sg_fast<false>(v[j], pk[j], lraw);
+          if (side == 0) epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
           else epi_chunk<LOSS, true, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         }
       }
       if (do_patch) {
-        const uint32_t bits = patch_bits;
+        // branch-free: every lane of a patch warp has a DIFFERENT pidx (== its lane within the chunk), so an if-chain
+        // here diverges 32 ways (measured: +4k cycles on each diagonal tile); selects cost 3 instructions per word
+        const bool odd = (pidx & 1) != 0;
+        const uint32_t keep = odd ? 0x0000FFFFu : 0xFFFF0000u;
+        const uint32_t ins = odd ? (static_cast<uint32_t>(patch_bits) << 16) : static_cast<uint32_t>(patch_bits);
+        const int pw = pidx >> 1;
 #pragma unroll
         for (int j = 0; j < NV; ++j)
 #pragma unroll
-          for (int i = 0; i < 16; ++i)
-            if (pidx == 32 * j + 2 * i) pk[j][i] = (pk[j][i] & 0xFFFF0000u) | bits;
-            else if (pidx == 32 * j + 2 * i + 1) pk[j][i] = (pk[j][i] & 0x0000FFFFu) | (bits << 16);
+          for (int i = 0; i < 16; ++i) {
+            const uint32_t patched = (pk[j][i] & keep) | ins;
+            pk[j][i] = (pw == 16 * j + i) ? patched : pk[j][i];
+          }
       }
       // G' goes back into TMEM over the first half of my own S' columns (two bf16 per column): the A operand of MMA2
 #pragma unroll
@@ -420,6 +444,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     // drain the accumulated gradient of the owned rows: this warp takes columns [h*DP/2, (h+1)*DP/2)
     mbar_wait(dx_full, 0);
     if (warp == 2 && lane == 0) NNCF_STAMP(4);
+    if (a.tl && warp == 2 && lane == 0) atomicMax(&a.tl[6], global_timer_ns());   // last CTA leaves its tile loop
     tc_fence_after();
     {
       // TMEM rows live in lanes, so a direct store would scatter 32 rows per instruction (measured: 4.4k cycles).
@@ -439,10 +464,15 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (a.fuse_sgd) fence_proxy_async();                                     // staged rows are read by the TMA engine
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");   // epilogue warps only
       if (a.fuse_sgd) {
-        // (the staged rows already carry the factor -lr, see g_scale) one bulk reduction per owned row
+        // (the staged rows already carry the factor -lr, see g_scale)
         const ShardPtrs& sh = side == 0 ? a.shards_u : a.shards_v;
         float* table = side == 0 ? a.table_u : a.table_v;
         const int32_t* ids = (side == 0 ? a.ids_u + r * a.ids_stride_u : a.ids_v + r * a.ids_stride_v) + ob * 128;
+#ifndef NNCF_DRAIN_MODE
+#define NNCF_DRAIN_MODE 0
+#endif
+#if NNCF_DRAIN_MODE == 0
+        // one bulk reduction (TMA engine, performed at the L2) per owned row
         const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
         if (row < 128 && ob * 128 + row < n_owner) {
           const int64_t id = ids[row];
@@ -451,6 +481,35 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           bulk_commit_group();
           bulk_wait_group_read0();                                 // shared memory must outlive the engine's reads
         }
+#elif NNCF_DRAIN_MODE == 2
+        // two bulk reductions per row (half a row per epilogue thread)
+        const int et = tid - 64, row = et >> 1, hf = et & 1;
+        const uint32_t hb = (static_cast<uint32_t>(a.d) * 2u + 15u) & ~15u;          // bytes of the first half (16-byte multiple)
+        if (ob * 128 + row < n_owner) {
+          const int64_t id = ids[row];
+          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
+          const uint32_t off = hf ? hb : 0u, len = hf ? static_cast<uint32_t>(a.d) * 4u - hb : hb;
+          if (len) bulk_reduce_add_f32_s2g(reinterpret_cast<uint8_t*>(trow) + off, reinterpret_cast<uint8_t*>(stage + row * LD) + off, len);
+          bulk_commit_group();
+          bulk_wait_group_read0();
+        }
+#else
+        // vector reductions from the staged rows: a warp instruction covers one whole row (coalesced 128 B lines)
+        const int nrow = min(128, n_owner - ob * 128);
+        int64_t myid = 0;
+        if (lane < 16 && ew + 8 * lane < nrow) myid = ids[ew + 8 * lane];
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          const int row = ew + 8 * k;
+          const int64_t id = __shfl_sync(0xffffffffu, myid, k);
+          if (row >= nrow) break;
+          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
+          for (int c = 4 * lane; c < a.d; c += 128) {
+            const float4 g4 = *reinterpret_cast<const float4*>(stage + row * LD + c);
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(trow + c), "f"(g4.x), "f"(g4.y), "f"(g4.z), "f"(g4.w) : "memory");
+          }
+        }
+#endif
       } else {
         float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
         for (int row = ew; row < 128; row += kScoreEpiWarps) {
@@ -465,7 +524,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (side == 0 && GROUP) atomicAdd(a.corrU + base + o, asum);
       if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
     }
-    if (side == 0) {
+    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {   // (balanced loss: both sides hold a share)
       if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
       lsum = warp_sum(lsum);
       if (lane == 0) {
@@ -473,7 +532,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         if (a.loss_count) {
           // last arriving warp of the replica (side-0 CTAs x epilogue warps) publishes the loss and re-arms the accumulators
           __threadfence();
-          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps;
+          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps *
+                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
           if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
             __threadfence();
             const double total = atomicAdd(&a.loss[r], 0.0);
@@ -508,6 +568,12 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     tmem_dealloc(tmem, C::kTmemCols);
   }
   if (tid == 0) NNCF_STAMP(6);
+  if (tid == 0 && dbg) dbg[41] = static_cast<long long>(global_timer_ns());
+  if (a.tl && tid == 0) {
+    const unsigned long long g1 = global_timer_ns();
+    atomicMax(&a.tl[5], g1);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) { a.tl[9] = static_cast<unsigned long long>(clock64() - tl_c0); a.tl[10] = g1 - tl_g0; }
+  }
 #undef NNCF_STAMP
 }
 

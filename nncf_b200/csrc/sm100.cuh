@@ -54,6 +54,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded spin: a protocol bug must surface as a trap (error code), never as a hung GPU box.
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+__device__ __forceinline__ unsigned int sm_id() {
+  unsigned int s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s;
+}
+
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {

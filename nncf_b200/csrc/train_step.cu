@@ -114,6 +114,7 @@ struct GatherArgs {
   uint8_t* img;              // [R][rows_pad/128][dp/64][16 KiB]
   float* dX;                 // [R][rows_pad][dp]  zeroed here
   float* corr;               // [R][rows_pad]      zeroed here
+  unsigned long long* tl;    // developer timeline (NNCF_TIMELINE): [0] first CTA start, [1] first CTA past the wait, [2] last end
 };
 
 __global__ void __launch_bounds__(256)
@@ -655,6 +656,12 @@ __global__ void reg_loss_kernel(const float* __restrict__ Uf, const float* __res
 // =================================================================================================
 using namespace nncf;
 
+__global__ void timeline_init_kernel(unsigned long long* tl, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = i & 15;
+  if (i < n) tl[i] = (k == 0 || k == 1 || k == 3 || k == 4) ? ~0ull : 0ull;   // min slots / max slots
+}
+
 struct nncf_trainer {
   nncf_step_config cfg;
   int rows;        // user-side rows per batch: B or (1+k)B
@@ -686,6 +693,11 @@ struct nncf_trainer {
   float* h_loss[kHostBufs] = {nullptr, nullptr, nullptr, nullptr};    // [R] device
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_ready[kHostBufs] = {}, ev_done[kHostBufs] = {}, ev_read[kHostBufs] = {};
+  // developer timeline (env NNCF_TIMELINE=<file>): per step 16 stamp slots written by the kernels themselves,
+  // dumped as text when the trainer is destroyed (tools/timeline.py reads it)
+  unsigned long long* timeline = nullptr;
+  int64_t tl_step = 0;
+  static constexpr int kTlSteps = 4096;
   // optional per-phase device timing (CUDA events on the launching stream)
   bool profile = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -742,6 +754,12 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
       rc |= dev_alloc(&t->uniq, nrow); rc |= dev_alloc(&t->inverse, nrow); rc |= dev_alloc(&t->nuniq, (size_t)R);
     }
   }
+  if (const char* tl = getenv("NNCF_TIMELINE")) {
+    if (*tl) {
+      rc |= dev_alloc(&t->timeline, (size_t)nncf_trainer::kTlSteps * 16);
+      if (!rc) timeline_init_kernel<<<ceil_div(nncf_trainer::kTlSteps * 16, 256), 256>>>(t->timeline, nncf_trainer::kTlSteps * 16);
+    }
+  }
   if (rc) { nncf_trainer_destroy(t); return NNCF_ECUDA; }
   *out = t;
   return NNCF_OK;
@@ -749,6 +767,21 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
 
 extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   if (!t) return NNCF_OK;
+  if (t->timeline) {
+    const int64_t n = t->tl_step < nncf_trainer::kTlSteps ? t->tl_step : nncf_trainer::kTlSteps;
+    std::vector<unsigned long long> h((size_t)nncf_trainer::kTlSteps * 16);
+    cudaDeviceSynchronize();
+    if (cudaMemcpy(h.data(), t->timeline, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+      if (FILE* f = fopen(getenv("NNCF_TIMELINE") ? getenv("NNCF_TIMELINE") : "/dev/null", "a")) {
+        fprintf(f, "# trainer R=%d B=%d d=%d steps=%lld (slot = step %% %d)\n", t->cfg.replicas, t->cfg.batch_size_p, t->cfg.dim, (long long)t->tl_step, nncf_trainer::kTlSteps);
+        for (int64_t i = 0; i < n; ++i) {
+          for (int k = 0; k < 16; ++k) fprintf(f, "%llu%c", h[i * 16 + k], k == 15 ? '\n' : ' ');
+        }
+        fclose(f);
+      }
+    }
+    cudaFree(t->timeline);
+  }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
                   t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -887,6 +920,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   gu.normalize = c.norm_u; gu.write_img = bf16; gu.zero_grad = bf16 ? 0 : 1;
   gu.write_xf = (!bf16 || c.norm_u || c.norm_v || pairwise || c.u_reg != 0.0f) ? 1 : 0; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
   gu.corr = t->corrU;
+  unsigned long long* tl = nullptr;
+  if (t->timeline) {
+    tl = t->timeline + (t->tl_step % nncf_trainer::kTlSteps) * 16;
+    if (t->tl_step >= nncf_trainer::kTlSteps) timeline_init_kernel<<<1, 16, 0, st>>>(tl, 16);
+    ++t->tl_step;
+  }
+  gu.tl = tl;
   GatherArgs gv = gu;
   gv.table = tb->item_table; gv.dense_rows = dense_items ? io->item_rows_dev : nullptr;
   gv.ids = item_ids; gv.ids_stride = item_stride; gv.count_dev = group ? t->nuniq : nullptr;
@@ -929,7 +969,9 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
-    if (next_uid && next_cid && !sharded && !dense_items && (d % 4 == 0)) {
+    ta.tl = tl;
+    static const bool prefetch_env = [] { const char* e = getenv("NNCF_PREFETCH"); return !e || atoi(e) != 0; }();
+    if (prefetch_env && next_uid && next_cid && !sharded && !dense_items && (d % 4 == 0)) {
       ta.next_ids_u = next_uid; ta.next_ids_v = next_cid; ta.next_count = R * B;
       ta.n_rows_u = tb->n_users; ta.n_rows_v = tb->n_items;
     }

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for pf in 1 0; do
+rm -f gpurun_out/s4e_timeline.txt
+NNCF_PREFETCH=$pf NNCF_TIMELINE=gpurun_out/s4e_timeline.txt timeout 600 python bench.py --steps 1500 --warmup 100 --no-eval --cpu-steps 20 > gpurun_out/s4e_bench.json 2> gpurun_out/s4e_bench.err; echo "prefetch=$pf rc=$?"; tail -2 gpurun_out/s4e_bench.err
+python tools/timeline.py gpurun_out/s4e_timeline.txt 200 2>&1 | head -30
+python - <<PY
+import json
+j=json.load(open("gpurun_out/s4e_bench.json")); print("value=%.3e"%j["value"], "ms/step=%.4f"%j["ms_per_step"], "e2e=%.3e"%j["e2e"]["value"])
+PY
+done
