@@ -32,7 +32,9 @@ extern "C" {
 #define NNCF_EUNSUPPORTED -4   /* shape / mode outside what the kernels implement */
 
 /* enums are plain ints in the ABI */
-enum { NNCF_SCHEME_NEG_SHARED = 0, NNCF_SCHEME_GROUP_NEG_SHARED = 1, NNCF_SCHEME_PAIRS = 2 };
+enum { NNCF_SCHEME_NEG_SHARED = 0, NNCF_SCHEME_GROUP_NEG_SHARED = 1, NNCF_SCHEME_PAIRS = 2,
+       NNCF_SCHEME_SAMPLED_NEG_SHARED = 3 /* B positives + k shared sampled negatives: rows_per_batch = B + k,
+                                             ref: models/model_framework.py:138-143, utils/objectives.py:120-161 */ };
 enum { NNCF_LOSS_SKIP_GRAM = 0, NNCF_LOSS_MSE = 1, NNCF_LOSS_LOG_LOSS = 2, NNCF_LOSS_MAX_MARGIN = 3 };
 enum { NNCF_PREC_FP32 = 0,   /* CUDA-core fp32 FMA, exact fp32 accumulate (1e-4 parity mode)            */
        NNCF_PREC_BF16 = 1 }; /* tcgen05 tensor cores: bf16 operands, fp32 accumulate in TMEM (1e-2 mode) */
@@ -83,6 +85,42 @@ int nncf_group_shuffle(const int32_t* train_dev, int64_t n_rows, int col, const 
 int nncf_assemble_pairs_batch(const int32_t* pos_dev, int B, int k, const int32_t* negs_dev, int neg_col,
                               int neg_sign, int32_t* out_dev, void* stream);
 
+/* presample: the whole epoch's N links with their k sampled negatives each, (1+k)N rows.  layout 0 = each positive
+ * followed by its k negatives (shuffle_st 'original' / 'reverse', ref: models/train_presample.py:46-60); layout 1 =
+ * the N positives, then positive p's negatives at N + p k + j (np.vstack((train_p, train_n)), :61-65).
+ * negs_dev [N k]; column neg_col of a negative row <- its sample, column 2 <- neg_sign. */
+int nncf_presample_assemble(const int32_t* pos_dev, int64_t n_links, int k, const int32_t* negs_dev, int neg_col,
+                            int neg_sign, int layout, int32_t* out_dev, void* stream);
+/* sampled_neg_shared: id arrays of n_batches batches of B + k rows: the B positives of train rows [b B, (b+1) B), then
+ * k rows (user 0, item negs[b k + j]).   ref: models/train_sampled_neg_shared.py:28,46-49 */
+int nncf_assemble_sns_batches(const int32_t* train_dev, int64_t n_batches, int B, int k, const int32_t* negs_dev,
+                              int32_t* user_ids_dev, int32_t* item_ids_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2b) GroupSampler (the batch source when group_shuffling_trick is False).   ref: configs/data_utils.py:244-408
+ *      (class GroupSampler: __init__ :248-304, sample :306-335, sample_with_negs :337-408), constructed at
+ *      models/train_group_neg_shared.py:33-37 and models/train_group_sample.py:31-36.
+ *      group_by: 0 = 'item' (groups are items, members users), 1 = 'user'.  neg_dist: 0 = 'unigram',
+ *      1 = 'uniform' (p_n/p_d corrected), 2 = 'uniform_no_correction'.  train_host = int32 [n_links, 3] HOST rows
+ *      (user, item, label), read once to build the CSR-by-group and the alias tables in device memory.
+ *      Every call draws a fresh block of the Philox stream selected by rand_seed.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct nncf_group_sampler nncf_group_sampler_t;
+int nncf_group_sampler_create(const int32_t* train_host, int64_t n_links, int group_by, int chop, int neg_dist,
+                              int neg_sign, double neg_sampling_power, uint64_t rand_seed, nncf_group_sampler_t** out);
+int nncf_group_sampler_destroy(nncf_group_sampler_t* g);
+/* n_batches independent results of GroupSampler.sample(batch_size_p) (strict_return_shape=True):
+ * out_dev int32 [n_batches][batch_size_p][3], rows (member, group, 1) (columns swapped for group_by user) */
+int nncf_group_sampler_sample(nncf_group_sampler_t* g, int batch_size_p, int n_batches, int32_t* out_dev, void* stream);
+/* n_batches independent results of GroupSampler.sample_with_negs(batch_size_p, k): out_dev int32
+ * [n_batches][batch_size_p * (1 + k)][3]: positives first (label 1), then negatives (label neg_sign), truncated to
+ * batch_size_p * (1 + k) rows; n_pos_dev[n_batches] (optional) = number of positive rows of each batch */
+int nncf_group_sampler_sample_with_negs(nncf_group_sampler_t* g, int batch_size_p, int k, int n_batches,
+                                        int32_t* out_dev, int32_t* n_pos_dev, void* stream);
+/* *failed_out = 1 if some sample_with_negs batch could not be filled within the reference's 10 top-up rounds (the
+ * reference asserts there, configs/data_utils.py:368-370).  Synchronises the device and clears the flag. */
+int nncf_group_sampler_check(nncf_group_sampler_t* g, int* failed_out);
+
 /* ------------------------------------------------------------------------------------------------
  * (3) Fused training step.   ref: models/model_framework.py:40-65,85-143 (graph), modules/interaction/
  *     interaction_dot.py:92-107 (scores), utils/objectives.py:35-220 (losses), utils/utilities.py:122-135
@@ -94,7 +132,7 @@ typedef struct {
   int32_t loss;            /* NNCF_LOSS_* */
   int32_t precision;       /* NNCF_PREC_* */
   int32_t batch_size_p;    /* B: positives per batch */
-  int32_t num_negatives;   /* k (PAIRS scheme only: the batch has (1+k)B rows) */
+  int32_t num_negatives;   /* k (PAIRS: the batch has (1+k)B rows; SAMPLED_NEG_SHARED: B + k rows) */
   int32_t dim;             /* d = user_dim = item_dim, 1..256 */
   int32_t norm_u;          /* l2-normalise user rows (emb_normalization, model_framework.py:62-63) */
   int32_t norm_v;          /* l2-normalise item rows (model_framework.py:109-111; not for 'mf') */
@@ -122,7 +160,7 @@ typedef struct {
 } nncf_tables;
 
 /* Runs `n_steps` consecutive steps; step s, replica r reads ids at  ids + (s * R + r) * rows_per_batch,
- * rows_per_batch = B (matmul schemes) or (1+k)B (PAIRS).  loss_out_dev[n_steps * R] receives each batch's
+ * rows_per_batch = B (matmul schemes), (1+k)B (PAIRS) or B + k (SAMPLED_NEG_SHARED).  loss_out_dev[n_steps * R] receives each batch's
  * loss (task loss + regulariser = what Keras' train_on_batch returns).  Lazy Adam's step counter t is kept
  * in the handle (advanced once per step).
  * Optional outputs of the LAST step, replica 0 (NULL to skip), used by parity tests and by framework
@@ -137,6 +175,10 @@ typedef struct {
   int32_t* inverse_dev;
   int32_t* n_unique_dev;
   const float* item_rows_dev;     /* dense item side only: [n_cols, d] */
+  const int32_t* response_dev;    /* PAIRS scheme, pointwise losses, optional: [n_steps * R * rows] response labels
+                                     (1 = positive; -1 / 0 = negative), the y_true of ref utils/objectives.py:59-70.
+                                     NULL = rows [0, B) of every batch are the positives (the reference's layout for
+                                     train_original / train_group_sample); presample's shuffled batches need it. */
 } nncf_step_io;
 
 int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,

@@ -16,7 +16,10 @@ EXPORTS = [
     "nncf_last_error", "nncf_version", "nncf_launch_count",
     "nncf_sampler_create", "nncf_sampler_destroy", "nncf_sampler_sample_batch_dev", "nncf_sampler_sample_batch_host",
     "nncf_sampler_seek", "nncf_sampler_export_table",
+    "nncf_group_sampler_create", "nncf_group_sampler_destroy", "nncf_group_sampler_sample",
+    "nncf_group_sampler_sample_with_negs", "nncf_group_sampler_check",
     "nncf_permute_rows", "nncf_group_shuffle_workspace_bytes", "nncf_group_shuffle", "nncf_assemble_pairs_batch",
+    "nncf_presample_assemble", "nncf_assemble_sns_batches",
     "nncf_trainer_create", "nncf_trainer_destroy", "nncf_train_steps", "nncf_train_steps_host", "nncf_trainer_set_profile",
     "nncf_trainer_get_profile", "nncf_unique_first_occurrence", "nncf_gather_rows", "nncf_updater_create",
     "nncf_updater_destroy", "nncf_updater_begin_step", "nncf_updater_apply",
@@ -25,7 +28,7 @@ EXPORTS = [
     "nncf_eval_topk_workspace_bytes", "nncf_eval_topk", "nncf_eval_metrics", "nncf_score_pairs", "nncf_eval_given",
 ]
 
-SCHEMES = {"neg_shared": 0, "group_neg_shared": 1, "pairs": 2}
+SCHEMES = {"neg_shared": 0, "group_neg_shared": 1, "pairs": 2, "sampled_neg_shared": 3}
 LOSSES = {"skip-gram": 0, "mse": 1, "log-loss": 2, "max-margin": 3}
 PRECISIONS = {"fp32": 0, "bf16": 1}
 OPTIMIZERS = {"none": 0, "sgd": 1, "lazy_adam": 2}
@@ -52,7 +55,7 @@ class StepIO(C.Structure):
     _fields_ = [
         ("loss_out_dev", C.c_void_p), ("grad_user_rows_dev", C.c_void_p), ("grad_item_rows_dev", C.c_void_p),
         ("unique_ids_dev", C.c_void_p), ("inverse_dev", C.c_void_p), ("n_unique_dev", C.c_void_p),
-        ("item_rows_dev", C.c_void_p),
+        ("item_rows_dev", C.c_void_p), ("response_dev", C.c_void_p),
     ]
 
 
@@ -72,10 +75,17 @@ def _load():
         "nncf_sampler_sample_batch_host": (i32, [vp, i64, vp]),
         "nncf_sampler_seek": (i32, [vp, C.c_uint64]),
         "nncf_sampler_export_table": (i32, [vp, vp, vp]),
+        "nncf_group_sampler_create": (i32, [vp, i64, i32, i32, i32, i32, C.c_double, C.c_uint64, C.POINTER(vp)]),
+        "nncf_group_sampler_destroy": (i32, [vp]),
+        "nncf_group_sampler_sample": (i32, [vp, i32, i32, vp, vp]),
+        "nncf_group_sampler_sample_with_negs": (i32, [vp, i32, i32, i32, vp, vp, vp]),
+        "nncf_group_sampler_check": (i32, [vp, C.POINTER(C.c_int)]),
         "nncf_permute_rows": (i32, [vp, i64, vp, vp, vp]),
         "nncf_group_shuffle_workspace_bytes": (sz, [i64, i64]),
         "nncf_group_shuffle": (i32, [vp, i64, i32, vp, i64, vp, vp, i32, vp, vp, sz, vp]),
         "nncf_assemble_pairs_batch": (i32, [vp, i32, i32, vp, i32, i32, vp, vp]),
+        "nncf_presample_assemble": (i32, [vp, i64, i32, vp, i32, i32, i32, vp, vp]),
+        "nncf_assemble_sns_batches": (i32, [vp, i64, i32, i32, vp, vp, vp, vp]),
         "nncf_trainer_create": (i32, [C.POINTER(StepConfig), C.POINTER(vp)]),
         "nncf_trainer_destroy": (i32, [vp]),
         "nncf_train_steps": (i32, [vp, C.POINTER(Tables), vp, vp, i64, C.POINTER(StepIO), vp]),

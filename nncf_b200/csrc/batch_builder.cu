@@ -193,6 +193,39 @@ assemble_pairs_kernel(const int32_t* __restrict__ pos, int B, int k, const int32
   out[r * 3] = row[0]; out[r * 3 + 1] = row[1]; out[r * 3 + 2] = row[2];
 }
 
+// presample: the whole epoch's links with their k sampled negatives in one array.
+//   layout 0 (shuffle_st 'original' / 'reverse'): row p(1+k) is positive p, the k rows after it are its negatives
+//            (train_p.repeat(1+k); column neg_col <- samples; train[::1+k] = train_p)   ref: models/train_presample.py:46-60
+//   layout 1 (all other shuffle_st): the N positives, then positive p's negatives at N + p k + j
+//            (np.vstack((train_p, train_n)))                                            ref: models/train_presample.py:61-65
+__global__ void __launch_bounds__(256)
+presample_assemble_kernel(const int32_t* __restrict__ pos, int64_t n, int k, const int32_t* __restrict__ negs, int neg_col,
+                          int neg_sign, int layout, int32_t* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n * (1 + k)) return;
+  int64_t p, j;                                     // positive index, negative slot (-1 = the positive itself)
+  if (layout == 0) { p = r / (1 + k); j = r % (1 + k) - 1; }
+  else if (r < n) { p = r; j = -1; }
+  else { p = (r - n) / k; j = (r - n) % k; }
+  int32_t row[3] = {pos[p * 3], pos[p * 3 + 1], pos[p * 3 + 2]};
+  if (j >= 0) { row[neg_col] = negs[p * k + j]; row[2] = neg_sign; }
+  out[r * 3] = row[0]; out[r * 3 + 1] = row[1]; out[r * 3 + 2] = row[2];
+}
+
+// sampled_neg_shared: batch b = its B positive rows followed by k rows (user 0, item negs[b k + j])
+//   ref: models/train_sampled_neg_shared.py:28,46-49 (train_batch_n = np.zeros((k, 3)); column 1 <- sample_batch(k))
+__global__ void __launch_bounds__(256)
+sns_assemble_kernel(const int32_t* __restrict__ train, int64_t n_batches, int B, int k, const int32_t* __restrict__ negs,
+                    int32_t* __restrict__ uid, int32_t* __restrict__ cid) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = B + k;
+  if (r >= n_batches * rows) return;
+  const int64_t b = r / rows;
+  const int i = static_cast<int>(r - b * rows);
+  if (i < B) { uid[r] = train[(b * B + i) * 3]; cid[r] = train[(b * B + i) * 3 + 1]; }
+  else { uid[r] = 0; cid[r] = negs[b * k + (i - B)]; }
+}
+
 }  // namespace nncf
 
 using namespace nncf;
@@ -282,6 +315,28 @@ extern "C" int nncf_assemble_pairs_batch(const int32_t* pos_dev, int B, int k, c
   NNCF_CHECK_ARG(neg_col == 0 || neg_col == 1, "nncf_assemble_pairs_batch: neg_col must be 0 or 1");
   assemble_pairs_kernel<<<ceil_div((int64_t)(1 + k) * B, 256), 256, 0, (cudaStream_t)stream>>>(pos_dev, B, k, negs_dev,
                                                                                                neg_col, neg_sign, out_dev);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+
+extern "C" int nncf_presample_assemble(const int32_t* pos_dev, int64_t n_links, int k, const int32_t* negs_dev, int neg_col,
+                                       int neg_sign, int layout, int32_t* out_dev, void* stream) {
+  NNCF_CHECK_ARG(pos_dev && negs_dev && out_dev, "nncf_presample_assemble: null argument");
+  NNCF_CHECK_ARG(n_links >= 1 && k >= 1, "nncf_presample_assemble: bad sizes");
+  NNCF_CHECK_ARG(neg_col == 0 || neg_col == 1, "nncf_presample_assemble: neg_col must be 0 or 1");
+  NNCF_CHECK_ARG(layout == 0 || layout == 1, "nncf_presample_assemble: layout must be 0 (interleaved) or 1 (stacked)");
+  presample_assemble_kernel<<<ceil_div(n_links * (1 + k), 256), 256, 0, (cudaStream_t)stream>>>(pos_dev, n_links, k, negs_dev,
+                                                                                              neg_col, neg_sign, layout, out_dev);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+
+extern "C" int nncf_assemble_sns_batches(const int32_t* train_dev, int64_t n_batches, int B, int k, const int32_t* negs_dev,
+                                         int32_t* user_ids_dev, int32_t* item_ids_dev, void* stream) {
+  NNCF_CHECK_ARG(train_dev && negs_dev && user_ids_dev && item_ids_dev, "nncf_assemble_sns_batches: null argument");
+  NNCF_CHECK_ARG(n_batches >= 1 && B >= 1 && k >= 1, "nncf_assemble_sns_batches: bad sizes");
+  sns_assemble_kernel<<<ceil_div(n_batches * (B + k), 256), 256, 0, (cudaStream_t)stream>>>(train_dev, n_batches, B, k, negs_dev,
+                                                                                          user_ids_dev, item_ids_dev);
   NNCF_LAUNCH_OK();
   return NNCF_OK;
 }

@@ -7,34 +7,9 @@
 #include <cstring>
 #include <vector>
 #include "common.cuh"
+#include "alias.cuh"
 
 namespace nncf {
-
-struct Philox {
-  static constexpr uint32_t kM0 = 0xD2511F53u, kM1 = 0xCD9E8D57u, kW0 = 0x9E3779B9u, kW1 = 0xBB67AE85u;
-  __host__ __device__ static inline void round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#ifdef __CUDA_ARCH__
-    const uint32_t hi0 = __umulhi(kM0, c[0]), hi1 = __umulhi(kM1, c[2]);
-#else
-    const uint32_t hi0 = static_cast<uint32_t>((static_cast<uint64_t>(kM0) * c[0]) >> 32);
-    const uint32_t hi1 = static_cast<uint32_t>((static_cast<uint64_t>(kM1) * c[2]) >> 32);
-#endif
-    const uint32_t lo0 = kM0 * c[0], lo1 = kM1 * c[2];
-    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-  }
-  // Philox4x32-10: counter (128 bit) x key (64 bit) -> 4 x 32 random bits
-  __host__ __device__ static inline void gen(uint64_t ctr, uint64_t key, uint32_t (&out)[4]) {
-    uint32_t c[4] = {static_cast<uint32_t>(ctr), static_cast<uint32_t>(ctr >> 32), 0u, 0u};
-    uint32_t k0 = static_cast<uint32_t>(key), k1 = static_cast<uint32_t>(key >> 32);
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-      round(c, k0, k1);
-      k0 += kW0; k1 += kW1;
-    }
-    out[0] = c[0]; out[1] = c[1]; out[2] = c[2]; out[3] = c[3];
-  }
-};
 
 // table entry: x = acceptance probability as float bits, y = alias id
 __global__ void __launch_bounds__(256)
@@ -44,11 +19,7 @@ sample_kernel(const uint2* __restrict__ table, uint32_t n, uint64_t key, uint64_
   if (i >= count) return;
   uint32_t r[4];
   Philox::gen(ctr0 + static_cast<uint64_t>(i), key, r);
-  const uint64_t x = (static_cast<uint64_t>(r[0]) << 32) | r[1];
-  const uint32_t bin = static_cast<uint32_t>(__umul64hi(x, static_cast<uint64_t>(n)));
-  const float u = static_cast<float>(r[2] >> 8) * (1.0f / 16777216.0f);
-  const uint2 e = __ldg(table + bin);
-  out[i] = (u < __uint_as_float(e.x)) ? static_cast<int32_t>(bin) : static_cast<int32_t>(e.y);
+  out[i] = alias_draw(table, n, r);
 }
 
 }  // namespace nncf
@@ -70,51 +41,19 @@ extern "C" int nncf_sampler_create(const double* dist_host, int dist_size, doubl
   NNCF_CHECK_ARG(dist_size >= 1, "nncf_sampler_create: dist_size must be >= 1");
   const int n = dist_size;
   std::vector<double> w(n);
-  double sum = 0.0;
-  int best = -1;
   for (int i = 0; i < n; ++i) {
     const double deg = dist_host[i];
     NNCF_CHECK_ARG(deg >= 0.0 && std::isfinite(deg), "nncf_sampler_create: dist must be finite and non-negative");
     w[i] = (deg == 0.0) ? 0.0 : std::pow(deg, neg_sampling_power);   // zero degree node will not be sampled
-    sum += w[i];
-    if (w[i] > 0.0 && (best < 0 || w[i] > w[best])) best = i;
-  }
-  NNCF_CHECK_ARG(best >= 0 && sum > 0.0, "nncf_sampler_create: distribution has no positive entry");
-  // Vose's alias method
-  std::vector<double> p(n);
-  std::vector<int32_t> alias(n), small, large;
-  small.reserve(n); large.reserve(n);
-  for (int i = 0; i < n; ++i) {
-    p[i] = w[i] / sum * n;
-    alias[i] = best;
-    (p[i] < 1.0 ? small : large).push_back(i);
-  }
-  while (!small.empty() && !large.empty()) {
-    const int s = small.back(); small.pop_back();
-    const int l = large.back();
-    alias[s] = l;
-    p[l] = (p[l] + p[s]) - 1.0;
-    if (p[l] < 1.0) { large.pop_back(); small.push_back(l); }
-  }
-  for (int i : large) p[i] = 1.0;
-  for (int i : small) {                       // numerical leftovers: ~1 for real ids, exactly 0 for zero-degree ids
-    if (w[i] > 0.0) p[i] = 1.0;
-    else { p[i] = 0.0; alias[i] = best; }
   }
   auto* s = new nncf_sampler();
   s->n = n;
   s->key = rand_seed;
-  s->prob_host.resize(n);
-  s->alias_host = alias;
-  std::vector<uint2> tab(n);
-  for (int i = 0; i < n; ++i) {
-    float pf = static_cast<float>(p[i]);
-    if (w[i] == 0.0) pf = 0.0f;
-    if (pf > 1.0f) pf = 1.0f;
-    s->prob_host[i] = pf;
-    uint32_t bits;
-    memcpy(&bits, &pf, 4);
-    tab[i] = make_uint2(bits, static_cast<uint32_t>(alias[i]));
+  std::vector<uint2> tab;
+  if (!build_alias_table(w, tab, s->prob_host, s->alias_host)) {
+    delete s;
+    set_error("nncf_sampler_create: distribution has no positive entry");
+    return NNCF_EINVAL;
   }
   cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&s->table), sizeof(uint2) * n);
   if (e == cudaSuccess) e = cudaMemcpy(s->table, tab.data(), sizeof(uint2) * n, cudaMemcpyHostToDevice);

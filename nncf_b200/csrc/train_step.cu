@@ -447,6 +447,7 @@ finalize_kernel(FinalizeArgs a0, FinalizeArgs a1) {
 
 }  // namespace nncf
 #include "row_kernels.cuh"
+#include "sns_kernels.cuh"
 namespace nncf {
 
 // =================================================================================================
@@ -526,6 +527,8 @@ struct PairsArgs {
   int optimizer; float lr;
   float* tableU; float* tableV;
   float* grad_out_u; float* grad_out_v;
+  const int32_t* resp;   // optional [R][n] response labels: pointwise losses take positive = (label == 1) from here
+                         // (ref: utils/objectives.py:59-70 weights by y_true); NULL = positives are rows [0, B)
 };
 
 __global__ void __launch_bounds__(256)
@@ -561,7 +564,8 @@ pairs_grad_kernel(PairsArgs a) {
   if (row >= n) return;
   const float* S = a.s + (int64_t)r * n;
   const float s = S[row];
-  const bool is_pos = row < B;
+  const bool pointwise = a.loss_kind <= NNCF_LOSS_MSE;
+  const bool is_pos = (pointwise && a.resp) ? (a.resp[(int64_t)r * n + row] == 1) : (row < B);
   const float invB = 1.0f / B, w = a.lambda / k;
   float g = 0.0f, l = 0.0f;
   if (a.loss_kind == NNCF_LOSS_SKIP_GRAM) {
@@ -678,6 +682,7 @@ struct nncf_trainer {
   int32_t *ownerU = nullptr, *ownerV = nullptr;
   int64_t ownerU_n = 0, ownerV_n = 0;
   float *ps = nullptr;   // PAIRS scores
+  float *dVn = nullptr;  // sampled_neg_shared: [R][k][d] accumulated dL/d(vhat_neg)
   bool tc_attr_set = false;
   const int32_t *hint_next_uid = nullptr, *hint_next_cid = nullptr;   // ids of the step after this call's last one (L2 prefetch hint)
   bool loss_published = false;   // the step's finalize launch already wrote loss_out and re-zeroed the accumulators
@@ -715,20 +720,24 @@ static int dev_alloc(T** p, size_t n) {
 
 extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t** out) {
   NNCF_CHECK_ARG(cfg && out, "nncf_trainer_create: null argument");
-  NNCF_CHECK_ARG(cfg->scheme >= 0 && cfg->scheme <= 2, "unknown scheme");
+  NNCF_CHECK_ARG(cfg->scheme >= 0 && cfg->scheme <= 3, "unknown scheme");
   NNCF_CHECK_ARG(cfg->loss >= 0 && cfg->loss <= 3, "[ERROR!] loss not specified.");
   NNCF_CHECK_ARG(cfg->precision == NNCF_PREC_FP32 || cfg->precision == NNCF_PREC_BF16, "unknown precision");
   NNCF_CHECK_ARG(cfg->batch_size_p >= 2, "batch_size_p must be >= 2");
   NNCF_CHECK_ARG(cfg->dim >= 1 && cfg->dim <= 256, "dim must be in [1, 256]");
   NNCF_CHECK_ARG(cfg->replicas >= 1 && cfg->replicas <= 1024, "replicas must be in [1, 1024]");
   NNCF_CHECK_ARG(cfg->optimizer >= 0 && cfg->optimizer <= 2, "unknown optimizer");
-  if (cfg->scheme == NNCF_SCHEME_PAIRS) NNCF_CHECK_ARG(cfg->num_negatives >= 1, "num_negatives must be >= 1");
+  if (cfg->scheme == NNCF_SCHEME_PAIRS || cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED)
+    NNCF_CHECK_ARG(cfg->num_negatives >= 1, "num_negatives must be >= 1");
+  if (cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED)
+    NNCF_CHECK_ARG((int64_t)cfg->num_negatives * cfg->dim * 4 <= 160 * 1024, "sampled_neg_shared: num_negatives * dim too large for the shared-memory accumulators");
   if (cfg->scheme == NNCF_SCHEME_GROUP_NEG_SHARED)
     NNCF_CHECK_ARG(cfg->batch_size_p <= 12288, "group_neg_shared supports batch_size_p <= 12288");
   auto* t = new nncf_trainer();
   t->cfg = *cfg;
   const int R = cfg->replicas;
-  t->rows = cfg->scheme == NNCF_SCHEME_PAIRS ? (1 + cfg->num_negatives) * cfg->batch_size_p : cfg->batch_size_p;
+  t->rows = cfg->scheme == NNCF_SCHEME_PAIRS ? (1 + cfg->num_negatives) * cfg->batch_size_p
+          : cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED ? cfg->batch_size_p + cfg->num_negatives : cfg->batch_size_p;
   t->rows_pad = (t->rows + 127) / 128 * 128;
   t->dp = cfg->dim <= 64 ? 64 : (cfg->dim <= 128 ? 128 : 256);   // tensor-core kernels exist for dp = 64 / 128 / 256
   t->nsub = t->dp / 64;
@@ -736,7 +745,11 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
   int rc = 0;
   rc |= dev_alloc(&t->loss, (size_t)R);
   rc |= dev_alloc(&t->loss_count, (size_t)R);
-  if (cfg->scheme == NNCF_SCHEME_PAIRS) {
+  if (cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED) {
+    rc |= dev_alloc(&t->dU, (size_t)R * t->rows * cfg->dim);
+    rc |= dev_alloc(&t->dV, (size_t)R * t->rows * cfg->dim);
+    rc |= dev_alloc(&t->dVn, (size_t)R * cfg->num_negatives * cfg->dim);
+  } else if (cfg->scheme == NNCF_SCHEME_PAIRS) {
     rc |= dev_alloc(&t->ps, (size_t)R * t->rows);
     rc |= dev_alloc(&t->invU, (size_t)R * t->rows);
     rc |= dev_alloc(&t->invV, (size_t)R * t->rows);
@@ -783,7 +796,7 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
     cudaFree(t->timeline);
   }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
-                  t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps};
+                  t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
@@ -1067,8 +1080,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   return NNCF_OK;
 }
 
+static int apply_row_grads(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid, int n, cudaStream_t st);
+
 static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
-                      const nncf_step_io* io, bool last, cudaStream_t st) {
+                      const nncf_step_io* io, bool last, const int32_t* resp, cudaStream_t st) {
   const nncf_step_config& c = t->cfg;
   NNCF_CHECK_ARG(tb->item_table, "PAIRS scheme needs an item embedding table");
   const int R = c.replicas, n = t->rows, d = c.dim;
@@ -1082,6 +1097,7 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
   pa.tableU = tb->user_table; pa.tableV = tb->item_table;
   pa.grad_out_u = (last && io) ? io->grad_user_rows_dev : nullptr;
   pa.grad_out_v = (last && io) ? io->grad_item_rows_dev : nullptr;
+  pa.resp = resp;
   dim3 g8(ceil_div(n, 8), R);
   NNCF_PROFILE_MARK(t, 0, st);
   pairs_score_kernel<<<g8, 256, 0, st>>>(pa);
@@ -1090,6 +1106,16 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
   pairs_grad_kernel<<<g8, 256, 0, st>>>(pa);
   NNCF_LAUNCH_OK();
   NNCF_PROFILE_MARK(t, 2, st);
+  if (int rc = apply_row_grads(t, tb, uid, cid, n, st)) return rc;
+  NNCF_PROFILE_MARK(t, 3, st);
+  return NNCF_OK;
+}
+
+// per-position row gradients t->dU / t->dV [R][n][d] -> sparse SGD (atomic scatter-add) or lazy Adam
+static int apply_row_grads(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid, int n, cudaStream_t st) {
+  const nncf_step_config& c = t->cfg;
+  const int R = c.replicas, d = c.dim;
+  dim3 g8(ceil_div(n, 8), R);
   if (c.optimizer == NNCF_OPT_SGD) {
     rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
     NNCF_LAUNCH_OK();
@@ -1107,6 +1133,36 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
     if (run_adam(t, cid, n, n, nullptr, n, d, d, t->ownerV, t->dV, tb->item_table, tb->item_m, tb->item_v, lr_t, st))
       return NNCF_ECUDA;
   }
+  return NNCF_OK;
+}
+
+// sampled_neg_shared: B positives + k shared sampled negatives per batch (ref: models/train_sampled_neg_shared.py)
+static int step_sns(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid, const int32_t* cid,
+                    const nncf_step_io* io, bool last, cudaStream_t st) {
+  const nncf_step_config& c = t->cfg;
+  NNCF_CHECK_ARG(tb->item_table, "sampled_neg_shared needs an item embedding table");
+  const int R = c.replicas, n = t->rows, d = c.dim, k = c.num_negatives, B = c.batch_size_p;
+  NNCF_CUDA(cudaMemsetAsync(t->loss, 0, sizeof(double) * R, st));
+  NNCF_CUDA(cudaMemsetAsync(t->dVn, 0, sizeof(float) * (size_t)R * k * d, st));
+  SnsArgs a{};
+  a.EU = tb->user_table; a.EV = tb->item_table; a.uid = uid; a.cid = cid; a.B = B; a.k = k; a.d = d;
+  a.norm_u = c.norm_u; a.norm_v = c.norm_v; a.loss_kind = c.loss; a.lambda = c.neg_loss_weight; a.gamma = c.loss_gamma;
+  a.u_reg = c.u_reg; a.loss = t->loss; a.dUrows = t->dU; a.dVrows = t->dV; a.dVn_hat = t->dVn;
+  a.grad_out_u = (last && io) ? io->grad_user_rows_dev : nullptr;
+  a.grad_out_v = (last && io) ? io->grad_item_rows_dev : nullptr;
+  const size_t sm = (size_t)k * d * sizeof(float);
+  if (sm > 48 * 1024 && !t->tc_attr_set) {
+    NNCF_CUDA(cudaFuncSetAttribute(sns_main_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    t->tc_attr_set = true;
+  }
+  NNCF_PROFILE_MARK(t, 0, st);
+  NNCF_PROFILE_MARK(t, 1, st);
+  sns_main_kernel<<<dim3(ceil_div(B, 8), R), 256, sm, st>>>(a);
+  NNCF_LAUNCH_OK();
+  sns_back_kernel<<<dim3(ceil_div(k, 8), R), 256, 0, st>>>(a);
+  NNCF_LAUNCH_OK();
+  NNCF_PROFILE_MARK(t, 2, st);
+  if (int rc = apply_row_grads(t, tb, uid, cid, n, st)) return rc;
   NNCF_PROFILE_MARK(t, 3, st);
   return NNCF_OK;
 }
@@ -1120,7 +1176,7 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
   if (dense_items) {
     NNCF_CHECK_ARG(io && io->item_rows_dev, "dense item side needs io->item_rows_dev");
     NNCF_CHECK_ARG(t->cfg.replicas == 1 && n_steps <= 1, "dense item side supports one batch per call");
-    NNCF_CHECK_ARG(t->cfg.scheme != NNCF_SCHEME_PAIRS, "dense item side is not available for the PAIRS scheme");
+    NNCF_CHECK_ARG(t->cfg.scheme < NNCF_SCHEME_PAIRS, "dense item side is available for the matmul schemes only");
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int R = t->cfg.replicas;
@@ -1131,7 +1187,10 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
     float* loss_out_step = (io && io->loss_out_dev) ? io->loss_out_dev + s * R : nullptr;
     t->loss_published = false;
     if (t->cfg.scheme == NNCF_SCHEME_PAIRS)
-      rc = step_pairs(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
+      rc = step_pairs(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last,
+                      (io && io->response_dev) ? io->response_dev + s * per_step : nullptr, st);
+    else if (t->cfg.scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED)
+      rc = step_sns(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
     else
       rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, loss_out_step,
                        last ? t->hint_next_uid : user_ids_dev + (s + 1) * per_step,

@@ -184,3 +184,50 @@ def group_shuffle_train(train, by='item', chop=0, iidx=None, rng=None):
         train[:] = train[row_perm]
         return out.cpu().numpy().astype(train.dtype)
     return out
+
+
+class GroupSampler(object):
+    """First sample a group/item, then sample its positive members/users, followed by sampling negative
+    members/users (whose number is decided).
+
+    ref: configs/data_utils.py:244-408.  Same constructor keywords, `sample(batch_size_p, strict_return_shape)` and
+    `sample_with_negs(batch_size_p, k, strict_return_shape)` returning host int arrays [rows, 3] like the reference;
+    the `*_device` variants return CUDA tensors holding many batches from one launch (what the trainers use).
+    Kept: group ~ degree^1, `chop` members with replacement, random_rounding(k * chop * p_n/p_d) negatives per group,
+    the top-up rounds, positives-then-negatives order, truncation, column swap for group_by='user'.
+    Declared: the reference reads an undefined global `conf` for neg_sampling_power and therefore ALWAYS uses 0.75
+    (:274-280); here 0.75 is the default and the power is a keyword.  Randomness comes from the device Philox stream
+    (the reference uses np.random + a time-seeded LCG), so parity is distributional.
+    """
+
+    def __init__(self, train, group_by='item', chop=1, neg_dist='unigram', neg_sign=0, neg_sampling_power=0.75, seed=0):
+        from . import ops
+        self.train = train
+        self.group_by = group_by
+        self.chop = chop
+        self.neg_dist = neg_dist
+        self.neg_sign = int(np.asarray(neg_sign).reshape(-1)[0])
+        self._dev = ops.DeviceGroupSampler(train, group_by, chop, neg_dist, self.neg_sign, neg_sampling_power, seed)
+
+    # ---- device variants (many batches per launch)
+    def sample_device(self, batch_size_p, n_batches=1):
+        return self._dev.sample(batch_size_p, n_batches)
+
+    def sample_with_negs_device(self, batch_size_p, k, n_batches=1):
+        return self._dev.sample_with_negs(batch_size_p, k, n_batches)
+
+    # ---- the reference's methods
+    def sample(self, batch_size_p, strict_return_shape=True):
+        if strict_return_shape:
+            return self._dev.sample(batch_size_p, 1)[0].cpu().numpy().astype(np.int64)
+        # non-strict: batch_size_p // chop whole groups, nothing truncated (:308-311, :334-335)
+        n = (batch_size_p // self.chop) * self.chop
+        return self._dev.sample(n, 1)[0].cpu().numpy().astype(np.int64)
+
+    def sample_with_negs(self, batch_size_p, k, strict_return_shape=True):
+        # the reference's non-strict branch returns an undefined name (`sample_batch`, :408) -> NameError there
+        assert strict_return_shape, 'sample_with_negs(strict_return_shape=False) is broken in the reference ' \
+                                    '(configs/data_utils.py:408) and not provided'
+        out, _ = self._dev.sample_with_negs(batch_size_p, k, 1)
+        self._dev.check()
+        return out[0].cpu().numpy().astype(np.int64)

@@ -11,8 +11,9 @@ that expose the Keras methods the trainers and the Evaluator call:
   model_dict['model_pred_pairs']        .predict([Uemb, Vemb, uid, cid], batch_size) -> [n, 1]
 
 All arithmetic is done by libnncf_b200.so kernels; the Dense/BatchNorm/ReLU of the mean-pool tower (and the CNN/RNN
-towers) stay torch modules feeding the fused score kernel, as the north_star prescribes.  Keys absent here
-(`model_sampled_neg_shared`, the two monitor dicts) belong to trainers outside the scoped train_scheme list.
+towers) stay torch modules feeding the fused score kernel, as the north_star prescribes.
+  model_dict['model_sampled_neg_shared'] .train_on_batch([uid, cid])  B positives + k shared sampled negatives
+Keys absent here: the two monitor dicts (the reference compiles them with the same loss, models/model_framework.py:179-187).
 """
 from __future__ import annotations
 
@@ -196,17 +197,25 @@ class MatmulView(_View):
 class PairsView(_View):
     """model: the row-wise 'mul' view used by train_original / train_group_sample (model_framework.py:123,147-149)."""
 
-    def train_on_batches(self, user_ids, item_ids, n_steps, loss_out=None):
+    def train_on_batches(self, user_ids, item_ids, n_steps, loss_out=None, responses=None):
+        """responses: optional int32 y_true per row (1 = positive).  Pointwise losses weight by it (ref:
+        utils/objectives.py:59-70), so batches whose positives are not the first B rows (presample's shuffles,
+        GroupSampler's ragged batches) train correctly; pairwise losses are positional in the reference too."""
         st = self.state
         assert st.item_table is not None
+        if st.conf.loss not in ('skip-gram', 'mse'):
+            responses = None
         return st.step('pairs').run(st.user_table, st.item_table, user_ids, item_ids, n_steps, adam_state=st.adam,
-                                    loss_out=loss_out)['loss']
+                                    loss_out=loss_out, responses=responses)['loss']
 
     def train_on_batch(self, x, y=None):
         st = self.state
         uid, cid = _dev_i32(x[0], st.device), _dev_i32(x[1], st.device)
         if st.item_table is not None:
-            return float(self.train_on_batches(uid, cid, 1).mean().item())
+            resp = None
+            if y is not None and y[0] is not None:
+                resp = _dev_i32(y[0], st.device)
+            return float(self.train_on_batches(uid, cid, 1, responses=resp).mean().item())
         # content tower: the unique items' embeddings act as a temporary item table indexed by tf.unique's inverse
         c = st.conf
         st.tower.train()
@@ -229,6 +238,22 @@ class PairsView(_View):
         compact.backward(g)
         st.tower_opt.step()
         return float(out['loss'][0].item())
+
+
+class SampledNegSharedView(_View):
+    """model_sampled_neg_shared: B positive rows + k shared sampled negative items per batch, scores [B, 1+k]
+    (models/model_framework.py:138-143,163-167; loss utils/objectives.py:120-161).  Embedding-table models."""
+
+    def train_on_batches(self, user_ids, item_ids, n_steps, loss_out=None):
+        st = self.state
+        assert st.item_table is not None, 'sampled_neg_shared runs on embedding-table models (mf)'
+        return st.step('sampled_neg_shared').run(st.user_table, st.item_table, user_ids, item_ids, n_steps,
+                                                 adam_state=st.adam, loss_out=loss_out)['loss']
+
+    def train_on_batch(self, x, y=None):
+        st = self.state
+        uid, cid = _dev_i32(x[0], st.device), _dev_i32(x[1], st.device)
+        return float(self.train_on_batches(uid, cid, 1).mean().item())
 
 
 class UserEmbView(_View):
@@ -257,6 +282,7 @@ def get_model(conf, data_helper, model_name):
     model_dict = {'model': PairsView(state),
                   'model_neg_shared': MatmulView(state, 'neg_shared'),
                   'model_group_neg_shared': MatmulView(state, 'group_neg_shared'),
+                  'model_sampled_neg_shared': SampledNegSharedView(state),
                   'model_user_emb': UserEmbView(state),
                   'model_item_emb': ItemEmbView(state),
                   'model_pred_pairs': PredPairsView(state),

@@ -76,6 +76,55 @@ class DeviceSampler:
         return prob, alias
 
 
+class DeviceGroupSampler:
+    """Handle on nncf_group_sampler_*: the reference's GroupSampler (configs/data_utils.py:244-408) on the device."""
+
+    NEG_DISTS = {"unigram": 0, "uniform": 1, "uniform_no_correction": 2}
+
+    def __init__(self, train: np.ndarray, group_by: str = "item", chop: int = 1, neg_dist: str = "unigram",
+                 neg_sign: int = 0, neg_sampling_power: float = 0.75, seed: int = 0):
+        if group_by not in ("item", "user"):
+            raise AssertionError("[ERROR] Illegal group_by {}".format(group_by))
+        if neg_dist not in self.NEG_DISTS:
+            raise AssertionError("[ERROR] Illegal neg_dist {}".format(neg_dist))
+        if not torch.cuda.is_available():
+            raise NNCFError("nncf_b200 needs a CUDA device (no CPU fallback)")
+        train = np.ascontiguousarray(train, dtype=np.int32)
+        assert train.ndim == 2 and train.shape[1] == 3
+        h = C.c_void_p()
+        check(lib.nncf_group_sampler_create(train.ctypes.data_as(C.c_void_p), train.shape[0], 0 if group_by == "item" else 1,
+                                            int(chop), self.NEG_DISTS[neg_dist], int(neg_sign), float(neg_sampling_power),
+                                            int(seed) & (2**64 - 1), C.byref(h)))
+        self._h = h
+        self.chop = int(chop)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.nncf_group_sampler_destroy(h)
+            self._h = None
+
+    def sample(self, batch_size_p: int, n_batches: int = 1) -> torch.Tensor:
+        """int32 CUDA tensor [n_batches, batch_size_p, 3]"""
+        out = torch.empty((int(n_batches), int(batch_size_p), 3), dtype=torch.int32, device="cuda")
+        check(lib.nncf_group_sampler_sample(self._h, int(batch_size_p), int(n_batches), _ptr(out), _stream()))
+        return out
+
+    def sample_with_negs(self, batch_size_p: int, k: int, n_batches: int = 1):
+        """(int32 CUDA tensor [n_batches, batch_size_p * (1 + k), 3], int32 [n_batches] positives per batch)"""
+        out = torch.empty((int(n_batches), int(batch_size_p) * (1 + int(k)), 3), dtype=torch.int32, device="cuda")
+        n_pos = torch.empty(int(n_batches), dtype=torch.int32, device="cuda")
+        check(lib.nncf_group_sampler_sample_with_negs(self._h, int(batch_size_p), int(k), int(n_batches), _ptr(out),
+                                                      _ptr(n_pos), _stream()))
+        return out, n_pos
+
+    def check(self) -> None:
+        """raises where the reference asserts: a batch was not filled within 10 top-up rounds (data_utils.py:368-370)"""
+        failed = C.c_int(0)
+        check(lib.nncf_group_sampler_check(self._h, C.byref(failed)))
+        assert not failed.value, "[WARNING] the code here should be optimized if this is shown."
+
+
 # ------------------------------------------------------------------------------------------------
 # batch builders
 # ------------------------------------------------------------------------------------------------
@@ -115,6 +164,29 @@ def assemble_pairs_batch(pos: torch.Tensor, k: int, negs: torch.Tensor, neg_col:
     return out
 
 
+def presample_assemble(pos: torch.Tensor, k: int, negs: torch.Tensor, neg_col: int, neg_sign: int, layout: int) -> torch.Tensor:
+    """(1+k)N rows of the presample trainer: layout 0 = interleaved, 1 = positives then negatives"""
+    _need_cuda(pos, negs)
+    pos, negs = _i32(pos), _i32(negs)
+    n = pos.shape[0]
+    assert negs.numel() >= n * k
+    out = torch.empty(((1 + k) * n, 3), dtype=torch.int32, device=pos.device)
+    check(lib.nncf_presample_assemble(_ptr(pos), n, int(k), _ptr(negs), int(neg_col), int(neg_sign), int(layout), _ptr(out),
+                                      _stream()))
+    return out
+
+
+def assemble_sns_batches(train: torch.Tensor, n_batches: int, B: int, k: int, negs: torch.Tensor):
+    """id arrays [n_batches * (B + k)] of the sampled_neg_shared trainer"""
+    _need_cuda(train, negs)
+    train, negs = _i32(train), _i32(negs)
+    assert train.shape[0] >= n_batches * B and negs.numel() >= n_batches * k
+    uid = torch.empty(n_batches * (B + k), dtype=torch.int32, device=train.device)
+    cid = torch.empty_like(uid)
+    check(lib.nncf_assemble_sns_batches(_ptr(train), int(n_batches), int(B), int(k), _ptr(negs), _ptr(uid), _ptr(cid), _stream()))
+    return uid, cid
+
+
 def unique_first_occurrence(ids: torch.Tensor):
     _need_cuda(ids)
     ids = _i32(ids)
@@ -131,7 +203,7 @@ def unique_first_occurrence(ids: torch.Tensor):
 # ------------------------------------------------------------------------------------------------
 @dataclass
 class StepSpec:
-    scheme: str = "neg_shared"          # neg_shared | group_neg_shared | pairs
+    scheme: str = "neg_shared"          # neg_shared | group_neg_shared | pairs | sampled_neg_shared
     loss: str = "skip-gram"
     precision: str = "bf16"             # fp32 (CUDA cores) | bf16 (tcgen05)
     batch_size_p: int = 512
@@ -169,7 +241,8 @@ class FusedStep:
         h = C.c_void_p()
         check(lib.nncf_trainer_create(C.byref(cfg), C.byref(h)))
         self._h = h
-        self.rows = (1 + spec.num_negatives) * spec.batch_size_p if spec.scheme == "pairs" else spec.batch_size_p
+        self.rows = ((1 + spec.num_negatives) * spec.batch_size_p if spec.scheme == "pairs" else
+                     spec.batch_size_p + spec.num_negatives if spec.scheme == "sampled_neg_shared" else spec.batch_size_p)
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -190,7 +263,8 @@ class FusedStep:
     def run(self, user_table: torch.Tensor, item_table: Optional[torch.Tensor], user_ids: torch.Tensor,
             item_ids: torch.Tensor, n_steps: int = 1, *, adam_state=None, want_grads: bool = False,
             item_rows: Optional[torch.Tensor] = None, inverse: Optional[torch.Tensor] = None,
-            n_unique: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None):
+            n_unique: Optional[torch.Tensor] = None, loss_out: Optional[torch.Tensor] = None,
+            responses: Optional[torch.Tensor] = None):
         """Runs n_steps steps (each over `replicas` batches).  Returns dict(loss=[n_steps*R] tensor, and if
         want_grads: grad_user_rows, grad_item_rows (+ unique_ids, inverse, n_unique for group_neg_shared))."""
         sp = self.spec
@@ -229,6 +303,13 @@ class FusedStep:
                 nu = torch.zeros(1, dtype=torch.int32, device=dev)
                 io.unique_ids_dev, io.inverse_dev, io.n_unique_dev = uq.data_ptr(), iv_.data_ptr(), nu.data_ptr()
                 out["unique_ids"], out["inverse"], out["n_unique"] = uq, iv_, nu
+        if responses is not None:
+            # PAIRS, pointwise losses: y_true per row (1 = positive), ref utils/objectives.py:59-70
+            _need_cuda(responses)
+            assert sp.scheme == "pairs" and responses.dtype == torch.int32 and responses.numel() >= need
+            responses = responses.contiguous()
+            keep.append(responses)
+            io.response_dev = responses.data_ptr()
         if item_rows is not None:
             item_rows = item_rows.contiguous()
             keep.append(item_rows)

@@ -139,12 +139,26 @@ def group_neg_shared_loss_grad(P, pos_col, loss, neg_loss_weight, gamma):
     return L, G
 
 
-def original_loss_grad(s, B, k, loss, neg_loss_weight, gamma):
+def original_loss_grad(s, B, k, loss, neg_loss_weight, gamma, y_true=None):
     """get_original_loss, utils/objectives.py:35-75.  s: [(1+k)B]; first B positives, then k consecutive
     negatives per positive (models/train_original.py:50-53).  y_true is implied by the scheme:
-    +1 for positives; -1 (skip-gram) or 0 (mse) for negatives (train_original.py:13-14).  Returns (loss, dL/ds)."""
+    +1 for positives; -1 (skip-gram) or 0 (mse) for negatives (train_original.py:13-14).  Returns (loss, dL/ds).
+    With an explicit y_true the pointwise losses weight each row by its own label exactly as the reference does
+    (:59-70), wherever the positives sit in the batch (models/train_presample.py feeds shuffled batches)."""
     s = np.asarray(s).reshape(-1)
     assert s.size == (1 + k) * B
+    if y_true is not None and loss in ("skip-gram", "mse"):
+        y = np.asarray(y_true, dtype=s.dtype).reshape(-1)
+        wv = neg_loss_weight / k
+        if loss == "skip-gram":
+            w = 1.0 + (1.0 - y) / 2.0 * (wv - 1.0)                   # :60-62
+            L = np.sum(-w * log_sigmoid(y * s)) / B                  # :63-64
+            g = -w * y * sigmoid(-y * s) / B
+        else:
+            w = 1.0 + (1.0 - y) * (wv - 1.0)                         # :66-68
+            L = np.sum(w * (y - s) ** 2) / B                         # :69-70
+            g = -2.0 * w * (y - s) / B
+        return L, g
     sp, sn = s[:B], s[B:]
     g = np.zeros_like(s)
     if loss == "skip-gram":
@@ -219,7 +233,7 @@ def step_matmul(EU, EV, uid, cid, scheme, loss, neg_loss_weight, gamma, u_reg=0.
                 dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], col_ids, dV))
 
 
-def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, norm_u=False, norm_v=False):
+def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, norm_u=False, norm_v=False, y_true=None):
     """One 'original' / 'group_sample' batch: (1+k)B listed pairs, row-wise dot
     (modules/interaction/interaction_dot.py:92-99), get_original_loss.  The regulariser averages over all
     (1+k)B gathered user rows (utils/utilities.py:129-135: K.mean over axis 0 of the layer output)."""
@@ -230,7 +244,7 @@ def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, no
     U, inv_u = l2_normalize(U_raw) if norm_u else (U_raw, None)
     V, inv_v = l2_normalize(V_raw) if norm_v else (V_raw, None)
     s = np.sum(U * V, axis=1)
-    L, g = original_loss_grad(s, B, k, loss, neg_loss_weight, gamma)
+    L, g = original_loss_grad(s, B, k, loss, neg_loss_weight, gamma, y_true)
     dU = g[:, None] * V
     dV = g[:, None] * U
     if norm_u:
@@ -240,6 +254,65 @@ def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, no
     reg = u_reg * np.sum(np.mean(U_raw ** 2, axis=0))
     dU = dU + 2.0 * u_reg * U_raw / n
     return dict(loss=L + reg, task_loss=L, s=s,
+                dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], cid, dV))
+
+
+def sampled_neg_shared_loss_grad(pred, loss, neg_loss_weight, gamma):
+    """get_sampled_neg_shared_loss, utils/objectives.py:120-161.  pred [B, 1+k]: column 0 = the positive's score,
+    columns 1.. = scores against the k shared sampled negatives.  Returns (loss, dL/dpred)."""
+    pred = np.asarray(pred)
+    B, k = pred.shape[0], pred.shape[1] - 1
+    G = np.zeros_like(pred)
+    if loss in ("max-margin", "log-loss"):
+        D = pred[:, :1] - pred[:, 1:]                                # :131, :135
+        if loss == "max-margin":
+            L = np.mean(np.maximum(gamma - D, 0.0))                  # :132
+            A = -((gamma - D) > 0).astype(pred.dtype) / (B * k)
+        else:
+            L = np.mean(-log_sigmoid(gamma * D))                     # :136
+            A = -gamma * sigmoid(-gamma * D) / (B * k)
+        G[:, 1:] = -A
+        G[:, 0] = A.sum(axis=1)
+    elif loss == "skip-gram":
+        w = np.ones_like(pred); w[:, 1:] = neg_loss_weight / k       # :138-141
+        y = np.ones_like(pred); y[:, 1:] = -1.0                      # :142-144
+        L = np.sum(-w * log_sigmoid(y * pred)) / B                   # :145-146
+        G = -w * y * sigmoid(-y * pred) / B
+    elif loss == "mse":
+        w = np.ones_like(pred); w[:, 1:] = neg_loss_weight / k       # :148-151
+        y = np.ones_like(pred); y[:, 1:] = 0.0                       # :152-154
+        L = np.sum(w * (pred - y) ** 2) / B                          # :155-156
+        G = 2.0 * w * (pred - y) / B
+    else:
+        raise AssertionError("[ERROR!] loss %s not specified." % loss)
+    return L, G
+
+
+def step_sampled_neg_shared(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, norm_u=False, norm_v=False):
+    """One 'sampled_neg_shared' batch of B + k rows: rows [0, B) are positive (user, item) links, rows [B, B+k) carry
+    the k sampled negative items (and a dummy user id, 0 in models/train_sampled_neg_shared.py:28).
+    Graph: models/model_framework.py:113-118 (front / back split), :138-143 (pred = [mul(front), matmul(U_front,
+    C_back^T)]); the activity regulariser sees the Embedding output of ALL B + k user ids (utils/utilities.py:129-135)."""
+    uid = np.asarray(uid); cid = np.asarray(cid)
+    n = uid.shape[0]
+    assert n == B + k
+    U_raw, V_raw = EU[uid], EV[cid]
+    U, inv_u = l2_normalize(U_raw) if norm_u else (U_raw, None)
+    V, inv_v = l2_normalize(V_raw) if norm_v else (V_raw, None)
+    Uf, Vf, Vb = U[:B], V[:B], V[B:]
+    pred = np.concatenate([np.sum(Uf * Vf, axis=1, keepdims=True), Uf @ Vb.T], axis=1)
+    L, G = sampled_neg_shared_loss_grad(pred, loss, neg_loss_weight, gamma)
+    dU = np.zeros_like(U); dV = np.zeros_like(V)
+    dU[:B] = G[:, :1] * Vf + G[:, 1:] @ Vb
+    dV[:B] = G[:, :1] * Uf
+    dV[B:] = G[:, 1:].T @ Uf
+    if norm_u:
+        dU = l2_normalize_bwd(U, inv_u, dU)
+    if norm_v:
+        dV = l2_normalize_bwd(V, inv_v, dV)
+    reg = u_reg * np.sum(np.mean(U_raw ** 2, axis=0))
+    dU = dU + 2.0 * u_reg * U_raw / n
+    return dict(loss=L + reg, task_loss=L, pred=pred, dU_rows=dU, dV_rows=dV,
                 dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], cid, dV))
 
 
@@ -353,6 +426,100 @@ def assemble_group_sample_batch(train_batch_p, k, neg_users, neg_sign):
 # ---------------------------------------------------------------------------------------------
 # negative sampler (sampler/nodesampler.cpp)
 # ---------------------------------------------------------------------------------------------
+def presample_rows(train_p, k, negs, neg_col, neg_sign, layout):
+    """The (1+k)N rows models/train_presample.py builds each epoch from the (already shuffled) positives and N k
+    sampled ids `negs` (negs[p k + j] = j-th negative of positive p).
+    layout 0 (shuffle_st 'original' / 'reverse', :46-60): train_p.repeat(1+k); column neg_col <- samples; column 2 <-
+    neg_sign; every (1+k)-th row restored to the positive.  layout 1 (:61-65): vstack((train_p, train_n))."""
+    train_p = np.asarray(train_p)
+    n = train_p.shape[0]
+    negs = np.asarray(negs).reshape(n, k)
+    if layout == 0:
+        out = train_p.repeat(1 + k, axis=0)
+        blk = out.reshape(n, 1 + k, 3)
+        blk[:, 1:, neg_col] = negs
+        blk[:, 1:, 2] = neg_sign
+        return blk.reshape(-1, 3)
+    train_n = train_p.repeat(k, axis=0)
+    train_n[:, neg_col] = negs.reshape(-1)
+    train_n[:, 2] = neg_sign
+    return np.vstack((train_p, train_n))
+
+
+def assemble_sns_batch(train_batch_p, k, neg_items):
+    """models/train_sampled_neg_shared.py:28,46-49: B positives + k rows (0, sampled item, 0)."""
+    train_batch_n = np.zeros((k, 3), dtype=train_batch_p.dtype)
+    train_batch_n[:, 1] = neg_items
+    return np.vstack((train_batch_p, train_batch_n))
+
+
+class GroupSamplerOracle(object):
+    """Restatement of class GroupSampler, configs/data_utils.py:244-408, with every random draw taken from one explicit
+    np.random.RandomState (the reference mixes np.random, `random` and its time-seeded C++ sampler).  The two inner
+    samplers are the analytic distributions of get_sampler (:193-215): p ∝ degree^power over ids with degree > 0."""
+
+    def __init__(self, train, group_by="item", chop=1, neg_dist="unigram", neg_sign=0, neg_sampling_power=0.75, rng=None):
+        self.rng = np.random.RandomState(0) if rng is None else rng
+        no_correction = neg_dist == "uniform_no_correction"           # :253-257
+        if no_correction:
+            neg_dist = "uniform"
+        self.chop, self.neg_sign, self.group_by = chop, neg_sign, group_by
+        gcol, mcol = (1, 0) if group_by == "item" else (0, 1)        # :267-272
+        train = np.asarray(train)
+        gdeg = np.bincount(train[:, gcol]).astype(np.float64)
+        mdeg = np.bincount(train[:, mcol]).astype(np.float64)
+        self.p_group = gdeg / gdeg.sum()                              # :281-282 unigram, power 1
+        mw = np.where(mdeg > 0, 1.0 if neg_dist == "uniform" else mdeg ** neg_sampling_power, 0.0)
+        self.p_member = mw / mw.sum()                                 # :283-285
+        gset = np.nonzero(gdeg)[0]
+        self.p_n_div_p_d = np.ones(gdeg.size)                         # :287-299
+        if neg_dist == "uniform" and not no_correction:
+            self.p_n_div_p_d[gset] = 1.0 / gset.size / self.p_group[gset]
+        order = np.argsort(train[:, gcol], kind="stable")            # :301-304 (members in train order)
+        self.members = train[order, mcol]
+        self.indptr = np.concatenate([[0], np.cumsum(np.bincount(train[:, gcol]))])
+
+    def _members(self, group, n):
+        lo, hi = self.indptr[group], self.indptr[group + 1]
+        return self.members[lo + self.rng.randint(0, hi - lo, size=n)]   # np.random.choice(gms, chop), :322
+
+    def sample(self, batch_size_p, strict_return_shape=True):
+        n_groups = int(np.ceil(float(batch_size_p) / self.chop)) if strict_return_shape else batch_size_p // self.chop
+        groups = self.rng.choice(self.p_group.size, size=n_groups, p=self.p_group)          # :318
+        mem = np.concatenate([self._members(g, self.chop) for g in groups])
+        out = np.stack([mem, np.repeat(groups, self.chop), np.ones(mem.size, dtype=np.int64)], 1)   # :324-329
+        if self.group_by == "user":
+            out = out[:, [1, 0, 2]]
+        return out[:batch_size_p] if strict_return_shape else out
+
+    def sample_with_negs(self, batch_size_p, k):
+        whole = batch_size_p * (1 + k)
+        gpos, mpos, gneg, mneg = [], [], [], []
+
+        def add(groups):                                              # :352-364
+            for g in groups:
+                mpos.append(self._members(g, self.chop)); gpos.extend([g] * self.chop)
+                x = k * self.chop * self.p_n_div_p_d[g]
+                nn = int(x) + int(self.rng.random_sample() < x - int(x))   # random_rounding
+                if nn > 0:
+                    gneg.extend([g] * nn)
+                    mneg.append(self.rng.choice(self.p_member.size, size=nn, p=self.p_member))
+
+        add(self.rng.choice(self.p_group.size, size=int(np.ceil(float(batch_size_p) / self.chop)), p=self.p_group))
+        for _ in range(10):                                           # :366-381
+            diff = whole - (len(gpos) + len(gneg))
+            if diff <= 0:
+                break
+            add(self.rng.choice(self.p_group.size, size=diff if diff <= 100 else diff // (self.chop * (1 + k)) + 100,
+                                p=self.p_group))
+        pos = np.stack([np.concatenate(mpos), np.array(gpos), np.ones(len(gpos), dtype=np.int64)], 1)
+        neg = np.stack([np.concatenate(mneg), np.array(gneg), np.full(len(gneg), self.neg_sign, dtype=np.int64)], 1)
+        out = np.vstack((pos, neg))                                   # :383-399
+        if self.group_by == "user":
+            out = out[:, [1, 0, 2]]
+        return out[:whole]
+
+
 def sampler_probabilities(dist, power):
     """Target distribution of NodeSampler::set_table, sampler/nodesampler.cpp:29-49: p_i ∝ deg_i^power for
     deg_i > 0, zero-degree ids never sampled (:34,:39)."""
