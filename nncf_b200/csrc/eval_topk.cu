@@ -111,7 +111,8 @@ __device__ __forceinline__ void coop_chunk(int L, const float* stage, uint32_t c
 
 // one 128-column tile held in registers as v[4][32]; lists = this warp's 32 rows x KP keys in shared memory
 __device__ __forceinline__ void filter_tile(const float (&v)[4][32], uint32_t col0, uint32_t col_end, RowState& st, bool row_ok,
-                                            uint64_t* lists_warp, int KP, int k, float* stage, int lane, unsigned own_mask) {
+                                            uint64_t* lists_warp, int KP, int k, float* stage, int lane, unsigned own_mask,
+                                            bool skip_hits = false) {
   float gm[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -127,6 +128,7 @@ __device__ __forceinline__ void filter_tile(const float (&v)[4][32], uint32_t co
   // several warps read the same 32 TMEM lanes; each handles only the rows it owns (own_mask), so the serial
   // candidate work of a quadrant is split between them while every row still has exactly one owner
   unsigned hits = __ballot_sync(0xffffffffu, row_ok && m >= st.thr) & own_mask;
+  if (skip_hits) { if (hits == 0x12345678u) st.minpos = 1; st.thr = fmaxf(st.thr, m - 1.0f); return; }   // developer switch: fast path only
   while (hits) {
     const int L = __ffs(hits) - 1;
     hits &= hits - 1;
@@ -211,7 +213,9 @@ struct EvalArgs {
   int nsplit, tiles_per_split;
   int nstages;                                // V stages in flight (shared memory left after the top-k sets)
   uint64_t* lists;                            // [n_user_blocks*128][nsplit][KP]  unsorted k-best sets per split
-  int dbg_mode;                               // developer switch (env NNCF_EVAL_DBG): 1 = skip the filter, 2 = also the TMEM loads
+  int prefetch_ahead;                         // second-generation kernel: L2 prefetch distance in tiles (0 = off)
+  int cap;                                    // second-generation kernel: keys per row buffer (multiple of 32, >= KP + 32)
+  int dbg_mode;                               // developer switch (env NNCF_EVAL_DBG): 1 = skip the filter, 2 = also the TMEM loads, 3 = row maxima + ballot only
 };
 
 constexpr int kEvalRowGroups = 2;                 // epilogue warps per TMEM lane quadrant; each owns 32 / kEvalRowGroups rows
@@ -337,13 +341,304 @@ eval_topk_tc_kernel(EvalArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
-      if (a.dbg_mode >= 1) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) rs.minpos = 1; continue; }
-      filter_tile(v, static_cast<uint32_t>((t0 + (j + rot) % nj) * 128), col_end, rs, row_ok, lists_warp, a.KP, a.k, stage, lane, own_mask);
+      if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) rs.minpos = 1; continue; }
+      filter_tile(v, static_cast<uint32_t>((t0 + (j + rot) % nj) * 128), col_end, rs, row_ok, lists_warp, a.KP, a.k, stage, lane, own_mask,
+                  a.dbg_mode == 3);
     }
     __syncwarp();
     const int64_t gstride = (int64_t)a.nsplit * a.KP;
     store_lists(lists_warp + rg * kOwn * a.KP, a.KP,
                 a.lists + ((int64_t)ub * 128 + q * 32 + rg * kOwn) * gstride + (int64_t)sp * a.KP, gstride, lane, kOwn);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();     // nobody exits while a peer may still multicast into it or signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// tcgen05 eval kernel, second generation (the default).  Measured on B200 with the kernel above (37,888 users x 1M
+// items, d = 128, k = 50): the MMA pipeline ALONE needed 1,326 cycles per 128 x 128 x 128 tile against a 512-cycle
+// tensor floor, because an SS-mode M = N = 128 MMA fetches 8 KiB of operands per 64 cycles = the whole 128 B/clk
+// shared-memory port, on top of the bulk-copy fills; and the exact streaming insertion cost ~1,900 warp-cycles per
+// candidate (a serial arg-min chain), 3,373 cycles per tile in total.  Changes:
+//   * the user block is the A operand of every MMA of the CTA: it is written ONCE into tensor memory (DP / 2 columns,
+//     two bf16 per column) and read from there (tcgen05.mma with a TMEM A operand), so shared memory serves only the
+//     item tiles; 3 accumulators of 128 columns (3 x 128 + DP / 2 <= 512 columns);
+//   * every accumulator is read from TMEM once: 4 epilogue warps, one per lane quadrant, 32 rows each (kEval2RowGroups);
+//   * top-k by APPEND + lazy compaction: a row keeps up to CAP > k keys in shared memory and a threshold that is exact
+//     as of its last compaction.  A 32-score chunk that reaches the threshold appends all its candidates with ONE
+//     ballot (no per-candidate loop); when fewer than 32 slots are left the warp selects the row's k largest keys
+//     (radix select on the ordered score bits in registers: 32 x REDUX, then ties by column) and raises the
+//     threshold.  A stale threshold only admits extra candidates, never loses one, so the result is still exact:
+//     score descending, then lowest column.  ~k (CAP - k)^-1 ln(I / k) compactions per row instead of an arg-min per
+//     candidate.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEval2RowGroups = 1;                // epilogue warps per TMEM lane quadrant.  Measured (37,888 x 1M, k = 50): 1 -> 19.5 ms,
+                                                  // 2 (both read the accumulator, 16 rows each, row maxima duplicated) -> 21.9 ms
+constexpr int kEval2EpiWarps = 4 * kEval2RowGroups;
+constexpr int kEval2Threads = 64 + 32 * kEval2EpiWarps;
+constexpr int kEval2Acc = 3;
+constexpr int kEval2MaxNK = 6;                    // CAP <= 192 keys per row
+
+__host__ __device__ inline size_t eval2_smem_bytes(int nsub, int nstages, int cap) {
+  return (size_t)nsub * kSubBytes * nstages + (size_t)128 * cap * 8 + kEval2EpiWarps * 32 * 4 + 1024 + 256;
+}
+
+// the row's n > k keys (buf[0..n)) -> its k largest at buf[0..k); returns the score of the k-th as the new threshold.
+// Warp-cooperative; n, k warp-uniform; keys are unique (they embed the column).
+__device__ __forceinline__ float compact_row(uint64_t* buf, int n, int k, int lane) {
+  uint32_t hi[kEval2MaxNK], lo[kEval2MaxNK];
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) {
+    const int idx = lane + 32 * i;
+    const uint64_t key = idx < n ? buf[idx] : 0ull;
+    hi[i] = static_cast<uint32_t>(key >> 32); lo[i] = static_cast<uint32_t>(key);
+  }
+  __syncwarp();
+  uint32_t T = 0;                                   // largest T with #(hi >= T) >= k  ==  high word of the k-th key
+#pragma unroll 1
+  for (int b = 31; b >= 0; --b) {
+    const uint32_t c = T | (1u << b);
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < kEval2MaxNK; ++i) cnt += (hi[i] >= c) ? 1 : 0;
+    if (__reduce_add_sync(0xffffffffu, cnt) >= k) T = c;
+  }
+  int gt = 0, eq = 0;
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) { gt += (hi[i] > T) ? 1 : 0; eq += (hi[i] == T) ? 1 : 0; }
+  gt = __reduce_add_sync(0xffffffffu, gt);
+  eq = __reduce_add_sync(0xffffffffu, eq);
+  const int need = k - gt;                          // 1 <= need <= eq keys of score T survive
+  uint32_t TL = 0;
+  if (eq > need) {                                  // equal scores straddle the boundary: lowest columns (largest low words) win
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+      const uint32_t c = TL | (1u << b);
+      int cnt = 0;
+#pragma unroll
+      for (int i = 0; i < kEval2MaxNK; ++i) cnt += (hi[i] == T && lo[i] >= c) ? 1 : 0;
+      if (__reduce_add_sync(0xffffffffu, cnt) >= need) TL = c;
+    }
+  }
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) {
+    const bool keep = hi[i] > T || (hi[i] == T && lo[i] >= TL && hi[i] != 0u);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(m & lt)] = (static_cast<uint64_t>(hi[i]) << 32) | lo[i];
+    base += __popc(m);
+  }
+  __syncwarp();
+  return key_score(static_cast<uint64_t>(T) << 32);
+}
+
+struct Row2 {
+  float thr;     // a lower bound of the row's k-th best score (exact as of the last compaction; -inf before k keys exist)
+  int cnt;       // keys in the row's buffer
+};
+
+__device__ __forceinline__ void filter_tile2(const float (&v)[4][32], uint32_t col0, uint32_t col_end, Row2& st, bool row_ok,
+                                             uint64_t* bufs_warp, int CAP, int k, float* stage, int lane, unsigned own_mask,
+                                             bool skip_hits) {
+  float gm[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float m8[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const float* w = v[c] + g * 8;
+      m8[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
+    }
+    gm[c] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+  }
+  const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+  unsigned hits = __ballot_sync(0xffffffffu, row_ok && m >= st.thr) & own_mask;
+  if (skip_hits) { if (hits == 0x12345678u) st.cnt = 1; st.thr = fmaxf(st.thr, m - 1.0f); return; }   // developer switch
+  const unsigned lt = (1u << lane) - 1u;
+  while (hits) {
+    const int L = __ffs(hits) - 1;
+    hits &= hits - 1;
+    float thr_l = __shfl_sync(0xffffffffu, st.thr, L);
+    int cnt_l = __shfl_sync(0xffffffffu, st.cnt, L);
+    uint64_t* buf = bufs_warp + (size_t)L * CAP;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float gmc = __shfl_sync(0xffffffffu, gm[c], L);
+      if (gmc >= thr_l && col0 + c * 32 < col_end) {    // warp-uniform
+        if (lane == L) {
+#pragma unroll
+          for (int t = 0; t < 32; t += 4)
+            *reinterpret_cast<float4*>(stage + t) = make_float4(v[c][t], v[c][t + 1], v[c][t + 2], v[c][t + 3]);
+        }
+        __syncwarp();
+        const float x = stage[lane];
+        const uint32_t col = col0 + c * 32 + lane;
+        const bool cand = (col < col_end) && (x >= thr_l);
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        if (cand) buf[cnt_l + __popc(cm & lt)] = make_key(x, col);
+        cnt_l += __popc(cm);
+        __syncwarp();
+        if (cnt_l > CAP - 32) {                         // fewer than 32 free slots: keep the k best, raise the threshold
+          thr_l = compact_row(buf, cnt_l, k, lane);
+          cnt_l = k;
+        }
+      }
+    }
+    if (lane == L) { st.thr = thr_l; st.cnt = cnt_l; }
+  }
+}
+
+template <int NSUB, int CL>
+__global__ void __launch_bounds__(kEval2Threads, 1)
+eval_topk_tc2_kernel(EvalArgs a) {
+  constexpr int DP = 64 * NSUB;
+  constexpr int kColU = kEval2Acc * 128;            // TMEM: 3 accumulators, then the user block (DP / 2 columns)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int nst = a.nstages, CAP = a.cap;
+  uint8_t* sV = smem;
+  uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);    // [128][CAP]
+  float* stage_all = reinterpret_cast<float*>(bufs_sm + 128 * CAP);                // [4 warps][32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + kEval2EpiWarps * 32);
+  uint64_t* u_full = bars;
+  uint64_t* v_full = bars + 1;    // [4]
+  uint64_t* v_empty = bars + 5;   // [4]
+  uint64_t* s_full = bars + 9;    // [3]
+  uint64_t* s_empty = bars + 13;  // [3]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ub = blockIdx.x, sp = blockIdx.y;
+  const int n_tiles = static_cast<int>((a.n_items + 127) >> 7);
+  const int t0 = sp * a.tiles_per_split;
+  const int t1 = min(n_tiles, t0 + a.tiles_per_split);
+  const int nj = max(0, t1 - t0);
+  const int rot = nj > 0 ? static_cast<int>((static_cast<unsigned>(ub / CL) * 37u + static_cast<unsigned>(sp) * 11u) % static_cast<unsigned>(nj)) : 0;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
+
+  if (tid == 0) {
+    mbar_init(u_full, 4);
+    for (int s = 0; s < 4; ++s) { mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], CL); }
+    for (int s = 0; s < kEval2Acc; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kEval2EpiWarps); }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();     // peers' barriers are initialised before anybody multicasts into this CTA
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nj > 0) {
+      for (int j = 0; j < nj; ++j) {
+        const int st = j % nst;
+        mbar_wait(&v_empty[st], ((j / nst) & 1) ^ 1);
+        mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
+        const int jj = (j + rot) % nj;
+        const uint8_t* gV = a.Vimg + (size_t)(t0 + jj) * NSUB * kSubBytes;
+        constexpr uint32_t kSlice = NSUB * kSubBytes / CL;        // my share of the tile, delivered to every CTA
+        if (a.prefetch_ahead > 0 && j + a.prefetch_ahead < nj) {
+          // the copy is latency-bound (3 stages cover ~1.5k cycles, a DRAM miss takes longer): pull my share of a tile
+          // further ahead into L2 now
+          const uint8_t* gP = a.Vimg + (size_t)(t0 + (j + a.prefetch_ahead + rot) % nj) * NSUB * kSubBytes + (size_t)crank * kSlice;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gP), "r"(kSlice) : "memory");
+        }
+        if (CL > 1) {
+          bulk_g2s_multicast(sV + st * NSUB * kSubBytes + crank * kSlice, gV + (size_t)crank * kSlice, kSlice, &v_full[st], kMask);
+        } else {
+          for (int s = 0; s < NSUB; ++s)
+            bulk_g2s(sV + (st * NSUB + s) * kSubBytes, gV + (size_t)s * kSubBytes, kSubBytes, &v_full[st]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nj > 0) {
+      const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      mbar_wait(u_full, 0);                                       // the user block sits in TMEM
+      tc_fence_after();
+      for (int j = 0; j < nj; ++j) {
+        const int st = j % nst, sb = j % kEval2Acc;
+        mbar_wait(&v_full[st], (j / nst) & 1);
+        mbar_wait(&s_empty[sb], ((j / kEval2Acc) & 1) ^ 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < DP / 16; ++k) {                       // K = 16 per MMA = 8 TMEM columns of the user block
+          const uint64_t bd = make_smem_desc(smem_u32(sV + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
+          umma_bf16_ts(tmem + sb * 128, tmem + kColU + 8 * k, bd, idesc, k > 0);
+        }
+        umma_commit(&s_full[sb]);
+        if (CL > 1) umma_commit_multicast(&v_empty[st], kMask);   // the stage is rewritten by all CL producers
+        else umma_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int il = q * 32 + lane;
+    const int64_t urow = (int64_t)ub * 128 + il;
+    const bool row_ok = urow < a.n_users;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const int rg = (warp - 2) >> 2;                                // row group inside the quadrant
+    constexpr int kOwn = 32 / kEval2RowGroups;
+    const unsigned own_mask = (kOwn == 32 ? 0xffffffffu : ((1u << kOwn) - 1u)) << (rg * kOwn);
+    // my user's row -> bf16 pairs -> TMEM columns kColU .. (row = lane): the A operand of every MMA of this CTA
+    if (rg == 0) {
+      const float* u = a.Uf + (row_ok ? urow : 0) * a.d;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + 2 * i;
+          const float x0 = (row_ok && c < a.d) ? __ldg(u + c) : 0.0f;
+          const float x1 = (row_ok && c + 1 < a.d) ? __ldg(u + c + 1) : 0.0f;
+          pk[i] = pack_bf16x2(x0, x1);
+        }
+        tmem_st16(tmem + lane_addr + kColU + c0 / 2, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(u_full);
+    }
+    Row2 rs; rs.thr = -INFINITY; rs.cnt = 0;
+    uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * CAP;
+    float* stage = stage_all + (warp - 2) * 32;
+    const uint32_t col_end = static_cast<uint32_t>(a.n_items);
+    for (int j = 0; j < nj; ++j) {
+      const int sb = j % kEval2Acc;
+      mbar_wait(&s_full[sb], (j / kEval2Acc) & 1);
+      tc_fence_after();
+      float v[4][32];
+      if (a.dbg_mode != 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+      if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) rs.cnt = 1; continue; }
+      filter_tile2(v, static_cast<uint32_t>((t0 + (j + rot) % nj) * 128), col_end, rs, row_ok, bufs_warp, CAP, a.k, stage, lane,
+                   own_mask, a.dbg_mode == 3);
+    }
+    __syncwarp();
+    // final compaction of every row to its k best, then the row's KP slots go to the global per-(user, split) lists
+    const int64_t gstride = (int64_t)a.nsplit * a.KP;
+    uint64_t* grow0 = a.lists + ((int64_t)ub * 128 + q * 32) * gstride + (int64_t)sp * a.KP;
+    for (int r = rg * kOwn; r < (rg + 1) * kOwn; ++r) {
+      int n = __shfl_sync(0xffffffffu, rs.cnt, r);
+      uint64_t* buf = bufs_warp + (size_t)r * CAP;
+      if (n > a.k) { compact_row(buf, n, a.k, lane); n = a.k; }
+      for (int i = lane; i < a.KP; i += 32) grow0[r * gstride + i] = i < n ? buf[i] : 0ull;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -554,6 +849,7 @@ static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 struct EvalPlan {
   int dp, nsub, KP, nsplit, nstages, tiles_per_split, n_tiles, cl;
+  int v2, cap, nstages2;      // second-generation tensor-core kernel: usable, keys per row buffer, V stages
   int64_t n_ub_grid;
   int64_t n_ub, users_pad, items_pad;
   size_t off_uimg, off_vimg, off_lists, off_end;
@@ -569,7 +865,7 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->KP = kpad_of(topk);
   p->n_ub = (n_users + 127) / 128;
   p->cl = (precision == NNCF_PREC_BF16 && p->n_ub >= kEvalCluster) ? kEvalCluster : 1;
-  { const char* e = getenv("NNCF_EVAL_CL"); if (e && precision == NNCF_PREC_BF16) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) p->cl = v; } }   // developer override
+  { const char* e = getenv("NNCF_EVAL_CL"); if (e && precision == NNCF_PREC_BF16) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) p->cl = v; } }   // developer override (8: second-generation kernel only)
   p->n_ub_grid = (p->n_ub + p->cl - 1) / p->cl * p->cl;
   p->users_pad = p->n_ub_grid * 128;
   p->n_tiles = static_cast<int>((n_items + 127) / 128);
@@ -588,9 +884,16 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->off_lists = take((size_t)p->users_pad * p->nsplit * p->KP * 8);
   p->off_end = off + 1024;
   p->nstages = 0;
+  p->v2 = 0; p->cap = 0; p->nstages2 = 0;
   if (precision == NNCF_PREC_BF16) {
     for (int st = 4; st >= 1; --st)
       if (eval_smem_bytes(p->nsub, st, p->KP) <= 232448) { p->nstages = st; break; }
+    // second generation: the largest row buffer (fewest compactions) that still leaves 3 (else 2) item-tile stages
+    static const bool v1_env = [] { const char* e = getenv("NNCF_EVAL_V1"); return e && atoi(e) != 0; }();
+    for (int st = 3; st >= 2 && !p->v2 && !v1_env; --st)
+      for (int cap = 2 * p->KP > 192 ? 192 : (2 * p->KP < 96 ? 96 : 2 * p->KP); cap >= p->KP + 32; cap -= 32)
+        if (eval2_smem_bytes(p->nsub, st, cap) <= 232448) { p->v2 = 1; p->cap = cap; p->nstages2 = st; break; }
+    if (p->v2) p->nstages = p->nstages2;
     if (p->nstages == 0) {
       set_error("eval (bf16): top-k sets of k > 64 do not fit next to dim > 128 operands; use k <= 64 or precision fp32");
       return NNCF_EUNSUPPORTED;
@@ -623,8 +926,32 @@ static int launch_eval_tc_cl(const EvalArgs& ea, const EvalPlan& p, cudaStream_t
   NNCF_LAUNCH_OK();
   return 0;
 }
+template <int NSUB, int CL>
+static int launch_eval_tc2_cl(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  const size_t smem = eval2_smem_bytes(NSUB, p.nstages2, p.cap);
+  NNCF_CUDA(cudaFuncSetAttribute(eval_topk_tc2_kernel<NSUB, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.n_ub_grid, p.nsplit, 1);
+  cfg.blockDim = dim3(kEval2Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNCF_CUDA(cudaLaunchKernelEx(&cfg, eval_topk_tc2_kernel<NSUB, CL>, ea));
+  NNCF_LAUNCH_OK();
+  return 0;
+}
 template <int NSUB>
 static int launch_eval_tc(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  if (p.v2) {
+    if (p.cl == 8) return launch_eval_tc2_cl<NSUB, 8>(ea, p, st);
+    if (p.cl == 4) return launch_eval_tc2_cl<NSUB, 4>(ea, p, st);
+    if (p.cl == 2) return launch_eval_tc2_cl<NSUB, 2>(ea, p, st);
+    return launch_eval_tc2_cl<NSUB, 1>(ea, p, st);
+  }
   if (p.cl == 4) return launch_eval_tc_cl<NSUB, 4>(ea, p, st);
   if (p.cl == 2) return launch_eval_tc_cl<NSUB, 2>(ea, p, st);
   return launch_eval_tc_cl<NSUB, 1>(ea, p, st);
@@ -645,13 +972,17 @@ extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const
   EvalArgs ea{};
   ea.Uf = user_rows_dev; ea.Vf = item_rows_dev; ea.n_users = n_users; ea.n_items = n_items; ea.d = dim; ea.dp = p.dp;
   ea.k = topk; ea.KP = p.KP; ea.nsplit = p.nsplit; ea.nstages = p.nstages; ea.tiles_per_split = p.tiles_per_split;
+  ea.cap = p.cap;
+  { const char* e = getenv("NNCF_EVAL_PF"); ea.prefetch_ahead = e ? atoi(e) : 0; }   // measured: no effect (the stream is not DRAM-latency-bound)
   { const char* e = getenv("NNCF_EVAL_DBG"); ea.dbg_mode = e ? atoi(e) : 0; }
   ea.lists = reinterpret_cast<uint64_t*>(ws + p.off_lists);
   if (precision == NNCF_PREC_BF16) {
     ea.Uimg = ws + p.off_uimg; ea.Vimg = ws + p.off_vimg;
-    rows_to_img_kernel<<<ceil_div(p.users_pad, 8), 256, 0, st>>>(user_rows_dev, n_users, dim, p.nsub,
-                                                                 const_cast<uint8_t*>(ea.Uimg), p.users_pad);
-    NNCF_LAUNCH_OK();
+    if (!p.v2) {   // (the second-generation kernel converts its user block itself, straight into tensor memory)
+      rows_to_img_kernel<<<ceil_div(p.users_pad, 8), 256, 0, st>>>(user_rows_dev, n_users, dim, p.nsub,
+                                                                   const_cast<uint8_t*>(ea.Uimg), p.users_pad);
+      NNCF_LAUNCH_OK();
+    }
     rows_to_img_kernel<<<ceil_div(p.items_pad, 8), 256, 0, st>>>(item_rows_dev, n_items, dim, p.nsub,
                                                                  const_cast<uint8_t*>(ea.Vimg), p.items_pad);
     NNCF_LAUNCH_OK();
