@@ -68,6 +68,30 @@ def synth_links_device(n_links, n_users, n_items, seed, torch):
     return out
 
 
+def synth_block_device(n_links, n_users_local, n_items_local, world, seed, torch):
+    """links of ONE stratified block with LOCAL ids: the rank's shard of a power-law id space is itself (about) a power
+    law over its local rows, p(j) ∝ (j + 10 / N)^-a (the ids of shard s are every N-th rank of a random permutation)"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+
+    def draw(n_ids, expo, perm_seed, n):
+        p = torch.pow(torch.arange(n_ids, device="cuda", dtype=torch.float64) + 10.0 / world, -expo)
+        cdf = torch.cumsum(p, 0)
+        cdf = cdf / cdf[-1]
+        r = torch.searchsorted(cdf, torch.rand(n, device="cuda", generator=g, dtype=torch.float64), right=True)
+        r.clamp_(max=n_ids - 1)
+        perm = torch.randperm(n_ids, device="cuda", generator=torch.Generator(device="cuda").manual_seed(perm_seed))
+        return perm[r].to(torch.int32)
+
+    uid = torch.empty(n_links, dtype=torch.int32, device="cuda")
+    cid = torch.empty(n_links, dtype=torch.int32, device="cuda")
+    chunk = 20_000_000
+    for s in range(0, n_links, chunk):
+        n = min(chunk, n_links - s)
+        uid[s:s + n] = draw(n_users_local, 0.8, 124, n)
+        cid[s:s + n] = draw(n_items_local, 1.0, 123, n)
+    return uid, cid
+
+
 class ClockSampler(threading.Thread):
     """samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
 
@@ -163,42 +187,73 @@ def run_ours(args):
     R, B, d = args.replicas, BATCH, DIM
     links_per_step = R * B
 
-    # ---- resident state.  N = 1: the two 1M x 128 tables live on the GPU.  N > 1: the SAME global tables are sharded by
-    #      row over the ranks (owner = id mod N, peer memory over NVLink) and every rank trains on its own links (weak
-    #      scaling: per-GPU work fixed).  Links are shuffled once on the device; np.random.shuffle semantics are
-    #      exercised by the parity tests, the order itself is not part of the timed hot path.
+    # ---- resident state.  N = 1: the two 1M x 128 tables live on the GPU.  N > 1 (weak scaling: per-GPU work fixed, every
+    #      rank trains on its own links of the SAME global 1M x 1M problem):
+    #        stratified (default): DSGD schedule, tables sharded by row, rank r owns user shard r and the item shards rotate
+    #          round the ring between sub-epochs; every step touches local rows only (nncf_b200/parallel.py)
+    #        peer: rows read and updated in the owners' shards over NVLink peer memory inside the step kernels
+    #      Links are shuffled once on the device; np.random.shuffle semantics are exercised by the parity tests, the
+    #      order itself is not part of the timed hot path.
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
     spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="sgd",
                     learn_rate=LR, replicas=R, neg_loss_weight=LAMBDA)
-    sharded = None
-    if world > 1:
-        from nncf_b200.parallel import ShardedTrainer
-        sharded = ShardedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
-        step, EU, EV = sharded.step, sharded.users.local, sharded.items.local
-    else:
-        EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
-        EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
-        step = FusedStep(spec)
+    sharded = strat = None
     n_links = args.links
-    train = synth_links_device(n_links, N_USERS, N_ITEMS, 2017 + rank, torch)
-    perm = torch.randperm(n_links, device="cuda", generator=g)
-    train = ops.permute_rows(train, perm)
-    uid_all = train[:, 0].contiguous()
-    cid_all = train[:, 1].contiguous()
-    del train, perm
-    steps_per_pass = n_links // links_per_step
-    assert steps_per_pass >= 1
     loss_buf = torch.empty(max(args.steps, args.warmup, 1) * R, dtype=torch.float32, device="cuda")
+    pos = {"step": 0, "rot": 0}
+    if world > 1 and args.parallelism == "stratified":
+        from nncf_b200.parallel import StratifiedTrainer, shard_rows
+        strat = StratifiedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
+        step = strat.step
+        links_per_block = n_links // world
+        blocks = [synth_block_device(links_per_block, strat.rows_u, shard_rows(N_ITEMS, v, world), world,
+                                     2017 + rank * world + v, torch) for v in range(world)]
+        steps_per_pass = links_per_block // links_per_step          # steps until the item shards rotate
+        assert steps_per_pass >= 1
+        tables = lambda: (strat.users, strat.items)                 # noqa: E731  (the item tensor changes at every rotation)
+        ids_now = lambda: blocks[strat.held]                        # noqa: E731
 
-    def run_steps(k, start_step):
-        """k consecutive steps starting at step index start_step (wraps around the link array between passes)"""
+        def end_of_pass():
+            strat.rotate()
+            pos["rot"] += 1
+    else:
+        if world > 1:
+            from nncf_b200.parallel import ShardedTrainer
+            sharded = ShardedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
+            step, EU, EV = sharded.step, sharded.users.local, sharded.items.local
+        else:
+            EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
+            EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
+            step = FusedStep(spec)
+        train = synth_links_device(n_links, N_USERS, N_ITEMS, 2017 + rank, torch)
+        perm = torch.randperm(n_links, device="cuda", generator=g)
+        train = ops.permute_rows(train, perm)
+        uid_all = train[:, 0].contiguous()
+        cid_all = train[:, 1].contiguous()
+        del train, perm
+        steps_per_pass = n_links // links_per_step
+        assert steps_per_pass >= 1
+        tables = lambda: (EU, EV)                                   # noqa: E731
+        ids_now = lambda: (uid_all, cid_all)                        # noqa: E731
+
+        def end_of_pass():
+            pass
+
+    def run_steps(k, start_step=None):
+        """k consecutive steps from the current position (wraps around the link array / moves to the next stratified
+        block, rotating the item shards, when a pass is exhausted)"""
         done = 0
         while done < k:
-            s0 = (start_step + done) % steps_per_pass
-            n = min(k - done, steps_per_pass - s0)
-            off = s0 * links_per_step
-            step.run(EU, EV, uid_all[off:], cid_all[off:], n, loss_out=loss_buf[done * R:])
+            n = min(k - done, steps_per_pass - pos["step"])
+            off = pos["step"] * links_per_step
+            u, c = ids_now()
+            tu, tv = tables()
+            step.run(tu, tv, u[off:], c[off:], n, loss_out=loss_buf[done * R:])
             done += n
+            pos["step"] += n
+            if pos["step"] == steps_per_pass:
+                pos["step"] = 0
+                end_of_pass()
 
     def barrier():
         if world > 1:
@@ -214,15 +269,25 @@ def run_ours(args):
 
     # ---- value: device-resident throughput ------------------------------------------------------------------
     run_steps(args.warmup, 0)
+    if strat is not None:
+        end_of_pass()            # untimed: the first send/recv sets up the NCCL peer-to-peer channels (~0.3 s)
+        pos["step"] = 0
+        run_steps(min(20, steps_per_pass))
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rot0 = pos["rot"]
     e0.record()
     run_steps(args.steps, args.warmup)
+    if strat is not None and pos["rot"] - rot0 < -(-args.steps // steps_per_pass):
+        # the timed window must carry its share of rotations even when it ends inside a block (rounded UP)
+        pos["step"] = 0
+        end_of_pass()
     e1.record()
     barrier()
+    rotations = pos["rot"] - rot0
     launches = ops.launch_count() - launches0
     sampler.stop_flag = True
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -235,7 +300,8 @@ def run_ours(args):
     #      runs the same number of profiled steps so that the device barriers of the sharded mode pair up)
     step.set_profile(True)
     nprof = min(200, steps_per_pass)
-    step.run(EU, EV, uid_all, cid_all, nprof)
+    pos["step"] = 0
+    run_steps(nprof)
     torch.cuda.synchronize()
     phase_ms, psteps = step.get_profile()
     step.set_profile(False)
@@ -245,9 +311,11 @@ def run_ours(args):
     #      every step copies its own ids H2D (overlapping the previous step's kernels) and its R losses D2H; wall clock
     #      around the call, which returns only when every step and copy has completed.  `per_call` is the same work issued
     #      as one blocking train_on_batch-style call per step (H2D, step, loss.cpu()) from Python.
-    e2e_steps = min(args.steps, 1000, steps_per_pass)
+    e2e_steps = max(1, min(args.steps, 1000, steps_per_pass - 5))
     h_uid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
     h_cid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
+    uid_all, cid_all = ids_now()
+    EU, EV = tables()
     h_uid.copy_(uid_all[:h_uid.numel()].view(h_uid.shape).cpu())
     h_cid.copy_(cid_all[:h_cid.numel()].view(h_cid.shape).cpu())
     h_loss = torch.empty((e2e_steps + 5) * R, dtype=torch.float32).pin_memory()
@@ -255,6 +323,11 @@ def run_ours(args):
     barrier()
     t0 = time.perf_counter()
     step.run_host(EU, EV, h_uid[5:], h_cid[5:], e2e_steps, h_loss)
+    if strat is not None:
+        # e2e carries the rotations of its window too (rounded up to one), synchronised like the step calls
+        end_of_pass()
+        torch.cuda.synchronize()
+        EU, EV = tables()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * e2e_steps * links_per_step / e2e_s
     assert np.isfinite(float(h_loss[:e2e_steps * R].mean())), "e2e training diverged"
@@ -285,12 +358,13 @@ def run_ours(args):
             dist.barrier()
             sharded.close()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same R, B, d)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
         if R == 37:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
@@ -351,8 +425,13 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "batch_size_p": B, "dim": d, "replicas_per_gpu": R, "links_per_step_per_gpu": links_per_step,
                    "links_resident_per_gpu": n_links, "optimizer": "sparse SGD (atomic scatter-add)",
                    "precision": "bf16 operands, fp32 accumulate (tcgen05)",
-                   "parallelism": "1 GPU" if world == 1 else "tables row-sharded over %d GPUs (owner = id mod N), rows read and "
-                                  "updated over NVLink peer memory inside the step kernels, 2 device barriers per step" % world,
+                   "parallelism": "1 GPU" if world == 1 else (
+                       "stratified SGD (DSGD) over %d GPUs: tables row-sharded (owner = id mod N), rank r owns user shard r, item "
+                       "shards rotate round the ring (NCCL send/recv) between sub-epochs of %d steps, every step touches local "
+                       "rows only; %d rotation(s) inside the timed region" % (world, steps_per_pass, rotations)
+                       if strat is not None else
+                       "tables row-sharded over %d GPUs (owner = id mod N), rows read and updated over NVLink peer memory "
+                       "inside the step kernels, 2 device barriers per step" % world),
                    "semantics": "each step = R independent neg_shared batches per GPU against one table snapshot (synchronous "
                                 "data-parallel virtual workers); R=1 (the reference's sequential loop) is reported in `sequential`",
                    "l2": "inputs larger than L2: 1.02 GB of embedding tables, random rows, batches never repeat within a pass"},
@@ -376,6 +455,7 @@ def run_ours(args):
         dist.barrier()
         sharded.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -390,6 +470,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=3000)
     ap.add_argument("--eval-users", type=int, default=75776)   # 4 full waves of 148 CTAs x 128 users
     ap.add_argument("--no-eval", action="store_true")
+    ap.add_argument("--parallelism", default="stratified", choices=["stratified", "peer"])   # N > 1 only
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

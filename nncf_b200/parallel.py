@@ -5,6 +5,18 @@
   `id % N` at local row `id // N`.  Shards are peer-visible allocations (CUDA IPC); the step kernels read and update
   remote rows directly over NVLink (include/nncf_b200.h, section 3b) — no all-to-all staging buffers.
 
+* `StratifiedTrainer`: the schedule that scales.  The step moves ~2 KB of embedding rows per positive link; at the
+  single-GPU rate (7e8 links/s) that is 1.4 TB/s of random row traffic per GPU, more than NVLink 5 carries (0.9 TB/s per
+  direction), so ANY scheme that fetches rows from their owners per step is NVLink-bound (measured with the peer-memory
+  mode: 5.3e8 links/s on 2 GPUs against 7.2e8 on one).  Stratified SGD (Gemulla et al., KDD'11, "DSGD") removes the
+  per-step exchange: links are partitioned into N x N blocks by (user % N, item % N); rank r owns user shard r for good
+  and, in sub-epoch t, holds item shard (r + t) % N and trains ONLY on block (r, (r + t) % N), so every row it touches
+  is local and the single-GPU kernels run unchanged; between sub-epochs the item shards (and their optimizer state)
+  rotate one rank down the ring (one NCCL send/recv of n_items / N rows per rank).  The blocks trained concurrently are
+  disjoint in users AND items, so a sub-epoch equals a sequential pass over its N blocks in any order (checked against
+  the oracle on 2 GPUs, tools/multi_gpu_check.py).  Declared difference to a single-GPU epoch: a batch's shared
+  negatives come from the item shard of its block (a random 1/N of the items under id % N).
+
 The reference is single-process / single-device (no collective anywhere); everything here is the
 B200-native extension and is exercised on CPU with the gloo backend for the host-side logic (tests/test_parallel_cpu.py).
 """
@@ -37,6 +49,43 @@ def local_row(ids, world: int):
 def shard_rows(n_rows: int, rank: int, world: int) -> int:
     """number of rows of a table with n_rows rows that live on `rank` under owner = id % world"""
     return (n_rows - rank + world - 1) // world
+
+
+def held_item_shard(rank: int, sub_epoch: int, world: int) -> int:
+    """item shard held (and trained on) by `rank` during sub-epoch `sub_epoch` of the stratified schedule"""
+    return (rank + sub_epoch) % world
+
+
+def partition_links_by_block(train, rank: int, world: int):
+    """Rows of `train` (int [n, 3]: user, item, label) owned by `rank` (user % world == rank), split by item shard.
+    Returns a list of `world` int32 arrays [n_v, 3] whose ids are LOCAL rows (id // world) of the two shards; the
+    original order is kept inside every block."""
+    train = np.asarray(train)
+    mine = train[train[:, 0] % world == rank]
+    out = []
+    for v in range(world):
+        b = mine[mine[:, 1] % world == v].astype(np.int32, copy=True)
+        b[:, 0] //= world
+        b[:, 1] //= world
+        out.append(b)
+    return out
+
+
+def ring_rotate(tensors, spares, rank: int, world: int, group=None):
+    """Every rank sends each tensor of `tensors` to rank - 1 and receives rank + 1's into the matching tensor of
+    `spares` (same shapes on every rank), then the two lists are swapped: after the call `tensors` holds what rank + 1
+    held.  NCCL on GPUs (ordered with the current stream), gloo on CPU tensors (tests)."""
+    import torch.distributed as dist
+    if world == 1:
+        return tensors, spares
+    dst, src = (rank - 1) % world, (rank + 1) % world
+    ops_ = []
+    for t, sp in zip(tensors, spares):
+        ops_.append(dist.P2POp(dist.isend, t, dst, group))
+        ops_.append(dist.P2POp(dist.irecv, sp, src, group))
+    for req in dist.batch_isend_irecv(ops_):
+        req.wait()
+    return spares, tensors
 
 
 def allreduce_metric_sums(sums, group=None):
@@ -167,3 +216,76 @@ class ShardedTrainer:
         self.step = None
         for m in (self.users.mem, self.items.mem, self.flags):
             m.close()
+
+
+class StratifiedTrainer:
+    """Stratified (DSGD-style) multi-GPU training: rank r keeps user shard r, item shards rotate round the ring between
+    sub-epochs, every step touches local rows only (see the module docstring).  Works with sparse SGD and lazy Adam
+    (the optimizer state of the item shard travels with it)."""
+
+    def __init__(self, spec, n_users: int, n_items: int, rank: int, world: int, seed: int = 7):
+        import torch
+        from .ops import FusedStep
+        self.spec, self.rank, self.world = spec, rank, world
+        self.n_users, self.n_items = n_users, n_items
+        self.rows_u = shard_rows(n_users, rank, world)
+        self.rows_i_max = shard_rows(n_items, 0, world)                 # shard 0 is the largest
+        dev = torch.device("cuda")
+        d = spec.dim
+        # shard s of a table is initialised from (seed, s), independent of the rank that builds it
+        self.users = self._init_shard(self.rows_u, d, seed + 1000 * rank, dev)
+        self.sub_epoch = 0
+        held = held_item_shard(rank, 0, world)
+        self.items = torch.zeros((self.rows_i_max, d), dtype=torch.float32, device=dev)
+        n_held = shard_rows(n_items, held, world)
+        self.items[:n_held] = self._init_shard(n_held, d, seed + 1 + 1000 * held, dev)
+        self._moving = [self.items]
+        self.adam = None
+        if spec.optimizer == "lazy_adam":
+            z = torch.zeros_like
+            self.adam = [z(self.users), z(self.users), z(self.items), z(self.items)]
+            self._moving += [self.adam[2], self.adam[3]]
+        self._spare = [torch.empty_like(t) for t in self._moving]
+        self.step = FusedStep(spec)
+
+    @staticmethod
+    def _init_shard(rows, d, seed, dev):
+        import torch
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        return (torch.rand((max(rows, 1), d), device=dev, generator=g) - 0.5) * 0.1      # Keras-1 'uniform'
+
+    @property
+    def held(self) -> int:
+        return held_item_shard(self.rank, self.sub_epoch, self.world)
+
+    def run_block(self, user_ids_local, item_ids_local, n_steps, loss_out=None):
+        """n_steps steps on links of block (rank, held): LOCAL ids (id // world) of the two shards"""
+        return self.step.run(self.users, self.items, user_ids_local, item_ids_local, n_steps, adam_state=self.adam,
+                             loss_out=loss_out)
+
+    def run_block_host(self, user_ids_host, item_ids_host, n_steps, loss_out_host=None):
+        return self.step.run_host(self.users, self.items, user_ids_host, item_ids_host, n_steps, loss_out_host)
+
+    def rotate(self):
+        """end of a sub-epoch: my item shard (and its optimizer state) goes to rank - 1, rank + 1's comes to me"""
+        self._moving, self._spare = ring_rotate(self._moving, self._spare, self.rank, self.world)
+        self.items = self._moving[0]
+        if self.adam is not None:
+            self.adam[2], self.adam[3] = self._moving[1], self._moving[2]
+        self.sub_epoch += 1
+
+    def train_epoch(self, blocks, rows_per_step=None):
+        """One stratified epoch: `blocks[v]` = (user_ids_local, item_ids_local) CUDA int32 arrays of block (rank, v).
+        Returns the list of per-step loss tensors.  Every rank calls it (the rotations pair up)."""
+        per = (rows_per_step or self.spec.replicas * self.spec.batch_size_p)
+        losses = []
+        for _ in range(self.world):
+            u, c = blocks[self.held]
+            n_steps = u.numel() // per
+            if n_steps > 0:
+                losses.append(self.run_block(u, c, n_steps)["loss"])
+            self.rotate()
+        return losses
+
+    def close(self):
+        self.step = None

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from nncf_b200.parallel import allreduce_metric_sums, local_row, owner_of, shard_range, shard_rows
+from nncf_b200.parallel import (allreduce_metric_sums, held_item_shard, local_row, owner_of, partition_links_by_block,
+                                ring_rotate, shard_range, shard_rows)
 
 
 @pytest.mark.parametrize("n,world", [(10, 1), (10, 2), (10, 3), (7, 8), (1000003, 8), (0, 4)])
@@ -73,3 +74,63 @@ def test_metric_sums_allreduce_gloo_world2():
     exp = [np.sum(kept * (u % 5) / 5.0), np.sum(kept * (u % 3) / 3.0), np.sum(kept * 0.1), kept.sum()]
     for r in range(world):
         np.testing.assert_allclose(res[r], exp, rtol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# stratified (DSGD) schedule
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_stratified_schedule_is_a_latin_square(world):
+    """in every sub-epoch the ranks hold distinct item shards, and over `world` sub-epochs every rank holds each once"""
+    for t in range(world):
+        assert sorted(held_item_shard(r, t, world) for r in range(world)) == list(range(world))
+    for r in range(world):
+        assert sorted(held_item_shard(r, t, world) for t in range(world)) == list(range(world))
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_partition_links_by_block_covers_every_link_once(world):
+    rng = np.random.RandomState(0)
+    train = np.stack([rng.randint(0, 101, 5000), rng.randint(0, 57, 5000), np.ones(5000, dtype=np.int64)], 1)
+    seen = []
+    for r in range(world):
+        blocks = partition_links_by_block(train, r, world)
+        assert len(blocks) == world
+        for v, b in enumerate(blocks):
+            assert b.dtype == np.int32
+            g = np.stack([b[:, 0].astype(np.int64) * world + r, b[:, 1].astype(np.int64) * world + v, b[:, 2]], 1)   # back to global ids
+            assert np.all(g[:, 0] % world == r) and np.all(g[:, 1] % world == v)
+            ref = train[(train[:, 0] % world == r) & (train[:, 1] % world == v)]
+            assert np.array_equal(g, ref)                       # order inside a block is the original order
+            seen.append(g)
+    assert sum(len(g) for g in seen) == len(train)
+
+
+def _rotate_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    held = [torch.full((4, 3), float(rank)), torch.full((2,), 10.0 + rank)]       # shard `rank` and its "optimizer state"
+    spare = [torch.empty_like(t) for t in held]
+    trace = []
+    for t in range(world):
+        trace.append((int(held[0][0, 0].item()), int(held[1][0].item()) - 10))
+        held, spare = ring_rotate(held, spare, rank, world)
+    q.put((rank, trace, int(held[0][0, 0].item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_ring_rotate_follows_the_schedule_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rotate_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+    for rank, trace, final in res:
+        assert trace == [(held_item_shard(rank, t, world),) * 2 for t in range(world)]       # tensors travel together
+        assert final == rank                                                                   # home again after N rotations

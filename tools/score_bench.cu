@@ -12,9 +12,15 @@
 namespace nncf { int launch_score_tc_nsub1(const ScoreTcArgs&, int, int, cudaStream_t) { return 0; } int launch_score_tc_nsub2(const ScoreTcArgs&, int, int, cudaStream_t) { return 0; } int launch_score_tc_nsub4(const ScoreTcArgs&, int, int, cudaStream_t) { return 0; }
 void set_error(const std::string&) {} std::atomic<int64_t> g_launches{0}; }
 using namespace nncf;
+// rewrites the tile images with generic stores from every SM, like the gather kernel does right before the score kernel
+__global__ void touch_images(uint4* a, uint4* b, size_t n16, unsigned salt) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    a[i] = make_uint4(salt & 0x3c003c00u, 0x3c003c00u & (unsigned)i, 0, 0); b[i] = make_uint4(0x3c003c00u & salt, 0, 0x38003800u & (unsigned)i, 0);
+  }
+}
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s line %d\n", cudaGetErrorString(e_), __LINE__); return 2; } } while (0)
 int main(int argc, char** argv) {
-  int B = argc > 1 ? atoi(argv[1]) : 512, R = argc > 2 ? atoi(argv[2]) : 1, fuse = argc > 3 ? atoi(argv[3]) : 0;
+  int B = argc > 1 ? atoi(argv[1]) : 512, R = argc > 2 ? atoi(argv[2]) : 1, fuse = argc > 3 ? atoi(argv[3]) : 0, touch = argc > 4 ? atoi(argv[4]) : 0; const double expo_scale = argc > 5 ? atof(argv[5]) : 1.0;
   constexpr int NSUB = 2, DP = 128;
   int rp = (B + 127) / 128 * 128, nblk = rp / 128;
   size_t img = (size_t)R * rp * DP * 2, nel = (size_t)R * rp * DP;
@@ -42,7 +48,7 @@ int main(int argc, char** argv) {
       std::uniform_real_distribution<double> U(0, acc);
       for (auto& x : out) { int r = int(std::lower_bound(cdf.begin(), cdf.end(), U(rng)) - cdf.begin()); x = perm[std::min(r, NR - 1)]; }
     };
-    std::vector<int> hu((size_t)R * B), hv((size_t)R * B); draw(0.8, hu); draw(1.0, hv);
+    std::vector<int> hu((size_t)R * B), hv((size_t)R * B); draw(0.8 * expo_scale, hu); draw(1.0 * expo_scale, hv);
     CK(cudaMalloc(&iu, hu.size() * 4)); CK(cudaMalloc(&iv, hv.size() * 4));
     CK(cudaMemcpy(iu, hu.data(), hu.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(iv, hv.data(), hv.size() * 4, cudaMemcpyHostToDevice));
     a.fuse_sgd = 1; a.d = DP; a.neg_lr = -0.01f; a.table_u = tu; a.table_v = tv; a.ids_u = iu; a.ids_v = iv; a.ids_stride_u = a.ids_stride_v = B;
@@ -58,7 +64,10 @@ int main(int argc, char** argv) {
   for (int it = 0; it < 3; ++it) score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
-  for (int it = 0; it < 20; ++it) score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
+  for (int it = 0; it < 20; ++it) {
+    if (touch) touch_images<<<1184, 256>>>((uint4*)U, (uint4*)V, img / 16, it);
+    score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
+  }
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
   float ms; cudaEventElapsedTime(&ms, e0, e1);
