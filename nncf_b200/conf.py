@@ -67,16 +67,50 @@ class Conf(object):
         self.contextual_temporal_gated_input = None
 
 
-def get_conf_default(data_name, param_dict=None):
-    return Conf(data_name, param_dict=param_dict)
+class CnnConf(Conf):
+    """configs/cnn_embedding_conf.py:10-60: the basic keys plus the convolutional content model's."""
+
+    def __init__(self, data_name, param_dict=None):
+        self.num_filters = [50]
+        self.filter_lengths = [[1, 3, 5]]
+        self.poolings = ['average']
+        self.pool_lengths = [-1]
+        self.conv_dropout_rate = 0.3
+        self.conv_activation = 'relu'
+        self.conv_batch_normalization = True
+        pd = {'u_reg': 1e-5, 'word_emb_dropout_rate': 0}
+        pd.update(param_dict or {})
+        super().__init__(data_name, pd)
+        for k in ('num_filters', 'filter_lengths', 'poolings', 'pool_lengths', 'conv_dropout_rate', 'conv_activation',
+                  'conv_batch_normalization'):
+            if param_dict and k in param_dict:
+                setattr(self, k, param_dict[k])
 
 
-def get_conf_best(data_name, param_dict=None):
+class RnnConf(Conf):
+    """configs/rnn_embedding_conf.py:10-60: the basic keys plus the recurrent content model's."""
+
+    def __init__(self, data_name, param_dict=None):
+        pd = {'u_reg': 1e-5, 'word_emb_dropout_rate': 0., 'rnn': 'lstm', 'bidirection': True, 'lstm_dims': [64],
+              'lstm_w_dropout_rate': 0., 'lstm_u_dropout_rate': 0., 'lstm_o_dropout_rate': 0.3, 'pooling': 'average',
+              'use_seq_for_dnn': True}
+        pd.update(param_dict or {})
+        super().__init__(data_name, pd)
+
+
+CONF_CLASSES = {'mf': Conf, 'basic_embedding': Conf, 'cnn_embedding': CnnConf, 'rnn_embedding': RnnConf}
+
+
+def get_conf_default(data_name, param_dict=None, model_choice='basic_embedding'):
+    return CONF_CLASSES[model_choice](data_name, param_dict=param_dict)
+
+
+def get_conf_best(data_name, param_dict=None, model_choice='basic_embedding'):
     """basic_embedding_conf.py:98-142: tuned per-dataset settings, then param_dict re-applied when it carries the key
     `reset_after_getconf` (the demo scripts always pass it, scripts/demos/run_neg_shared.sh:37).  As in the
     reference the re-apply is a plain __dict__.update: derived fields (emb_normalization, optimizer) keep the values
     computed in Conf.__init__, where param_dict had already been applied once."""
-    conf = Conf(data_name, param_dict=param_dict)
+    conf = CONF_CLASSES[model_choice](data_name, param_dict=param_dict)
     conf.c_reg = 0
     conf.num_negatives = 10
     if data_name.startswith('news'):
@@ -95,10 +129,10 @@ def get_conf_best(data_name, param_dict=None):
     return conf
 
 
-def get_conf(data_name, conf_choice, param_dict=None):
+def get_conf(data_name, conf_choice, param_dict=None, model_choice='basic_embedding'):
     if conf_choice == 'best':
-        return get_conf_best(data_name, param_dict)
+        return get_conf_best(data_name, param_dict, model_choice)
     elif conf_choice in ('default', 'evaluation'):
-        return get_conf_default(data_name, param_dict)
+        return get_conf_default(data_name, param_dict, model_choice)
     else:
         assert False, '[ERROR] conf_choice %s unknown' % conf_choice

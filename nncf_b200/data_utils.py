@@ -83,6 +83,29 @@ def make_synthetic(user_count=5551, item_count=16980, n_links=204986, content_le
             'test_seen': test_seen.astype(np.int32), 'train_items': train_items.tolist(), 'test_items': test_items.tolist()}
 
 
+def create_val(data, val_ratio=0.1, rng=None):
+    """Validation split of a `data_split_cold_item` dictionary, in place: a random `val_ratio` of the TRAIN items becomes
+    the new cold-start test set (their links leave `train`), `test_seen` = the first len(test) remaining train rows.
+    ref: data/create_val.py:8,16-40 (same steps, same np.random.shuffle of train_items, same sanity checks)."""
+    rng = np.random if rng is None else rng
+    train_items = list(data['train_items'])
+    train = data['train']
+    num_train_items, num_train = len(train_items), train.shape[0]
+    rng.shuffle(train_items)
+    test_len = int(len(train_items) * val_ratio)
+    test_items = train_items[:test_len]
+    train_items = train_items[test_len:]
+    tt_idx = np.isin(train[:, 1], np.asarray(test_items, dtype=train.dtype))
+    test = train[tt_idx]
+    train = train[~tt_idx]
+    data['train_items'], data['test_items'] = train_items, test_items
+    data['train'], data['test'], data['test_seen'] = train, test, train[:test.shape[0]]
+    assert len(train_items) + len(test_items) == num_train_items
+    assert data['train'].shape[0] + data['test'].shape[0] == num_train
+    assert len(set(test_items).intersection(train_items)) == 0
+    return data
+
+
 def _get_data(data_name):
     """Loads the reference's `data_split_cold_item.pkl` (a Python-2 pickle of NumPy arrays, keys per
     data/readme.txt:3-9) when present under ./data, else builds the synthetic stand-in of the same shape."""
@@ -102,6 +125,8 @@ def _get_data(data_name):
             data_helper.data = pickle.load(fp, encoding='latin1')
     elif data_name.startswith('synthetic_small'):
         data_helper.data = make_synthetic(600, 1500, 20000, content_len=40, vocab=500, seed=11)
+        if data_name.endswith('_val'):
+            create_val(data_helper.data, rng=np.random.RandomState(3))
     elif split_file is not None or data_name.startswith('synthetic'):
         print('[INFO] %s: data blob not found, using the synthetic CiteULike-shaped stand-in' % data_name)
         data_helper.data = make_synthetic()

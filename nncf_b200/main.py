@@ -38,13 +38,13 @@ def run(argv=None):
     print('model_choice: %s \nconf_choice: %s' % (model_choice, conf_choice))
 
     # load confs and related (main.py:46-58)
-    if model_choice in ('mf', 'basic_embedding'):
+    if model_choice in ('mf', 'basic_embedding', 'cnn_embedding', 'rnn_embedding'):
         from .conf import get_conf
-    elif model_choice in ('pretrained', 'cnn_embedding', 'rnn_embedding'):
-        assert False, 'model choice %s is outside the scoped hot path (SURVEY.md §2 rows 14-15)' % model_choice
+    elif model_choice == 'pretrained':
+        assert False, 'model choice pretrained needs the pretrained vector blobs (absent, SURVEY.md §8f3)'
     else:
         assert False, 'model choice %s not defined' % model_choice
-    conf = get_conf(data_name, conf_choice, param_dict)
+    conf = get_conf(data_name, conf_choice, param_dict, model_choice)
     # basic postprocessing (main.py:60-63)
     if eval_scheme.find('@') > 0:
         p = eval_scheme.find('@')

@@ -86,13 +86,16 @@ class SharedState(object):
         self.item_table = None
         if model_name == 'mf':
             self.item_table = (torch.rand((spec.item_count, d), generator=g, device=dev) - 0.5) * 0.1
-        elif model_name == 'basic_embedding':
+        elif model_name in ('basic_embedding', 'cnn_embedding', 'rnn_embedding'):
             content = torch.from_numpy(np.ascontiguousarray(data_helper.data['C'], dtype=np.int32)).to(dev)
-            self.tower = MeanPoolTower(spec, conf, content, g).to(dev)
+            if model_name == 'basic_embedding':
+                self.tower = MeanPoolTower(spec, conf, content, g).to(dev)
+            else:
+                from .towers import CNNTower, RNNTower          # plain torch modules (models/model_framework.py:89-96)
+                self.tower = (CNNTower if model_name == 'cnn_embedding' else RNNTower)(spec, conf, content, g).to(dev)
             self.tower_opt = torch.optim.Adam(self.tower.parameters(), lr=self.lr, eps=1e-8)   # Keras Adam(lr)
         else:
-            assert False, '[ERROR] Model name {} unknown (cnn/rnn towers: plug a torch module with the MeanPoolTower ' \
-                          'contract into SharedState.tower)'.format(model_name)
+            assert False, '[ERROR] Model name {} unknown'.format(model_name)
         self.norm_u = bool(conf.emb_normalization)
         # reference quirk: the 'mf' branch never l2-normalises the item embedding (models/model_framework.py:85-88)
         self.norm_v = bool(conf.emb_normalization) and model_name != 'mf'

@@ -41,6 +41,22 @@ def test_basic_embedding_tower_runs(scheme, loss, capsys):
     assert 'epoch 1 (' in out and 'test recall/map' in out
 
 
+@pytest.mark.parametrize("model,scheme,loss", [("cnn_embedding", "neg_shared", "skip-gram"), ("rnn_embedding", "group_neg_shared", "log-loss"),
+                                               ("cnn_embedding", "original", "mse")])
+def test_cnn_rnn_towers_run(model, scheme, loss, capsys):
+    _run(model, scheme, loss, 'whole@10', {'max_epoch': 1, 'lstm_dims': [16]})
+    out = capsys.readouterr().out
+    assert 'epoch 1 (' in out and 'test recall/map' in out
+
+
+def test_validation_split_data_runs(capsys):
+    from nncf_b200.main import run
+    np.random.seed(0)
+    run(['--data_name', 'synthetic_small_val', '--model_choice', 'mf', '--conf_choice', 'default', '--train_scheme', 'neg_shared',
+         '--eval_scheme', 'whole@10', '--param_dict', "{'max_epoch': 1, 'batch_size_p': 128, 'user_dim': 32, 'item_dim': 32}"])
+    assert 'test recall/map' in capsys.readouterr().out
+
+
 def test_given_eval_runs(capsys):
     _run('mf', 'neg_shared', 'skip-gram', 'given@-1', {'max_epoch': 1})
     out = capsys.readouterr().out

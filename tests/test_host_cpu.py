@@ -120,3 +120,49 @@ def test_golden_original_and_metric_cases():
     np.testing.assert_allclose(got, g["ev_per_user"], rtol=1e-12)
     goto = np.array([O.eval_multiple_original(truth[u], pred[u], -1) for u in kept])
     np.testing.assert_allclose(goto, g["evo_per_user"], rtol=1e-12)
+
+
+def test_create_val_follows_reference_split():
+    """data/create_val.py: 10% of the train items become cold test items; nothing lost, nothing shared"""
+    from nncf_b200.data_utils import create_val, make_synthetic
+    data = make_synthetic(200, 300, 5000, content_len=10, vocab=50, seed=1)
+    n_train, items = data['train'].shape[0], sorted(data['train_items'])
+    rs = np.random.RandomState(5)
+    expect = list(items); rs.shuffle(expect)                    # the reference shuffles train_items with np.random
+    create_val(data, rng=np.random.RandomState(5))
+    assert data['test_items'] == expect[:int(len(items) * 0.1)] and data['train_items'] == expect[int(len(items) * 0.1):]
+    assert data['train'].shape[0] + data['test'].shape[0] == n_train
+    assert set(data['test'][:, 1]) <= set(data['test_items']) and not (set(data['train'][:, 1]) & set(data['test_items']))
+    assert np.array_equal(data['test_seen'], data['train'][:data['test'].shape[0]])
+
+
+def test_cnn_and_rnn_towers_shapes_and_gradients():
+    """the CNN / RNN item towers (plain torch modules) honour the tower contract: ids -> [n, d], differentiable"""
+    import torch
+    from nncf_b200.conf import get_conf
+    from nncf_b200.towers import CNNTower, RNNTower
+
+    class DS:
+        word_count = 120
+        W_pretrain = None
+    content = torch.from_numpy(np.random.RandomState(0).randint(0, 120, (40, 12)).astype(np.int32))
+    g = torch.Generator().manual_seed(0)
+    cases = [('cnn_embedding', CNNTower, {}),
+             ('cnn_embedding', CNNTower, {'filter_lengths': [3, 5], 'num_filters': [6, 5], 'poolings': ['max', 'average'], 'pool_lengths': [2, -1]}),
+             ('rnn_embedding', RNNTower, {'lstm_dims': [8]}),
+             ('rnn_embedding', RNNTower, {'rnn': 'gru', 'bidirection': False, 'use_seq_for_dnn': False, 'lstm_dims': [8, 6]})]
+    for mc, T, extra in cases:
+        pd = {'user_dim': 16, 'item_dim': 16, 'word_dim': 8}
+        pd.update(extra)
+        conf = get_conf('synthetic_small', 'default', pd, mc)
+        assert conf.u_reg == 1e-5                              # cnn / rnn conf default (configs/cnn_embedding_conf.py:34)
+        tower = T(DS, conf, content, g)
+        tower.train()
+        out = tower(torch.arange(9))
+        assert out.shape == (9, 16)
+        out.square().sum().backward()
+        assert tower.word_embedding.grad is not None and torch.isfinite(tower.word_embedding.grad).all()
+        tower.eval()
+        with torch.no_grad():
+            a, b = tower(torch.arange(5)), tower(torch.arange(5))
+        assert torch.equal(a, b)                               # test phase: dropout off, BN running statistics
