@@ -102,6 +102,27 @@ class ClockSampler(threading.Thread):
         self.stop_flag = False
 
     def run(self):
+        # NVML directly (nvidia_ml_py): a sample costs ~0.1 ms, so even a 50 ms timed region gets dozens of samples;
+        # rows have the layout of the nvidia-smi query below, which is the fallback
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
+                    ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
+                    ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
+                    ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4))]
+            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = reasons_fn(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.rows.append([str(sm), str(mx), "%.1f" % pw] + ["Active" if (r & b) else "Not Active" for _, b in bits])
+                time.sleep(0.002)
+            return
+        except Exception:
+            pass
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
@@ -120,8 +141,9 @@ class ClockSampler(threading.Thread):
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in self.rows if len(r) >= 7)]
+        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -353,6 +375,28 @@ def run_ours(args):
     per_call_value = world * per_call_steps * links_per_step / per_call_s
     barrier()
 
+    # ---- extra: whole@k users/sec, users sharded over the ranks (C4 shape: every rank scores its own users against all
+    #      2M items, k = 50; no data-path collective, the metric sums would be all-reduced).  Time = max over ranks.
+    extra = {}
+    if not args.no_eval:
+        n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
+        ge = torch.Generator(device="cuda").manual_seed(99)
+        Ve = torch.randn((n_eval_items, d), device="cuda", generator=ge) / d ** 0.5            # replicated item table
+        Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5             # this rank's user shard
+        ops.eval_topk(Ue[:1024], Ve, k, "bf16")
+        barrier()
+        e0.record()
+        ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
+        e1.record()
+        barrier()
+        ems = max_over_ranks(e0.elapsed_time(e1))
+        etf = 2.0 * world * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
+        extra = {"whole_at_k": {"users_per_sec": world * n_eval_users / (ems * 1e-3), "k": k, "users": world * n_eval_users,
+                                "items": n_eval_items, "dim": d, "ms": ems, "sharding": "users over %d GPU(s)" % world,
+                                "roofline": {"bound": "tensor", "achieved": etf, "peak": world * peaks["bf16_burst"],
+                                             "unit": "TFLOP/s", "frac": etf / (world * peaks["bf16_burst"])}}}
+        del Ue, Ve, ids
+
     if rank != 0:
         if sharded is not None:
             dist.barrier()
@@ -382,7 +426,7 @@ def run_ours(args):
                 "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / step_s / 1e9,
                              "peak_gbs": peaks["hbm"], "frac": step_bytes / step_s / 1e9 / peaks["hbm"]}}
 
-    seq_info, extra, cpu = None, {}, None
+    seq_info, cpu = None, None
     if world == 1:
         # ---- sequential reference semantics (R = 1) ----------------------------------------------------------
         seq = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
@@ -395,24 +439,6 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         seq_info = {"value": nseq * B / (e0.elapsed_time(e1) * 1e-3), "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq}
-        # ---- extra: whole@k users/sec on a C4-shaped shard (all 2M items, k = 50) -----------------------------
-        if not args.no_eval:
-            n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
-            Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5
-            Ve = torch.randn((n_eval_items, d), device="cuda", generator=g) / d ** 0.5
-            ops.eval_topk(Ue[:1024], Ve, k, "bf16")
-            torch.cuda.synchronize()
-            e0.record()
-            ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
-            e1.record()
-            torch.cuda.synchronize()
-            ems = e0.elapsed_time(e1)
-            etf = 2.0 * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
-            extra = {"whole_at_k": {"users_per_sec": n_eval_users / (ems * 1e-3), "k": k, "users": n_eval_users,
-                                    "items": n_eval_items, "dim": d, "ms": ems,
-                                    "roofline": {"bound": "tensor", "achieved": etf, "peak": peaks["bf16_burst"],
-                                                 "unit": "TFLOP/s", "frac": etf / peaks["bf16_burst"]}}}
-            del Ue, Ve, ids
         # ---- cpu baseline: bounded sample on the box's host cores (rank 0, N = 1 only) ------------------------
         cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
         cpu = {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",

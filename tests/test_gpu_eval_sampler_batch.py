@@ -261,3 +261,25 @@ def test_meanpool_fwd_bwd_match_oracle():
     meanpool_bwd(dW, tC, tid, n, torch.from_numpy(dX).cuda())
     ref = O.meanpool_bwd(W.shape, C[ids], dX.astype(np.float64))
     assert np.max(np.abs(dW.cpu().numpy() - ref)) <= 1e-4 * np.max(np.abs(ref))
+
+
+@pytest.mark.parametrize("k", [10, 50, 100])
+def test_topk_c4_item_count_property_check(k):
+    """BASELINE config 4's candidate count (2M items, d = 128) with a shard of 512 users: exactness properties of the
+    append + compaction top-k at full width — sorted output, exact scores, nothing outside the list beats the k-th, and
+    the same ids as torch.topk on the bf16-rounded operands for sampled users (continuous scores: no ties)."""
+    from nncf_b200.ops import eval_topk
+    g = torch.Generator(device="cuda").manual_seed(2)
+    nu, ni, d = 512, 2_000_000, 128
+    U = torch.randn((nu, d), device="cuda", generator=g) / d ** 0.5
+    V = torch.randn((ni, d), device="cuda", generator=g) / d ** 0.5
+    ids, sc = eval_topk(U, V, k, "bf16")
+    assert bool((sc[:, :-1] >= sc[:, 1:]).all()) and bool(((ids >= 0) & (ids < ni)).all())
+    Ub, Vb = U.bfloat16().float(), V.bfloat16().float()
+    for u in [0, 101, 511]:
+        s_all = Vb @ Ub[u]
+        ref = torch.topk(s_all, k)
+        # fp32 accumulation order differs between the tensor core and torch: allow swaps between scores closer than 1e-5
+        assert torch.allclose(sc[u], ref.values, rtol=1e-4, atol=1e-5)
+        same = (ids[u].long() == ref.indices)
+        assert bool(same.all()) or float((sc[u][~same] - ref.values[~same]).abs().max()) < 1e-5

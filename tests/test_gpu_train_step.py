@@ -308,3 +308,61 @@ def test_fused_sgd_drain_matches_oracle(scheme, loss, B, d, replicas):
     out2 = step.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
     torch.cuda.synchronize()
     assert np.all(out2["loss"].cpu().numpy() < 1.5 * got + 1.0) and np.all(np.isfinite(out2["loss"].cpu().numpy()))
+
+
+@pytest.mark.parametrize("loss,norm", [("max-margin", True), ("skip-gram", False)])
+def test_c5_full_size_loss_and_update_match_torch_fp32(loss, norm):
+    """BASELINE config 5 at its full size (batch 16,384, dim 256): the oracle would need minutes, so the check is an
+    independent fp32 torch evaluation of the same formulas on the GPU (score matrix materialised: 1 GiB) — loss within
+    the bf16 tolerance, and the SGD update of a sample of rows against autograd."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    B, d, nu, ni = 16384, 256, 50000, 40000
+    lam, gamma, lr = 128.0, 0.1, 1.0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    tU = (torch.rand((nu, d), device="cuda", generator=g) - 0.5)
+    tV = (torch.rand((ni, d), device="cuda", generator=g) - 0.5)
+    if not norm:
+        tU *= 0.1; tV *= 0.1
+    uid = torch.randperm(nu, device="cuda", generator=g)[:B].to(torch.int32)        # distinct ids: rows map 1:1 to updates
+    cid = torch.randperm(ni, device="cuda", generator=g)[:B].to(torch.int32)
+    U0 = tU[uid.long()].clone().requires_grad_(True)
+    V0 = tV[cid.long()].clone().requires_grad_(True)
+    Uh = torch.nn.functional.normalize(U0, dim=1, eps=1e-12) if norm else U0
+    Vh = torch.nn.functional.normalize(V0, dim=1, eps=1e-12) if norm else V0
+    S = Uh @ Vh.T
+    if loss == "max-margin":                                                        # utils/objectives.py:91-94
+        D = torch.diagonal(S)[None, :] - S
+        M = gamma * (1.0 - torch.eye(B, device="cuda"))
+        L = torch.relu(M - D).mean()
+    else:                                                                           # :99-105
+        w = lam / (B - 1)
+        L = (-(torch.nn.functional.logsigmoid(torch.diagonal(S))).sum() - w * (torch.nn.functional.logsigmoid(-S).sum()
+             - torch.nn.functional.logsigmoid(-torch.diagonal(S)).sum())) / B
+    L.backward()
+    EU_before, EV_before = tU.clone(), tV.clone()
+    spec = StepSpec(scheme="neg_shared", loss=loss, precision="bf16", batch_size_p=B, dim=d, norm_u=norm, norm_v=norm,
+                    optimizer="sgd", learn_rate=lr, neg_loss_weight=lam, loss_gamma=gamma)
+    out = FusedStep(spec).run(tU, tV, uid, cid, 1)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss"][0]) - float(L)) <= 1e-2 * abs(float(L)), (float(out["loss"][0]), float(L))
+    gU = (EU_before[uid.long()] - tU[uid.long()]) / lr
+    gV = (EV_before[cid.long()] - tV[cid.long()]) / lr
+    if loss == "skip-gram":      # (max-margin gradients are indicators: bf16 operand rounding flips entries near the margin)
+        assert float((gU - U0.grad).abs().max() / U0.grad.abs().max()) <= 2e-2
+        assert float((gV - V0.grad).abs().max() / V0.grad.abs().max()) <= 2e-2
+    else:
+        cos = torch.nn.functional.cosine_similarity(gU.flatten(), U0.grad.flatten(), dim=0)
+        assert float(cos) > 0.98, float(cos)
+    # rows outside the batch are untouched
+    mask = torch.ones(nu, dtype=torch.bool, device="cuda"); mask[uid.long()] = False
+    assert torch.equal(tU[mask], EU_before[mask])
+
+
+def test_zero_steps_is_a_no_op():
+    from nncf_b200.ops import FusedStep, StepSpec
+    tU = torch.rand((100, 64), device="cuda"); tV = torch.rand((100, 64), device="cuda")
+    a, b = tU.clone(), tV.clone()
+    ids = torch.zeros(128, dtype=torch.int32, device="cuda")
+    out = FusedStep(StepSpec(batch_size_p=128, dim=64)).run(tU, tV, ids, ids, 0)
+    torch.cuda.synchronize()
+    assert out["loss"].numel() == 0 and torch.equal(tU, a) and torch.equal(tV, b)
