@@ -144,6 +144,11 @@ typedef struct {
   float u_reg;             /* activity L2 on the un-normalised user rows */
   float learn_rate;
   float beta1, beta2, epsilon;   /* lazy Adam */
+  int32_t interaction_bias;      /* 0 none, 1 user, 2 item, 3 both (ref: modules/interaction/interaction_dot.py:26-34,
+                                    96-107).  When non-zero `dim` = embedding dim + 2 and every table row carries two
+                                    extra columns: users (ubias, 1), items (1, cbias), so the bias terms come out of the
+                                    same contraction; those columns are excluded from l2-normalisation and the regulariser
+                                    and the gradient of the constant column (and of an unused bias) is dropped. */
 } nncf_step_config;
 
 typedef struct nncf_trainer nncf_trainer_t;

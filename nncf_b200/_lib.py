@@ -32,6 +32,7 @@ SCHEMES = {"neg_shared": 0, "group_neg_shared": 1, "pairs": 2, "sampled_neg_shar
 LOSSES = {"skip-gram": 0, "mse": 1, "log-loss": 2, "max-margin": 3}
 PRECISIONS = {"fp32": 0, "bf16": 1}
 OPTIMIZERS = {"none": 0, "sgd": 1, "lazy_adam": 2}
+BIASES = {None: 0, "user": 1, "item": 2, "both": 3}
 
 
 class StepConfig(C.Structure):
@@ -40,7 +41,7 @@ class StepConfig(C.Structure):
         ("num_negatives", C.c_int32), ("dim", C.c_int32), ("norm_u", C.c_int32), ("norm_v", C.c_int32),
         ("optimizer", C.c_int32), ("replicas", C.c_int32),
         ("neg_loss_weight", C.c_float), ("loss_gamma", C.c_float), ("u_reg", C.c_float), ("learn_rate", C.c_float),
-        ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float),
+        ("beta1", C.c_float), ("beta2", C.c_float), ("epsilon", C.c_float), ("interaction_bias", C.c_int32),
     ]
 
 

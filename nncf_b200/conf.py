@@ -67,6 +67,19 @@ class Conf(object):
         self.contextual_temporal_gated_input = None
 
 
+class MfConf(Conf):
+    """configs/pretrained_conf.py:10-41, the Conf main.py gives `--model_choice mf` (main.py:47-48): its own defaults
+    (64-link batches, 5 negatives, neg_loss_weight 1, uniform negatives, item interaction bias ...).  get_conf_best then
+    applies pretrained_conf.py:121-142 (30 epochs, 10 negatives, no bias, per-dataset u_reg)."""
+
+    def __init__(self, data_name, param_dict=None):
+        pd = {'max_epoch': 20, 'num_negatives': 5, 'batch_size_p': 64, 'neg_loss_weight': 1, 'interaction_bias': 'item',
+              'learn_rate': 0.01, 'u_reg': 1e-5, 'neg_dist': 'uniform', 'neg_sampling_power': 1, 'chop_size': 1,
+              'shuffle_st': 'by_item', 'interaction_multiplier': False, 'evaluation_mode': False}
+        pd.update(param_dict or {})
+        super().__init__(data_name, pd)
+
+
 class CnnConf(Conf):
     """configs/cnn_embedding_conf.py:10-60: the basic keys plus the convolutional content model's."""
 
@@ -98,7 +111,7 @@ class RnnConf(Conf):
         super().__init__(data_name, pd)
 
 
-CONF_CLASSES = {'mf': Conf, 'basic_embedding': Conf, 'cnn_embedding': CnnConf, 'rnn_embedding': RnnConf}
+CONF_CLASSES = {'mf': MfConf, 'basic_embedding': Conf, 'cnn_embedding': CnnConf, 'rnn_embedding': RnnConf}
 
 
 def get_conf_default(data_name, param_dict=None, model_choice='basic_embedding'):
@@ -113,7 +126,11 @@ def get_conf_best(data_name, param_dict=None, model_choice='basic_embedding'):
     conf = CONF_CLASSES[model_choice](data_name, param_dict=param_dict)
     conf.c_reg = 0
     conf.num_negatives = 10
-    if data_name.startswith('news'):
+    if model_choice == 'mf':                               # pretrained_conf.py:128-142
+        conf.max_epoch = 30
+        conf.interaction_bias = None
+        conf.u_reg = 1e-5 if data_name.startswith('news_title_only') else 1e-6
+    elif data_name.startswith('news'):
         conf.max_epoch = 20
         conf.u_reg = 1e-5 if data_name.startswith('news_title_only') else 1e-6
         conf.word_emb_dropout_rate = 0.3

@@ -114,6 +114,8 @@ struct GatherArgs {
   uint8_t* img;              // [R][rows_pad/128][dp/64][16 KiB]
   float* dX;                 // [R][rows_pad][dp]  zeroed here
   float* corr;               // [R][rows_pad]      zeroed here
+  int d_emb;                 // columns [0, d_emb) are the embedding (l2-normalised if asked); [d_emb, d) are interaction-bias
+                             // plumbing (a bias and a constant 1) that passes through unscaled.  0 = all d columns
   unsigned long long* tl;    // developer timeline (NNCF_TIMELINE): [0] first CTA start, [1] first CTA past the wait, [2] last end
 };
 
@@ -150,14 +152,15 @@ gather_rows_kernel(GatherArgs a0, GatherArgs a1) {
   }
   float inv = 1.0f;
   if (a.normalize) {
+    const int de = a.d_emb > 0 ? a.d_emb : a.d;   // interaction-bias columns are not part of the embedding
     float ss = 0.0f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) ss += x[m] * x[m];
+    for (int m = 0; m < 8; ++m) { const int c = (m >> 1) * 64 + 2 * lane + (m & 1); ss += (c < de) ? x[m] * x[m] : 0.0f; }
     ss = warp_sum(ss);
     inv = rsqrtf(fmaxf(ss, 1e-12f));   // tf.nn.l2_normalize: x * rsqrt(max(sum(x^2), 1e-12))
     if (row >= count) inv = 1.0f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) x[m] *= inv;
+    for (int m = 0; m < 8; ++m) { const int c = (m >> 1) * 64 + 2 * lane + (m & 1); if (c < de) x[m] *= inv; }
   }
   const int64_t rowoff = ((int64_t)r * a.rows_pad + row);
   float* xf = a.Xf + rowoff * a.dp;
@@ -337,6 +340,8 @@ struct FinalizeArgs {
   int write_back;            // store the finalised row gradient back to dX (lazy Adam reads it)
   int need_x;                // rows of Xf are read (normalise-backward, corrections or regulariser)
   float reg_scale;           // 2 * u_reg / rows  (user side) else 0
+  int d_emb;                 // embedding columns (normalise-backward and regulariser act on [0, d_emb)); 0 = all
+  int frozen0, frozen1;      // columns whose gradient is dropped (interaction-bias plumbing: the constant 1, an unused bias), -1 = none
   // optimizer
   int optimizer;
   float lr;
@@ -407,24 +412,26 @@ finalize_kernel(FinalizeArgs a0, FinalizeArgs a1) {
     }
   }
   float invn = 1.0f;
+  const int de = a.d_emb > 0 ? a.d_emb : a.dp;
   if (a.normalize) {
     invn = a.inv[base + row];
     float dot = 0.0f;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) dot += g[m] * xv[m];
+    for (int m = 0; m < 8; ++m) dot += (lane + 32 * m < de) ? g[m] * xv[m] : 0.0f;
     dot = warp_sum(dot);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) g[m] = (g[m] - xv[m] * dot) * invn;
+    for (int m = 0; m < 8; ++m) if (lane + 32 * m < de) g[m] = (g[m] - xv[m] * dot) * invn;
   }
   if (a.reg_scale != 0.0f) {
     // regulariser acts on the UN-normalised row: x_raw = xhat / inv
     const float s = a.reg_scale / invn;
 #pragma unroll
-    for (int m = 0; m < 8; ++m) g[m] = fmaf(s, xv[m], g[m]);
+    for (int m = 0; m < 8; ++m) if (lane + 32 * m < de) g[m] = fmaf(s, xv[m], g[m]);
   }
 #pragma unroll
   for (int m = 0; m < 8; ++m) {
     const int c = lane + 32 * m;
+    if (c == a.frozen0 || c == a.frozen1) g[m] = 0.0f;
     if (c < a.dp) dx[c] = g[m];
   }
   if (a.grad_out && r == 0) {
@@ -527,6 +534,8 @@ struct PairsArgs {
   int optimizer; float lr;
   float* tableU; float* tableV;
   float* grad_out_u; float* grad_out_v;
+  int d_emb;             // embedding columns (0 = all d); [d_emb, d) = interaction-bias plumbing, see GatherArgs
+  int fu0, fu1, fv0, fv1;   // frozen columns of the user / item rows (-1 = none)
   const int32_t* resp;   // optional [R][n] response labels: pointwise losses take positive = (label == 1) from here
                          // (ref: utils/objectives.py:59-70 weights by y_true); NULL = positives are rows [0, B)
 };
@@ -539,17 +548,19 @@ pairs_score_kernel(PairsArgs a) {
   if (row >= n) return;
   const float* u = a.EU + (int64_t)a.uid[r * a.ids_stride + row] * a.d;
   const float* v = a.EV + (int64_t)a.cid[r * a.ids_stride + row] * a.d;
-  float su = 0.0f, sv = 0.0f, dot = 0.0f;
+  const int de = a.d_emb > 0 ? a.d_emb : a.d;
+  float su = 0.0f, sv = 0.0f, dot = 0.0f, dotb = 0.0f;
   for (int c = lane; c < a.d; c += 32) {
     const float x = __ldg(u + c), y = __ldg(v + c);
-    su = fmaf(x, x, su); sv = fmaf(y, y, sv); dot = fmaf(x, y, dot);
+    if (c < de) { su = fmaf(x, x, su); sv = fmaf(y, y, sv); dot = fmaf(x, y, dot); }
+    else dotb = fmaf(x, y, dotb);                 // ubias * 1 + 1 * cbias (ref: interaction_dot.py:96-99)
   }
-  su = warp_sum(su); sv = warp_sum(sv); dot = warp_sum(dot);
+  su = warp_sum(su); sv = warp_sum(sv); dot = warp_sum(dot); dotb = warp_sum(dotb);
   const float iu = a.norm_u ? rsqrtf(fmaxf(su, 1e-12f)) : 1.0f;
   const float iv = a.norm_v ? rsqrtf(fmaxf(sv, 1e-12f)) : 1.0f;
   if (lane == 0) {
     const int64_t o = (int64_t)r * n + row;
-    a.s[o] = dot * iu * iv;
+    a.s[o] = dot * iu * iv + dotb;
     a.invu[o] = iu;
     a.invv[o] = iv;
     if (a.u_reg != 0.0f) atomicAdd(&a.loss[r], static_cast<double>(a.u_reg * su / n));
@@ -604,15 +615,25 @@ pairs_grad_kernel(PairsArgs a) {
   const int64_t o = (int64_t)r * n + row;
   const float iu = a.invu[o], iv = a.invv[o];
   // dU_hat = g * V_hat, dV_hat = g * U_hat; then normalise-backward: dx = (dxhat - xhat (xhat . dxhat)) * inv
-  // with xhat . dxhat = g * s for both sides.
+  // with xhat . dxhat = g * s_emb for both sides (s_emb = the embedding part of the score: bias columns pass through).
+  const int de = a.d_emb > 0 ? a.d_emb : a.d;
+  float se = s;
+  if (de < a.d) {
+    float dote = 0.0f;
+    for (int c = lane; c < de; c += 32) dote = fmaf(__ldg(u + c), __ldg(v + c), dote);
+    se = warp_sum(dote) * iu * iv;
+  }
   const float reg = 2.0f * a.u_reg / n;
   for (int c = lane; c < a.d; c += 32) {
     const float x = __ldg(u + c), y = __ldg(v + c);
-    const float xh = x * iu, yh = y * iv;
+    const bool emb = c < de;
+    const float xh = emb ? x * iu : x, yh = emb ? y * iv : y;
     float du = g * yh, dv = g * xh;
-    if (a.norm_u) du = (du - xh * (g * s)) * iu;
-    if (a.norm_v) dv = (dv - yh * (g * s)) * iv;
-    du = fmaf(reg, x, du);
+    if (a.norm_u && emb) du = (du - xh * (g * se)) * iu;
+    if (a.norm_v && emb) dv = (dv - yh * (g * se)) * iv;
+    if (emb) du = fmaf(reg, x, du);
+    if (c == a.fu0 || c == a.fu1) du = 0.0f;
+    if (c == a.fv0 || c == a.fv1) dv = 0.0f;
     if (a.dUrows) { a.dUrows[o * a.d + c] = du; a.dVrows[o * a.d + c] = dv; }
     if (a.grad_out_u && r == 0) a.grad_out_u[(int64_t)row * a.d + c] = du;
     if (a.grad_out_v && r == 0) a.grad_out_v[(int64_t)row * a.d + c] = dv;
@@ -636,7 +657,7 @@ __global__ void loss_out_kernel(const double* __restrict__ loss, int R, float* o
   if (r < R) out[r] = static_cast<float>(loss[r]);
 }
 __global__ void reg_loss_kernel(const float* __restrict__ Uf, const float* __restrict__ inv, int rows_pad, int dp,
-                                int rows, float u_reg, double* loss) {
+                                int rows, float u_reg, double* loss, int d_emb) {
   // u_reg * sum_d mean_b U_raw[b,d]^2, U_raw = Uf / inv        ref: utils/utilities.py:129-135
   const int r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -645,7 +666,7 @@ __global__ void reg_loss_kernel(const float* __restrict__ Uf, const float* __res
   const int64_t base = (int64_t)r * rows_pad + row;
   const float* x = Uf + base * dp;
   float ss = 0.0f;
-  for (int c = lane; c < dp; c += 32) ss = fmaf(x[c], x[c], ss);
+  for (int c = lane; c < (d_emb > 0 ? d_emb : dp); c += 32) ss = fmaf(x[c], x[c], ss);   // embedding columns only
   ss = warp_sum(ss);
   if (lane == 0) {
     const float iv = inv[base];
@@ -727,6 +748,11 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
   NNCF_CHECK_ARG(cfg->dim >= 1 && cfg->dim <= 256, "dim must be in [1, 256]");
   NNCF_CHECK_ARG(cfg->replicas >= 1 && cfg->replicas <= 1024, "replicas must be in [1, 1024]");
   NNCF_CHECK_ARG(cfg->optimizer >= 0 && cfg->optimizer <= 2, "unknown optimizer");
+  NNCF_CHECK_ARG(cfg->interaction_bias >= 0 && cfg->interaction_bias <= 3, "ERROR! Unknown interation bias");
+  if (cfg->interaction_bias) {
+    NNCF_CHECK_ARG(cfg->dim >= 3, "interaction bias: dim counts the two bias columns");
+    NNCF_CHECK_ARG(cfg->scheme != NNCF_SCHEME_SAMPLED_NEG_SHARED, "interaction bias is not available for sampled_neg_shared");
+  }
   if (cfg->scheme == NNCF_SCHEME_PAIRS || cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED)
     NNCF_CHECK_ARG(cfg->num_negatives >= 1, "num_negatives must be >= 1");
   if (cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED)
@@ -898,6 +924,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool pairwise = c.loss >= NNCF_LOSS_LOG_LOSS;
   const bool bf16 = c.precision == NNCF_PREC_BF16;
   const bool dense_items = tb->item_table == nullptr;
+  // interaction bias (ref: modules/interaction/interaction_dot.py:96-107): the tables carry two extra columns, users
+  // (ubias, 1), items (1, cbias), so that <u, v> = <u_emb, v_emb> + ubias + cbias comes out of the same contraction;
+  // they are excluded from l2-normalisation and the regulariser, and the gradient of a constant / unused column is dropped
+  const int bias = c.interaction_bias;
+  const int d_emb = bias ? d - 2 : 0;
   NNCF_PROFILE_MARK(t, 0, st);
   const bool want_row_grads = last && io && (io->grad_user_rows_dev || io->grad_item_rows_dev);
   // plain sparse SGD with nothing to post-process: the score kernel's drain applies the update itself, one bulk async
@@ -905,7 +936,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // (A first version issued red.global.add.v4 from the epilogue warps: +9.7 us in the kernel for the 11 us it saved.)
   static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return !e || atoi(e) != 0; }();
   const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
-                        (d % 4 == 0) && !dense_items && !want_row_grads;
+                        (d % 4 == 0) && !dense_items && !want_row_grads && !bias;
   // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
   // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
   t->loss_published = true;   // by the last finalize launch, or by the score kernel itself in fused mode
@@ -940,6 +971,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ++t->tl_step;
   }
   gu.tl = tl;
+  gu.d_emb = d_emb;
   GatherArgs gv = gu;
   gv.table = tb->item_table; gv.dense_rows = dense_items ? io->item_rows_dev : nullptr;
   gv.ids = item_ids; gv.ids_stride = item_stride; gv.count_dev = group ? t->nuniq : nullptr;
@@ -950,7 +982,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     gu.shards.n = gv.shards.n = t->n_shards;
     for (int i = 0; i < t->n_shards; ++i) { gu.shards.p[i] = t->ushards[i]; gv.shards.p[i] = t->ishards[i]; }
   }
-  const bool vec = (d % 4 == 0);   // 16-byte aligned rows: 128-bit loads / vector reductions
+  const bool vec = (d % 4 == 0) && !bias;   // 16-byte aligned rows: 128-bit loads / vector reductions (the scalar kernels carry the bias-column logic)
   // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
   // reads what its predecessor wrote, so only launch latency and prologues overlap
   if (vec && dp <= 128) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<1>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
@@ -963,7 +995,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     NNCF_LAUNCH_OK();
   }
   if (c.u_reg != 0.0f) {
-    reg_loss_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss);
+    reg_loss_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss, d_emb);
     NNCF_LAUNCH_OK();
   }
   NNCF_PROFILE_MARK(t, 1, st);
@@ -1017,9 +1049,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   fu.dX = t->dU; fu.dO = t->dV; fu.corr_self = group ? t->corrU : t->corrV; fu.inverse = group ? t->inverse : nullptr;
   fu.count = B; fu.rows_pad = rp; fu.d = d; fu.dp = dp; fu.normalize = c.norm_u; fu.need_x = (c.norm_u || pairwise || c.u_reg != 0.0f) ? 1 : 0;
   fu.write_back = (c.optimizer == NNCF_OPT_LAZY_ADAM) ? 1 : 0;
+  fu.d_emb = d_emb; fu.frozen0 = bias ? d - 1 : -1; fu.frozen1 = (bias && !(bias & 1)) ? d - 2 : -1;   // users: (ubias, 1)
   fu.reg_scale = 2.0f * c.u_reg / B; fu.optimizer = c.optimizer; fu.lr = c.learn_rate; fu.table = tb->user_table;
   fu.ids = uid; fu.ids_stride = B; fu.grad_out = (last && io) ? io->grad_user_rows_dev : nullptr;
   FinalizeArgs fv = fu;
+  fv.frozen0 = bias ? d - 2 : -1; fv.frozen1 = (bias && !(bias & 2)) ? d - 1 : -1;                      // items: (1, cbias)
   fv.side = 1; fv.Xf = t->Vf; fv.Of = t->Uf; fv.inv = t->invV; fv.dX = t->dV; fv.dO = nullptr; fv.corr_self = t->corrV;
   fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.need_x = (c.norm_v || pairwise) ? 1 : 0; fv.reg_scale = 0.0f;
   fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
@@ -1098,6 +1132,10 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
   pa.grad_out_u = (last && io) ? io->grad_user_rows_dev : nullptr;
   pa.grad_out_v = (last && io) ? io->grad_item_rows_dev : nullptr;
   pa.resp = resp;
+  { const int bias = c.interaction_bias;
+    pa.d_emb = bias ? d - 2 : 0;
+    pa.fu0 = bias ? d - 1 : -1; pa.fu1 = (bias && !(bias & 1)) ? d - 2 : -1;
+    pa.fv0 = bias ? d - 2 : -1; pa.fv1 = (bias && !(bias & 2)) ? d - 1 : -1; }
   dim3 g8(ceil_div(n, 8), R);
   NNCF_PROFILE_MARK(t, 0, st);
   pairs_score_kernel<<<g8, 256, 0, st>>>(pa);

@@ -63,6 +63,20 @@ class MeanPoolTower(torch.nn.Module):
         return h
 
 
+class BiasedTower(torch.nn.Module):
+    """item tower output [n, d] -> [n, d + 2] = (embedding, 1, cbias[id]): the interaction-bias columns of the item side
+    (ref: modules/interaction/interaction_dot.py:64-69,104-107; init 'zero').  cbias is trained by the tower's optimizer."""
+
+    def __init__(self, tower, item_count, item_bias):
+        super().__init__()
+        self.tower = tower
+        self.cbias = torch.nn.Parameter(torch.zeros(item_count, device='cuda'), requires_grad=item_bias)
+
+    def forward(self, item_ids):
+        h = self.tower(item_ids)
+        return torch.cat([h, torch.ones_like(h[:, :1]), self.cbias[item_ids.long()][:, None]], dim=1)
+
+
 class SharedState(object):
     """Parameters shared by every view (the reference's single Keras graph)."""
 
@@ -77,15 +91,26 @@ class SharedState(object):
         g = torch.Generator(device='cuda').manual_seed(int(getattr(conf, 'seed', 0)) + 7)
         d = conf.user_dim
         assert conf.user_dim == conf.item_dim, 'dot-product interaction needs user_dim == item_dim'
-        assert conf.interaction_bias is None, 'interaction_bias is outside the scoped path (SURVEY.md §8f)'
-        self.dim = d
+        assert conf.interaction_bias in ['user', 'item', 'both', None], \
+            "ERROR! Unknown interation bias {}".format(conf.interaction_bias)
+        # interaction bias (modules/interaction/interaction_dot.py:96-107): two extra columns per row, users (ubias, 1),
+        # items (1, cbias), biases initialised to zero; the kernels treat them as bias plumbing (include/nncf_b200.h)
+        self.bias = conf.interaction_bias
+        self.emb_dim = d
+        self.dim = d + 2 if self.bias else d
+
+        def with_bias_cols(t, ones_first):
+            if not self.bias:
+                return t
+            z, o = torch.zeros_like(t[:, :1]), torch.ones_like(t[:, :1])
+            return torch.cat([t, o, z] if ones_first else [t, z, o], dim=1).contiguous()
         # Keras-1 Embedding init 'uniform' = U(-0.05, 0.05)
-        self.user_table = (torch.rand((spec.user_count, d), generator=g, device=dev) - 0.5) * 0.1
+        self.user_table = with_bias_cols((torch.rand((spec.user_count, d), generator=g, device=dev) - 0.5) * 0.1, False)
         self.opt_kind, self.lr = conf.optimizer
         self.tower = None
         self.item_table = None
         if model_name == 'mf':
-            self.item_table = (torch.rand((spec.item_count, d), generator=g, device=dev) - 0.5) * 0.1
+            self.item_table = with_bias_cols((torch.rand((spec.item_count, d), generator=g, device=dev) - 0.5) * 0.1, True)
         elif model_name in ('basic_embedding', 'cnn_embedding', 'rnn_embedding'):
             content = torch.from_numpy(np.ascontiguousarray(data_helper.data['C'], dtype=np.int32)).to(dev)
             if model_name == 'basic_embedding':
@@ -93,7 +118,10 @@ class SharedState(object):
             else:
                 from .towers import CNNTower, RNNTower          # plain torch modules (models/model_framework.py:89-96)
                 self.tower = (CNNTower if model_name == 'cnn_embedding' else RNNTower)(spec, conf, content, g).to(dev)
-            self.tower_opt = torch.optim.Adam(self.tower.parameters(), lr=self.lr, eps=1e-8)   # Keras Adam(lr)
+            if self.bias:
+                self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
+            self.tower_opt = torch.optim.Adam([p for p in self.tower.parameters() if p.requires_grad], lr=self.lr,
+                                              eps=1e-8)                                      # Keras Adam(lr)
         else:
             assert False, '[ERROR] Model name {} unknown'.format(model_name)
         self.norm_u = bool(conf.emb_normalization)
@@ -116,13 +144,20 @@ class SharedState(object):
                 num_negatives=c.num_negatives, dim=self.dim, norm_u=self.norm_u, norm_v=self.norm_v,
                 optimizer=self.opt_kind, replicas=(c.replicas if self.item_table is not None else 1),
                 neg_loss_weight=float(c.neg_loss_weight), loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg),
-                learn_rate=float(self.lr)))
+                learn_rate=float(self.lr), interaction_bias=self.bias))
         return self._steps[scheme]
+
+    def _norm_emb(self, rows):
+        """l2-normalise the embedding columns only (the bias columns pass through)"""
+        if not self.bias:
+            return torch.nn.functional.normalize(rows, dim=-1, eps=1e-6)
+        e = self.emb_dim
+        return torch.cat([torch.nn.functional.normalize(rows[:, :e], dim=-1, eps=1e-6), rows[:, e:]], dim=1)
 
     # ---- embeddings as the views see them (test phase: dropout off, BN running statistics)
     def user_emb(self, ids):
         rows = ops.gather_rows(self.user_table, ids)
-        return torch.nn.functional.normalize(rows, dim=-1, eps=1e-6) if self.norm_u else rows
+        return self._norm_emb(rows) if self.norm_u else rows
 
     def item_emb(self, ids):
         if self.item_table is not None:
@@ -131,7 +166,7 @@ class SharedState(object):
             self.tower.eval()
             with torch.no_grad():
                 rows = self.tower(ids)
-        return torch.nn.functional.normalize(rows, dim=-1, eps=1e-6) if self.norm_v else rows
+        return self._norm_emb(rows) if self.norm_v else rows
 
 
 class _View(object):
@@ -230,7 +265,7 @@ class PairsView(_View):
             st._steps[key] = FusedStep(StepSpec(
                 scheme='pairs', loss=c.loss, precision='fp32', batch_size_p=c.batch_size_p, num_negatives=c.num_negatives,
                 dim=st.dim, norm_u=st.norm_u, norm_v=st.norm_v, optimizer='none', neg_loss_weight=float(c.neg_loss_weight),
-                loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg)))
+                loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg), interaction_bias=st.bias))
             st._user_updater = SparseUpdater(st.opt_kind, st.lr)
         out = st._steps[key].run(st.user_table, compact.detach().contiguous(), uid, inv, 1, want_grads=True)
         st._user_updater.begin_step()

@@ -9,7 +9,7 @@ from typing import Optional
 import numpy as np
 import torch
 
-from ._lib import (LOSSES, OPTIMIZERS, PRECISIONS, SCHEMES, NNCFError, StepConfig, StepIO, Tables, check, lib)
+from ._lib import (BIASES, LOSSES, OPTIMIZERS, PRECISIONS, SCHEMES, NNCFError, StepConfig, StepIO, Tables, check, lib)
 
 
 def _stream() -> int:
@@ -220,6 +220,7 @@ class StepSpec:
     beta1: float = 0.9
     beta2: float = 0.999
     epsilon: float = 1e-8
+    interaction_bias: Optional[str] = None   # None | user | item | both: `dim` then counts the two bias columns
 
     def to_c(self) -> StepConfig:
         if self.loss not in LOSSES:
@@ -227,7 +228,7 @@ class StepSpec:
         return StepConfig(SCHEMES[self.scheme], LOSSES[self.loss], PRECISIONS[self.precision], self.batch_size_p,
                           self.num_negatives, self.dim, int(self.norm_u), int(self.norm_v), OPTIMIZERS[self.optimizer],
                           self.replicas, self.neg_loss_weight, self.loss_gamma, self.u_reg, self.learn_rate, self.beta1,
-                          self.beta2, self.epsilon)
+                          self.beta2, self.epsilon, BIASES[self.interaction_bias])
 
 
 class FusedStep:

@@ -196,11 +196,13 @@ def _scatter_rows(n_rows, ids, rows):
 
 
 def step_matmul(EU, EV, uid, cid, scheme, loss, neg_loss_weight, gamma, u_reg=0.0,
-                norm_u=False, norm_v=False):
+                norm_u=False, norm_v=False, ubias=None, cbias=None):
     """One neg_shared / group_neg_shared batch on plain embedding tables.
     Graph: models/model_framework.py:40-65 (user side), :85-88 / :98-111 (item side), :126-136 (scores),
     modules/interaction/interaction_dot.py:100-107 ('matmul'), loss per scheme, activity regulariser
     utils/utilities.py:122-135 on the un-normalised user rows.
+    ubias [U] / cbias [I] (optional): InteractionDot's bias terms, S += ubias[uid][:, None] + cbias[col_ids][None, :]
+    (modules/interaction/interaction_dot.py:104-107); their gradients come back as dubias / dcbias.
     Returns dict(loss, task_loss, dEU [U,d], dEV [I,d], S)."""
     uid = np.asarray(uid); cid = np.asarray(cid)
     B = uid.shape[0]
@@ -210,6 +212,10 @@ def step_matmul(EU, EV, uid, cid, scheme, loss, neg_loss_weight, gamma, u_reg=0.
         V_raw = EV[cid]
         V, inv_v = l2_normalize(V_raw) if norm_v else (V_raw, None)
         S = U @ V.T
+        if ubias is not None:
+            S = S + np.asarray(ubias)[uid][:, None]
+        if cbias is not None:
+            S = S + np.asarray(cbias)[cid][None, :]
         L, G = neg_shared_loss_grad(S, loss, neg_loss_weight, gamma)
         col_ids = cid
     elif scheme == "group_neg_shared":
@@ -217,6 +223,10 @@ def step_matmul(EU, EV, uid, cid, scheme, loss, neg_loss_weight, gamma, u_reg=0.
         V_raw = EV[cid_u]
         V, inv_v = l2_normalize(V_raw) if norm_v else (V_raw, None)
         S = U @ V.T
+        if ubias is not None:
+            S = S + np.asarray(ubias)[uid][:, None]
+        if cbias is not None:
+            S = S + np.asarray(cbias)[cid_u][None, :]
         L, G = group_neg_shared_loss_grad(S, cid_x, loss, neg_loss_weight, gamma)
         col_ids = cid_u
     else:
@@ -229,11 +239,17 @@ def step_matmul(EU, EV, uid, cid, scheme, loss, neg_loss_weight, gamma, u_reg=0.
         dV = l2_normalize_bwd(V, inv_v, dV)
     reg = u_reg * np.sum(np.mean(U_raw ** 2, axis=0))
     dU = dU + 2.0 * u_reg * U_raw / B
-    return dict(loss=L + reg, task_loss=L, S=S,
-                dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], col_ids, dV))
+    out = dict(loss=L + reg, task_loss=L, S=S,
+               dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], col_ids, dV))
+    if ubias is not None:
+        out["dubias"] = _scatter_rows(EU.shape[0], uid, G.sum(axis=1, keepdims=True))[:, 0]
+    if cbias is not None:
+        out["dcbias"] = _scatter_rows(EV.shape[0], col_ids, G.sum(axis=0)[:, None])[:, 0]
+    return out
 
 
-def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, norm_u=False, norm_v=False, y_true=None):
+def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, norm_u=False, norm_v=False, y_true=None,
+             ubias=None, cbias=None):
     """One 'original' / 'group_sample' batch: (1+k)B listed pairs, row-wise dot
     (modules/interaction/interaction_dot.py:92-99), get_original_loss.  The regulariser averages over all
     (1+k)B gathered user rows (utils/utilities.py:129-135: K.mean over axis 0 of the layer output)."""
@@ -244,6 +260,10 @@ def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, no
     U, inv_u = l2_normalize(U_raw) if norm_u else (U_raw, None)
     V, inv_v = l2_normalize(V_raw) if norm_v else (V_raw, None)
     s = np.sum(U * V, axis=1)
+    if ubias is not None:                                             # interaction_dot.py:96-99
+        s = s + np.asarray(ubias)[uid]
+    if cbias is not None:
+        s = s + np.asarray(cbias)[cid]
     L, g = original_loss_grad(s, B, k, loss, neg_loss_weight, gamma, y_true)
     dU = g[:, None] * V
     dV = g[:, None] * U
@@ -253,8 +273,13 @@ def step_mul(EU, EV, uid, cid, B, k, loss, neg_loss_weight, gamma, u_reg=0.0, no
         dV = l2_normalize_bwd(V, inv_v, dV)
     reg = u_reg * np.sum(np.mean(U_raw ** 2, axis=0))
     dU = dU + 2.0 * u_reg * U_raw / n
-    return dict(loss=L + reg, task_loss=L, s=s,
-                dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], cid, dV))
+    out = dict(loss=L + reg, task_loss=L, s=s,
+               dEU=_scatter_rows(EU.shape[0], uid, dU), dEV=_scatter_rows(EV.shape[0], cid, dV))
+    if ubias is not None:
+        out["dubias"] = _scatter_rows(EU.shape[0], uid, g[:, None])[:, 0]
+    if cbias is not None:
+        out["dcbias"] = _scatter_rows(EV.shape[0], cid, g[:, None])[:, 0]
+    return out
 
 
 def sampled_neg_shared_loss_grad(pred, loss, neg_loss_weight, gamma):

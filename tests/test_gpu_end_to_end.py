@@ -49,6 +49,27 @@ def test_cnn_rnn_towers_run(model, scheme, loss, capsys):
     assert 'epoch 1 (' in out and 'test recall/map' in out
 
 
+@pytest.mark.parametrize("model,scheme,bias", [("mf", "neg_shared", "item"), ("mf", "original", "both"),
+                                               ("basic_embedding", "group_neg_shared", "item"), ("basic_embedding", "original", "user")])
+def test_interaction_bias_models_run_and_learn_bias(model, scheme, bias, capsys):
+    """InteractionDot(bias=...) end to end (the default Conf of --model_choice mf has interaction_bias='item')"""
+    tr = _run(model, scheme, 'skip-gram', 'whole@10', {'max_epoch': 1, 'interaction_bias': bias, 'learn_rate': 0.05})
+    out = capsys.readouterr().out
+    assert 'epoch 1 (' in out and 'test recall/map' in out
+    st = tr.model_dict['_state']
+    d = st.emb_dim
+    assert st.dim == d + 2 and bool((st.user_table[:, d + 1] == 1).all())                 # the constant column never moves
+    if bias in ('user', 'both'):
+        assert float(st.user_table[:, d].abs().max()) > 0                                  # the user bias was trained
+    else:
+        assert float(st.user_table[:, d].abs().max()) == 0
+    if st.item_table is not None:
+        assert bool((st.item_table[:, d] == 1).all())
+        assert (float(st.item_table[:, d + 1].abs().max()) > 0) == (bias in ('item', 'both'))
+    else:
+        assert (float(st.tower.cbias.abs().max()) > 0) == (bias in ('item', 'both'))
+
+
 def test_validation_split_data_runs(capsys):
     from nncf_b200.main import run
     np.random.seed(0)

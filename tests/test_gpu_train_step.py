@@ -366,3 +366,71 @@ def test_zero_steps_is_a_no_op():
     out = FusedStep(StepSpec(batch_size_p=128, dim=64)).run(tU, tV, ids, ids, 0)
     torch.cuda.synchronize()
     assert out["loss"].numel() == 0 and torch.equal(tU, a) and torch.equal(tV, b)
+
+
+def _augment(EU, EV, ub, cb):
+    """tables with the two interaction-bias columns: users (ubias, 1), items (1, cbias)"""
+    one_u, one_v = np.ones((EU.shape[0], 1), np.float32), np.ones((EV.shape[0], 1), np.float32)
+    return (np.concatenate([EU, ub[:, None].astype(np.float32), one_u], 1),
+            np.concatenate([EV, one_v, cb[:, None].astype(np.float32)], 1))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("scheme,loss,norm,bias", [("neg_shared", "skip-gram", False, "both"), ("neg_shared", "log-loss", True, "item"),
+                                                   ("group_neg_shared", "mse", False, "user"), ("group_neg_shared", "max-margin", True, "both"),
+                                                   ("pairs", "skip-gram", True, "item"), ("pairs", "log-loss", False, "both")])
+def test_interaction_bias_matches_oracle(scheme, loss, norm, bias, precision):
+    """InteractionDot(bias=...) (ref: modules/interaction/interaction_dot.py:96-107) through the augmented-column tables:
+    loss, embedding gradients and bias gradients against the oracle; constant columns and unused biases stay put."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    if scheme == "pairs" and precision == "bf16":
+        pytest.skip("the PAIRS scheme is fp32 only")
+    rng = np.random.RandomState(3)
+    nu, ni, d, B, k, lr = 200, 90, 50, 96, 3, 2.0
+    EU, EV = _tables(nu, ni, d, seed=1)
+    ub = rng.uniform(-0.3, 0.3, nu) * (bias in ("user", "both"))
+    cb = rng.uniform(-0.3, 0.3, ni) * (bias in ("item", "both"))
+    if loss == "max-margin" and precision == "bf16":
+        EU = torch.from_numpy(EU).bfloat16().float().numpy(); EV = torch.from_numpy(EV).bfloat16().float().numpy()
+        ub = torch.from_numpy(ub).bfloat16().double().numpy(); cb = torch.from_numpy(cb).bfloat16().double().numpy()
+    rows = (1 + k) * B if scheme == "pairs" else B
+    uid = rng.randint(0, nu, rows).astype(np.int32); cid = rng.randint(0, ni, rows).astype(np.int32)
+    lam, gamma = _params(loss)
+    kw = dict(u_reg=1e-3, norm_u=norm, norm_v=norm, ubias=ub if bias in ("user", "both") else None,
+              cbias=cb if bias in ("item", "both") else None)
+    if scheme == "pairs":
+        ref = O.step_mul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, B, k, loss, lam, gamma, **kw)
+    else:
+        ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, scheme, loss, lam, gamma, **kw)
+    AU, AV = _augment(EU, EV, ub, cb)
+    spec = StepSpec(scheme=scheme, loss=loss, precision=precision, batch_size_p=B, num_negatives=k, dim=d + 2, norm_u=norm,
+                    norm_v=norm, optimizer="sgd", learn_rate=lr, neg_loss_weight=lam, loss_gamma=gamma, u_reg=1e-3,
+                    interaction_bias=bias)
+    tU, tV = torch.from_numpy(AU).cuda(), torch.from_numpy(AV).cuda()
+    out = FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
+    torch.cuda.synchronize()
+    tol = TOL[precision]
+    assert abs(float(out["loss"][0]) - ref["loss"]) <= tol * abs(ref["loss"])
+    gU = (AU.astype(np.float64) - tU.cpu().numpy()) / lr
+    gV = (AV.astype(np.float64) - tV.cpu().numpy()) / lr
+    if not (loss == "max-margin" and precision == "bf16"):
+        assert _rel(gU[:, :d], ref["dEU"]) <= max(tol, 1e-3)
+        assert _rel(gV[:, :d], ref["dEV"]) <= max(tol, 1e-3)
+        scale = np.max(np.abs(ref["dEU"]))
+
+        def bias_grad_ok(got, want):
+            # pairwise losses compare scores that share the bias (neg_shared: same item column, group: same user row), so
+            # that bias has an exactly zero gradient: check it absolutely, against the scale of the embedding gradients
+            if np.max(np.abs(want)) < 1e-9 * scale:
+                return np.max(np.abs(got)) <= max(tol, 1e-3) * scale
+            return _rel(got, want) <= max(tol, 1e-3)
+        if bias in ("user", "both"):
+            assert bias_grad_ok(gU[:, d], ref["dubias"])
+        if bias in ("item", "both"):
+            assert bias_grad_ok(gV[:, d + 1], ref["dcbias"])
+    # the constant columns never move; an unused bias column stays zero
+    assert np.array_equal(tU.cpu().numpy()[:, d + 1], np.ones(nu, np.float32)) and np.array_equal(tV.cpu().numpy()[:, d], np.ones(ni, np.float32))
+    if bias == "item":
+        assert np.all(tU.cpu().numpy()[:, d] == 0)
+    if bias == "user":
+        assert np.all(tV.cpu().numpy()[:, d + 1] == 0)

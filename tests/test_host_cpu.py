@@ -166,3 +166,15 @@ def test_cnn_and_rnn_towers_shapes_and_gradients():
         with torch.no_grad():
             a, b = tower(torch.arange(5)), tower(torch.arange(5))
         assert torch.equal(a, b)                               # test phase: dropout off, BN running statistics
+
+
+def test_mf_conf_follows_pretrained_conf():
+    """main.py:47-48 gives --model_choice mf the Conf of configs/pretrained_conf.py"""
+    from nncf_b200.conf import get_conf
+    c = get_conf('citeulike_title_only_fold1', 'default', None, 'mf')
+    assert (c.max_epoch, c.num_negatives, c.batch_size_p, c.neg_loss_weight, c.interaction_bias) == (20, 5, 64, 1, 'item')
+    assert (c.neg_dist, c.chop_size, c.shuffle_st, c.u_reg) == ('uniform', 1, 'by_item', 1e-5)
+    b = get_conf('citeulike_title_only_fold1', 'best', None, 'mf')             # pretrained_conf.py:121-142
+    assert (b.max_epoch, b.num_negatives, b.interaction_bias, b.u_reg) == (30, 10, None, 1e-6)
+    assert get_conf('news_title_only_fold1', 'best', None, 'mf').u_reg == 1e-5
+    assert get_conf('x', 'default', {'interaction_bias': None, 'batch_size_p': 512}, 'mf').batch_size_p == 512
