@@ -39,6 +39,17 @@ class Conf(object):
         self.interaction_bias = None
         self.use_content_id = False
         self.v_reg = 0
+        # pretrained content embedding                (:68-76).  The reference always points at its vector blobs; they are
+        # absent here (.MISSING_LARGE_BLOBS), so the dict is only created when the files exist or param_dict supplies one
+        # ({'wordvec_filepath', 'sentvec_filepath', 'pretrain_combine_dropout', '..._mode', '..._actv'}; the arrays may
+        # also be handed over as 'W_pretrain' / 'C_pretrain').  None = the reference's conf_var 'sup' (supervised only).
+        self.pretrain = None
+        from .data_utils import get_pretrain_folder
+        import os as _os
+        folder = get_pretrain_folder(data_name, aug=True)
+        if folder is not None and _os.path.exists(folder + 'sentence_vectors_50d.pkl'):
+            self.pretrain = {'wordvec_filepath': folder + 'word_vectors_50d.pkl',
+                             'sentvec_filepath': folder + 'sentence_vectors_50d.pkl'}
         # engine keys (not in the reference)
         self.precision = 'bf16'          # 'bf16' = tcgen05 tensor cores, 'fp32' = CUDA-core exact mode
         self.replicas = 1                # independent batches per device step (1 = the reference's sequential loop)
@@ -50,6 +61,10 @@ class Conf(object):
         self._post_init()
 
     def _post_init(self):
+        if self.pretrain:
+            for key, val in (('pretrain_combine_dropout', 0.5), ('pretrain_combine_mode', 'concat'),
+                             ('pretrain_combine_actv', 'relu')):
+                self.pretrain.setdefault(key, val)
         if self.emb_normalization is None:
             self.emb_normalization = True \
                 if self.loss == 'max-margin' or self.loss == 'log-loss' else False
@@ -111,7 +126,23 @@ class RnnConf(Conf):
         super().__init__(data_name, pd)
 
 
-CONF_CLASSES = {'mf': MfConf, 'basic_embedding': Conf, 'cnn_embedding': CnnConf, 'rnn_embedding': RnnConf}
+class PretrainedConf(MfConf):
+    """configs/pretrained_conf.py:10-65 for `--model_choice pretrained`: the 'mf' keys plus the pretrain dict (doc2vec
+    item vectors of the un-augmented corpus, `transform` False = use them as the item embedding as they are)."""
+
+    def __init__(self, data_name, param_dict=None):
+        super().__init__(data_name, param_dict)
+        from .data_utils import get_pretrain_folder
+        given = dict(self.pretrain) if isinstance(self.pretrain, dict) else {}
+        folder = get_pretrain_folder(data_name, aug=False)
+        self.pretrain = {'wordvec_filepath': None,
+                         'sentvec_filepath': (folder + 'sentence_vectors_50d.txt') if folder else None,
+                         'transform': False, 'pretrain_combine_dropout': 0.5, 'pretrain_combine_actv': 'relu',
+                         'pretrain_combine_mode': None}
+        self.pretrain.update(given)
+
+
+CONF_CLASSES = {'pretrained': PretrainedConf, 'mf': MfConf, 'basic_embedding': Conf, 'cnn_embedding': CnnConf, 'rnn_embedding': RnnConf}
 
 
 def get_conf_default(data_name, param_dict=None, model_choice='basic_embedding'):
@@ -126,7 +157,7 @@ def get_conf_best(data_name, param_dict=None, model_choice='basic_embedding'):
     conf = CONF_CLASSES[model_choice](data_name, param_dict=param_dict)
     conf.c_reg = 0
     conf.num_negatives = 10
-    if model_choice == 'mf':                               # pretrained_conf.py:128-142
+    if model_choice in ('mf', 'pretrained'):               # pretrained_conf.py:128-142
         conf.max_epoch = 30
         conf.interaction_bias = None
         conf.u_reg = 1e-5 if data_name.startswith('news_title_only') else 1e-6
@@ -134,10 +165,19 @@ def get_conf_best(data_name, param_dict=None, model_choice='basic_embedding'):
         conf.max_epoch = 20
         conf.u_reg = 1e-5 if data_name.startswith('news_title_only') else 1e-6
         conf.word_emb_dropout_rate = 0.3
+        if conf.pretrain:
+            conf.pretrain['pretrain_combine_dropout'] = 0.1
     else:  # citeulike_* and the synthetic stand-ins of the same shape
         conf.max_epoch = 30
         conf.u_reg = 1e-6
         conf.word_emb_dropout_rate = 0.5
+        if conf.pretrain:
+            conf.pretrain['pretrain_combine_dropout'] = 0.3
+    conf_var = (param_dict or {}).get('conf_var')          # basic_embedding_conf.py:131-136
+    if conf_var == 'sup':
+        conf.pretrain = None
+    elif isinstance(conf_var, str) and conf_var.startswith('unsup_dropout') and conf.pretrain:
+        conf.pretrain['pretrain_combine_dropout'] = float(conf_var[conf_var.find('=') + 1:])
     try:
         param_dict['reset_after_getconf']
         conf.__dict__.update(param_dict)

@@ -216,6 +216,9 @@ struct EvalArgs {
   int prefetch_ahead;                         // second-generation kernel: L2 prefetch distance in tiles (0 = off)
   int cap;                                    // second-generation kernel: keys per row buffer (multiple of 32, >= KP + 32)
   int dbg_mode;                               // developer switch (env NNCF_EVAL_DBG): 1 = skip the filter, 2 = also the TMEM loads, 3 = row maxima + ballot only
+  unsigned long long* stats;                  // developer counters (env NNCF_EVAL_STATS): [0] tiles x warps, [1] tiles with a hit, [2] hit rows,
+                                              // [3] keys appended, [4] compactions, [5] cycles in the hit path, [6] cycles in the tile loop
+  int dbg_pipe;                               // developer switch (env NNCF_EVAL_PIPE), second generation: bit 0 = no item copies after the first fill, bit 1 = no MMAs, bit 2 = exact (radix-select) compaction on the hot path
 };
 
 constexpr int kEvalRowGroups = 2;                 // epilogue warps per TMEM lane quadrant; each owns 32 / kEvalRowGroups rows
@@ -233,12 +236,12 @@ __global__ void __launch_bounds__(kEvalThreads, 1)
 eval_topk_tc_kernel(EvalArgs a) {
   constexpr int DP = 64 * NSUB;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST)
   const int nst = a.nstages;
   uint8_t* sU = smem;
   uint8_t* sV = sU + NSUB * kSubBytes;
   uint64_t* lists_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);   // [128][KP]
-  float* stage_all = reinterpret_cast<float*>(lists_sm + 128 * a.KP);              // [4 warps][32]
+  float* stage_all = reinterpret_cast<float*>(lists_sm + 128 * a.KP);              // [8 warps][32]
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + 8 * 32);
   uint64_t* u_full = bars;
   uint64_t* v_full = bars + 1;    // [4]
@@ -385,12 +388,12 @@ constexpr int kEval2Acc = 3;
 constexpr int kEval2MaxNK = 6;                    // CAP <= 192 keys per row
 
 __host__ __device__ inline size_t eval2_smem_bytes(int nsub, int nstages, int cap) {
-  return (size_t)nsub * kSubBytes * nstages + (size_t)128 * cap * 8 + kEval2EpiWarps * 32 * 4 + 1024 + 256;
+  return (size_t)nsub * kSubBytes * nstages + (size_t)128 * (cap + 1) * 8 + kEval2EpiWarps * 128 * 4 + 1024 + 256;
 }
 
 // the row's n > k keys (buf[0..n)) -> its k largest at buf[0..k); returns the score of the k-th as the new threshold.
 // Warp-cooperative; n, k warp-uniform; keys are unique (they embed the column).
-__device__ __forceinline__ float compact_row(uint64_t* buf, int n, int k, int lane) {
+__device__ __noinline__ float compact_row(uint64_t* buf, int n, int k, int lane) {
   uint32_t hi[kEval2MaxNK], lo[kEval2MaxNK];
 #pragma unroll
   for (int i = 0; i < kEval2MaxNK; ++i) {
@@ -438,14 +441,93 @@ __device__ __forceinline__ float compact_row(uint64_t* buf, int n, int k, int la
   return key_score(static_cast<uint64_t>(T) << 32);
 }
 
+// Coarse compaction (the hot-path variant): one histogram round instead of a 32-step radix select.  The row's keys are
+// bucketed by score into 32 equal bins between the row's smallest and largest score (monotone in the score), the bins are
+// suffix-summed, and every key in or above the highest bin B whose suffix count reaches k is kept: kept >= k keys, all
+// greater than every dropped key, so the smallest kept score is a valid lower bound of the row's k-th best and no key that
+// can still belong to the top k is lost (exactness is preserved; the final per-row compaction is the exact one).
+// ~300 cycles against ~2,500: a compaction holds up its whole CTA pair (an accumulator is recycled only when all 8 filter
+// warps have read it), and with ~0.5 compactions per tile per pair that stall, not the per-candidate work, was what
+// held whole@k at ~2,200 cycles per tile.  Falls back to the exact select when the bins cannot separate (ties).
+// Returns the new threshold; *n_out = keys kept.
+__device__ __noinline__ float compact_row_coarse(uint64_t* buf, int n, int k, int max_keep, int lane, int* hist, int* n_out) {
+  uint32_t hi[kEval2MaxNK], lo[kEval2MaxNK];
+  uint32_t hmax = 0u, hmin = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) {
+    const int idx = lane + 32 * i;
+    const uint64_t key = idx < n ? buf[idx] : 0ull;
+    hi[i] = static_cast<uint32_t>(key >> 32); lo[i] = static_cast<uint32_t>(key);
+    if (hi[i]) { hmax = max(hmax, hi[i]); hmin = min(hmin, hi[i]); }
+  }
+  hist[lane] = 0;
+  hmax = __reduce_max_sync(0xffffffffu, hmax);
+  hmin = __reduce_min_sync(0xffffffffu, hmin);
+  const float smax = key_score(static_cast<uint64_t>(hmax) << 32), smin = key_score(static_cast<uint64_t>(hmin) << 32);
+  const float scale = 32.0f / (smax - smin);
+  __syncwarp();
+  int bin[kEval2MaxNK];
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) {
+    bin[i] = -1;
+    if (hi[i]) {
+      const float sc = key_score(static_cast<uint64_t>(hi[i]) << 32);
+      bin[i] = min(31, max(0, static_cast<int>((sc - smin) * scale)));
+      atomicAdd(&hist[bin[i]], 1);
+    }
+  }
+  __syncwarp();
+  int suf = hist[lane];
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_down_sync(0xffffffffu, suf, d);
+    if (lane + d < 32) suf += t;
+  }
+  const unsigned okm = __ballot_sync(0xffffffffu, suf >= k);      // suf is non-increasing in the bin index; bin 0 holds all n >= k keys
+  const int B = 31 - __clz(okm | 1u);
+  const int kept = __shfl_sync(0xffffffffu, suf, B);
+  if (!(smax > smin) || kept > max_keep || kept < k) {             // bins cannot separate (equal scores): exact select
+    __syncwarp();
+    *n_out = k;
+    return compact_row(buf, n, k, lane);
+  }
+  uint32_t kmin = 0xffffffffu;
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) if (bin[i] >= B) kmin = min(kmin, hi[i]);
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  int base = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int i = 0; i < kEval2MaxNK; ++i) {
+    const bool keep = bin[i] >= B;
+    const unsigned mk = __ballot_sync(0xffffffffu, keep);
+    if (keep) buf[base + __popc(mk & lt)] = (static_cast<uint64_t>(hi[i]) << 32) | lo[i];
+    base += __popc(mk);
+  }
+  __syncwarp();
+  *n_out = kept;
+  return key_score(static_cast<uint64_t>(kmin) << 32);
+}
+
+#ifdef NNCF_EVAL_STATS_BUILD
+struct FStat { unsigned tiles_hit, hit_rows, appended, compactions; };
+#define FSTAT_ADD(field, x) do { fstat.field += (x); } while (0)
+#else
+struct FStat {};
+#define FSTAT_ADD(field, x) do { } while (0)
+#endif
+
 struct Row2 {
   float thr;     // a lower bound of the row's k-th best score (exact as of the last compaction; -inf before k keys exist)
   int cnt;       // keys in the row's buffer
 };
 
+// (A compact variant of this filter - one run-time loop over the row's passing chunks, compactions out of line, 38 KB of
+// SASS instead of 160 KB - was SLOWER (17.8 vs 15.7 ms at k = 50): the cost is the dependent chain per hit row, not
+// instruction fetch.  The third generation takes the candidate path off the reading warps instead.)
 __device__ __forceinline__ void filter_tile2(const float (&v)[4][32], uint32_t col0, uint32_t col_end, Row2& st, bool row_ok,
                                              uint64_t* bufs_warp, int CAP, int k, float* stage, int lane, unsigned own_mask,
-                                             bool skip_hits) {
+                                             bool skip_hits, bool exact_compaction, FStat& fstat) {
   float gm[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -461,12 +543,13 @@ __device__ __forceinline__ void filter_tile2(const float (&v)[4][32], uint32_t c
   unsigned hits = __ballot_sync(0xffffffffu, row_ok && m >= st.thr) & own_mask;
   if (skip_hits) { if (hits == 0x12345678u) st.cnt = 1; st.thr = fmaxf(st.thr, m - 1.0f); return; }   // developer switch
   const unsigned lt = (1u << lane) - 1u;
+  FSTAT_ADD(tiles_hit, hits ? 1 : 0); FSTAT_ADD(hit_rows, __popc(hits));
   while (hits) {
     const int L = __ffs(hits) - 1;
     hits &= hits - 1;
     float thr_l = __shfl_sync(0xffffffffu, st.thr, L);
     int cnt_l = __shfl_sync(0xffffffffu, st.cnt, L);
-    uint64_t* buf = bufs_warp + (size_t)L * CAP;
+    uint64_t* buf = bufs_warp + (size_t)L * (CAP + 1);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const float gmc = __shfl_sync(0xffffffffu, gm[c], L);
@@ -483,10 +566,14 @@ __device__ __forceinline__ void filter_tile2(const float (&v)[4][32], uint32_t c
         const unsigned cm = __ballot_sync(0xffffffffu, cand);
         if (cand) buf[cnt_l + __popc(cm & lt)] = make_key(x, col);
         cnt_l += __popc(cm);
+        FSTAT_ADD(appended, __popc(cm));
         __syncwarp();
-        if (cnt_l > CAP - 32) {                         // fewer than 32 free slots: keep the k best, raise the threshold
-          thr_l = compact_row(buf, cnt_l, k, lane);
-          cnt_l = k;
+        if (cnt_l > CAP - 32) {                         // fewer than 32 free slots: keep (about) the k best, raise the threshold
+          int kept = k;
+          FSTAT_ADD(compactions, 1);
+          if (exact_compaction) thr_l = compact_row(buf, cnt_l, k, lane);
+          else thr_l = compact_row_coarse(buf, cnt_l, k, CAP - 48, lane, reinterpret_cast<int*>(stage), &kept);
+          cnt_l = kept;
         }
       }
     }
@@ -500,12 +587,12 @@ eval_topk_tc2_kernel(EvalArgs a) {
   constexpr int DP = 64 * NSUB;
   constexpr int kColU = kEval2Acc * 128;            // TMEM: 3 accumulators, then the user block (DP / 2 columns)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST)
   const int nst = a.nstages, CAP = a.cap;
   uint8_t* sV = smem;
-  uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);    // [128][CAP]
-  float* stage_all = reinterpret_cast<float*>(bufs_sm + 128 * CAP);                // [4 warps][32]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + kEval2EpiWarps * 32);
+  uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);    // [128][CAP + 1] (padded rows)
+  float* stage_all = reinterpret_cast<float*>(bufs_sm + 128 * (CAP + 1));          // [filter warps][128]: a hit row's passing chunks / the compaction histogram
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + kEval2EpiWarps * 128);
   uint64_t* u_full = bars;
   uint64_t* v_full = bars + 1;    // [4]
   uint64_t* v_empty = bars + 5;   // [4]
@@ -541,6 +628,7 @@ eval_topk_tc2_kernel(EvalArgs a) {
       for (int j = 0; j < nj; ++j) {
         const int st = j % nst;
         mbar_wait(&v_empty[st], ((j / nst) & 1) ^ 1);
+        if ((a.dbg_pipe & 1) && j >= nst) { mbar_arrive(&v_full[st]); continue; }   // developer switch: stale stage contents
         mbar_expect_tx(&v_full[st], NSUB * kSubBytes);
         const int jj = (j + rot) % nj;
         const uint8_t* gV = a.Vimg + (size_t)(t0 + jj) * NSUB * kSubBytes;
@@ -560,8 +648,13 @@ eval_topk_tc2_kernel(EvalArgs a) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nj > 0) {
+    if (nj > 0) {
+      // The whole warp runs this loop (warp-uniform control flow and operands -> uniform registers); one elected lane issues.
+      // An `if (lane == 0)` body made ptxas rebuild the descriptor and move the tensor-memory addresses through an
+      // ELECT / R2UR.BROADCAST / BRA.U.ANY sequence before every MMA: 163 cycles per instruction against 64 of tensor work.
       const uint32_t idesc = make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t desc0 = make_smem_desc(smem_u32(sV), 16, 1024);
       mbar_wait(u_full, 0);                                       // the user block sits in TMEM
       tc_fence_after();
       for (int j = 0; j < nj; ++j) {
@@ -569,14 +662,20 @@ eval_topk_tc2_kernel(EvalArgs a) {
         mbar_wait(&v_full[st], (j / nst) & 1);
         mbar_wait(&s_empty[sb], ((j / kEval2Acc) & 1) ^ 1);
         tc_fence_after();
+        if (elect_one()) {
+          if (!(a.dbg_pipe & 2)) {
+            const uint64_t dst = desc0 + static_cast<uint64_t>((st * NSUB * kSubBytes) >> 4);
+            const uint32_t dcol = tmem_u + sb * 128;
 #pragma unroll
-        for (int k = 0; k < DP / 16; ++k) {                       // K = 16 per MMA = 8 TMEM columns of the user block
-          const uint64_t bd = make_smem_desc(smem_u32(sV + (st * NSUB + (k >> 2)) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          umma_bf16_ts(tmem + sb * 128, tmem + kColU + 8 * k, bd, idesc, k > 0);
+            for (int k = 0; k < DP / 16; ++k)                     // K = 16 per MMA = 8 TMEM columns of the user block
+              umma_bf16_ts(dcol, tmem_u + kColU + 8 * k, dst + static_cast<uint64_t>(((k >> 2) * kSubBytes + (k & 3) * 32) >> 4),
+                           idesc, k > 0);
+          }
+          umma_commit(&s_full[sb]);
+          if (CL > 1) umma_commit_multicast(&v_empty[st], kMask);   // the stage is rewritten by all CL producers
+          else umma_commit(&v_empty[st]);
         }
-        umma_commit(&s_full[sb]);
-        if (CL > 1) umma_commit_multicast(&v_empty[st], kMask);   // the stage is rewritten by all CL producers
-        else umma_commit(&v_empty[st]);
+        __syncwarp();
       }
     }
   } else {
@@ -609,8 +708,10 @@ eval_topk_tc2_kernel(EvalArgs a) {
       if (lane == 0) mbar_arrive(u_full);
     }
     Row2 rs; rs.thr = -INFINITY; rs.cnt = 0;
-    uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * CAP;
-    float* stage = stage_all + (warp - 2) * 32;
+    FStat fstat{};
+    long long cyc_hit = 0; (void)cyc_hit;
+    uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * (CAP + 1);
+    float* stage = stage_all + (warp - 2) * 128;
     const uint32_t col_end = static_cast<uint32_t>(a.n_items);
     for (int j = 0; j < nj; ++j) {
       const int sb = j % kEval2Acc;
@@ -626,8 +727,8 @@ eval_topk_tc2_kernel(EvalArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[sb]);
       if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) rs.cnt = 1; continue; }
-      filter_tile2(v, static_cast<uint32_t>((t0 + (j + rot) % nj) * 128), col_end, rs, row_ok, bufs_warp, CAP, a.k, stage, lane,
-                   own_mask, a.dbg_mode == 3);
+      const uint32_t col0 = static_cast<uint32_t>((t0 + (j + rot) % nj) * 128);
+      filter_tile2(v, col0, col_end, rs, row_ok, bufs_warp, CAP, a.k, stage, lane, own_mask, a.dbg_mode == 3, (a.dbg_pipe & 4) != 0, fstat);
     }
     __syncwarp();
     // final compaction of every row to its k best, then the row's KP slots go to the global per-(user, split) lists
@@ -635,7 +736,7 @@ eval_topk_tc2_kernel(EvalArgs a) {
     uint64_t* grow0 = a.lists + ((int64_t)ub * 128 + q * 32) * gstride + (int64_t)sp * a.KP;
     for (int r = rg * kOwn; r < (rg + 1) * kOwn; ++r) {
       int n = __shfl_sync(0xffffffffu, rs.cnt, r);
-      uint64_t* buf = bufs_warp + (size_t)r * CAP;
+      uint64_t* buf = bufs_warp + (size_t)r * (CAP + 1);
       if (n > a.k) { compact_row(buf, n, a.k, lane); n = a.k; }
       for (int i = lane; i < a.KP; i += 32) grow0[r * gstride + i] = i < n ? buf[i] : 0ull;
     }
@@ -646,6 +747,313 @@ eval_topk_tc2_kernel(EvalArgs a) {
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Third generation: a CTA PAIR (cluster of 2 = the two SMs of a TPC) on one tcgen05.mma.cta_group::2.
+//   M = 256 users (128 per CTA, each CTA's block in its OWN tensor memory as the A operand), N = 128 items of which
+//   each CTA stages only 64 rows (the first / second 8 KiB of every 16 KiB sub-tile of the item image): an item tile
+//   enters each SM once per 256 users, so the L2 -> SM stream per SM is half of the second generation's, and a stage
+//   is half as big, so the same shared memory holds twice as many tiles in flight.
+//   Leader (cluster rank 0): warp 1 lane 0 issues the MMAs and commits with a multicast arrive to both CTAs' barriers.
+//   Peer: warp 1 lane 0 relays "my half of stage st has landed" to the leader's p_full[st] (remote mbarrier arrive);
+//   the epilogue warps of both CTAs release accumulators on the leader's s_empty (remote arrive).
+//   Epilogue (filter) identical to the second generation.
+// ------------------------------------------------------------------------------------------------
+constexpr int kEval3MaxStages = 8;
+// Warp roles of the third generation: 0 producer, 1 MMA issuer / relay, 2..5 readers (one per TMEM lane quadrant), 6..9 selectors.
+// A reader loads its 32 x 128 scores, releases the accumulator, takes the row / chunk maxima, and - for rows that reach their
+// threshold - only STAGES the passing 32-column chunks into a shared-memory ring; it never touches the k-best sets.  The
+// selector of the same quadrant owns the row buffers and thresholds: it drains the ring (compare, ballot, append,
+// compaction) and publishes each raised threshold for the reader's next tiles (a stale threshold only forwards extra
+// chunks: the result stays exact).  Why: ncu pc-sampling of the one-warp filter (profiles/r01c) showed the four filter
+// warps busy 83 % of the time, 3/4 of it in the candidate path, every sample a fixed-latency dependency stall - one warp
+// per scheduler, nothing to hide a ~700-cycle chain per hit row behind - while an accumulator is recycled only when all
+// 8 filter warps of the pair have read it.  Variants measured first (37,888 users x 1M items, k = 50; 15.7 ms before):
+// two readers per quadrant with 16 rows each 18.6 ms (duplicated TMEM reads), per-lane compare-and-branch 30 ms,
+// per-lane branch-free scan down the maxima hierarchy 19.9 ms.
+constexpr int kEval3Ring = 32;                    // staged chunks per quadrant ring (power of two, >= 32 = one chunk of every row)
+constexpr int kEval3Threads = 64 + 32 * 8;
+constexpr int kEvalDefaultGen = 2;                // NNCF_EVAL_GEN overrides (2 = second generation, 3 = CTA pair)
+
+__host__ __device__ inline size_t eval3_smem_bytes(int nsub, int nstages, int cap) {
+  return (size_t)nsub * (kSubBytes / 2) * nstages + (size_t)128 * (cap + 1) * 8 + 4 * kEval3Ring * (128 + 8) /*ring + meta*/ +
+         4 * 128 /*histograms*/ + 128 * 4 /*thresholds*/ + 64 /*ring counters*/ + 1024 + 512;
+}
+
+template <int NSUB>
+__global__ void __launch_bounds__(kEval3Threads, 1)
+eval_topk_tc3_kernel(EvalArgs a) {
+  constexpr int DP = 64 * NSUB;
+  constexpr int kHalf = kSubBytes / 2;              // 64 item rows x 64 bf16 of one sub-tile
+  constexpr int kStage = NSUB * kHalf;
+  constexpr int kColU = kEval2Acc * 128;            // TMEM: 3 accumulators, then the user block (DP / 2 columns)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // (pointer arithmetic keeps the shared address space: LDS / STS, not generic LD / ST)
+  const int nst = a.nstages, CAP = a.cap;
+  uint8_t* sV = smem;
+  uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + (size_t)nst * kStage);      // [128][CAP + 1] (padded rows)
+  float* ring = reinterpret_cast<float*>(bufs_sm + 128 * (CAP + 1));               // [4 quadrants][kEval3Ring][32] staged chunks
+  uint2* ring_meta = reinterpret_cast<uint2*>(ring + 4 * kEval3Ring * 32);         // [4][kEval3Ring] (row inside the quadrant, first column)
+  int* hist_all = reinterpret_cast<int*>(ring_meta + 4 * kEval3Ring);              // [4][32] compaction histograms
+  float* thr_sm = reinterpret_cast<float*>(hist_all + 4 * 32);                     // [128] thresholds published by the selectors
+  volatile int* ring_ctl = reinterpret_cast<volatile int*>(thr_sm + 128);          // [4] head, [4] tail, [4] finished
+  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(ring_ctl) + 16);
+  uint64_t* u_full = bars;                          // leader's: both user blocks are in tensor memory (8 warp arrivals)
+  uint64_t* v_full = bars + 1;                      // [8] my half of the stage has landed
+  uint64_t* p_full = bars + 9;                      // [8] leader's: the peer's half has landed (relayed)
+  uint64_t* v_empty = bars + 17;                    // [8] the MMAs reading the stage have completed (multicast commit)
+  uint64_t* s_full = bars + 25;                     // [3] accumulator ready (multicast commit)
+  uint64_t* s_empty = bars + 28;                    // [3] leader's: accumulator drained by the 8 epilogue warps of the pair
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int ub = blockIdx.x, sp = blockIdx.y;
+  const int n_tiles = static_cast<int>((a.n_items + 127) >> 7);
+  const int t0 = sp * a.tiles_per_split;
+  const int t1 = min(n_tiles, t0 + a.tiles_per_split);
+  const int nj = max(0, t1 - t0);
+  const int rot = nj > 0 ? static_cast<int>((static_cast<unsigned>(ub >> 1) * 37u + static_cast<unsigned>(sp) * 11u) % static_cast<unsigned>(nj)) : 0;
+  const uint32_t crank = cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (tid == 0) {
+    mbar_init(u_full, 2 * 4);
+    for (int s = 0; s < kEval3MaxStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&p_full[s], 1); mbar_init(&v_empty[s], 1); }
+    for (int s = 0; s < kEval2Acc; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2 * 4); }
+    mbar_fence_init();
+  }
+  if (tid < 128) thr_sm[tid] = -INFINITY;
+  if (tid < 16) ring_ctl[tid] = 0;
+  if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // both CTAs' barriers and tensor memory exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0 && nj > 0) {
+      for (int j = 0; j < nj; ++j) {
+        const int st = j % nst;
+        mbar_wait(&v_empty[st], ((j / nst) & 1) ^ 1);
+        if ((a.dbg_pipe & 1) && j >= nst) { mbar_arrive(&v_full[st]); continue; }   // developer switch: stale stage contents
+        mbar_expect_tx(&v_full[st], kStage);
+        const uint8_t* gV = a.Vimg + (size_t)(t0 + (j + rot) % nj) * NSUB * kSubBytes + (size_t)crank * kHalf;
+#pragma unroll
+        for (int s = 0; s < NSUB; ++s)
+          bulk_g2s(sV + (size_t)st * kStage + s * kHalf, gV + (size_t)s * kSubBytes, kHalf, &v_full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (nj > 0) {
+      if (leader) {
+        // warp-uniform loop, one elected lane issues (see the second generation)
+        const uint32_t idesc = make_idesc_bf16(256, 128, 0, 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t desc0 = make_smem_desc(smem_u32(sV), 16, 1024);
+        mbar_wait(u_full, 0);                                       // both user blocks sit in tensor memory
+        tc_fence_after();
+        for (int j = 0; j < nj; ++j) {
+          const int st = j % nst, sb = j % kEval2Acc;
+          mbar_wait(&v_full[st], (j / nst) & 1);
+          mbar_wait(&p_full[st], (j / nst) & 1);
+          mbar_wait(&s_empty[sb], ((j / kEval2Acc) & 1) ^ 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (!(a.dbg_pipe & 2)) {
+              const uint64_t dst = desc0 + static_cast<uint64_t>((st * kStage) >> 4);
+              const uint32_t dcol = tmem_u + sb * 128;
+#pragma unroll
+              for (int k = 0; k < DP / 16; ++k)                     // K = 16 per MMA = 8 TMEM columns of the user blocks
+                umma_bf16_ts_pair(dcol, tmem_u + kColU + 8 * k, dst + static_cast<uint64_t>(((k >> 2) * kHalf + (k & 3) * 32) >> 4),
+                                  idesc, k > 0);
+            }
+            umma_commit_pair(&s_full[sb], 3);
+            umma_commit_pair(&v_empty[st], 3);
+          }
+          __syncwarp();
+        }
+      } else if (lane == 0) {
+        const uint32_t p_full0 = mapa_shared(smem_u32(p_full), 0);
+        for (int j = 0; j < nj; ++j) {
+          const int st = j % nst;
+          mbar_wait(&v_full[st], (j / nst) & 1);
+          mbar_arrive_cluster(p_full0 + 8u * st);
+        }
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------------------ readers (one per TMEM lane quadrant)
+    const int q = warp & 3;
+    const int il = q * 32 + lane;
+    const int64_t urow = (int64_t)ub * 128 + il;
+    const bool row_ok = urow < a.n_users;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    const uint32_t u_full0 = mapa_shared(smem_u32(u_full), 0);
+    const uint32_t s_empty0 = mapa_shared(smem_u32(s_empty), 0);
+    // my user's row -> bf16 pairs -> TMEM columns kColU .. (row = lane): my CTA's half of the A operand of every MMA
+    {
+      const float* u = a.Uf + (row_ok ? urow : 0) * a.d;
+#pragma unroll 1
+      for (int c0 = 0; c0 < DP; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int c = c0 + 2 * i;
+          const float x0 = (row_ok && c < a.d) ? __ldg(u + c) : 0.0f;
+          const float x1 = (row_ok && c + 1 < a.d) ? __ldg(u + c + 1) : 0.0f;
+          pk[i] = pack_bf16x2(x0, x1);
+        }
+        tmem_st16(tmem + lane_addr + kColU + c0 / 2, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(u_full0);
+    }
+    float* my_ring = ring + q * kEval3Ring * 32;
+    uint2* my_meta = ring_meta + q * kEval3Ring;
+    volatile float* my_thr = thr_sm + il;
+    volatile int* head_sm = ring_ctl + q;
+    volatile int* tail_sm = ring_ctl + 4 + q;
+    int head = 0, tail_seen = 0;
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t col_end = static_cast<uint32_t>(a.n_items);
+    for (int j = 0; j < nj; ++j) {
+      const int sb = j % kEval2Acc;
+      mbar_wait(&s_full[sb], (j / kEval2Acc) & 1);
+      tc_fence_after();
+      float v[4][32];
+      if (a.dbg_mode != 2) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(s_empty0 + 8u * sb);
+      if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) head = 1; continue; }
+      const uint32_t col0 = static_cast<uint32_t>((t0 + (j + rot) % nj) * 128);
+      float gm[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float m8[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const float* w = v[c] + g * 8;
+          m8[g] = fmaxf(fmaxf(fmaxf(w[0], w[1]), fmaxf(w[2], w[3])), fmaxf(fmaxf(w[4], w[5]), fmaxf(w[6], w[7])));
+        }
+        gm[c] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
+      }
+      const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+      const float thr = *my_thr;                          // possibly stale (lower): forwards extra chunks, never loses one
+      const bool hit = row_ok && m >= thr;
+      if (!__any_sync(0xffffffffu, hit) || a.dbg_mode == 3) continue;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const bool pc = hit && gm[c] >= thr && col0 + c * 32 < col_end;
+        const unsigned bc = __ballot_sync(0xffffffffu, pc);
+        if (!bc) continue;
+        const int nc = __popc(bc);
+        if (head + nc - tail_seen > kEval3Ring) {         // ring full: wait for the selector
+          uint32_t spins = 0;
+          do {
+            tail_seen = *tail_sm;
+            if (++spins > 20000000u) __trap();
+          } while (head + nc - tail_seen > kEval3Ring);
+        }
+        if (pc) {
+          const int slot = (head + __popc(bc & lt)) & (kEval3Ring - 1);
+          float* dst = my_ring + slot * 32;
+#pragma unroll
+          for (int t = 0; t < 32; t += 4)
+            *reinterpret_cast<float4*>(dst + t) = make_float4(v[c][t], v[c][t + 1], v[c][t + 2], v[c][t + 3]);
+          my_meta[slot] = make_uint2(static_cast<uint32_t>(lane), col0 + c * 32);
+        }
+        head += nc;
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) *head_sm = head;
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) ring_ctl[8 + q] = 1;                   // finished: the selector drains what is left and writes the lists
+  } else {
+    // ------------------------------------------------------------------------------ selectors (own the k-best sets)
+    const int q = warp & 3;
+    const float* my_ring = ring + q * kEval3Ring * 32;
+    const uint2* my_meta = ring_meta + q * kEval3Ring;
+    volatile int* head_sm = ring_ctl + q;
+    volatile int* tail_sm = ring_ctl + 4 + q;
+    volatile int* fin_sm = ring_ctl + 8 + q;
+    int* hist = hist_all + q * 32;
+    uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * (CAP + 1);
+    const unsigned lt = (1u << lane) - 1u;
+    const uint32_t col_end = static_cast<uint32_t>(a.n_items);
+    const bool exact_compaction = (a.dbg_pipe & 4) != 0;
+    float thr = -INFINITY;                                // lane = row inside the quadrant
+    int cnt = 0, tail = 0;
+    uint32_t idle = 0;
+    for (;;) {
+      const int fin = *fin_sm;                            // (read before head: a chunk published before `finished` is seen)
+      const int head = *head_sm;
+      if (head == tail) {
+        if (fin) break;
+        if (++idle > 40000000u) __trap();
+        __nanosleep(20);
+        continue;
+      }
+      idle = 0;
+      __threadfence_block();
+#pragma unroll 1
+      for (; tail != head; ++tail) {
+        const int slot = tail & (kEval3Ring - 1);
+        const uint2 me = my_meta[slot];
+        const float x = my_ring[slot * 32 + lane];
+        const int L = static_cast<int>(me.x);
+        float thr_l = __shfl_sync(0xffffffffu, thr, L);
+        const uint32_t col = me.y + lane;
+        const bool cand = (col < col_end) && (x >= thr_l);
+        const unsigned cm = __ballot_sync(0xffffffffu, cand);
+        if (!cm) continue;
+        int cnt_l = __shfl_sync(0xffffffffu, cnt, L);
+        uint64_t* buf = bufs_warp + (size_t)L * (CAP + 1);
+        if (cand) buf[cnt_l + __popc(cm & lt)] = make_key(x, col);
+        cnt_l += __popc(cm);
+        if (cnt_l > CAP - 32) {                           // fewer than 32 free slots: keep (about) the k best, raise the threshold
+          __syncwarp();
+          int kept = a.k;
+          if (exact_compaction) thr_l = compact_row(buf, cnt_l, a.k, lane);
+          else thr_l = compact_row_coarse(buf, cnt_l, a.k, CAP - 48, lane, hist, &kept);
+          cnt_l = kept;
+          if (lane == L) { thr = thr_l; thr_sm[q * 32 + L] = thr_l; }
+        }
+        if (lane == L) cnt = cnt_l;
+      }
+      __syncwarp();
+      if (lane == 0) *tail_sm = tail;                     // the slots up to here may be overwritten
+    }
+    __syncwarp();
+    // final (exact) compaction of every row to its k best, then the row's KP slots go to the global per-(user, split) lists
+    const int64_t gstride = (int64_t)a.nsplit * a.KP;
+    uint64_t* grow0 = a.lists + ((int64_t)ub * 128 + q * 32) * gstride + (int64_t)sp * a.KP;
+    for (int r = 0; r < 32; ++r) {
+      int n = __shfl_sync(0xffffffffu, cnt, r);
+      uint64_t* buf = bufs_warp + (size_t)r * (CAP + 1);
+      if (n > a.k) { compact_row(buf, n, a.k, lane); n = a.k; }
+      __syncwarp();
+      for (int i = lane; i < a.KP; i += 32) grow0[r * gstride + i] = i < n ? buf[i] : 0ull;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                 // the pair's MMAs read both shared memories and write both tensor memories: leave together
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem, 512);
   }
 }
 
@@ -850,6 +1258,7 @@ static int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 struct EvalPlan {
   int dp, nsub, KP, nsplit, nstages, tiles_per_split, n_tiles, cl;
   int v2, cap, nstages2;      // second-generation tensor-core kernel: usable, keys per row buffer, V stages
+  int v3;                     // third generation (CTA pair, cta_group::2) selected: cap / nstages2 describe it, cl = 2
   int64_t n_ub_grid;
   int64_t n_ub, users_pad, items_pad;
   size_t off_uimg, off_vimg, off_lists, off_end;
@@ -866,8 +1275,11 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
   p->n_ub = (n_users + 127) / 128;
   p->cl = (precision == NNCF_PREC_BF16 && p->n_ub >= kEvalCluster) ? kEvalCluster : 1;
   { const char* e = getenv("NNCF_EVAL_CL"); if (e && precision == NNCF_PREC_BF16) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) p->cl = v; } }   // developer override (8: second-generation kernel only)
-  p->n_ub_grid = (p->n_ub + p->cl - 1) / p->cl * p->cl;
-  p->users_pad = p->n_ub_grid * 128;
+  {
+    const int padto = (precision == NNCF_PREC_BF16 && p->n_ub >= 2 && p->cl < 2) ? 2 : p->cl;   // a CTA pair needs an even block count
+    p->n_ub_grid = (p->n_ub + p->cl - 1) / p->cl * p->cl;
+    p->users_pad = (p->n_ub + padto - 1) / padto * padto * 128;
+  }
   p->n_tiles = static_cast<int>((n_items + 127) / 128);
   p->items_pad = (int64_t)p->n_tiles * 128;
   // enough CTAs to fill 148 SMs twice when the user dimension alone cannot
@@ -890,10 +1302,31 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
       if (eval_smem_bytes(p->nsub, st, p->KP) <= 232448) { p->nstages = st; break; }
     // second generation: the largest row buffer (fewest compactions) that still leaves 3 (else 2) item-tile stages
     static const bool v1_env = [] { const char* e = getenv("NNCF_EVAL_V1"); return e && atoi(e) != 0; }();
-    for (int st = 3; st >= 2 && !p->v2 && !v1_env; --st)
-      for (int cap = 2 * p->KP > 192 ? 192 : (2 * p->KP < 96 ? 96 : 2 * p->KP); cap >= p->KP + 32; cap -= 32)
+    int st_hi = 3, cap_hi = 2 * p->KP > 192 ? 192 : (2 * p->KP < 96 ? 96 : 2 * p->KP);
+    { const char* e = getenv("NNCF_EVAL_NST"); if (e) { const int v = atoi(e); if (v >= 2 && v <= 4) st_hi = v; } }     // developer overrides
+    { const char* e = getenv("NNCF_EVAL_CAP"); if (e) { const int v = atoi(e); if (v % 32 == 0 && v >= p->KP + 32 && v <= 192) cap_hi = v; } }
+    for (int st = st_hi; st >= 2 && !p->v2 && !v1_env; --st)
+      for (int cap = cap_hi; cap >= p->KP + 32; cap -= 32)
         if (eval2_smem_bytes(p->nsub, st, cap) <= 232448) { p->v2 = 1; p->cap = cap; p->nstages2 = st; break; }
     if (p->v2) p->nstages = p->nstages2;
+    // third generation (CTA pair): half-size stages; prefer >= 4 stages in flight, then the largest row buffer
+    const int gen_env = [] { const char* e = getenv("NNCF_EVAL_GEN"); return e ? atoi(e) : kEvalDefaultGen; }();
+    p->v3 = 0;
+    if (p->v2 && gen_env >= 3 && p->n_ub >= 2) {
+      int best_st = 0, best_cap = 0;
+      for (int want = 4; want >= 2 && !best_st; --want)
+        for (int cap = cap_hi; cap >= p->KP + 32 && !best_st; cap -= 32) {
+          int st = 0;
+          for (int t = kEval3MaxStages; t >= want; --t) if (eval3_smem_bytes(p->nsub, t, cap) <= 232448) { st = t; break; }
+          if (st) { best_st = st; best_cap = cap; }
+        }
+      { const char* e = getenv("NNCF_EVAL_NST3"); if (e && best_st) { const int v = atoi(e); if (v >= 2 && v <= best_st) best_st = v; } }   // developer override
+      if (best_st) {
+        p->v3 = 1; p->cap = best_cap; p->nstages2 = best_st; p->nstages = best_st; p->cl = 2;
+        p->n_ub_grid = (p->n_ub + 1) / 2 * 2;
+        // (the workspace offsets above were sized with the cluster size in force then; the pair needs users_pad even in blocks)
+      }
+    }
     if (p->nstages == 0) {
       set_error("eval (bf16): top-k sets of k > 64 do not fit next to dim > 128 operands; use k <= 64 or precision fp32");
       return NNCF_EUNSUPPORTED;
@@ -945,7 +1378,26 @@ static int launch_eval_tc2_cl(const EvalArgs& ea, const EvalPlan& p, cudaStream_
   return 0;
 }
 template <int NSUB>
+static int launch_eval_tc3(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  const size_t smem = eval3_smem_bytes(NSUB, p.nstages2, p.cap);
+  NNCF_CUDA(cudaFuncSetAttribute(eval_topk_tc3_kernel<NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)p.n_ub_grid, p.nsplit, 1);
+  cfg.blockDim = dim3(kEval3Threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  NNCF_CUDA(cudaLaunchKernelEx(&cfg, eval_topk_tc3_kernel<NSUB>, ea));
+  NNCF_LAUNCH_OK();
+  return 0;
+}
+template <int NSUB>
 static int launch_eval_tc(const EvalArgs& ea, const EvalPlan& p, cudaStream_t st) {
+  if (p.v3) return launch_eval_tc3<NSUB>(ea, p, st);
   if (p.v2) {
     if (p.cl == 8) return launch_eval_tc2_cl<NSUB, 8>(ea, p, st);
     if (p.cl == 4) return launch_eval_tc2_cl<NSUB, 4>(ea, p, st);
@@ -975,6 +1427,15 @@ extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const
   ea.cap = p.cap;
   { const char* e = getenv("NNCF_EVAL_PF"); ea.prefetch_ahead = e ? atoi(e) : 0; }   // measured: no effect (the stream is not DRAM-latency-bound)
   { const char* e = getenv("NNCF_EVAL_DBG"); ea.dbg_mode = e ? atoi(e) : 0; }
+  { const char* e = getenv("NNCF_EVAL_PIPE"); ea.dbg_pipe = e ? atoi(e) : 0; }
+#ifdef NNCF_EVAL_STATS_BUILD
+  static unsigned long long* stats_dev = nullptr;
+  if (getenv("NNCF_EVAL_STATS")) {
+    if (!stats_dev) cudaMalloc(&stats_dev, 8 * sizeof(unsigned long long));
+    cudaMemsetAsync(stats_dev, 0, 8 * sizeof(unsigned long long), st);
+    ea.stats = stats_dev;
+  }
+#endif
   ea.lists = reinterpret_cast<uint64_t*>(ws + p.off_lists);
   if (precision == NNCF_PREC_BF16) {
     ea.Uimg = ws + p.off_uimg; ea.Vimg = ws + p.off_vimg;
@@ -1003,6 +1464,16 @@ extern "C" int nncf_eval_topk(const float* user_rows_dev, int64_t n_users, const
   topk_merge_kernel<<<ceil_div(n_users, 4), 128, 0, st>>>(ea.lists, n_users, p.nsplit, p.KP, topk, pow2_ge(2 * p.KP),
                                                           topk_ids_dev, topk_scores_dev);
   NNCF_LAUNCH_OK();
+#ifdef NNCF_EVAL_STATS_BUILD
+  if (ea.stats) {
+    unsigned long long h[8];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, ea.stats, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[eval stats] warp-tiles %llu, with a hit %.3f, hit rows / warp-tile %.3f, appended / warp-tile %.3f, compactions / warp-tile %.4f, "
+            "filter cycles / warp-tile %.0f (lane-0 counts are per warp for appended only in the per-lane filter)\n",
+            h[0], (double)h[1] / h[0], (double)h[2] / h[0], (double)h[3] / h[0], (double)h[4] / h[0], (double)h[5] / h[0]);
+  }
+#endif
   return NNCF_OK;
 }
 

@@ -292,43 +292,58 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp runs the loop (warp-uniform control flow, descriptors and tensor-memory addresses in uniform
+    // registers, one UIADD3.64 per MMA); one elected lane issues.  Under `if (lane == 0)` ptxas rebuilt every descriptor
+    // and moved the addresses through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence: ~160 cycles per MMA, against 32-64
+    // cycles of tensor work.
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, TN, 0, 0);
       const uint32_t idesc_dx = make_idesc_bf16(128, DP, 0, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t xdesc0 = make_smem_desc(smem_u32(sX), 16, 1024);            // K-major X block
+      const uint64_t ydesc0 = make_smem_desc(smem_u32(sY), 16, 1024);            // K-major view of a Y stage (MMA1)
+      const uint64_t ydesc0_mn = make_smem_desc(smem_u32(sY), C::kYBytes, 1024); // MN-major view of the same bytes (MMA2)
       auto issue_mma1 = [&](int t) {
         const int st = t % C::kStages, sb = t & 1;
         mbar_wait(&y_full[st], (t / C::kStages) & 1);
-        // buffer sb was last read by MMA2(t - 2), issued earlier by this thread: the tensor pipe runs in issue order
+        // buffer sb was last read by MMA2(t - 2), issued earlier by this warp: the tensor pipe runs in issue order
+        if (elect_one()) {
+          const uint64_t yd = ydesc0 + static_cast<uint64_t>((st * NSUB * C::kYBytes) >> 4);
+          const uint32_t dcol = tmem_u + sb * TN;
 #pragma unroll
-        for (int k = 0; k < DP / 16; ++k) {
-          const uint64_t ad = make_smem_desc(smem_u32(sX + (k >> 2) * kSubBytes) + (k & 3) * 32, 16, 1024);
-          const uint64_t bd = make_smem_desc(smem_u32(sY + (st * NSUB + (k >> 2)) * C::kYBytes) + (k & 3) * 32, 16, 1024);
-          umma_bf16(tmem + sb * TN, ad, bd, idesc_s, k > 0);
+          for (int k = 0; k < DP / 16; ++k)
+            umma_bf16(dcol, xdesc0 + static_cast<uint64_t>(((k >> 2) * kSubBytes + (k & 3) * 32) >> 4),
+                      yd + static_cast<uint64_t>(((k >> 2) * C::kYBytes + (k & 3) * 32) >> 4), idesc_s, k > 0);
+          umma_commit(&s_full[sb]);
         }
-        umma_commit(&s_full[sb]);
+        __syncwarp();
       };
       mbar_wait(x_full, 0);
-      NNCF_STAMP(1);
+      if (lane == 0) NNCF_STAMP(1);
       issue_mma1(0);
-      NNCF_STAMP(2);
+      if (lane == 0) NNCF_STAMP(2);
       for (int t = 0; t < nt; ++t) {
         const int st = t % C::kStages, sb = t & 1;
         if (t + 1 < nt) issue_mma1(t + 1);
         mbar_wait(&g_full[sb], (t >> 1) & 1);
-        if (t < 8) NNCF_STAMP(8 + t);
+        if (lane == 0 && t < 8) NNCF_STAMP(8 + t);
         tc_fence_after();
-        const uint8_t* y = sY + st * NSUB * C::kYBytes;
+        if (elect_one()) {
+          const uint64_t yd = ydesc0_mn + static_cast<uint64_t>((st * NSUB * C::kYBytes) >> 4);
+          const uint32_t acol0 = tmem_u + sb * TN;
 #pragma unroll
-        for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA = 8 TMEM columns of G'
-          // K rows 16k.. were written by epilogue column-half (16k) / CW at column offset ((16k) % CW) / 2 of its own range
-          const uint32_t acol = sb * TN + ((16 * k) / CW) * CW + ((16 * k) % CW) / 2;
-          const uint64_t bd = make_smem_desc(smem_u32(y) + k * 2048, C::kYBytes, 1024);
-          umma_bf16_ts(tmem + C::kColDX, tmem + acol, bd, idesc_dx, (t > 0) || (k > 0));
+          for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA = 8 TMEM columns of G'
+            // K rows 16k.. were written by epilogue column-half (16k) / CW at column offset ((16k) % CW) / 2 of its own range
+            umma_bf16_ts(tmem_u + C::kColDX, acol0 + ((16 * k) / CW) * CW + ((16 * k) % CW) / 2,
+                         yd + static_cast<uint64_t>((k * 2048) >> 4), idesc_dx, (t > 0) || (k > 0));
+          }
+          umma_commit(&y_empty[st]);
         }
-        umma_commit(&y_empty[st]);
+        __syncwarp();
       }
-      umma_commit(dx_full);
-      NNCF_STAMP(3);
+      if (elect_one()) umma_commit(dx_full);    // (elect.sync picks the same lane for the same mask: all MMAs are its own)
+      __syncwarp();
+      if (lane == 0) NNCF_STAMP(3);
     }
   } else if (warp < 2 + kScoreEpiWarps) {
     // ------------------------------------------------------------------------------ epilogue warps

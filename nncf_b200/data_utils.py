@@ -135,6 +135,64 @@ def _get_data(data_name):
     return data_helper
 
 
+def get_pretrain_folder(data_name, aug=True):
+    """configs/data_utils.py:107-126: <data_root>/<family>/<kind>/pretrain/<aug|''>/ ; None for a data_name outside the
+    four families (the synthetic stand-ins), where the reference asserts."""
+    for family, prefix in (('citeulike', 'citeulike_'), ('news', 'news_')):
+        for kind in ('title_only', 'title_and_abstract'):
+            if data_name.startswith(prefix + kind):
+                return data_root + '/%s/%s/pretrain/%s/' % (family, kind, 'aug' if aug else '')
+    return None
+
+
+def get_pretrained_vectors(conf, data_spec, data_helper):
+    """configs/data_utils.py:129-185: (W_pretrain [word_count, dw] | None, C_pretrain [item_count, dc] | None) from
+    `conf.pretrain`.  A '.pkl' file holds the matrix itself (Python-2 pickle: latin1); the text formats are word2vec's
+    (first line skipped, `word v0 v1 ... ` with a trailing blank column; words resolved through `data_helper.word2id`)
+    and doc2vec's (`_*<item id> v0 v1 ... `; ids >= item_count dropped).  Engine addition: the arrays may be handed
+    over directly as conf.pretrain['W_pretrain'] / ['C_pretrain']."""
+    pre = getattr(conf, 'pretrain', None) or {}
+    W_pretrain = C_pretrain = None
+    wordvec_filepath, sentvec_filepath = pre.get('wordvec_filepath'), pre.get('sentvec_filepath')
+    if pre.get('W_pretrain') is not None:
+        W_pretrain = np.asarray(pre['W_pretrain'])
+    elif wordvec_filepath and os.path.exists(wordvec_filepath):
+        if wordvec_filepath.endswith('pkl'):
+            with open(wordvec_filepath, 'rb') as fp:
+                W_pretrain = np.asarray(pickle.load(fp, encoding='latin1'))
+        else:
+            word2id = getattr(data_helper, 'word2id', None) or {}
+            with open(wordvec_filepath) as fp:
+                fp.readline()
+                for line in fp:
+                    tok = line.rstrip().split(' ')
+                    if W_pretrain is None:
+                        W_pretrain = np.zeros((data_spec.word_count, len(tok) - 1))
+                    wid = word2id.get(tok[0])
+                    if wid is not None and wid < data_spec.word_count:
+                        W_pretrain[wid] = [float(x) for x in tok[1:]]
+    if pre.get('C_pretrain') is not None:
+        C_pretrain = np.asarray(pre['C_pretrain'])
+    elif sentvec_filepath and os.path.exists(sentvec_filepath):
+        if sentvec_filepath.endswith('pkl'):
+            with open(sentvec_filepath, 'rb') as fp:
+                C_pretrain = np.asarray(pickle.load(fp, encoding='latin1'))
+        else:
+            with open(sentvec_filepath) as fp:
+                for line in fp:
+                    tok = line.rstrip().split(' ')
+                    if C_pretrain is None:
+                        C_pretrain = np.zeros((data_spec.item_count, len(tok) - 1))
+                    iid = int(tok[0][2:])                       # '_*<id>'
+                    if iid < data_spec.item_count:
+                        C_pretrain[iid] = [float(x) for x in tok[1:]]
+    if W_pretrain is not None:
+        assert W_pretrain.shape[0] == data_spec.word_count, 'W_pretrain rows != word_count'
+    if C_pretrain is not None:
+        assert C_pretrain.shape[0] == data_spec.item_count, 'C_pretrain rows != item_count'
+    return W_pretrain, C_pretrain
+
+
 def get_data(data_name, conf, reverse_samping=False):
     """configs/data_utils.py:15-70 (the misspelt keyword `reverse_samping` is the reference's, main.py:67)."""
     data_helper = _get_data(data_name)
@@ -147,6 +205,7 @@ def get_data(data_name, conf, reverse_samping=False):
     max_content_len = C.shape[1]
     data_spec = DataSpec(user_count, word_count, item_count, max_content_len)
     if conf is not None:
+        data_spec.W_pretrain, data_spec.C_pretrain = get_pretrained_vectors(conf, data_spec, data_helper)   # :37
         neg_dist = conf.neg_dist
         try:
             neg_sampling_power = conf.neg_sampling_power

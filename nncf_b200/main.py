@@ -38,10 +38,8 @@ def run(argv=None):
     print('model_choice: %s \nconf_choice: %s' % (model_choice, conf_choice))
 
     # load confs and related (main.py:46-58)
-    if model_choice in ('mf', 'basic_embedding', 'cnn_embedding', 'rnn_embedding'):
-        from .conf import get_conf
-    elif model_choice == 'pretrained':
-        assert False, 'model choice pretrained needs the pretrained vector blobs (absent, SURVEY.md §8f3)'
+    if model_choice in ('mf', 'pretrained', 'basic_embedding', 'cnn_embedding', 'rnn_embedding'):
+        from .conf import get_conf                         # ('pretrained' needs conf.pretrain to name / carry the vectors)
     else:
         assert False, 'model choice %s not defined' % model_choice
     conf = get_conf(data_name, conf_choice, param_dict, model_choice)

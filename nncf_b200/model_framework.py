@@ -30,6 +30,18 @@ def _dev_i32(x, device):
     return torch.from_numpy(np.ascontiguousarray(np.asarray(x).reshape(-1), dtype=np.int32)).to(device)
 
 
+def _tower_backward(tower, rows, grad_rows):
+    """backward through the item tower from the kernel's dL/d(rows); an activity regulariser the tower carries
+    (`reg_loss`, e.g. use_content_id's v_reg term) joins the same pass.  Returns the regulariser's value (added to the
+    reported loss like Keras adds regularisers)."""
+    reg = getattr(tower, 'reg_loss', None)
+    if reg is None:
+        rows.backward(grad_rows)
+        return 0.0
+    torch.autograd.backward([rows, reg], [grad_rows, None])
+    return float(reg.item())
+
+
 class MeanPoolTower(torch.nn.Module):
     """word Embedding -> mean over all L positions -> Dense -> BatchNorm -> relu   (modules/content/mean_pool.py:46-110).
     The gather-mean is the nncf_meanpool kernel; BN uses Keras-1 defaults (epsilon 1e-3, momentum 0.99)."""
@@ -74,6 +86,7 @@ class BiasedTower(torch.nn.Module):
 
     def forward(self, item_ids):
         h = self.tower(item_ids)
+        self.reg_loss = getattr(self.tower, 'reg_loss', None)
         return torch.cat([h, torch.ones_like(h[:, :1]), self.cbias[item_ids.long()][:, None]], dim=1)
 
 
@@ -118,10 +131,42 @@ class SharedState(object):
             else:
                 from .towers import CNNTower, RNNTower          # plain torch modules (models/model_framework.py:89-96)
                 self.tower = (CNNTower if model_name == 'cnn_embedding' else RNNTower)(spec, conf, content, g).to(dev)
+            if conf.use_content_id:                 # ref: modules/content/mean_pool.py:102-108 (same in the CNN / RNN models)
+                from .towers import ContentIdTower
+                self.tower = ContentIdTower(self.tower, spec.item_count, conf.item_dim, conf.v_reg, g, dev)
+            if getattr(spec, 'C_pretrain', None) is not None and getattr(conf, 'pretrain', None):
+                # ref: models/model_framework.py:99-100 -> modules/shared/vec2vec.py:17-64
+                from .towers import PretrainCombinedTower
+                self.tower.eval()
+                with torch.no_grad():
+                    tower_dim = int(self.tower(torch.zeros(2, dtype=torch.int32, device=dev)).shape[1])
+                self.tower = PretrainCombinedTower(self.tower, spec.C_pretrain, conf, tower_dim).to(dev)
             if self.bias:
                 self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
             self.tower_opt = torch.optim.Adam([p for p in self.tower.parameters() if p.requires_grad], lr=self.lr,
                                               eps=1e-8)                                      # Keras Adam(lr)
+        elif model_name == 'pretrained':
+            # ref: models/model_framework.py:69-84 + configs/pretrained_conf.py:57-65,77-105
+            from .towers import FrozenItemTable, PretrainCombinedTower
+            pre = conf.pretrain or {}
+            if getattr(conf, 'evaluation_mode', False):        # given user / item embeddings, nothing trainable
+                ue, ie = np.asarray(pre['user_emb'], dtype=np.float32), np.asarray(pre['item_emb'], dtype=np.float32)
+                assert ue.shape == (spec.user_count, d) and ie.shape[1] == d, 'evaluation_mode: embedding shapes'
+                self.user_table = with_bias_cols(torch.from_numpy(ue).to(dev), False)
+                self.tower = FrozenItemTable(ie).to(dev)
+                self.opt_kind, self.lr = 'sgd', 0.0                                          # conf.optimizer = SGD(0)
+            else:
+                assert spec.C_pretrain is not None, \
+                    '[ERROR] model_choice pretrained needs pretrained item vectors (conf.pretrain sentvec_filepath / C_pretrain)'
+                if pre.get('transform'):
+                    self.tower = PretrainCombinedTower(None, spec.C_pretrain, conf).to(dev)
+                else:
+                    assert spec.C_pretrain.shape[1] == d, 'pretrained item vectors must have item_dim columns without transform'
+                    self.tower = FrozenItemTable(spec.C_pretrain).to(dev)
+            if self.bias:
+                self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
+            params = [p for p in self.tower.parameters() if p.requires_grad]
+            self.tower_opt = torch.optim.Adam(params, lr=self.lr, eps=1e-8) if params else None
         else:
             assert False, '[ERROR] Model name {} unknown'.format(model_name)
         self.norm_u = bool(conf.emb_normalization)
@@ -214,10 +259,12 @@ class MatmulView(_View):
             rows = compact[inv.long()]                                 # C_emb = C_emb_compact[cid_x]
             out = step.run(st.user_table, None, uid, cid, 1, adam_state=st.adam, want_grads=True, item_rows=rows.detach())
             g = out['grad_item_rows']
-        st.tower_opt.zero_grad(set_to_none=True)
-        rows.backward(g)
-        st.tower_opt.step()
-        return float(out['loss'][0].item())
+        reg = 0.0
+        if st.tower_opt is not None:
+            st.tower_opt.zero_grad(set_to_none=True)
+            reg = _tower_backward(st.tower, rows, g)
+            st.tower_opt.step()
+        return float(out['loss'][0].item()) + reg
 
     def predict_on_batch(self, x):
         """[users, items] -> float32 [len(users), len(items)] score matrix (host), for API compatibility with
@@ -272,10 +319,12 @@ class PairsView(_View):
         st._user_updater.apply(st.user_table, uid, out['grad_user_rows'], *(st.adam[:2] if st.adam else (None, None)))
         g = torch.zeros_like(compact)
         g.index_add_(0, inv.long(), out['grad_item_rows'])
-        st.tower_opt.zero_grad(set_to_none=True)
-        compact.backward(g)
-        st.tower_opt.step()
-        return float(out['loss'][0].item())
+        reg = 0.0
+        if st.tower_opt is not None:
+            st.tower_opt.zero_grad(set_to_none=True)
+            reg = _tower_backward(st.tower, compact, g)
+            st.tower_opt.step()
+        return float(out['loss'][0].item()) + reg
 
 
 class SampledNegSharedView(_View):

@@ -9,7 +9,12 @@ Flatten -> Dense -> BatchNorm -> activation -> Dropout; LSTM / GRU stacks, optio
 backwards, concatenation, pooling over time when `use_seq_for_dnn`.
 Declared (third-party Keras-1.2.2 arithmetic, not under /root/reference): torch's LSTM/GRU gates use sigmoid where the
 reference asks Keras for `hard_sigmoid`; recurrent dropout (dropout_W / dropout_U) is not applied; the contextual gating
-layers (modules/shared/gatings.py, off by default) and `use_content_id` are not provided.
+layers (modules/shared/gatings.py, off by default) are not provided.
+
+Two wrappers complete the item side of the reference graph for every content model (mean-pool, CNN, RNN):
+`ContentIdTower` (`use_content_id`: + Emb_Cid[cid], ref: modules/content/mean_pool.py:102-108, cnn_model.py:134-140,
+rnn_model.py:126-132) and `PretrainCombinedTower` (the supervised / pretrained sentence-vector combination, ref:
+modules/shared/vec2vec.py:17-64, applied at models/model_framework.py:99-100).
 """
 from __future__ import annotations
 
@@ -28,7 +33,6 @@ class _ContentTower(torch.nn.Module):
         dev = content.device
         assert not conf.contextual_temporal_gated_input and not conf.contextual_spatial_gated_input, \
             'contextual gating (modules/shared/gatings.py) is not provided'
-        assert not conf.use_content_id, 'use_content_id is not provided'
         w = (torch.rand((data_spec.word_count, conf.word_dim), generator=generator, device=dev) - 0.5) * 0.1
         if getattr(data_spec, 'W_pretrain', None) is not None:
             w = torch.as_tensor(data_spec.W_pretrain, dtype=torch.float32, device=dev)
@@ -142,3 +146,93 @@ class RNNTower(_ContentTower):
             else:
                 assert False, 'pooling %s not recognized.' % self.pooling
         return self.head(h)
+
+
+class ContentIdTower(torch.nn.Module):
+    """`use_content_id`: h + Emb_Cid[cid] with Emb_Cid [item_count, item_dim] (Keras-1 'uniform' init) and the activity
+    regulariser `v_reg * sum_d mean_b E[b, d]^2` on its output (ref: modules/content/mean_pool.py:102-108;
+    utils/utilities.py:122-135).  `reg_loss` holds the regulariser of the last training forward (None when v_reg = 0):
+    the trainer adds it to the backward pass of the tower."""
+
+    def __init__(self, tower, item_count, item_dim, v_reg, generator=None, device=None):
+        super().__init__()
+        self.tower = tower
+        dev = device if device is not None else next(tower.parameters()).device
+        self.emb_cid = torch.nn.Parameter((torch.rand((item_count, item_dim), generator=generator, device=dev) - 0.5) * 0.1)
+        self.v_reg = float(v_reg)
+        self.reg_loss = None
+
+    def forward(self, item_ids):
+        e = self.emb_cid[item_ids.long()]
+        self.reg_loss = self.v_reg * (e * e).mean(dim=0).sum() if (self.training and self.v_reg > 0) else None
+        h = self.tower(item_ids)
+        assert h.shape[1] == e.shape[1], 'use_content_id: the content model must end in item_dim columns'
+        return h + e
+
+
+class PretrainCombinedTower(torch.nn.Module):
+    """ItemCombination (ref: modules/shared/vec2vec.py:17-64): frozen pretrained item vectors `C_pretrain[cid]` (Keras-1
+    Embedding dropout = whole table rows dropped, the rest rescaled by 1/(1-p); skipped entirely when the dropout is >= 1)
+    merged with the content model's output (`pretrain_combine_mode`: concat | sum | mul | ave | max), then
+    Dense(user_dim) -> activation.  No BatchNorm: the reference forces `conf.no_BN = True` right before its test
+    (vec2vec.py:52-59).  `tower=None` is the 'pretrained' model's transform branch (models/model_framework.py:78-79)."""
+
+    def __init__(self, tower, C_pretrain, conf, tower_dim=None):
+        super().__init__()
+        pre = conf.pretrain
+        self.tower = tower
+        self.p_drop = float(pre.get('pretrain_combine_dropout', 0.5))
+        self.mode = pre.get('pretrain_combine_mode', 'concat')
+        self.actv = _actv(pre.get('pretrain_combine_actv', 'relu'))
+        assert self.mode in ('concat', 'sum', 'mul', 'ave', 'max'), 'unknown pretrain_combine_mode %s' % self.mode
+        C = torch.as_tensor(C_pretrain, dtype=torch.float32)
+        self.register_buffer('c_pretrain', C)
+        pdim = C.shape[1]
+        if tower is None:
+            assert self.p_drop < 1, 'pretrained transform without a content model needs the pretrained vectors'
+            in_dim = pdim
+        elif self.p_drop >= 1:
+            in_dim = tower_dim
+        elif self.mode == 'concat':
+            in_dim = tower_dim + pdim
+        else:
+            assert tower_dim == pdim, 'merge mode %s needs equal widths (%d vs %d)' % (self.mode, tower_dim, pdim)
+            in_dim = pdim
+        self.dense = torch.nn.Linear(in_dim, conf.user_dim)
+        self.reg_loss = None
+
+    def forward(self, item_ids):
+        h = self.tower(item_ids) if self.tower is not None else None
+        self.reg_loss = getattr(self.tower, 'reg_loss', None)
+        if self.p_drop < 1:
+            p = self.c_pretrain[item_ids.long()]
+            if self.training and self.p_drop > 0:
+                # a mask per TABLE row: every occurrence of an item in the batch shares it (the batch holds unique ids anyway)
+                keep = (torch.rand((self.c_pretrain.shape[0], 1), device=p.device) >= self.p_drop).float() / (1.0 - self.p_drop)
+                p = p * keep[item_ids.long()]
+            if h is None:
+                h = p
+            elif self.mode == 'concat':
+                h = torch.cat([h, p], dim=1)
+            elif self.mode == 'sum':
+                h = h + p
+            elif self.mode == 'mul':
+                h = h * p
+            elif self.mode == 'ave':
+                h = 0.5 * (h + p)
+            else:
+                h = torch.maximum(h, p)
+        return self.actv(self.dense(h))
+
+
+class FrozenItemTable(torch.nn.Module):
+    """model_choice 'pretrained' without transform: item embeddings are the frozen pretrained vectors themselves
+    (ref: models/model_framework.py:80-83: Embedding(..., trainable=False, weights=[C_pretrain]))."""
+
+    def __init__(self, C_pretrain):
+        super().__init__()
+        self.register_buffer('table', torch.as_tensor(C_pretrain, dtype=torch.float32))
+        self.reg_loss = None
+
+    def forward(self, item_ids):
+        return self.table[item_ids.long()]
