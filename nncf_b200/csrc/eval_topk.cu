@@ -388,12 +388,12 @@ constexpr int kEval2Acc = 3;
 constexpr int kEval2MaxNK = 6;                    // CAP <= 192 keys per row
 
 __host__ __device__ inline size_t eval2_smem_bytes(int nsub, int nstages, int cap) {
-  return (size_t)nsub * kSubBytes * nstages + (size_t)128 * (cap + 1) * 8 + kEval2EpiWarps * 128 * 4 + 1024 + 256;
+  return (size_t)nsub * kSubBytes * nstages + (size_t)128 * (cap + 1) * 8 + kEval2EpiWarps * 32 * 4 + 1024 + 256;
 }
 
 // the row's n > k keys (buf[0..n)) -> its k largest at buf[0..k); returns the score of the k-th as the new threshold.
 // Warp-cooperative; n, k warp-uniform; keys are unique (they embed the column).
-__device__ __noinline__ float compact_row(uint64_t* buf, int n, int k, int lane) {
+__device__ __forceinline__ float compact_row(uint64_t* buf, int n, int k, int lane) {
   uint32_t hi[kEval2MaxNK], lo[kEval2MaxNK];
 #pragma unroll
   for (int i = 0; i < kEval2MaxNK; ++i) {
@@ -450,7 +450,7 @@ __device__ __noinline__ float compact_row(uint64_t* buf, int n, int k, int lane)
 // warps have read it), and with ~0.5 compactions per tile per pair that stall, not the per-candidate work, was what
 // held whole@k at ~2,200 cycles per tile.  Falls back to the exact select when the bins cannot separate (ties).
 // Returns the new threshold; *n_out = keys kept.
-__device__ __noinline__ float compact_row_coarse(uint64_t* buf, int n, int k, int max_keep, int lane, int* hist, int* n_out) {
+__device__ __forceinline__ float compact_row_coarse(uint64_t* buf, int n, int k, int max_keep, int lane, int* hist, int* n_out) {
   uint32_t hi[kEval2MaxNK], lo[kEval2MaxNK];
   uint32_t hmax = 0u, hmin = 0xffffffffu;
 #pragma unroll
@@ -507,6 +507,13 @@ __device__ __noinline__ float compact_row_coarse(uint64_t* buf, int n, int k, in
   __syncwarp();
   *n_out = kept;
   return key_score(static_cast<uint64_t>(kmin) << 32);
+}
+
+// out-of-line copies for the selector warps of the third generation (few live registers around the call; the
+// second generation inlines: a call there spills the 128 score registers)
+__device__ __noinline__ float compact_row_call(uint64_t* buf, int n, int k, int lane) { return compact_row(buf, n, k, lane); }
+__device__ __noinline__ float compact_row_coarse_call(uint64_t* buf, int n, int k, int max_keep, int lane, int* hist, int* n_out) {
+  return compact_row_coarse(buf, n, k, max_keep, lane, hist, n_out);
 }
 
 #ifdef NNCF_EVAL_STATS_BUILD
@@ -592,7 +599,7 @@ eval_topk_tc2_kernel(EvalArgs a) {
   uint8_t* sV = smem;
   uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + nst * NSUB * kSubBytes);    // [128][CAP + 1] (padded rows)
   float* stage_all = reinterpret_cast<float*>(bufs_sm + 128 * (CAP + 1));          // [filter warps][128]: a hit row's passing chunks / the compaction histogram
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + kEval2EpiWarps * 128);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_all + kEval2EpiWarps * 32);
   uint64_t* u_full = bars;
   uint64_t* v_full = bars + 1;    // [4]
   uint64_t* v_empty = bars + 5;   // [4]
@@ -711,7 +718,7 @@ eval_topk_tc2_kernel(EvalArgs a) {
     FStat fstat{};
     long long cyc_hit = 0; (void)cyc_hit;
     uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * (CAP + 1);
-    float* stage = stage_all + (warp - 2) * 128;
+    float* stage = stage_all + (warp - 2) * 32;
     const uint32_t col_end = static_cast<uint32_t>(a.n_items);
     for (int j = 0; j < nj; ++j) {
       const int sb = j % kEval2Acc;
@@ -762,24 +769,29 @@ eval_topk_tc2_kernel(EvalArgs a) {
 //   Epilogue (filter) identical to the second generation.
 // ------------------------------------------------------------------------------------------------
 constexpr int kEval3MaxStages = 8;
-// Warp roles of the third generation: 0 producer, 1 MMA issuer / relay, 2..5 readers (one per TMEM lane quadrant), 6..9 selectors.
-// A reader loads its 32 x 128 scores, releases the accumulator, takes the row / chunk maxima, and - for rows that reach their
-// threshold - only STAGES the passing 32-column chunks into a shared-memory ring; it never touches the k-best sets.  The
-// selector of the same quadrant owns the row buffers and thresholds: it drains the ring (compare, ballot, append,
-// compaction) and publishes each raised threshold for the reader's next tiles (a stale threshold only forwards extra
-// chunks: the result stays exact).  Why: ncu pc-sampling of the one-warp filter (profiles/r01c) showed the four filter
+// Warp roles of the third generation: 0 producer, 1 MMA issuer / relay, 2..9 readers (two per TMEM lane quadrant: columns
+// 0..63 and 64..127 of every accumulator, so nothing is read twice), 10..17 selectors (two per quadrant: rows 0..15 and
+// 16..31 of the quadrant; one ring per (reader, row half)).
+// A reader loads its 32 x 64 scores, releases the accumulator, takes the row / chunk maxima, and - for rows that reach their
+// threshold - only STAGES the passing 32-column chunks into its shared-memory ring; it never touches the k-best sets.  The
+// selector of a row half owns its row buffers and thresholds: it drains its two rings (two entries at a time, two
+// independent dependency chains: compare, ballot, append, compaction) and publishes each raised threshold for the
+// readers' next tiles (a stale threshold only forwards extra chunks: the result stays exact).  Why: ncu pc-sampling of the one-warp filter (profiles/r01c) showed the four filter
 // warps busy 83 % of the time, 3/4 of it in the candidate path, every sample a fixed-latency dependency stall - one warp
 // per scheduler, nothing to hide a ~700-cycle chain per hit row behind - while an accumulator is recycled only when all
 // 8 filter warps of the pair have read it.  Variants measured first (37,888 users x 1M items, k = 50; 15.7 ms before):
 // two readers per quadrant with 16 rows each 18.6 ms (duplicated TMEM reads), per-lane compare-and-branch 30 ms,
-// per-lane branch-free scan down the maxima hierarchy 19.9 ms.
-constexpr int kEval3Ring = 32;                    // staged chunks per quadrant ring (power of two, >= 32 = one chunk of every row)
-constexpr int kEval3Threads = 64 + 32 * 8;
-constexpr int kEvalDefaultGen = 2;                // NNCF_EVAL_GEN overrides (2 = second generation, 3 = CTA pair)
+// per-lane branch-free scan down the maxima hierarchy 19.9 ms; one reader + one selector per quadrant 14.3 ms (the
+// reader alone: wait 310, TMEM load 210, 128 maxima 430, staging 700 cycles per tile); two readers + one selector
+// 12.4 ms (selector 100 % busy, ~150 dependent instructions per pair of entries).
+constexpr int kEval3Ring = 16;                    // staged chunks per ring (power of two, >= 16 = one chunk of every row of a row half)
+constexpr int kEval3Threads = 64 + 32 * 16;
+constexpr int kEvalDefaultGen = 3;                // NNCF_EVAL_GEN overrides (2 = second generation, 3 = CTA pair; the plan falls back to 2 when
+                                                  // the pair's rings and row buffers leave fewer than 2 item stages, e.g. k > 64, or for a single user block)
 
 __host__ __device__ inline size_t eval3_smem_bytes(int nsub, int nstages, int cap) {
-  return (size_t)nsub * (kSubBytes / 2) * nstages + (size_t)128 * (cap + 1) * 8 + 4 * kEval3Ring * (128 + 8) /*ring + meta*/ +
-         4 * 128 /*histograms*/ + 128 * 4 /*thresholds*/ + 64 /*ring counters*/ + 1024 + 512;
+  return (size_t)nsub * (kSubBytes / 2) * nstages + (size_t)128 * (cap + 1) * 8 + 16 * kEval3Ring * (128 + 8) /*rings + meta*/ +
+         8 * 128 /*histograms*/ + 128 * 4 /*thresholds*/ + 256 /*ring counters*/ + 1024 + 512;
 }
 
 template <int NSUB>
@@ -794,12 +806,12 @@ eval_topk_tc3_kernel(EvalArgs a) {
   const int nst = a.nstages, CAP = a.cap;
   uint8_t* sV = smem;
   uint64_t* bufs_sm = reinterpret_cast<uint64_t*>(sV + (size_t)nst * kStage);      // [128][CAP + 1] (padded rows)
-  float* ring = reinterpret_cast<float*>(bufs_sm + 128 * (CAP + 1));               // [4 quadrants][kEval3Ring][32] staged chunks
-  uint2* ring_meta = reinterpret_cast<uint2*>(ring + 4 * kEval3Ring * 32);         // [4][kEval3Ring] (row inside the quadrant, first column)
-  int* hist_all = reinterpret_cast<int*>(ring_meta + 4 * kEval3Ring);              // [4][32] compaction histograms
-  float* thr_sm = reinterpret_cast<float*>(hist_all + 4 * 32);                     // [128] thresholds published by the selectors
-  volatile int* ring_ctl = reinterpret_cast<volatile int*>(thr_sm + 128);          // [4] head, [4] tail, [4] finished
-  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(ring_ctl) + 16);
+  float* ring = reinterpret_cast<float*>(bufs_sm + 128 * (CAP + 1));               // [16 = (quadrant, column half, row half)][kEval3Ring][32] staged chunks
+  uint2* ring_meta = reinterpret_cast<uint2*>(ring + 16 * kEval3Ring * 32);        // [16][kEval3Ring] (row inside the quadrant, first column)
+  int* hist_all = reinterpret_cast<int*>(ring_meta + 16 * kEval3Ring);             // [8 selectors][32] compaction histograms
+  float* thr_sm = reinterpret_cast<float*>(hist_all + 8 * 32);                     // [128] thresholds published by the selectors
+  volatile int* ring_ctl = reinterpret_cast<volatile int*>(thr_sm + 128);          // [16] head, [16] tail, [16] finished
+  uint64_t* bars = reinterpret_cast<uint64_t*>(const_cast<int*>(ring_ctl) + 64);
   uint64_t* u_full = bars;                          // leader's: both user blocks are in tensor memory (8 warp arrivals)
   uint64_t* v_full = bars + 1;                      // [8] my half of the stage has landed
   uint64_t* p_full = bars + 9;                      // [8] leader's: the peer's half has landed (relayed)
@@ -821,11 +833,11 @@ eval_topk_tc3_kernel(EvalArgs a) {
   if (tid == 0) {
     mbar_init(u_full, 2 * 4);
     for (int s = 0; s < kEval3MaxStages; ++s) { mbar_init(&v_full[s], 1); mbar_init(&p_full[s], 1); mbar_init(&v_empty[s], 1); }
-    for (int s = 0; s < kEval2Acc; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2 * 4); }
+    for (int s = 0; s < kEval2Acc; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 2 * 8); }
     mbar_fence_init();
   }
   if (tid < 128) thr_sm[tid] = -INFINITY;
-  if (tid < 16) ring_ctl[tid] = 0;
+  if (tid < 64) ring_ctl[tid] = 0;
   if (warp == 1) tmem_alloc_pair(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
@@ -884,17 +896,19 @@ eval_topk_tc3_kernel(EvalArgs a) {
         }
       }
     }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------------------------ readers (one per TMEM lane quadrant)
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------------------ readers (two per TMEM lane quadrant)
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;                        // my column half of every accumulator
+    const int rid = q * 2 + h;                            // my ring
     const int il = q * 32 + lane;
     const int64_t urow = (int64_t)ub * 128 + il;
     const bool row_ok = urow < a.n_users;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    const uint32_t u_full0 = mapa_shared(smem_u32(u_full), 0);
     const uint32_t s_empty0 = mapa_shared(smem_u32(s_empty), 0);
     // my user's row -> bf16 pairs -> TMEM columns kColU .. (row = lane): my CTA's half of the A operand of every MMA
-    {
+    if (h == 0) {
+      const uint32_t u_full0 = mapa_shared(smem_u32(u_full), 0);
       const float* u = a.Uf + (row_ok ? urow : 0) * a.d;
 #pragma unroll 1
       for (int c0 = 0; c0 < DP; c0 += 32) {
@@ -913,32 +927,40 @@ eval_topk_tc3_kernel(EvalArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(u_full0);
     }
-    float* my_ring = ring + q * kEval3Ring * 32;
-    uint2* my_meta = ring_meta + q * kEval3Ring;
+    float* my_ring = ring + rid * 2 * kEval3Ring * 32;    // my two rings: row halves 0 and 1
+    uint2* my_meta = ring_meta + rid * 2 * kEval3Ring;
     volatile float* my_thr = thr_sm + il;
-    volatile int* head_sm = ring_ctl + q;
-    volatile int* tail_sm = ring_ctl + 4 + q;
-    int head = 0, tail_seen = 0;
+    volatile int* head_sm = ring_ctl + rid * 2;
+    volatile int* tail_sm = ring_ctl + 16 + rid * 2;
+    int head0 = 0, head1 = 0, pub0 = 0, pub1 = 0, tail_seen0 = 0, tail_seen1 = 0;
     const unsigned lt = (1u << lane) - 1u;
+    const int rh = lane >> 4;                             // my row's half of the quadrant
     const uint32_t col_end = static_cast<uint32_t>(a.n_items);
+    auto publish = [&]() {                                // make the staged chunks visible, then the new heads
+      if (head0 != pub0 || head1 != pub1) {
+        __syncwarp();                                     // (orders the lanes' stores before lane 0's release)
+        if (lane == 0) { if (head0 != pub0) st_release_cta_smem(head_sm, head0); if (head1 != pub1) st_release_cta_smem(head_sm + 1, head1); }
+        pub0 = head0; pub1 = head1;
+      }
+    };
     for (int j = 0; j < nj; ++j) {
       const int sb = j % kEval2Acc;
       mbar_wait(&s_full[sb], (j / kEval2Acc) & 1);
       tc_fence_after();
-      float v[4][32];
+      float v[2][32];
       if (a.dbg_mode != 2) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + c * 32, v[c]);
+        for (int c = 0; c < 2; ++c) tmem_ld32(tmem + lane_addr + sb * 128 + h * 64 + c * 32, v[c]);
         tmem_ld_wait();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(s_empty0 + 8u * sb);
-      if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) head = 1; continue; }
-      const uint32_t col0 = static_cast<uint32_t>((t0 + (j + rot) % nj) * 128);
-      float gm[4];
+      if (a.dbg_mode == 1 || a.dbg_mode == 2) { if (a.dbg_mode < 2 && v[0][0] == 123456.0f) head0 = 1; continue; }
+      const uint32_t col0 = static_cast<uint32_t>((t0 + (j + rot) % nj) * 128 + h * 64);
+      float gm[2];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         float m8[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -947,103 +969,140 @@ eval_topk_tc3_kernel(EvalArgs a) {
         }
         gm[c] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
       }
-      const float m = fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));
+      const float m = fmaxf(gm[0], gm[1]);
       const float thr = *my_thr;                          // possibly stale (lower): forwards extra chunks, never loses one
       const bool hit = row_ok && m >= thr;
       if (!__any_sync(0xffffffffu, hit) || a.dbg_mode == 3) continue;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         const bool pc = hit && gm[c] >= thr && col0 + c * 32 < col_end;
         const unsigned bc = __ballot_sync(0xffffffffu, pc);
         if (!bc) continue;
-        const int nc = __popc(bc);
-        if (head + nc - tail_seen > kEval3Ring) {         // ring full: wait for the selector
+        const int n0 = __popc(bc & 0x0000ffffu), n1 = __popc(bc & 0xffff0000u);
+        if (head0 + n0 - tail_seen0 > kEval3Ring || head1 + n1 - tail_seen1 > kEval3Ring) {   // a ring is full: wait for its selector
+          publish();                                      // (it can only drain what it can see)
           uint32_t spins = 0;
-          do {
-            tail_seen = *tail_sm;
+          for (;;) {
+            tail_seen0 = ld_acquire_cta_smem(tail_sm); tail_seen1 = ld_acquire_cta_smem(tail_sm + 1);
+            if (head0 + n0 - tail_seen0 <= kEval3Ring && head1 + n1 - tail_seen1 <= kEval3Ring) break;
+            __nanosleep(40);                              // (a hot spin would take issue slots from the selectors on this scheduler)
             if (++spins > 20000000u) __trap();
-          } while (head + nc - tail_seen > kEval3Ring);
+          }
         }
         if (pc) {
-          const int slot = (head + __popc(bc & lt)) & (kEval3Ring - 1);
+          const int pos = rh ? head1 + __popc(bc & 0xffff0000u & lt) : head0 + __popc(bc & 0x0000ffffu & lt);
+          const int slot = rh * kEval3Ring + (pos & (kEval3Ring - 1));
           float* dst = my_ring + slot * 32;
 #pragma unroll
           for (int t = 0; t < 32; t += 4)
             *reinterpret_cast<float4*>(dst + t) = make_float4(v[c][t], v[c][t + 1], v[c][t + 2], v[c][t + 3]);
           my_meta[slot] = make_uint2(static_cast<uint32_t>(lane), col0 + c * 32);
         }
-        head += nc;
-        __syncwarp();
-        __threadfence_block();
-        if (lane == 0) *head_sm = head;
+        head0 += n0; head1 += n1;
       }
+      publish();
     }
     __syncwarp();
-    __threadfence_block();
-    if (lane == 0) ring_ctl[8 + q] = 1;                   // finished: the selector drains what is left and writes the lists
+    if (lane == 0) { st_release_cta_smem(ring_ctl + 32 + rid * 2, 1); st_release_cta_smem(ring_ctl + 32 + rid * 2 + 1, 1); }   // finished: the selectors drain what is left and write the lists
   } else {
     // ------------------------------------------------------------------------------ selectors (own the k-best sets)
     const int q = warp & 3;
-    const float* my_ring = ring + q * kEval3Ring * 32;
-    const uint2* my_meta = ring_meta + q * kEval3Ring;
-    volatile int* head_sm = ring_ctl + q;
-    volatile int* tail_sm = ring_ctl + 4 + q;
-    volatile int* fin_sm = ring_ctl + 8 + q;
-    int* hist = hist_all + q * 32;
-    uint64_t* bufs_warp = bufs_sm + (size_t)q * 32 * (CAP + 1);
+    const int rh = (warp - 10) >> 2;                      // my row half: rows 16 rh .. 16 rh + 15 of the quadrant
+    const int ra = ((q * 2 + 0) * 2 + rh), rb = ((q * 2 + 1) * 2 + rh);   // my rings: column halves 0 and 1
+    const float* ring_a = ring + ra * kEval3Ring * 32;
+    const float* ring_b = ring + rb * kEval3Ring * 32;
+    const uint2* meta_a = ring_meta + ra * kEval3Ring;
+    const uint2* meta_b = ring_meta + rb * kEval3Ring;
+    volatile int* ctl = ring_ctl;                         // [r] head, [16 + r] tail, [32 + r] finished
+    int* hist = hist_all + (warp - 10) * 32;
+    uint64_t* bufs_warp = bufs_sm + q * 32 * (CAP + 1);
     const unsigned lt = (1u << lane) - 1u;
     const uint32_t col_end = static_cast<uint32_t>(a.n_items);
     const bool exact_compaction = (a.dbg_pipe & 4) != 0;
+    const int k = a.k;
     float thr = -INFINITY;                                // lane = row inside the quadrant
-    int cnt = 0, tail = 0;
+    int cnt = 0, tail_a = 0, tail_b = 0;
     uint32_t idle = 0;
+    // fewer than 32 free slots in row L: keep (about) the k best, raise and publish the threshold
+    auto make_room = [&](int L, uint64_t* buf, int& cnt_l) {
+      if (cnt_l > CAP - 32) {
+        __syncwarp();
+        int kept = k;
+        const float t = exact_compaction ? compact_row_call(buf, cnt_l, k, lane) : compact_row_coarse_call(buf, cnt_l, k, CAP - 48, lane, hist, &kept);
+        cnt_l = kept;
+        if (lane == L) { thr = t; thr_sm[q * 32 + L] = t; }
+      }
+    };
+    auto do_one = [&](const uint2 me, const float x) {
+      const int L = static_cast<int>(me.x);
+      const float thr_l = __shfl_sync(0xffffffffu, thr, L);
+      const uint32_t col = me.y + lane;
+      const bool cand = (col < col_end) && (x >= thr_l);
+      const unsigned cm = __ballot_sync(0xffffffffu, cand);
+      if (!cm) return;
+      int cnt_l = __shfl_sync(0xffffffffu, cnt, L);
+      uint64_t* buf = bufs_warp + L * (CAP + 1);
+      if (cand) buf[cnt_l + __popc(cm & lt)] = make_key(x, col);
+      cnt_l += __popc(cm);
+      make_room(L, buf, cnt_l);
+      if (lane == L) cnt = cnt_l;
+    };
     for (;;) {
-      const int fin = *fin_sm;                            // (read before head: a chunk published before `finished` is seen)
-      const int head = *head_sm;
-      if (head == tail) {
+      const int fin = ld_acquire_cta_smem(ctl + 32 + ra) & ld_acquire_cta_smem(ctl + 32 + rb);                  // (read before the heads: what was published before `finished` is seen)
+      const int head_a = ld_acquire_cta_smem(ctl + ra), head_b = ld_acquire_cta_smem(ctl + rb);
+      if (head_a == tail_a && head_b == tail_b) {
         if (fin) break;
         if (++idle > 40000000u) __trap();
         __nanosleep(20);
         continue;
       }
       idle = 0;
-      __threadfence_block();
+      // two entries per step while both rings have some: two independent dependency chains
 #pragma unroll 1
-      for (; tail != head; ++tail) {
-        const int slot = tail & (kEval3Ring - 1);
-        const uint2 me = my_meta[slot];
-        const float x = my_ring[slot * 32 + lane];
-        const int L = static_cast<int>(me.x);
-        float thr_l = __shfl_sync(0xffffffffu, thr, L);
-        const uint32_t col = me.y + lane;
-        const bool cand = (col < col_end) && (x >= thr_l);
-        const unsigned cm = __ballot_sync(0xffffffffu, cand);
-        if (!cm) continue;
-        int cnt_l = __shfl_sync(0xffffffffu, cnt, L);
-        uint64_t* buf = bufs_warp + (size_t)L * (CAP + 1);
-        if (cand) buf[cnt_l + __popc(cm & lt)] = make_key(x, col);
-        cnt_l += __popc(cm);
-        if (cnt_l > CAP - 32) {                           // fewer than 32 free slots: keep (about) the k best, raise the threshold
-          __syncwarp();
-          int kept = a.k;
-          if (exact_compaction) thr_l = compact_row(buf, cnt_l, a.k, lane);
-          else thr_l = compact_row_coarse(buf, cnt_l, a.k, CAP - 48, lane, hist, &kept);
-          cnt_l = kept;
-          if (lane == L) { thr = thr_l; thr_sm[q * 32 + L] = thr_l; }
-        }
-        if (lane == L) cnt = cnt_l;
+      while (tail_a != head_a && tail_b != head_b) {
+        const int sa = tail_a & (kEval3Ring - 1), sb2 = tail_b & (kEval3Ring - 1);
+        ++tail_a; ++tail_b;
+        const uint2 ma = meta_a[sa], mb = meta_b[sb2];
+        const float xa = ring_a[sa * 32 + lane], xb = ring_b[sb2 * 32 + lane];
+        const int La = static_cast<int>(ma.x), Lb = static_cast<int>(mb.x);
+        if (La == Lb) { do_one(ma, xa); do_one(mb, xb); continue; }     // same row: one buffer, in sequence
+        const float thr_a = __shfl_sync(0xffffffffu, thr, La), thr_b = __shfl_sync(0xffffffffu, thr, Lb);
+        const uint32_t col_a = ma.y + lane, col_b = mb.y + lane;
+        const bool cand_a = (col_a < col_end) && (xa >= thr_a), cand_b = (col_b < col_end) && (xb >= thr_b);
+        const unsigned cm_a = __ballot_sync(0xffffffffu, cand_a), cm_b = __ballot_sync(0xffffffffu, cand_b);
+        if (!(cm_a | cm_b)) continue;
+        int cnt_a = __shfl_sync(0xffffffffu, cnt, La), cnt_b = __shfl_sync(0xffffffffu, cnt, Lb);
+        uint64_t* buf_a = bufs_warp + La * (CAP + 1);
+        uint64_t* buf_b = bufs_warp + Lb * (CAP + 1);
+        if (cand_a) buf_a[cnt_a + __popc(cm_a & lt)] = make_key(xa, col_a);
+        if (cand_b) buf_b[cnt_b + __popc(cm_b & lt)] = make_key(xb, col_b);
+        cnt_a += __popc(cm_a); cnt_b += __popc(cm_b);
+        make_room(La, buf_a, cnt_a);
+        make_room(Lb, buf_b, cnt_b);
+        if (lane == La) cnt = cnt_a;
+        if (lane == Lb) cnt = cnt_b;
+      }
+#pragma unroll 1
+      for (; tail_a != head_a; ++tail_a) {
+        const int sl = tail_a & (kEval3Ring - 1);
+        do_one(meta_a[sl], ring_a[sl * 32 + lane]);
+      }
+#pragma unroll 1
+      for (; tail_b != head_b; ++tail_b) {
+        const int sl = tail_b & (kEval3Ring - 1);
+        do_one(meta_b[sl], ring_b[sl * 32 + lane]);
       }
       __syncwarp();
-      if (lane == 0) *tail_sm = tail;                     // the slots up to here may be overwritten
+      if (lane == 0) { st_release_cta_smem(ctl + 16 + ra, tail_a); st_release_cta_smem(ctl + 16 + rb, tail_b); }   // the slots up to here may be overwritten
     }
     __syncwarp();
     // final (exact) compaction of every row to its k best, then the row's KP slots go to the global per-(user, split) lists
     const int64_t gstride = (int64_t)a.nsplit * a.KP;
     uint64_t* grow0 = a.lists + ((int64_t)ub * 128 + q * 32) * gstride + (int64_t)sp * a.KP;
-    for (int r = 0; r < 32; ++r) {
+    for (int r = 16 * rh; r < 16 * rh + 16; ++r) {
       int n = __shfl_sync(0xffffffffu, cnt, r);
-      uint64_t* buf = bufs_warp + (size_t)r * (CAP + 1);
-      if (n > a.k) { compact_row(buf, n, a.k, lane); n = a.k; }
+      uint64_t* buf = bufs_warp + r * (CAP + 1);
+      if (n > a.k) { compact_row_call(buf, n, a.k, lane); n = a.k; }
       __syncwarp();
       for (int i = lane; i < a.KP; i += 32) grow0[r * gstride + i] = i < n ? buf[i] : 0ull;
     }
@@ -1309,12 +1368,12 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
       for (int cap = cap_hi; cap >= p->KP + 32; cap -= 32)
         if (eval2_smem_bytes(p->nsub, st, cap) <= 232448) { p->v2 = 1; p->cap = cap; p->nstages2 = st; break; }
     if (p->v2) p->nstages = p->nstages2;
-    // third generation (CTA pair): half-size stages; prefer >= 4 stages in flight, then the largest row buffer
+    // third generation (CTA pair): half-size stages; the largest row buffer that leaves >= 3 (else 2) stages in flight
     const int gen_env = [] { const char* e = getenv("NNCF_EVAL_GEN"); return e ? atoi(e) : kEvalDefaultGen; }();
     p->v3 = 0;
     if (p->v2 && gen_env >= 3 && p->n_ub >= 2) {
       int best_st = 0, best_cap = 0;
-      for (int want = 4; want >= 2 && !best_st; --want)
+      for (int want = 3; want >= 2 && !best_st; --want)   // (measured: 4 stages 876, 2 stages 1,266 cycles per tile for the pipeline alone)
         for (int cap = cap_hi; cap >= p->KP + 32 && !best_st; cap -= 32) {
           int st = 0;
           for (int t = kEval3MaxStages; t >= want; --t) if (eval3_smem_bytes(p->nsub, t, cap) <= 232448) { st = t; break; }

@@ -259,6 +259,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// release / acquire accesses to a shared-memory word at CTA scope (ring counters between warps of one CTA): lighter than
+// __threadfence_block(), which compiles to MEMBAR.SC.CTA
+__device__ __forceinline__ void st_release_cta_smem(volatile int* p, int v) {
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cta_smem(volatile int* p) {
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<int*>(p))) : "memory");
+  return v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns; thread t of the warp gets lane (base+t)
 // ----------------------------------------------------------------------------------------------

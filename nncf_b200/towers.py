@@ -182,7 +182,7 @@ class PretrainCombinedTower(torch.nn.Module):
         pre = conf.pretrain
         self.tower = tower
         self.p_drop = float(pre.get('pretrain_combine_dropout', 0.5))
-        self.mode = pre.get('pretrain_combine_mode', 'concat')
+        self.mode = pre.get('pretrain_combine_mode') or 'concat'       # (None in configs/pretrained_conf.py:63: nothing to merge there)
         self.actv = _actv(pre.get('pretrain_combine_actv', 'relu'))
         assert self.mode in ('concat', 'sum', 'mul', 'ave', 'max'), 'unknown pretrain_combine_mode %s' % self.mode
         C = torch.as_tensor(C_pretrain, dtype=torch.float32)

@@ -122,3 +122,38 @@ def test_evaluator_matches_oracle_whole_eval(precision, tol):
     for got, ref in ((a, ra), (b, rb)):
         assert abs(got['map@20'] - ref['map']) <= tol * max(ref['map'], 1e-9)
         assert abs(got['recall@20'] - ref['recall']) <= tol * max(ref['recall'], 1e-9)
+
+
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared", "original"])
+def test_use_content_id_trains_the_id_embedding(scheme, capsys):
+    """use_content_id (ref: modules/content/mean_pool.py:102-108): the item tower adds Emb_Cid[cid]; it is trained, its
+    v_reg activity regulariser joins the loss"""
+    tr = _run('basic_embedding', scheme, 'skip-gram', 'whole@10', {'max_epoch': 1, 'use_content_id': True, 'v_reg': 1e-4})
+    out = capsys.readouterr().out
+    assert 'epoch 1 (' in out and 'test recall/map' in out
+    st = tr.model_dict['_state']
+    from nncf_b200.towers import ContentIdTower
+    assert isinstance(st.tower, ContentIdTower)
+    touched = (st.tower.emb_cid.abs() > 0.05 + 1e-6).any() or st.tower.emb_cid.grad is not None
+    assert bool(touched)
+
+
+@pytest.mark.parametrize("model,transform", [("basic_embedding", None), ("pretrained", False), ("pretrained", True)])
+def test_pretrained_item_vectors_models_run(model, transform, capsys):
+    """the supervised / pretrained combination (ref: modules/shared/vec2vec.py:17-64, models/model_framework.py:69-84,99-100)
+    with in-memory vectors standing in for the absent sentence-vector blobs"""
+    C = np.random.RandomState(5).randn(1500, 32).astype(np.float32) * 0.1       # synthetic_small has 1,500 items
+    pre = {'C_pretrain': C.tolist(), 'pretrain_combine_dropout': 0.3}      # (--param_dict goes through ast.literal_eval)
+    if transform is not None:
+        pre['transform'] = transform
+    tr = _run(model, 'neg_shared', 'skip-gram', 'whole@10', {'max_epoch': 1, 'pretrain': pre, 'interaction_bias': None})
+    out = capsys.readouterr().out
+    assert 'epoch 1 (' in out and 'test recall/map' in out
+    st = tr.model_dict['_state']
+    from nncf_b200.towers import PretrainCombinedTower, FrozenItemTable
+    if model == 'pretrained' and not transform:
+        assert isinstance(st.tower, FrozenItemTable) and st.tower_opt is None
+        assert np.allclose(st.tower.table.cpu().numpy(), C)                      # trainable=False
+    else:
+        assert isinstance(st.tower, PretrainCombinedTower)
+        assert np.allclose(st.tower.c_pretrain.cpu().numpy(), C)

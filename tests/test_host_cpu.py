@@ -178,3 +178,111 @@ def test_mf_conf_follows_pretrained_conf():
     assert (b.max_epoch, b.num_negatives, b.interaction_bias, b.u_reg) == (30, 10, None, 1e-6)
     assert get_conf('news_title_only_fold1', 'best', None, 'mf').u_reg == 1e-5
     assert get_conf('x', 'default', {'interaction_bias': None, 'batch_size_p': 512}, 'mf').batch_size_p == 512
+
+
+def test_content_id_and_pretrain_combination_towers():
+    """use_content_id (ref: modules/content/mean_pool.py:102-108) and ItemCombination (ref: modules/shared/vec2vec.py:17-64)
+    as wrappers round any item tower: shapes, the v_reg activity regulariser, merge modes, frozen pretrained vectors."""
+    import torch
+    from nncf_b200.conf import get_conf
+    from nncf_b200.towers import ContentIdTower, PretrainCombinedTower, FrozenItemTable
+
+    class Inner(torch.nn.Module):
+        def __init__(self, n, d):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.arange(n * d, dtype=torch.float32).reshape(n, d) / (n * d))
+
+        def forward(self, ids):
+            return self.w[ids.long()]
+
+    g = torch.Generator().manual_seed(0)
+    n_items, d = 30, 8
+    ids = torch.tensor([3, 7, 7, 11], dtype=torch.int32)
+    t = ContentIdTower(Inner(n_items, d), n_items, d, v_reg=0.5, generator=g, device='cpu')
+    t.train()
+    out = t(ids)
+    e = t.emb_cid[ids.long()]
+    assert torch.allclose(out, t.tower(ids) + e)
+    # utils/utilities.py:129-135: v_reg * sum_d mean_b E[b, d]^2
+    assert torch.allclose(t.reg_loss, 0.5 * (e * e).mean(0).sum())
+    assert (t.emb_cid.abs() <= 0.05).all()                                   # Keras-1 'uniform'
+    t.eval()
+    t(ids)
+    assert t.reg_loss is None
+
+    C = np.random.RandomState(1).randn(n_items, 5).astype(np.float32)
+    for mode, pdim in (('concat', 5), ('sum', d), ('mul', d), ('ave', d), ('max', d)):
+        Cm = C if pdim == 5 else np.random.RandomState(2).randn(n_items, d).astype(np.float32)
+        conf = get_conf('synthetic_small', 'default', {'user_dim': 6, 'item_dim': 6, 'pretrain': {
+            'C_pretrain': Cm, 'pretrain_combine_mode': mode, 'pretrain_combine_dropout': 0.0, 'pretrain_combine_actv': 'relu'}})
+        assert conf.pretrain['pretrain_combine_actv'] == 'relu'
+        pt = PretrainCombinedTower(Inner(n_items, d), Cm, conf, tower_dim=d)
+        pt.train()
+        o = pt(ids)
+        assert o.shape == (4, 6) and (o >= 0).all()
+        assert not pt.c_pretrain.requires_grad and 'c_pretrain' not in dict(pt.named_parameters())   # trainable=False
+        o.sum().backward()
+        assert pt.dense.weight.grad is not None and pt.tower.w.grad is not None
+        h, p = pt.tower(ids), torch.from_numpy(Cm)[ids.long()]
+        merged = {'concat': lambda: torch.cat([h, p], 1), 'sum': lambda: h + p, 'mul': lambda: h * p, 'ave': lambda: 0.5 * (h + p),
+                  'max': lambda: torch.maximum(h, p)}[mode]()
+        assert torch.allclose(o, torch.relu(pt.dense(merged)), atol=1e-6)
+    # dropout >= 1: the pretrained vectors are not used at all (vec2vec.py:29,45-47)
+    conf = get_conf('synthetic_small', 'default', {'user_dim': 6, 'item_dim': 6, 'pretrain': {'C_pretrain': C, 'pretrain_combine_dropout': 1.0}})
+    pt = PretrainCombinedTower(Inner(n_items, d), C, conf, tower_dim=d)
+    assert pt.dense.in_features == d
+    # row dropout: whole table rows, rescaled by 1 / (1 - p); the two occurrences of item 7 share the mask
+    conf = get_conf('synthetic_small', 'default', {'user_dim': 6, 'item_dim': 6, 'pretrain': {'C_pretrain': C, 'pretrain_combine_dropout': 0.5}})
+    pt = PretrainCombinedTower(None, C, conf)
+    pt.train()
+    torch.manual_seed(0)
+    pt.dense.weight.data = torch.eye(6, 5)
+    pt.dense.bias.data.zero_()
+    pt.actv = lambda x: x
+    o = pt(ids)
+    ref = torch.from_numpy(C)[ids.long()]
+    for r in range(4):
+        assert torch.allclose(o[r, :5], torch.zeros(5)) or torch.allclose(o[r, :5], 2.0 * ref[r], atol=1e-6)
+    assert torch.allclose(o[1], o[2])
+    ft = FrozenItemTable(C)
+    assert torch.equal(ft(ids), torch.from_numpy(C)[ids.long()]) and len(list(ft.parameters())) == 0
+
+
+def test_pretrained_vectors_loader_and_conf(tmp_path):
+    """configs/data_utils.py:129-185 (pkl and text formats) and the pretrain keys of the Conf classes"""
+    import pickle
+    from nncf_b200 import data_utils as DU
+    from nncf_b200.conf import get_conf
+
+    class Spec:
+        word_count, item_count = 6, 5
+
+    class Helper:
+        word2id = {'alpha': 1, 'beta': 4, 'zzz': 99}
+
+    W = np.arange(12, dtype=np.float64).reshape(6, 2)
+    wp = tmp_path / 'word_vectors_50d.pkl'
+    with open(wp, 'wb') as fp:
+        pickle.dump(W, fp, protocol=2)
+    sp = tmp_path / 'sentence_vectors_50d.txt'
+    sp.write_text('_*0 0.5 1.5 \n_*3 -1.0 2.0 \n_*9 7.0 7.0 \n')
+    conf = get_conf('synthetic_small', 'default', {'pretrain': {'wordvec_filepath': str(wp), 'sentvec_filepath': str(sp)}})
+    Wl, Cl = DU.get_pretrained_vectors(conf, Spec, Helper)
+    assert np.array_equal(Wl, W)
+    assert Cl.shape == (5, 2) and np.array_equal(Cl[3], [-1.0, 2.0]) and np.array_equal(Cl[1], [0.0, 0.0])   # id 9 >= item_count dropped
+    wt = tmp_path / 'words.txt'
+    wt.write_text('2 2\nalpha 1.0 2.0 \nbeta 3.0 4.0 \nzzz 5.0 6.0 \n')
+    conf = get_conf('synthetic_small', 'default', {'pretrain': {'wordvec_filepath': str(wt), 'sentvec_filepath': None}})
+    Wl, Cl = DU.get_pretrained_vectors(conf, Spec, Helper)
+    assert Cl is None and np.array_equal(Wl[1], [1.0, 2.0]) and np.array_equal(Wl[4], [3.0, 4.0]) and not Wl[0].any()
+    assert DU.get_pretrained_vectors(get_conf('synthetic_small', 'default', None), Spec, Helper) == (None, None)
+    # get_conf_best: per-dataset combine dropout (basic_embedding_conf.py:109-128) and the conf_var switches (:131-136)
+    pre = {'sentvec_filepath': str(sp)}
+    assert get_conf('citeulike_title_only', 'best', {'pretrain': dict(pre)}).pretrain['pretrain_combine_dropout'] == 0.3
+    assert get_conf('news_title_only', 'best', {'pretrain': dict(pre)}).pretrain['pretrain_combine_dropout'] == 0.1
+    assert get_conf('citeulike_title_only', 'best', {'pretrain': dict(pre), 'conf_var': 'sup'}).pretrain is None
+    assert get_conf('citeulike_title_only', 'best', {'pretrain': dict(pre), 'conf_var': 'unsup_dropout=0.7'}).pretrain['pretrain_combine_dropout'] == 0.7
+    # model_choice 'pretrained' (configs/pretrained_conf.py:57-65): transform off by default
+    c = get_conf('citeulike_title_only', 'default', None, 'pretrained')
+    assert c.pretrain['transform'] is False and c.pretrain['sentvec_filepath'].endswith('pretrain//sentence_vectors_50d.txt')
+    assert DU.get_pretrain_folder('news_title_and_abstract_fold2', aug=True).endswith('news/title_and_abstract/pretrain/aug/')

@@ -69,3 +69,11 @@ if which == "stats":
     run("g3 new filter", GEN=3)
     run("g3 old filter (dbg4) exact compaction", GEN=3, DBG=4, PIPE=4)
     run("g3 old filter (dbg4) k=10", kk=10, GEN=3, DBG=4)
+if which == "quick2":
+    for kk in (10, 50, 100):
+        run("g2 default", kk=kk)
+        run("g3 default", kk=kk, GEN=3)
+        run("g3 default (again)", kk=kk, GEN=3)
+    run("g3 exact compaction", GEN=3, PIPE=4)
+    run("g3 maxima only (dbg3)", GEN=3, DBG=3)
+    run("g3 pipeline only (dbg2)", GEN=3, DBG=2)
