@@ -783,7 +783,11 @@ constexpr int kEval3MaxStages = 8;
 // two readers per quadrant with 16 rows each 18.6 ms (duplicated TMEM reads), per-lane compare-and-branch 30 ms,
 // per-lane branch-free scan down the maxima hierarchy 19.9 ms; one reader + one selector per quadrant 14.3 ms (the
 // reader alone: wait 310, TMEM load 210, 128 maxima 430, staging 700 cycles per tile); two readers + one selector
-// 12.4 ms (selector 100 % busy, ~150 dependent instructions per pair of entries).
+// 12.4 ms (selector 100 % busy, ~150 dependent instructions per pair of entries); two readers + two selectors 12.1 ms
+// (this version; readers 80 % busy: TMEM load 215, 64 maxima 260, threshold 125, staging + publishing 345 cycles per tile);
+// four readers (32 columns each) + two selectors on multi-producer rings (slots reserved with a shared-memory atomic,
+// made visible by a lap tag) 12.8 ms: the fixed cost per reader and tile (barrier wait, fences, arrive; the pipeline
+// alone went from 959 to 1,010 cycles per tile with 26 warps) outweighs the smaller chunk.
 constexpr int kEval3Ring = 16;                    // staged chunks per ring (power of two, >= 16 = one chunk of every row of a row half)
 constexpr int kEval3Threads = 64 + 32 * 16;
 constexpr int kEvalDefaultGen = 3;                // NNCF_EVAL_GEN overrides (2 = second generation, 3 = CTA pair; the plan falls back to 2 when
@@ -945,6 +949,8 @@ eval_topk_tc3_kernel(EvalArgs a) {
     };
     for (int j = 0; j < nj; ++j) {
       const int sb = j % kEval2Acc;
+      const float thr = *my_thr;                          // possibly stale (lower): forwards extra chunks, never loses one;
+                                                          // read before the wait so that its latency hides behind it
       mbar_wait(&s_full[sb], (j / kEval2Acc) & 1);
       tc_fence_after();
       float v[2][32];
@@ -970,7 +976,6 @@ eval_topk_tc3_kernel(EvalArgs a) {
         gm[c] = fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3]));
       }
       const float m = fmaxf(gm[0], gm[1]);
-      const float thr = *my_thr;                          // possibly stale (lower): forwards extra chunks, never loses one
       const bool hit = row_ok && m >= thr;
       if (!__any_sync(0xffffffffu, hit) || a.dbg_mode == 3) continue;
 #pragma unroll

@@ -264,6 +264,14 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void st_release_cta_smem(volatile int* p, int v) {
   asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"(smem_u32(const_cast<int*>(p))), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_release_cta_smem_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta_smem_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
 __device__ __forceinline__ int ld_acquire_cta_smem(volatile int* p) {
   int v;
   asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(const_cast<int*>(p))) : "memory");
