@@ -69,6 +69,16 @@ struct ScoreTcArgs {
   const int32_t* ids_u; const int32_t* ids_v; // table row of each owner row: ids_x[r * stride_x + row]
   int64_t ids_stride_u, ids_stride_v;
   ShardPtrs shards_u, shards_v;
+  // self-gather (fused SGD, neg_shared, dp <= 128, one table, the whole grid co-resident): there is no gather kernel.
+  // Every CTA gathers ITS OWN 128 rows (ids -> fp32 rows -> bf16 tile image) straight into its shared-memory X block
+  // and into the global image, where the CTAs of the other side read them as their Y tiles once the block's flag
+  // carries this step's sequence number.  The tables are read and updated inside one kernel now, so no drain may
+  // start before every CTA has finished reading: gather_count (monotonic) must reach gather_target first.
+  int self_gather;
+  int gather_seq;                             // this step's sequence number (> 0, increasing)
+  int* gather_flags;                          // [R][2][rows_pad / 128]
+  unsigned long long* gather_count;           // CTAs that have finished gathering, summed over all steps
+  unsigned long long gather_target;           // = gather_seq * (active CTAs per step)
 };
 
 // declared here, defined in score_tc_nsub{1,2,4}.cu (one translation unit per NSUB so they compile in parallel)
@@ -278,10 +288,20 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   if (warp == 0) {
     // ------------------------------------------------------------------------------ producer
     if (lane == 0) {
-      mbar_expect_tx(x_full, NSUB * kSubBytes);
-      for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
+      if (!a.self_gather) {
+        mbar_expect_tx(x_full, NSUB * kSubBytes);
+        for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
+      }
+      int ready_blk = -1;                                // self-gather: blocks of the swept side known to be in the image
       for (int t = 0; t < nt; ++t) {
         const int st = t % C::kStages;
+        if (a.self_gather && ((t * TN) >> 7) > ready_blk) {
+          ready_blk = (t * TN) >> 7;
+          const int* flag = a.gather_flags + (r * 2 + (1 - side)) * nblk + ready_blk;
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(flag) != a.gather_seq) { __nanosleep(20); if (++spins > 20000000u) __trap(); }
+          fence_proxy_async_global();                    // the rows were written by generic stores; the bulk copy reads them
+        }
         mbar_wait(&y_empty[st], ((t / C::kStages) & 1) ^ 1);
         mbar_expect_tx(&y_full[st], NSUB * C::kYBytes);
         // rows [t TN, (t+1) TN) of the swept side: a contiguous piece of each [128 x 64] sub-tile of block (t TN) / 128
@@ -371,6 +391,46 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     const int32_t* inv_row = GROUP ? a.inverse + base : nullptr;
     const float* spos_row = a.spos + base;
     float lsum = 0.0f, asum = 0.0f, lraw = 0.0f;
+
+    if (a.self_gather) {
+      // gather my CTA's 128 rows: this warp takes rows 16 ew .. 16 ew + 15 (ids first: the id -> row dependency is two
+      // L2 round trips; the rows were pulled into L2 by the previous step's prefetch warps)
+      const int32_t* gids = (side == 0 ? a.ids_u + r * a.ids_stride_u : a.ids_v + r * a.ids_stride_v) + ob * 128 + ew * 16;
+      const float* gtab = side == 0 ? a.table_u : a.table_v;
+      const int rows_here = n_owner - (ob * 128 + ew * 16);                     // valid rows of my 16
+      int64_t myid = -1;
+      if (lane < 16 && lane < rows_here) myid = gids[lane];
+      const int c = 4 * lane;                                                   // my 4 columns of every row
+      uint8_t* gimg = const_cast<uint8_t*>(gX);
+#pragma unroll 1
+      for (int k0 = 0; k0 < 16; k0 += 8) {                                      // 8 row loads in flight (the register budget is 80)
+        float4 x[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int64_t id = __shfl_sync(0xffffffffu, myid, k0 + k);
+          x[k] = (id >= 0 && c < a.d) ? __ldg(reinterpret_cast<const float4*>(gtab + id * a.d + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (c < DP) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint2 pk2;
+            pk2.x = pack_bf16x2(x[k].x, x[k].y);
+            pk2.y = pack_bf16x2(x[k].z, x[k].w);
+            const uint32_t off = (c >> 6) * kSubBytes + sw128_offset(ew * 16 + k0 + k, c & 63);
+            *reinterpret_cast<uint2*>(sX + off) = pk2;                           // my X operand
+            *reinterpret_cast<uint2*>(gimg + off) = pk2;                         // the other side's Y tiles
+          }
+        }
+      }
+      fence_proxy_async();                                                      // sX is read by the tensor core (async proxy)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");    // epilogue warps only; orders their image
+                                                                                // stores before the (cumulative) release below
+      if (tid == 64) {
+        st_release_gpu(a.gather_flags + (r * 2 + side) * nblk + ob, a.gather_seq);
+        atomicAdd(a.gather_count, 1ull);
+        mbar_arrive(x_full);
+      }
+    }
 
     for (int t = 0; t < nt; ++t) {
       const int sb = t & 1;
@@ -477,6 +537,12 @@ score_grad_tc_kernel(ScoreTcArgs a) {
               make_float4(v[u] * ec.g_scale, v[u + 1] * ec.g_scale, v[u + 2] * ec.g_scale, v[u + 3] * ec.g_scale);
       }
       if (a.fuse_sgd) fence_proxy_async();                                     // staged rows are read by the TMA engine
+      if (a.self_gather && tid == 64) {
+        // nobody may still be READING the tables when the first update lands (all CTAs of the grid are co-resident and
+        // their gathers ended ~20 us ago: this never spins in practice, it makes the one-snapshot semantics unconditional)
+        uint32_t spins = 0;
+        while (ld_acquire_gpu_u64(a.gather_count) < a.gather_target) { __nanosleep(64); if (++spins > 20000000u) __trap(); }
+      }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * kScoreEpiWarps) : "memory");   // epilogue warps only
       if (a.fuse_sgd) {
         // (the staged rows already carry the factor -lr, see g_scale)

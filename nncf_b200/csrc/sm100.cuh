@@ -259,6 +259,23 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// release / acquire accesses to global words at GPU scope (flags and counters between CTAs of one grid)
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// orders this thread's earlier generic-proxy observations of global memory before its later async-proxy (bulk copy) reads
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 // release / acquire accesses to a shared-memory word at CTA scope (ring counters between warps of one CTA): lighter than
 // __threadfence_block(), which compiles to MEMBAR.SC.CTA
 __device__ __forceinline__ void st_release_cta_smem(volatile int* p, int v) {

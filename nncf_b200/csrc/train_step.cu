@@ -699,6 +699,10 @@ struct nncf_trainer {
   uint8_t *Uimg = nullptr, *Vimg = nullptr;
   double* loss = nullptr;
   unsigned int* loss_count = nullptr;   // fused mode: per-replica arrival counters of the in-kernel loss hand-off
+  int* gather_flags = nullptr;          // self-gather mode (score_tc.cuh): [R][2][rows_pad / 128] step sequence numbers
+  unsigned long long* gather_count = nullptr;
+  int gather_seq = 0;
+  int resident_ctas = 0;                // CTAs of the score kernel that fit on the device at once
   int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
   int32_t *ownerU = nullptr, *ownerV = nullptr;
   int64_t ownerU_n = 0, ownerV_n = 0;
@@ -771,6 +775,14 @@ extern "C" int nncf_trainer_create(const nncf_step_config* cfg, nncf_trainer_t**
   int rc = 0;
   rc |= dev_alloc(&t->loss, (size_t)R);
   rc |= dev_alloc(&t->loss_count, (size_t)R);
+  rc |= dev_alloc(&t->gather_flags, (size_t)R * 2 * (t->rows_pad / 128));
+  rc |= dev_alloc(&t->gather_count, (size_t)1);
+  {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    t->resident_ctas = 2 * sms;         // ScoreTcCfg::kMinBlocks = 2 for dp <= 128 (the only shapes that self-gather)
+  }
   if (cfg->scheme == NNCF_SCHEME_SAMPLED_NEG_SHARED) {
     rc |= dev_alloc(&t->dU, (size_t)R * t->rows * cfg->dim);
     rc |= dev_alloc(&t->dV, (size_t)R * t->rows * cfg->dim);
@@ -822,7 +834,8 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
     cudaFree(t->timeline);
   }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
-                  t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn};
+                  t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn,
+                  t->gather_flags, t->gather_count};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
@@ -983,12 +996,23 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     for (int i = 0; i < t->n_shards; ++i) { gu.shards.p[i] = t->ushards[i]; gv.shards.p[i] = t->ishards[i]; }
   }
   const bool vec = (d % 4 == 0) && !bias;   // 16-byte aligned rows: 128-bit loads / vector reductions (the scalar kernels carry the bias-column logic)
+  // self-gather (opt-in, NNCF_SELF_GATHER=1): the score kernel's CTAs gather their own rows (no gather launch, no hand-off).
+  // Needs the fused drain (nothing else reads the staging buffers), one local table, dp <= 128 and the whole grid resident
+  // at once: CTAs wait for each other's image blocks, and no drain may start before the last gather has ended.
+  // Measured on B200 and NOT the default: 27.9 vs 26.9 us per step at R = 37, 18.8 vs 15.1 us at R = 1 (B = 512, d = 128,
+  // uniform ids).  The separate gather kernel has 1,184 CTAs x 8 warps x 4 rows in flight and its launch overlaps the score
+  // kernel's prologue through programmatic dependent launch; 8 warps x 8 rows per CTA behind the prologue do not beat it.
+  const bool self_env = [] { const char* e = getenv("NNCF_SELF_GATHER"); return e && atoi(e) != 0; }();   // (read per step: the tests switch it)
+  const int active_ctas = ceil_div(B, 128) * 2 * R;
+  const bool self_gather = self_env && fuse_sgd && vec && !group && !sharded && dp <= 128 && !t->timeline &&
+                           active_ctas <= t->resident_ctas;
   // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
   // reads what its predecessor wrote, so only launch latency and prologues overlap
-  if (vec && dp <= 128) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<1>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
+  if (self_gather) { /* the score kernel gathers */ }
+  else if (vec && dp <= 128) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<1>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
   else if (vec) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<2>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
   else NNCF_CUDA(launch_pdl(gather_rows_kernel, dim3(rp / 8, R, 2), dim3(256), 0, st, gu, gv));
-  count_launch();
+  if (!self_gather) count_launch();
   if (pairwise) {
     pos_score_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->Vf, group ? t->inverse : nullptr, rp, dp, B,
                                                               bf16 ? 1 : 0, t->spos);
@@ -1015,6 +1039,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
     ta.tl = tl;
+    if (self_gather) {
+      ta.self_gather = 1; ta.gather_seq = ++t->gather_seq; ta.gather_flags = t->gather_flags; ta.gather_count = t->gather_count;
+      ta.gather_target = static_cast<unsigned long long>(t->gather_seq) * static_cast<unsigned long long>(active_ctas);
+    }
     static const bool prefetch_env = [] { const char* e = getenv("NNCF_PREFETCH"); return !e || atoi(e) != 0; }();
     if (prefetch_env && next_uid && next_cid && !sharded && !dense_items && (d % 4 == 0)) {
       ta.next_ids_u = next_uid; ta.next_ids_v = next_cid; ta.next_count = R * B;

@@ -275,10 +275,12 @@ def test_host_fed_steps_match_device_fed(replicas, n_steps):
         b.run_host(hU, hV, h_uid.cuda(), h_cid.cuda(), 1)
 
 
+@pytest.mark.parametrize("self_gather", ["1", "0"])
 @pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
 @pytest.mark.parametrize("loss", ["skip-gram", "mse"])
 @pytest.mark.parametrize("B,d,replicas", [(128, 64, 1), (200, 128, 2), (512, 128, 3), (130, 256, 1), (96, 52, 1)])
-def test_fused_sgd_drain_matches_oracle(scheme, loss, B, d, replicas):
+def test_fused_sgd_drain_matches_oracle(scheme, loss, B, d, replicas, self_gather, monkeypatch):
+    monkeypatch.setenv("NNCF_SELF_GATHER", self_gather)     # neg_shared, dp <= 128: the score kernel gathers its own rows (or not)
     """bf16 + sparse SGD + pointwise loss is the fused mode: the score kernel's drain applies -lr * dX to the table rows
     with one bulk async reduction per row (duplicates, also across replicas, must sum) and publishes the loss itself.
     Checked against the oracle's table delta summed over the replicas, for three consecutive steps' worth of re-use."""
@@ -308,6 +310,33 @@ def test_fused_sgd_drain_matches_oracle(scheme, loss, B, d, replicas):
     out2 = step.run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1)
     torch.cuda.synchronize()
     assert np.all(out2["loss"].cpu().numpy() < 1.5 * got + 1.0) and np.all(np.isfinite(out2["loss"].cpu().numpy()))
+
+
+@pytest.mark.parametrize("B,d,replicas,steps", [(512, 128, 37, 6), (512, 128, 1, 8), (300, 64, 5, 4)])
+def test_self_gather_equals_separate_gather_over_consecutive_steps(B, d, replicas, steps, monkeypatch):
+    """the self-gathering score kernel (no gather launch; image blocks handed between CTAs through flags; drains held back
+    until every CTA has read its rows) against the two-launch step on the same ids, several dependent steps in one call:
+    the same losses and the same tables (the only freedom is the order of the fp32 reductions at the L2)"""
+    from nncf_b200.ops import FusedStep, StepSpec
+    nu, ni, lr = 4000, 1500, 0.05
+    EU, EV = _tables(nu, ni, d, seed=B + replicas)
+    rng = np.random.RandomState(steps)
+    n = B * replicas * steps
+    uid = torch.from_numpy(rng.randint(0, nu, size=n).astype(np.int32)).cuda()
+    cid = torch.from_numpy((rng.zipf(1.3, size=n) % ni).astype(np.int32)).cuda()       # hot items: duplicates inside and across steps
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NNCF_SELF_GATHER", mode)
+        step = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="sgd",
+                                  learn_rate=lr, replicas=replicas, neg_loss_weight=128.0, loss_gamma=10.0))
+        tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+        out = step.run(tU, tV, uid, cid, steps)
+        torch.cuda.synchronize()
+        res[mode] = (out["loss"].cpu().numpy().copy(), tU.cpu().numpy(), tV.cpu().numpy())
+    assert np.all(np.isfinite(res["1"][0])) and res["1"][0].shape == res["0"][0].shape
+    assert np.allclose(res["1"][0], res["0"][0], rtol=1e-4), (res["1"][0][:4], res["0"][0][:4])
+    assert _rel(res["1"][1] - EU, res["0"][1] - EU) <= 1e-3
+    assert _rel(res["1"][2] - EV, res["0"][2] - EV) <= 1e-3
 
 
 @pytest.mark.parametrize("loss,norm", [("max-margin", True), ("skip-gram", False)])
