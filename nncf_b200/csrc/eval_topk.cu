@@ -1365,7 +1365,7 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
     for (int st = 4; st >= 1; --st)
       if (eval_smem_bytes(p->nsub, st, p->KP) <= 232448) { p->nstages = st; break; }
     // second generation: the largest row buffer (fewest compactions) that still leaves 3 (else 2) item-tile stages
-    static const bool v1_env = [] { const char* e = getenv("NNCF_EVAL_V1"); return e && atoi(e) != 0; }();
+    const bool v1_env = [] { const char* e = getenv("NNCF_EVAL_V1"); return e && atoi(e) != 0; }();
     int st_hi = 3, cap_hi = 2 * p->KP > 192 ? 192 : (2 * p->KP < 96 ? 96 : 2 * p->KP);
     { const char* e = getenv("NNCF_EVAL_NST"); if (e) { const int v = atoi(e); if (v >= 2 && v <= 4) st_hi = v; } }     // developer overrides
     { const char* e = getenv("NNCF_EVAL_CAP"); if (e) { const int v = atoi(e); if (v % 32 == 0 && v >= p->KP + 32 && v <= 192) cap_hi = v; } }

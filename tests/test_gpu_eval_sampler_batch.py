@@ -14,6 +14,28 @@ def _int_embeddings(n, d, seed):
     return np.random.RandomState(seed).randint(-4, 5, size=(n, d)).astype(np.float32)
 
 
+@pytest.mark.parametrize("gen", ["3", "2", "1"])
+@pytest.mark.parametrize("nu,ni,d,k", [(300, 2500, 50, 50), (700, 9000, 128, 10), (385, 4100, 96, 32), (260, 1500, 200, 40),
+                                       (1100, 20000, 128, 64), (130, 1000, 128, 100)])
+def test_topk_generations_bit_exact(gen, nu, ni, d, k, monkeypatch):
+    """the three tensor-core generations of whole@k (CTA pair with readers / selectors = default, one CTA per 128 users,
+    streaming exact sets) on tie-heavy integer embeddings: odd numbers of user blocks (a padded pair), ragged item tiles,
+    several item splits, d = 200 (NSUB = 4), k = 100 (falls back to the second generation): ids and scores bit-exact"""
+    from nncf_b200.ops import eval_topk
+    if gen == "1":
+        monkeypatch.setenv("NNCF_EVAL_V1", "1")
+    else:
+        monkeypatch.setenv("NNCF_EVAL_GEN", gen)
+    U, V = _int_embeddings(nu, d, 11), _int_embeddings(ni, d, 12)
+    ids, sc = eval_topk(torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda(), k, "bf16")
+    ids, sc = ids.cpu().numpy(), sc.cpu().numpy()
+    S = U.astype(np.float64) @ V.astype(np.float64).T
+    for u in range(0, nu, 3):
+        exp = O.topk_indices(S[u], k)
+        np.testing.assert_array_equal(ids[u], exp)
+        np.testing.assert_array_equal(sc[u], S[u, exp].astype(np.float32))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("nu,ni,d,k", [(37, 500, 16, 10), (300, 2500, 50, 50), (130, 1000, 128, 100), (64, 40, 8, 50),
                                        (5, 129, 200, 128)])
