@@ -788,6 +788,8 @@ constexpr int kEval3MaxStages = 8;
 // four readers (32 columns each) + two selectors on multi-producer rings (slots reserved with a shared-memory atomic,
 // made visible by a lap tag) 12.8 ms: the fixed cost per reader and tile (barrier wait, fences, arrive; the pipeline
 // alone went from 959 to 1,010 cycles per tile with 26 warps) outweighs the smaller chunk.
+// Also slower: a reader that keeps one TMEM load in flight behind the processing of the other chunk (13.2 ms): it holds
+// the accumulator one chunk longer, and the accumulator ring (3 deep) is what the MMA waits for.
 constexpr int kEval3Ring = 16;                    // staged chunks per ring (power of two, >= 16 = one chunk of every row of a row half)
 constexpr int kEval3Threads = 64 + 32 * 16;
 constexpr int kEvalDefaultGen = 3;                // NNCF_EVAL_GEN overrides (2 = second generation, 3 = CTA pair; the plan falls back to 2 when
