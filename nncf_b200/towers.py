@@ -8,8 +8,9 @@ concatenated, optional BatchNorm + activation + dropout, average / max pooling (
 Flatten -> Dense -> BatchNorm -> activation -> Dropout; LSTM / GRU stacks, optional second stack reading the sequence
 backwards, concatenation, pooling over time when `use_seq_for_dnn`.
 Declared (third-party Keras-1.2.2 arithmetic, not under /root/reference): torch's LSTM/GRU gates use sigmoid where the
-reference asks Keras for `hard_sigmoid`; recurrent dropout (dropout_W / dropout_U) is not applied; the contextual gating
-layers (modules/shared/gatings.py, off by default) are not provided.
+reference asks Keras for `hard_sigmoid`; recurrent dropout (dropout_W / dropout_U) is not applied.
+The contextual gating layers of modules/shared/gatings.py (off in every Conf) are `SpatialGate` / `TemporalGate` below,
+applied to the word embeddings in the reference's order (temporal, then spatial: cnn_model.py:53-59, rnn_model.py:46-52).
 
 Two wrappers complete the item side of the reference graph for every content model (mean-pool, CNN, RNN):
 `ContentIdTower` (`use_content_id`: + Emb_Cid[cid], ref: modules/content/mean_pool.py:102-108, cnn_model.py:134-140,
@@ -25,14 +26,58 @@ def _actv(name):
     return {'relu': torch.relu, 'tanh': torch.tanh, 'linear': (lambda x: x), 'sigmoid': torch.sigmoid}[name]
 
 
+class SpatialGate(torch.nn.Module):
+    """X' = X * sigmoid(Dense(mean_steps(f(Dense(X))))): one gate per embedding dimension, shared by all steps
+    (ref: modules/shared/gatings.py:63-80; conf_dict keys gating_hidden_dim, gating_hidden_actv)"""
+
+    def __init__(self, x_dim, conf_dict):
+        super().__init__()
+        self.hidden = torch.nn.Linear(x_dim, conf_dict['gating_hidden_dim'])
+        self.actv = _actv(conf_dict['gating_hidden_actv'])
+        self.out = torch.nn.Linear(conf_dict['gating_hidden_dim'], x_dim)
+
+    def forward(self, x):                                   # [n, steps, x_dim]
+        g = torch.sigmoid(self.out(self.actv(self.hidden(x)).mean(dim=1)))
+        return x * g[:, None, :]
+
+
+class TemporalGate(torch.nn.Module):
+    """X' = X * c * sigmoid(<X_t, q>), q = Dense(mean_steps(f(Dense(X)))) (optionally after BatchNorm): one gate per step
+    (ref: modules/shared/gatings.py:83-118; conf_dict keys gating_hidden_dim, gating_hidden_actv, scale, nl_choice in
+    'nl' | 'bn+nl' | 'bn+l'; the reference's softmax variant is dead code there)"""
+
+    def __init__(self, x_dim, conf_dict):
+        super().__init__()
+        hd = conf_dict['gating_hidden_dim']
+        self.hidden = torch.nn.Linear(x_dim, hd)
+        self.actv = _actv(conf_dict['gating_hidden_actv'])
+        nl = conf_dict['nl_choice']
+        assert nl in ('nl', 'bn+nl', 'bn+l'), 'nonononon'
+        self.bn = torch.nn.BatchNorm1d(hd, eps=1e-3, momentum=0.01) if nl.startswith('bn') else None
+        self.out = torch.nn.Linear(hd, x_dim)
+        self.out_actv = torch.relu if nl.endswith('+nl') or nl == 'nl' else (lambda t: t)
+        self.c = torch.nn.Parameter(torch.ones(1)) if conf_dict.get('scale') else None
+
+    def forward(self, x):                                   # [n, steps, x_dim]
+        q = self.actv(self.hidden(x)).mean(dim=1)
+        if self.bn is not None:
+            q = self.bn(q)
+        q = self.out_actv(self.out(q))                      # [n, x_dim]
+        g = torch.sigmoid((x * q[:, None, :]).sum(dim=-1, keepdim=True))      # [n, steps, 1]
+        y = x * g
+        return y * self.c if self.c is not None else y
+
+
 class _ContentTower(torch.nn.Module):
     """shared head and tail: word embedding (Keras-1 row dropout) ... Dense -> BN -> actv -> dropout"""
 
     def __init__(self, data_spec, conf, content, generator, flat_dim):
         super().__init__()
         dev = content.device
-        assert not conf.contextual_temporal_gated_input and not conf.contextual_spatial_gated_input, \
-            'contextual gating (modules/shared/gatings.py) is not provided'
+        self.temporal_gate = TemporalGate(conf.word_dim, conf.contextual_temporal_gated_input) \
+            if conf.contextual_temporal_gated_input else None
+        self.spatial_gate = SpatialGate(conf.word_dim, conf.contextual_spatial_gated_input) \
+            if conf.contextual_spatial_gated_input else None
         w = (torch.rand((data_spec.word_count, conf.word_dim), generator=generator, device=dev) - 0.5) * 0.1
         if getattr(data_spec, 'W_pretrain', None) is not None:
             w = torch.as_tensor(data_spec.W_pretrain, dtype=torch.float32, device=dev)
@@ -53,7 +98,12 @@ class _ContentTower(torch.nn.Module):
         if self.training and self.word_dropout > 0:
             keep = (torch.rand((W.shape[0], 1), device=W.device) >= self.word_dropout).float() / (1.0 - self.word_dropout)
             W = W * keep
-        return W[self.content[item_ids.long()].long()]                  # [n, L, word_dim]
+        x = W[self.content[item_ids.long()].long()]                     # [n, L, word_dim]
+        if self.temporal_gate is not None:
+            x = self.temporal_gate(x)
+        if self.spatial_gate is not None:
+            x = self.spatial_gate(x)
+        return x
 
     def head(self, h):
         if self.dense is None:

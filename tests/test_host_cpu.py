@@ -286,3 +286,38 @@ def test_pretrained_vectors_loader_and_conf(tmp_path):
     c = get_conf('citeulike_title_only', 'default', None, 'pretrained')
     assert c.pretrain['transform'] is False and c.pretrain['sentvec_filepath'].endswith('pretrain//sentence_vectors_50d.txt')
     assert DU.get_pretrain_folder('news_title_and_abstract_fold2', aug=True).endswith('news/title_and_abstract/pretrain/aug/')
+
+
+def test_contextual_gating_layers():
+    """modules/shared/gatings.py:63-118 as torch modules, wired into the CNN / RNN towers in the reference's order"""
+    import torch
+    from nncf_b200.conf import get_conf
+    from nncf_b200.towers import SpatialGate, TemporalGate, CNNTower
+    torch.manual_seed(0)
+    x = torch.randn(5, 7, 6)
+    sg = SpatialGate(6, {'gating_hidden_dim': 4, 'gating_hidden_actv': 'tanh'})
+    g = torch.sigmoid(sg.out(torch.tanh(sg.hidden(x)).mean(1)))
+    assert torch.allclose(sg(x), x * g[:, None, :])
+    for nl, scale in (('nl', False), ('bn+nl', True), ('bn+l', True)):
+        tg = TemporalGate(6, {'gating_hidden_dim': 4, 'gating_hidden_actv': 'relu', 'scale': scale, 'nl_choice': nl})
+        tg.eval()
+        y = tg(x)
+        assert y.shape == x.shape
+        ratio = (y / x)                                              # one gate per (sample, step), shared by the dims
+        assert torch.allclose(ratio, ratio[:, :, :1].expand_as(ratio), atol=1e-5)
+        assert (ratio > 0).all() and (ratio < 1.0 + 1e-6).all()
+        assert (tg.c is not None) == scale
+
+    class DS:
+        word_count = 50
+        W_pretrain = None
+    content = torch.from_numpy(np.random.RandomState(0).randint(0, 50, (20, 9)).astype(np.int32))
+    gd = {'gating_hidden_dim': 5, 'gating_hidden_actv': 'relu', 'scale': True, 'nl_choice': 'nl'}
+    conf = get_conf('synthetic_small', 'default', {'user_dim': 8, 'item_dim': 8, 'word_dim': 6}, 'cnn_embedding')
+    conf.contextual_temporal_gated_input = gd
+    conf.contextual_spatial_gated_input = gd
+    t = CNNTower(DS, conf, content, torch.Generator().manual_seed(0))
+    out = t(torch.arange(4))
+    assert out.shape == (4, 8)
+    out.sum().backward()
+    assert t.temporal_gate.hidden.weight.grad is not None and t.spatial_gate.out.weight.grad is not None
