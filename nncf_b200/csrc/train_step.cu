@@ -511,6 +511,106 @@ __global__ void adam_reset_kernel(const int32_t* __restrict__ ids, int64_t ids_s
   if (row >= cnt) return;
   owner[ids[r * ids_stride + row]] = 0x7fffffff;
 }
+// ---- vectorised, both tables per launch, programmatic dependent launch (the matmul schemes with 16-byte aligned rows).
+// The four kernels above are 8 dependent launches per step for the two tables (+ gather, score, finalize = 11): at
+// R = 37, B = 512 the step took 90 us, most of it launch gaps.  Here: 3 launches for both tables (owner, combine,
+// apply), the reset folded into apply (the owner row re-arms owner[id] itself: any value != my position still means
+// "not the owner" to a duplicate that looks later), 128-bit accesses, several rows in flight per warp.
+struct AdamSide {
+  const int32_t* ids; int64_t ids_stride; int count; const int32_t* count_dev;
+  int32_t* owner; float* dX; float* table; float* m; float* v;
+};
+__global__ void adam_owner2_kernel(AdamSide s0, AdamSide s1, int rows_pad) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const AdamSide& s = blockIdx.z ? s1 : s0;
+  if (!s.ids) return;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  const int cnt = s.count_dev ? s.count_dev[r] : s.count;
+  if (row >= cnt) return;
+  atomicMin(&s.owner[s.ids[r * s.ids_stride + row]], r * rows_pad + row);
+}
+template <int NV>   // float4 chunks per lane: 1 for dp <= 128, 2 for dp = 256
+__global__ void __launch_bounds__(256)
+adam_combine_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int dp) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const AdamSide& s = blockIdx.z ? s1 : s0;
+  if (!s.ids) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
+  const int cnt = s.count_dev ? s.count_dev[r] : s.count;
+  if (row >= cnt) return;
+  const int me = r * rows_pad + row;
+  const int own = s.owner[s.ids[r * s.ids_stride + row]];
+  if (own == me) return;
+  const float* src = s.dX + (int64_t)me * dp;
+  float* dst = s.dX + (int64_t)own * dp;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    const int c = 4 * (lane + 32 * v);
+    if (c < dp) {
+      const float4 g4 = *reinterpret_cast<const float4*>(src + c);
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(g4.x), "f"(g4.y), "f"(g4.z), "f"(g4.w) : "memory");
+    }
+  }
+}
+template <int NV>
+__global__ void __launch_bounds__(256)
+adam_apply_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int d, int dp, float lr_t, float beta1, float beta2, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const AdamSide& s = blockIdx.z ? s1 : s0;
+  if (!s.ids) return;
+  constexpr int kRows = 4;                              // rows in flight per warp (id -> owner -> rows: dependent loads)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + warp) * kRows, r = blockIdx.y;
+  const int cnt = s.count_dev ? s.count_dev[r] : s.count;
+  if (row0 >= cnt) return;
+  int64_t myid = -1;
+  if (lane < kRows && row0 + lane < cnt) {
+    const int64_t id = s.ids[r * s.ids_stride + row0 + lane];
+    if (s.owner[id] == r * rows_pad + row0 + lane) myid = id;       // only the owner row applies (it holds the summed gradient)
+  }
+  float4 g[kRows][NV], mm[kRows][NV], vv[kRows][NV], pp[kRows][NV];
+  int64_t ids[kRows];
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    ids[k] = __shfl_sync(0xffffffffu, myid, k);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (lane + 32 * v);
+      if (ids[k] >= 0 && c < d) {
+        g[k][v] = *reinterpret_cast<const float4*>(s.dX + (int64_t)(r * rows_pad + row0 + k) * dp + c);
+        const int64_t o = ids[k] * d + c;
+        mm[k][v] = *reinterpret_cast<const float4*>(s.m + o);
+        vv[k][v] = *reinterpret_cast<const float4*>(s.v + o);
+        pp[k][v] = *reinterpret_cast<const float4*>(s.table + o);
+      }
+    }
+  }
+  const float c1 = 1.0f - beta1, c2 = 1.0f - beta2;
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    if (ids[k] < 0) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (lane + 32 * v);
+      if (c < d) {
+        float4 G = g[k][v], M = mm[k][v], V = vv[k][v], P = pp[k][v];
+        M.x = beta1 * M.x + c1 * G.x; M.y = beta1 * M.y + c1 * G.y; M.z = beta1 * M.z + c1 * G.z; M.w = beta1 * M.w + c1 * G.w;
+        V.x = beta2 * V.x + c2 * G.x * G.x; V.y = beta2 * V.y + c2 * G.y * G.y; V.z = beta2 * V.z + c2 * G.z * G.z; V.w = beta2 * V.w + c2 * G.w * G.w;
+        P.x -= lr_t * M.x / (sqrtf(V.x) + eps); P.y -= lr_t * M.y / (sqrtf(V.y) + eps);
+        P.z -= lr_t * M.z / (sqrtf(V.z) + eps); P.w -= lr_t * M.w / (sqrtf(V.w) + eps);
+        const int64_t o = ids[k] * d + c;
+        *reinterpret_cast<float4*>(s.m + o) = M;
+        *reinterpret_cast<float4*>(s.v + o) = V;
+        *reinterpret_cast<float4*>(s.table + o) = P;
+      }
+    }
+    if (lane == 0) s.owner[ids[k]] = 0x7fffffff;          // re-arm (was adam_reset_kernel)
+  }
+}
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -911,6 +1011,23 @@ static int ensure_owner(int32_t** owner, int64_t* have, int64_t need, cudaStream
   return 0;
 }
 
+static int run_adam2(nncf_trainer* t, const AdamSide& su, const AdamSide& sv, int rows_stride, int d, int dp, float lr_t,
+                     cudaStream_t st) {
+  const int R = t->cfg.replicas;
+  const int count = su.count > sv.count ? su.count : sv.count;
+  NNCF_CUDA(launch_pdl(adam_owner2_kernel, dim3(ceil_div(count, 256), R, 2), dim3(256), 0, st, su, sv, rows_stride));
+  if (dp <= 128) {
+    NNCF_CUDA(launch_pdl(adam_combine_vec_kernel<1>, dim3(ceil_div(count, 8), R, 2), dim3(256), 0, st, su, sv, rows_stride, dp));
+    NNCF_CUDA(launch_pdl(adam_apply_vec_kernel<1>, dim3(ceil_div(count, 32), R, 2), dim3(256), 0, st, su, sv, rows_stride, d, dp, lr_t,
+                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon));
+  } else {
+    NNCF_CUDA(launch_pdl(adam_combine_vec_kernel<2>, dim3(ceil_div(count, 8), R, 2), dim3(256), 0, st, su, sv, rows_stride, dp));
+    NNCF_CUDA(launch_pdl(adam_apply_vec_kernel<2>, dim3(ceil_div(count, 32), R, 2), dim3(256), 0, st, su, sv, rows_stride, d, dp, lr_t,
+                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon));
+  }
+  return 0;
+}
+
 static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int count, const int32_t* count_dev,
                     int rows_stride, int d, int dp, int32_t* owner, float* dX, float* table, float* m, float* v,
                     float lr_t, cudaStream_t st) {
@@ -950,6 +1067,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return !e || atoi(e) != 0; }();
   const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
                         (d % 4 == 0) && !dense_items && !want_row_grads && !bias;
+  // lazy Adam with nothing to post-process: the score kernel publishes the loss itself (as in the fused SGD mode) and
+  // writes the finished gradient blocks, the Adam kernels read them: no finalize launch
+  const bool adam_plain = bf16 && c.optimizer == NNCF_OPT_LAZY_ADAM && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
+                          (d % 4 == 0) && !dense_items && !want_row_grads && !bias && t->n_shards <= 1;
   // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
   // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
   t->loss_published = true;   // by the last finalize launch, or by the score kernel itself in fused mode
@@ -1034,7 +1155,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.Uimg = t->Uimg; ta.Vimg = t->Vimg; ta.dU = t->dU; ta.dV = t->dV; ta.corrU = t->corrU; ta.corrV = t->corrV;
     ta.spos = t->spos; ta.inverse = sa.inverse; ta.ncols_dev = sa.ncols_dev; ta.loss = t->loss; ta.rows_pad = rp;
     ta.B = B; ta.scheme = c.scheme; ta.loss_kind = c.loss; ta.lambda = c.neg_loss_weight; ta.gamma = c.loss_gamma;
-    ta.loss_count = fuse_sgd ? t->loss_count : nullptr; ta.loss_out = fuse_sgd ? loss_out_step : nullptr;
+    ta.loss_count = (fuse_sgd || adam_plain) ? t->loss_count : nullptr; ta.loss_out = (fuse_sgd || adam_plain) ? loss_out_step : nullptr;
     ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
@@ -1100,6 +1221,8 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   };
   if (fuse_sgd) {
     // nothing left to do: the update was applied by the score kernel's drain
+  } else if (adam_plain) {
+    // nothing to post-process: the Adam kernels below read the gradient blocks as the score kernel left them
   } else if (group && pairwise) {
     // the user side adds the positive-column corrections into the item accumulators: strictly before the item side
     launch_finalize(fu, fu, 1);
@@ -1123,14 +1246,24 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     const double b1t = pow((double)c.beta1, (double)t->adam_t), b2t = pow((double)c.beta2, (double)t->adam_t);
     const float lr_t = (float)(c.learn_rate * sqrt(1.0 - b2t) / (1.0 - b1t));   // optimizer.py:109-111
     if (ensure_owner(&t->ownerU, &t->ownerU_n, tb->n_users, st)) return NNCF_ECUDA;
-    if (run_adam(t, uid, B, B, nullptr, rp, d, dp, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v, lr_t, st))
-      return NNCF_ECUDA;
     if (!dense_items) {
       NNCF_CHECK_ARG(tb->item_m && tb->item_v, "lazy Adam needs item_m / item_v");
       if (ensure_owner(&t->ownerV, &t->ownerV_n, tb->n_items, st)) return NNCF_ECUDA;
-      if (run_adam(t, item_ids, item_stride, B, group ? t->nuniq : nullptr, rp, d, dp, t->ownerV, t->dV, tb->item_table,
-                   tb->item_m, tb->item_v, lr_t, st))
+    }
+    if (vec) {
+      // both tables per launch, 3 launches (owner, combine, apply + re-arm), 128-bit accesses, programmatic dependent launch
+      AdamSide su{uid, B, B, nullptr, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v};
+      AdamSide sv{};
+      if (!dense_items) sv = AdamSide{item_ids, item_stride, B, group ? t->nuniq : nullptr, t->ownerV, t->dV, tb->item_table, tb->item_m, tb->item_v};
+      if (run_adam2(t, su, sv, rp, d, dp, lr_t, st)) return NNCF_ECUDA;
+    } else {
+      if (run_adam(t, uid, B, B, nullptr, rp, d, dp, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v, lr_t, st))
         return NNCF_ECUDA;
+      if (!dense_items) {
+        if (run_adam(t, item_ids, item_stride, B, group ? t->nuniq : nullptr, rp, d, dp, t->ownerV, t->dV, tb->item_table,
+                     tb->item_m, tb->item_v, lr_t, st))
+          return NNCF_ECUDA;
+      }
     }
   }
   NNCF_PROFILE_MARK(t, 3, st);
