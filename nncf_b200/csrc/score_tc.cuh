@@ -516,6 +516,33 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (lane == 0) mbar_arrive(&g_full[sb]);
       if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(24 + t);
     }
+    // (the loss hand-off comes BEFORE the drain: its values are final once the tile loop has ended, and its two gpu-scope
+    //  fences would otherwise sit behind ~20 MB of bulk reductions: 19 % of this kernel's stall samples were there)
+    // per-row sums of dL/dD: the two column halves of a row live in two warps -> atomics on two addends only
+    if (kPairwise && row_ok) {
+      if (side == 0 && GROUP) atomicAdd(a.corrU + base + o, asum);
+      if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
+    }
+    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {   // (balanced loss: both sides hold a share)
+      if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
+      lsum = warp_sum(lsum);
+      if (lane == 0) {
+        atomicAdd(&a.loss[r], static_cast<double>(lsum));
+        if (a.loss_count) {
+          // last arriving warp of the replica (side-0 CTAs x epilogue warps) publishes the loss and re-arms the accumulators
+          __threadfence();
+          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps *
+                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
+          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
+            __threadfence();
+            const double total = atomicAdd(&a.loss[r], 0.0);
+            if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
+            a.loss[r] = 0.0;
+            a.loss_count[r] = 0u;
+          }
+        }
+      }
+    }
     // drain the accumulated gradient of the owned rows: this warp takes columns [h*DP/2, (h+1)*DP/2)
     mbar_wait(dx_full, 0);
     if (warp == 2 && lane == 0) NNCF_STAMP(4);
@@ -597,31 +624,6 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           if (ob * 128 + row >= n_owner) break;
           const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
           for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
-        }
-      }
-    }
-    // per-row sums of dL/dD: the two column halves of a row live in two warps -> atomics on two addends only
-    if (kPairwise && row_ok) {
-      if (side == 0 && GROUP) atomicAdd(a.corrU + base + o, asum);
-      if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
-    }
-    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {   // (balanced loss: both sides hold a share)
-      if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
-      lsum = warp_sum(lsum);
-      if (lane == 0) {
-        atomicAdd(&a.loss[r], static_cast<double>(lsum));
-        if (a.loss_count) {
-          // last arriving warp of the replica (side-0 CTAs x epilogue warps) publishes the loss and re-arms the accumulators
-          __threadfence();
-          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps *
-                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
-          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
-            __threadfence();
-            const double total = atomicAdd(&a.loss[r], 0.0);
-            if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
-            a.loss[r] = 0.0;
-            a.loss_count[r] = 0u;
-          }
         }
       }
     }
