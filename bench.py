@@ -167,6 +167,9 @@ def cpu_links_per_sec(n_steps, warmup, n_rows=N_USERS):
     return n_steps * BATCH / dt, dt
 
 
+_OUT = sys.stdout
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -187,7 +190,8 @@ def run_reference(args):
         "e2e": {"value": v, "unit": "links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -508,7 +512,8 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "extra": extra,
     }
-    print(json.dumps(line))
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
     if sharded is not None:
         dist.barrier()
         sharded.close()
@@ -530,6 +535,12 @@ def main():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--parallelism", default="stratified", choices=["stratified", "peer"])   # N > 1 only
     args = ap.parse_args()
+    # stdout carries ONE JSON line and nothing else: libraries that print to the process's stdout (NCCL's "NCCL version ..."
+    # banner under torchrun, for one) are sent to stderr for the whole run, the line goes to the saved descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
