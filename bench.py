@@ -475,6 +475,52 @@ def run_ours(args):
             del state, adam
         except Exception as ex:      # an extra must never cost the headline line
             seq_info["lazy_adam"] = {"error": str(ex)[:200]}
+        # ---- the other batch sizes SURVEY.md 8 names for C3 (same tables, same links; fewer replicas so that a step still
+        #      fills the 148 SMs once) and the tensor-bound C5 shape are reported beside the headline -----------------------
+        sweep = {}
+        for Bx, Rx in ((4096, 5), (8192, 2)):
+            try:
+                sx = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=Bx, dim=d,
+                                        optimizer="sgd", learn_rate=LR, replicas=Rx, neg_loss_weight=LAMBDA))
+                nx = min(300, n_links // (Rx * Bx) - 12)
+                sx.run(EU, EV, uid_all, cid_all, 10)
+                torch.cuda.synchronize()
+                e0.record()
+                sx.run(EU, EV, uid_all, cid_all, nx)
+                e1.record()
+                torch.cuda.synchronize()
+                xms = e0.elapsed_time(e1) / nx
+                sweep[str(Bx)] = {"value": Rx * Bx / (xms * 1e-3), "unit": "links/s", "replicas_per_gpu": Rx, "ms_per_step": xms,
+                                  "tflops_algorithmic": 6.0 * Bx * Bx * d * Rx / (xms * 1e-3) / 1e12}
+                del sx
+            except Exception as ex:
+                sweep[str(Bx)] = {"error": str(ex)[:200]}
+        seq_info["batch_size_sweep"] = sweep
+        # ---- BASELINE config 5: neg_shared max-margin, batch 16,384, dim 256, l2-normalised rows (tensor-bound contraction)
+        try:
+            g5 = torch.Generator(device="cuda").manual_seed(55)
+            U5 = (torch.rand((1_000_000, 256), device="cuda", generator=g5) - 0.5) * 0.1
+            V5 = (torch.rand((1_000_000, 256), device="cuda", generator=g5) - 0.5) * 0.1
+            n5 = 40
+            u5 = torch.randint(0, 1_000_000, ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
+            c5 = torch.randint(0, 1_000_000, ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
+            s5 = FusedStep(StepSpec(scheme="neg_shared", loss="max-margin", precision="bf16", batch_size_p=16384, dim=256, norm_u=True,
+                                    norm_v=True, optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA, loss_gamma=0.1))
+            s5.run(U5, V5, u5, c5, 5)
+            torch.cuda.synchronize()
+            e0.record()
+            s5.run(U5, V5, u5[5 * 16384:], c5[5 * 16384:], n5)
+            e1.record()
+            torch.cuda.synchronize()
+            ms5 = e0.elapsed_time(e1) / n5
+            tf5 = 6.0 * 16384 * 16384 * 256 / (ms5 * 1e-3) / 1e12
+            seq_info["c5_max_margin_b16384_d256"] = {"value": 16384 / (ms5 * 1e-3), "unit": "links/s", "ms_per_step": ms5,
+                                                     "roofline": {"bound": "tensor", "achieved": tf5, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                                                                  "frac": tf5 / peaks["bf16_burst"],
+                                                                  "note": "algorithmic 6 B^2 d; the one-sided kernel executes 8 B^2 d"}}
+            del U5, V5, u5, c5, s5
+        except Exception as ex:
+            seq_info["c5_max_margin_b16384_d256"] = {"error": str(ex)[:200]}
         # ---- cpu baseline: bounded sample on the box's host cores (rank 0, N = 1 only) ------------------------
         cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
         cpu = {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
