@@ -89,7 +89,13 @@ int launch_score_tc_nsub4(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st
 template <int NSUB>
 struct ScoreTcCfg {
   static constexpr int DP = 64 * NSUB;
-  static constexpr int TN = NSUB <= 2 ? 64 : 128;     // swept rows per tile = columns of one S' tile
+#ifndef NNCF_SCORE_TN4
+#define NNCF_SCORE_TN4 64
+#endif
+  // swept rows per tile = columns of one S' tile.  dp = 256 used 128-row tiles with 2 stages of 64 KiB: a stage is held
+  // from MMA1 through the epilogue to MMA2, so the next-but-one tile's copy (64 KiB, ~2k cycles) could only start after
+  // MMA2 and was fully exposed (tensor pipe ~50 % busy at C5).  64-row tiles: 32 KiB stages, four of them in flight.
+  static constexpr int TN = NSUB <= 2 ? 64 : NNCF_SCORE_TN4;
   static constexpr int CW = TN / 2;                   // S' columns per epilogue warp
   static constexpr int kYBytes = TN * 128;            // one [TN rows x 64 bf16] piece of a Y tile (8 or 16 KiB)
 #ifndef NNCF_SCORE_STAGES
@@ -97,7 +103,7 @@ struct ScoreTcCfg {
 #endif
   // Two resident CTAs of a tcgen05 kernel have (228 KiB - 2 x (1 KiB reserved + 1 KiB tcgen05 block)) / 2 = 112 KiB of
   // dynamic shared memory each (measured with tools/occ_probe.cu), barriers included.
-  static constexpr int kStages = NSUB <= 2 ? NNCF_SCORE_STAGES : 2;   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
+  static constexpr int kStages = (NSUB <= 2 || TN == 64) ? NNCF_SCORE_STAGES : 2;   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
   static constexpr int kColDX = 2 * TN;               // S' is double buffered in TMEM columns [0, 2 TN)
   static constexpr int kTmemCols = (kColDX + DP) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = NSUB <= 2 ? 2 : 1;   // resident CTAs per SM
