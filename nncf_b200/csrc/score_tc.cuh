@@ -187,7 +187,41 @@ __device__ __forceinline__ void epi_val(const EpiConst& c, float s, float w, flo
     const float t = (c.gamma - posf * c.ns_margin) - (sp - s);                  // M - D
     if (NEED_LOSS) l = fmaxf(t, 0.0f) * c.inv_cnt;
     a = (t > 0.0f) ? -c.inv_cnt : 0.0f;
-    g = -a;
+    g = (t > 0.0f) ? 1.0f : 0.0f;                                               // G' is an indicator; 1 / count is applied at the drain (g_scale)
+  }
+}
+
+// max-margin fast path: 32 scores of a full tile without positives.  The gradient of relu(gamma - (sp - s)) is an
+// indicator: G' = 1 or 0 as a bf16 bit pattern (one add, one compare, one select per element), scaled by 1 / count at the
+// drain; the hinge sum and the number of active elements are accumulated raw and scaled once per chunk.
+template <bool SIDE1, bool GROUP>
+__device__ __forceinline__ void epi_chunk_mm_fast(const EpiConst& c, const float (&v)[32], int x0, bool row_ok, float my_sp,
+                                                  const float* __restrict__ spos_row, float& lsum, float& asum, uint32_t (&pk)[16]) {
+  constexpr bool kSpMine = (SIDE1 != GROUP);        // positive score constant along my row
+  float hinge = 0.0f;
+  int cnt = 0;
+  const float gs_mine = c.gamma - my_sp;
+#pragma unroll
+  for (int u4 = 0; u4 < 32; u4 += 4) {
+    float4 sv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!kSpMine) sv = __ldg(reinterpret_cast<const float4*>(spos_row + x0 + u4));
+    const float gs[4] = {kSpMine ? gs_mine : c.gamma - sv.x, kSpMine ? gs_mine : c.gamma - sv.y,
+                         kSpMine ? gs_mine : c.gamma - sv.z, kSpMine ? gs_mine : c.gamma - sv.w};
+#pragma unroll
+    for (int k = 0; k < 4; k += 2) {
+      const float t0 = gs[k] + v[u4 + k], t1 = gs[k + 1] + v[u4 + k + 1];       // M - D with M = gamma (no positive here)
+      const bool p0 = t0 > 0.0f, p1 = t1 > 0.0f;
+      pk[(u4 + k) >> 1] = (p0 ? 0x00003F80u : 0u) | (p1 ? 0x3F800000u : 0u);    // bf16 (1.0 | 0.0) pair
+      if (!SIDE1) hinge += fmaxf(t0, 0.0f) + fmaxf(t1, 0.0f);
+      cnt += (p0 ? 1 : 0) + (p1 ? 1 : 0);
+    }
+  }
+  if (row_ok) {
+    if (!SIDE1) lsum += hinge * c.inv_cnt;
+    asum -= static_cast<float>(cnt) * c.inv_cnt;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) pk[i] = 0u;
   }
 }
 
@@ -387,7 +421,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     ec.inv_cnt = 1.0f / (static_cast<float>(a.B) * static_cast<float>(nc));
     ec.ns_margin = GROUP ? 0.0f : a.gamma;
     ec.inv_wneg = 1.0f / ec.w_neg;
-    ec.g_scale = (LOSS == NNCF_LOSS_SKIP_GRAM) ? ec.w_neg * ec.inv_b : 1.0f;
+    ec.g_scale = (LOSS == NNCF_LOSS_SKIP_GRAM) ? ec.w_neg * ec.inv_b : ((LOSS == NNCF_LOSS_MAX_MARGIN) ? ec.inv_cnt : 1.0f);
     if (a.fuse_sgd) ec.g_scale *= a.neg_lr;     // the drain adds -lr * dX straight into the table rows
     const bool row_ok = o < n_owner;
     // side 0: the positive column of my row.  side 1 (neg_shared): my own index (the diagonal).
@@ -493,6 +527,9 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         } else if (kFastSg) {
           if (loss_here) epi_chunk_sg_fast<true>(v[j], pk[j], lraw);
           else epi_chunk_sg_fast<false>(v[j], pk[j], lraw);
+        } else if (LOSS == NNCF_LOSS_MAX_MARGIN) {
+          if (side == 0) epi_chunk_mm_fast<false, GROUP>(ec, v[j], x0 + 32 * j, row_ok, my_sp, spos_row, lsum, asum, pk[j]);
+          else epi_chunk_mm_fast<true, GROUP>(ec, v[j], x0 + 32 * j, row_ok, my_sp, spos_row, lsum, asum, pk[j]);
         } else {
           if (side == 0) epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
           else epi_chunk<LOSS, true, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
