@@ -286,6 +286,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   uint64_t* g_full = bars + 11;     // [2]  G'(t) has replaced it
   uint64_t* dx_full = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* loss_slots = reinterpret_cast<float*>(bars + 20);   // [8] per-epilogue-warp loss sums, handed to warp 0 (see below)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
@@ -348,6 +349,30 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         const uint8_t* src = gY + (size_t)((t * TN) >> 7) * NSUB * kSubBytes + (size_t)((t * TN) & 127) * 128;
         for (int s = 0; s < NSUB; ++s)
           bulk_g2s(sY + (st * NSUB + s) * C::kYBytes, src + (size_t)s * kSubBytes, C::kYBytes, &y_full[st]);
+      }
+    }
+    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {
+      // loss hand-off for the whole CTA (the epilogue warps have moved on to the drain)
+      __syncwarp();                                      // lane 0 comes out of the producer loop: the barrier below is .aligned
+      asm volatile("bar.sync 2, %0;" ::"n"(32 * kScoreEpiWarps + 32) : "memory");
+      if (lane == 0) {
+        float cta_loss = 0.0f;
+#pragma unroll
+        for (int w = 0; w < kScoreEpiWarps; ++w) cta_loss += loss_slots[w];
+        atomicAdd(&a.loss[r], static_cast<double>(cta_loss));
+        if (a.loss_count) {
+          // last arriving CTA of the replica publishes the loss and re-arms the accumulators
+          __threadfence();
+          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) *
+                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
+          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
+            __threadfence();
+            const double total = atomicAdd(&a.loss[r], 0.0);
+            if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
+            a.loss[r] = 0.0;
+            a.loss_count[r] = 0u;
+          }
+        }
       }
     }
   } else if (warp == 1) {
@@ -567,24 +592,15 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
     }
     if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {   // (balanced loss: both sides hold a share)
+      // The replica's loss is summed with a gpu-scope atomic, a fence and an arrival counter (the last arriver publishes):
+      // ~4 us when the epilogue warps did it themselves in front of (or behind) the drain - the in-kernel timeline showed
+      // the drain + update is only 2.6 us.  The warps now leave their sums in shared memory, arrive on a named barrier
+      // without waiting, and the idle producer warp does the hand-off while they drain.
       if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
       lsum = warp_sum(lsum);
-      if (lane == 0) {
-        atomicAdd(&a.loss[r], static_cast<double>(lsum));
-        if (a.loss_count) {
-          // last arriving warp of the replica (side-0 CTAs x epilogue warps) publishes the loss and re-arms the accumulators
-          __threadfence();
-          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * kScoreEpiWarps *
-                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
-          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
-            __threadfence();
-            const double total = atomicAdd(&a.loss[r], 0.0);
-            if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
-            a.loss[r] = 0.0;
-            a.loss_count[r] = 0u;
-          }
-        }
-      }
+      if (lane == 0) loss_slots[ew] = lsum;
+      __syncwarp();
+      asm volatile("bar.arrive 2, %0;" ::"n"(32 * kScoreEpiWarps + 32) : "memory");
     }
     // drain the accumulated gradient of the owned rows: this warp takes columns [h*DP/2, (h+1)*DP/2)
     mbar_wait(dx_full, 0);
