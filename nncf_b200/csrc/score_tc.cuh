@@ -361,12 +361,14 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         for (int w = 0; w < kScoreEpiWarps; ++w) cta_loss += loss_slots[w];
         atomicAdd(&a.loss[r], static_cast<double>(cta_loss));
         if (a.loss_count) {
-          // last arriving CTA of the replica publishes the loss and re-arms the accumulators
-          __threadfence();
+          // last arriving CTA of the replica publishes the loss and re-arms the accumulators.  One acq_rel atomic on the
+          // counter orders my loss contribution before it and everybody's contributions before the read below
+          // (instead of __threadfence() = MEMBAR.SC.GPU on either side of a relaxed atomic)
           const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) *
                                       ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
-          if (atomicAdd(&a.loss_count[r], 1u) + 1u == expect) {
-            __threadfence();
+          unsigned int arrived;
+          asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(a.loss_count + r) : "memory");
+          if (arrived + 1u == expect) {
             const double total = atomicAdd(&a.loss[r], 0.0);
             if (a.loss_out) a.loss_out[r] = static_cast<float>(total);
             a.loss[r] = 0.0;
