@@ -17,18 +17,24 @@ __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
   pdl_launch_dependents();      // the score kernel may set up its barriers / TMEM while the rows are gathered
   if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[0], global_timer_ns());
-  pdl_wait();                   // the previous step's update (and this step's tf.unique) must have landed
-  if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[1], global_timer_ns());
   const GatherArgs& a = blockIdx.z ? a1 : a0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row0 = (blockIdx.x * 8 + warp) * kRowsPerWarp;
   const int r = blockIdx.y;
+  // ids of my four rows (one load instruction for the warp).  Link ids are inputs of the step, nothing in the stream
+  // writes them: they are fetched BEFORE waiting for the previous kernel, which takes one of the two dependent round
+  // trips (id -> row) off the critical path.  (The compact item ids of the group scheme are produced by this step's
+  // unique kernel: those wait first.)
+  const bool early_ids = a.count_dev == nullptr;
+  int64_t myid = 0;
+  if (early_ids && row0 < a.rows_pad && lane < kRowsPerWarp && row0 + lane < a.count && a.table)
+    myid = a.ids[r * a.ids_stride + row0 + lane];
+  pdl_wait();                   // the previous step's update (and this step's tf.unique) must have landed
+  if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[1], global_timer_ns());
   if (row0 >= a.rows_pad) return;
   const int count = a.count_dev ? a.count_dev[r] : a.count;
   const int nchunk = a.dp / 64;
-  // ids of my four rows (one load instruction for the warp)
-  int64_t myid = 0;
-  if (lane < kRowsPerWarp && row0 + lane < count && a.table) myid = a.ids[r * a.ids_stride + row0 + lane];
+  if (!early_ids && lane < kRowsPerWarp && row0 + lane < count && a.table) myid = a.ids[r * a.ids_stride + row0 + lane];
   float4 x[kRowsPerWarp][NV];
 #pragma unroll
   for (int k = 0; k < kRowsPerWarp; ++k) {
