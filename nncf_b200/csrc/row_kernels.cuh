@@ -11,15 +11,19 @@
 namespace nncf {
 
 constexpr int kRowsPerWarp = 4;
+// The gather runs while the NEXT score kernel's CTAs are already resident (768 threads per SM, prologue overlap): with 4
+// rows per warp the gather grid is 2,048 threads per SM at R = 37 and needed 1.6 waves next to them; 8 rows per warp halve
+// the grid (1,024 threads per SM): one wave, and twice the loads in flight per warp.
+// (a small grid - R = 1 - is faster with 4: 12.7 vs 13.6 us per step: the host picks)
 
-template <int NV>   // float4 chunks per lane: 1 for dp <= 128, 2 for dp = 256
+template <int NV, int kGatherRowsPerWarp>   // NV: float4 chunks per lane (1 for dp <= 128, 2 for dp = 256); rows in flight per warp: 4 or 8
 __global__ void __launch_bounds__(256)
 gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
   pdl_launch_dependents();      // the score kernel may set up its barriers / TMEM while the rows are gathered
   if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[0], global_timer_ns());
   const GatherArgs& a = blockIdx.z ? a1 : a0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row0 = (blockIdx.x * 8 + warp) * kRowsPerWarp;
+  const int row0 = (blockIdx.x * 8 + warp) * kGatherRowsPerWarp;
   const int r = blockIdx.y;
   // ids of my four rows (one load instruction for the warp).  Link ids are inputs of the step, nothing in the stream
   // writes them: they are fetched BEFORE waiting for the previous kernel, which takes one of the two dependent round
@@ -27,17 +31,17 @@ gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
   // unique kernel: those wait first.)
   const bool early_ids = a.count_dev == nullptr;
   int64_t myid = 0;
-  if (early_ids && row0 < a.rows_pad && lane < kRowsPerWarp && row0 + lane < a.count && a.table)
+  if (early_ids && row0 < a.rows_pad && lane < kGatherRowsPerWarp && row0 + lane < a.count && a.table)
     myid = a.ids[r * a.ids_stride + row0 + lane];
   pdl_wait();                   // the previous step's update (and this step's tf.unique) must have landed
   if (a0.tl && threadIdx.x == 0) atomicMin(&a0.tl[1], global_timer_ns());
   if (row0 >= a.rows_pad) return;
   const int count = a.count_dev ? a.count_dev[r] : a.count;
   const int nchunk = a.dp / 64;
-  if (!early_ids && lane < kRowsPerWarp && row0 + lane < count && a.table) myid = a.ids[r * a.ids_stride + row0 + lane];
-  float4 x[kRowsPerWarp][NV];
+  if (!early_ids && lane < kGatherRowsPerWarp && row0 + lane < count && a.table) myid = a.ids[r * a.ids_stride + row0 + lane];
+  float4 x[kGatherRowsPerWarp][NV];
 #pragma unroll
-  for (int k = 0; k < kRowsPerWarp; ++k) {
+  for (int k = 0; k < kGatherRowsPerWarp; ++k) {
     const int row = row0 + k;
     const int64_t id = __shfl_sync(0xffffffffu, myid, k);
     const float* src = a.shards.n > 1 ? a.shards.p[id % a.shards.n] + (id / a.shards.n) * a.d
@@ -49,7 +53,7 @@ gather_rows_vec_kernel(GatherArgs a0, GatherArgs a1) {
     }
   }
 #pragma unroll
-  for (int k = 0; k < kRowsPerWarp; ++k) {
+  for (int k = 0; k < kGatherRowsPerWarp; ++k) {
     const int row = row0 + k;
     if (row >= a.rows_pad) break;
     float inv = 1.0f;

@@ -1130,8 +1130,17 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
   // reads what its predecessor wrote, so only launch latency and prologues overlap
   if (self_gather) { /* the score kernel gathers */ }
-  else if (vec && dp <= 128) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<1>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
-  else if (vec) NNCF_CUDA(launch_pdl(gather_rows_vec_kernel<2>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv));
+  else if (vec) {
+    // rows per warp: 8 when the grid at 4 would not fit in one wave next to the resident CTAs of the following score kernel
+    // (768 of an SM's 2,048 threads), else 4
+    const bool fat = (size_t)2 * R * rp * 8 > (size_t)(t->resident_ctas / 2) * 1280;
+    cudaError_t ge;
+    if (dp <= 128) ge = fat ? launch_pdl(gather_rows_vec_kernel<1, 8>, dim3(rp / 64, R, 2), dim3(256), 0, st, gu, gv)
+                            : launch_pdl(gather_rows_vec_kernel<1, 4>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv);
+    else ge = fat ? launch_pdl(gather_rows_vec_kernel<2, 8>, dim3(rp / 64, R, 2), dim3(256), 0, st, gu, gv)
+                  : launch_pdl(gather_rows_vec_kernel<2, 4>, dim3(rp / 32, R, 2), dim3(256), 0, st, gu, gv);
+    NNCF_CUDA(ge);
+  }
   else NNCF_CUDA(launch_pdl(gather_rows_kernel, dim3(rp / 8, R, 2), dim3(256), 0, st, gu, gv));
   if (!self_gather) count_launch();
   if (pairwise) {
