@@ -321,3 +321,22 @@ def test_contextual_gating_layers():
     assert out.shape == (4, 8)
     out.sum().backward()
     assert t.temporal_gate.hidden.weight.grad is not None and t.spatial_gate.out.weight.grad is not None
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (library banners go to stderr); the reference arm runs without a GPU"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "6", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert p.returncode == 0, p.stderr[-500:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, p.stdout[:500]
+    j = json.loads(lines[0])
+    assert j["impl"] == "reference" and j["unit"] == "links/s" and j["higher_is_better"] is True
+    assert j["steps"] == 6 and j["warmup"] == 3 and j["n_gpus"] == 1 and j["value"] > 0
+    assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
+    assert j["config"]["workload"].startswith("C3")
