@@ -135,7 +135,7 @@ typedef struct {
   int32_t num_negatives;   /* k (PAIRS: the batch has (1+k)B rows; SAMPLED_NEG_SHARED: B + k rows) */
   int32_t dim;             /* d = user_dim = item_dim, 1..256 */
   int32_t norm_u;          /* l2-normalise user rows (emb_normalization, model_framework.py:62-63) */
-  int32_t norm_v;          /* l2-normalise item rows (model_framework.py:109-111; not for 'mf') */
+  int32_t norm_v;          /* l2-normalise item rows (model_framework.py:109-111; not for 'mf' / 'pretrained': :85-88) */
   int32_t optimizer;       /* NNCF_OPT_* */
   int32_t replicas;        /* R >= 1 independent batches per call (synchronous data-parallel virtual workers
                               on one GPU; R = 1 is the reference's sequential loop) */
@@ -224,6 +224,14 @@ int nncf_peer_close(void* ptr);
 int nncf_peer_free(void* ptr);
 int nncf_peer_barrier(void* const* flag_ptrs /* [n_ranks] 64-byte flag arrays */, int n_ranks, int rank, unsigned int epoch,
                       void* stream);
+/* Stream-ordered transfer between two device pointers, either of which may be a peer mapping (nncf_peer_open): runs on
+ * the copy engines over NVLink, no SM involved.  With the two flag calls below it is the transport of the pipelined
+ * stratum rotation (nncf_b200/parallel.py): copy, then signal the receiver's flag; the receiver's stream waits on it. */
+int nncf_peer_copy(void* dst, const void* src, size_t bytes, void* stream);
+/* *flag = value, ordered after the stream's earlier work (system-scope fences); flag may live on a peer. */
+int nncf_peer_signal(void* flag_ptr, unsigned int value, void* stream);
+/* blocks the STREAM (not the host) until *flag >= value (wrap-safe compare); bounded spin, traps after ~30 s. */
+int nncf_peer_wait(const void* flag_ptr, unsigned int value, void* stream);
 int nncf_trainer_set_shards(nncf_trainer_t* t, int n_shards, int rank, void* const* user_shards, void* const* item_shards,
                             void* const* barrier_flags);
 
@@ -274,11 +282,14 @@ int nncf_eval_metrics(const int32_t* topk_ids_dev, int64_t n_users, int topk, co
 /* given@k: scores of listed (user, item) pairs = row-wise dot (interaction_dot.py:92-99). */
 int nncf_score_pairs(const float* user_table_dev, const float* item_table_dev, int dim, const int32_t* user_ids_dev,
                      const int32_t* item_ids_dev, int64_t n_pairs, float* scores_dev, void* stream);
-/* given@-1 metrics: pairs grouped by user (seg_indptr [n_groups+1] over the pair list), full descending sort per
- * group (ties: lowest position first), AP over the whole list and AUC (Mann-Whitney, average ranks).
- * per_group_dev [n_groups, 2] = (AP, AUC). */
+/* given@k metrics (utils/objectives.py:259-294 with metrics_ranking.py:6-61): pairs grouped by user (seg_indptr
+ * [n_groups+1] over the pair list), full descending sort per group (ties: lowest position first).  topk = -1: AP over
+ * the whole list (eval_multiple_original); topk >= 1: AP / recall / precision over the first k ranked entries with
+ * nhits counted over the whole list and denominator min(nhits, k) (eval_multiple; a list shorter than k is ranked
+ * whole).  AUC (Mann-Whitney, average ranks) is over the whole list either way.
+ * per_group_dev [n_groups, 4] = (AP@k, AUC, recall@k, precision@k). */
 int nncf_eval_given(const float* scores_dev, const int32_t* truth_dev, const int64_t* seg_indptr_dev, int64_t n_groups,
-                    float* per_group_dev, void* stream);
+                    int topk, float* per_group_dev, void* stream);
 
 #ifdef __cplusplus
 }

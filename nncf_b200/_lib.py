@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnncf_b200.so")
+# NNCF_LIB_PATH: developer switch, loads an alternative build of the same library (tools/ablate.sh builds ablated variants)
+LIB_PATH = os.environ.get("NNCF_LIB_PATH") or os.path.join(_HERE, "libnncf_b200.so")
 
 # every symbol include/nncf_b200.h declares (tests check that the library exports all of them)
 EXPORTS = [
@@ -24,7 +25,7 @@ EXPORTS = [
     "nncf_trainer_get_profile", "nncf_unique_first_occurrence", "nncf_gather_rows", "nncf_updater_create",
     "nncf_updater_destroy", "nncf_updater_begin_step", "nncf_updater_apply",
     "nncf_meanpool_fwd", "nncf_meanpool_bwd",
-    "nncf_peer_alloc", "nncf_peer_open", "nncf_peer_close", "nncf_peer_free", "nncf_peer_barrier", "nncf_trainer_set_shards",
+    "nncf_peer_alloc", "nncf_peer_open", "nncf_peer_close", "nncf_peer_free", "nncf_peer_barrier", "nncf_peer_copy", "nncf_peer_signal", "nncf_peer_wait", "nncf_trainer_set_shards",
     "nncf_eval_topk_workspace_bytes", "nncf_eval_topk", "nncf_eval_metrics", "nncf_score_pairs", "nncf_eval_given",
 ]
 
@@ -104,6 +105,9 @@ def _load():
         "nncf_peer_close": (i32, [vp]),
         "nncf_peer_free": (i32, [vp]),
         "nncf_peer_barrier": (i32, [vp, i32, i32, C.c_uint, vp]),
+        "nncf_peer_copy": (i32, [vp, vp, sz, vp]),
+        "nncf_peer_signal": (i32, [vp, C.c_uint, vp]),
+        "nncf_peer_wait": (i32, [vp, C.c_uint, vp]),
         "nncf_trainer_set_shards": (i32, [vp, i32, i32, vp, vp, vp]),
         "nncf_meanpool_fwd": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
         "nncf_meanpool_bwd": (i32, [vp, i32, vp, i32, vp, i32, vp, vp]),
@@ -111,7 +115,7 @@ def _load():
         "nncf_eval_topk": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
         "nncf_eval_metrics": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),
         "nncf_score_pairs": (i32, [vp, vp, i32, vp, vp, i64, vp, vp]),
-        "nncf_eval_given": (i32, [vp, vp, vp, i64, vp, vp]),
+        "nncf_eval_given": (i32, [vp, vp, vp, i64, i32, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)          # AttributeError here = the library does not export a declared symbol

@@ -1275,14 +1275,15 @@ score_pairs_kernel(const float* __restrict__ EU, const float* __restrict__ EV, i
 // One warp per group.  rank-by-counting (O(n^2 / 32)); groups in the 'given' test lists are small.
 __global__ void __launch_bounds__(128)
 eval_given_kernel(const float* __restrict__ scores, const int32_t* __restrict__ truth, const int64_t* __restrict__ indptr,
-                  int64_t n_groups, float* __restrict__ out) {
+                  int64_t n_groups, int topk, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gidx = (int64_t)blockIdx.x * 4 + warp;
   if (gidx >= n_groups) return;
   const int64_t b = indptr[gidx], e = indptr[gidx + 1];
   const int64_t n = e - b;
+  const int64_t k = topk >= 0 ? topk : n;          // eval_multiple_original: k = len(rec) when topk < 0 (metrics_ranking.py:45)
   double ap_acc = 0.0, rank_sum = 0.0;
-  int64_t npos = 0;
+  int64_t npos = 0, hits_k = 0;
   for (int64_t i = lane; i < n; i += 32) {
     if (truth[b + i] == 0) continue;
     ++npos;
@@ -1297,20 +1298,27 @@ eval_given_kernel(const float* __restrict__ scores, const int32_t* __restrict__ 
       less += (sj < si);
       equal += (sj == si);
     }
-    ap_acc += static_cast<double>(better_pos + 1) / static_cast<double>(better + 1);
+    if (better < k) {                                // inside the top k of this user's list
+      ap_acc += static_cast<double>(better_pos + 1) / static_cast<double>(better + 1);
+      ++hits_k;
+    }
     rank_sum += static_cast<double>(less) + 0.5 * static_cast<double>(equal + 1);   // average rank (1-based)
   }
   for (int o = 16; o > 0; o >>= 1) {
     ap_acc += __shfl_xor_sync(0xffffffffu, ap_acc, o);
     rank_sum += __shfl_xor_sync(0xffffffffu, rank_sum, o);
     npos += __shfl_xor_sync(0xffffffffu, npos, o);
+    hits_k += __shfl_xor_sync(0xffffffffu, hits_k, o);
   }
   if (lane == 0) {
     const int64_t nneg = n - npos;
-    out[gidx * 2 + 0] = npos > 0 ? static_cast<float>(ap_acc / static_cast<double>(npos)) : 0.0f;
-    out[gidx * 2 + 1] = (npos > 0 && nneg > 0)
+    const double denom = static_cast<double>(npos < k ? npos : k);          // min(nhits, k)
+    out[gidx * 4 + 0] = (npos > 0 && k > 0) ? static_cast<float>(ap_acc / denom) : 0.0f;
+    out[gidx * 4 + 1] = (npos > 0 && nneg > 0)
                             ? static_cast<float>((rank_sum - 0.5 * npos * (npos + 1)) / (static_cast<double>(npos) * nneg))
                             : NAN;
+    out[gidx * 4 + 2] = npos > 0 ? static_cast<float>(static_cast<double>(hits_k) / static_cast<double>(npos)) : 0.0f;
+    out[gidx * 4 + 3] = (npos > 0 && k > 0) ? static_cast<float>(static_cast<double>(hits_k) / static_cast<double>(k)) : 0.0f;
   }
 }
 
@@ -1571,11 +1579,12 @@ extern "C" int nncf_score_pairs(const float* user_table_dev, const float* item_t
 }
 
 extern "C" int nncf_eval_given(const float* scores_dev, const int32_t* truth_dev, const int64_t* seg_indptr_dev,
-                               int64_t n_groups, float* per_group_dev, void* stream) {
+                               int64_t n_groups, int topk, float* per_group_dev, void* stream) {
   NNCF_CHECK_ARG(scores_dev && truth_dev && seg_indptr_dev && per_group_dev, "nncf_eval_given: null argument");
   if (n_groups == 0) return NNCF_OK;
+  NNCF_CHECK_ARG(topk == -1 || topk >= 1, "nncf_eval_given: topk must be -1 (whole list) or >= 1");
   eval_given_kernel<<<ceil_div(n_groups, 4), 128, 0, (cudaStream_t)stream>>>(scores_dev, truth_dev, seg_indptr_dev,
-                                                                             n_groups, per_group_dev);
+                                                                             n_groups, topk, per_group_dev);
   NNCF_LAUNCH_OK();
   return NNCF_OK;
 }

@@ -34,8 +34,11 @@ struct GsArgs {
   int* err;
 };
 
-__device__ __forceinline__ uint64_t gs_ctr(uint64_t call, uint64_t batch, uint64_t slot) {
-  return (call << 44) ^ (batch << 24) ^ slot;        // 2^20 calls x 2^20 batches x 2^24 slots per purpose key
+// Philox counter of (batch, slot): 2^24 slots per batch (range-checked by the entry points), batches up to 2^40.  The call
+// number is not packed into the counter (its field used to overlap the batch field after 2^20 batches or calls): it is
+// mixed into the KEY on the host (gs_args), so no two calls share a stream however large an epoch is.
+__device__ __forceinline__ uint64_t gs_ctr(uint64_t /*call*/, uint64_t batch, uint64_t slot) {
+  return (batch << 24) ^ slot;
 }
 
 __device__ __forceinline__ void gs_write(const GsArgs& a, int32_t* row, int32_t member, int32_t group, int32_t label) {
@@ -231,7 +234,13 @@ extern "C" int nncf_group_sampler_create(const int32_t* train_host, int64_t n_li
 static GsArgs gs_args(nncf_group_sampler* g, int B, int k, int32_t* out, int32_t* n_pos) {
   GsArgs a{};
   a.group_table = g->group_table; a.n_groups = g->n_groups; a.member_table = g->member_table; a.n_members = g->n_members;
-  a.indptr = g->indptr; a.members = g->members; a.pnd = g->pnd; a.key = g->key; a.call = g->call++;
+  a.indptr = g->indptr; a.members = g->members; a.pnd = g->pnd;
+  a.call = g->call++;
+  {  // per-call key: splitmix64 of (seed key, call number)
+    uint64_t z = g->key + 0x9E3779B97F4A7C15ull * (a.call + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    a.key = z;
+  }
   a.chop = g->chop; a.B = B; a.k = k; a.neg_sign = g->neg_sign; a.group_by_user = g->group_by_user;
   a.out = out; a.n_pos = n_pos; a.err = g->err;
   return a;
@@ -240,7 +249,7 @@ static GsArgs gs_args(nncf_group_sampler* g, int B, int k, int32_t* out, int32_t
 extern "C" int nncf_group_sampler_sample(nncf_group_sampler_t* g, int batch_size_p, int n_batches, int32_t* out_dev,
                                          void* stream) {
   NNCF_CHECK_ARG(g && out_dev, "nncf_group_sampler_sample: null argument");
-  NNCF_CHECK_ARG(batch_size_p >= 1 && n_batches >= 0 && n_batches < (1 << 20), "nncf_group_sampler_sample: bad sizes");
+  NNCF_CHECK_ARG(batch_size_p >= 1 && batch_size_p < (1 << 24) && n_batches >= 0, "nncf_group_sampler_sample: bad sizes");
   if (n_batches == 0) return NNCF_OK;
   GsArgs a = gs_args(g, batch_size_p, 0, out_dev, nullptr);
   const int64_t n = (int64_t)n_batches * batch_size_p;
@@ -252,8 +261,7 @@ extern "C" int nncf_group_sampler_sample(nncf_group_sampler_t* g, int batch_size
 extern "C" int nncf_group_sampler_sample_with_negs(nncf_group_sampler_t* g, int batch_size_p, int k, int n_batches,
                                                    int32_t* out_dev, int32_t* n_pos_dev, void* stream) {
   NNCF_CHECK_ARG(g && out_dev, "nncf_group_sampler_sample_with_negs: null argument");
-  NNCF_CHECK_ARG(batch_size_p >= 1 && k >= 1 && n_batches >= 0 && n_batches < (1 << 20),
-                 "nncf_group_sampler_sample_with_negs: bad sizes");
+  NNCF_CHECK_ARG(batch_size_p >= 1 && k >= 1 && n_batches >= 0, "nncf_group_sampler_sample_with_negs: bad sizes");
   NNCF_CHECK_ARG((int64_t)batch_size_p * (1 + k) < (1 << 24), "nncf_group_sampler_sample_with_negs: batch too large");
   if (n_batches == 0) return NNCF_OK;
   const int ng0 = (batch_size_p + g->chop - 1) / g->chop;

@@ -32,6 +32,24 @@ __global__ void peer_barrier_kernel(PeerFlags p, int n, int rank, unsigned int e
   }
 }
 
+// Flag words in peer-visible memory for stream-ordered hand-offs between GPUs (the pipelined stratum rotation of
+// nncf_b200/parallel.py): a producer's stream stores a monotonically increasing value AFTER the copies it covers, a
+// consumer's stream waits until the word has reached the value it needs.  Bounded spin (~30 s): a lost peer traps.
+__global__ void peer_signal_kernel(unsigned int* flag, unsigned int value) {
+  __threadfence_system();                                // the stream's earlier peer writes are ordered before the flag
+  *reinterpret_cast<volatile unsigned int*>(flag) = value;
+  __threadfence_system();
+}
+__global__ void peer_wait_kernel(const unsigned int* flag, unsigned int value) {
+  const volatile unsigned int* f = flag;
+  unsigned int spins = 0;
+  while (static_cast<int>(*f - value) < 0) {
+    __nanosleep(256);
+    if (++spins > 120000000u) __trap();
+  }
+  __threadfence_system();
+}
+
 }  // namespace nncf
 
 using namespace nncf;
@@ -77,6 +95,27 @@ extern "C" int nncf_peer_barrier(void* const* flag_ptrs, int n_ranks, int rank, 
   PeerFlags p{};
   for (int i = 0; i < n_ranks; ++i) p.flags[i] = static_cast<unsigned int*>(flag_ptrs[i]);
   peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, n_ranks, rank, epoch);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+
+
+// ---- stream-ordered transfers between peer-visible allocations (copy engines over NVLink; no SM is used) ----------------
+extern "C" int nncf_peer_copy(void* dst, const void* src, size_t bytes, void* stream) {
+  NNCF_CHECK_ARG(dst && src, "nncf_peer_copy: null argument");
+  if (bytes == 0) return NNCF_OK;
+  NNCF_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+  return NNCF_OK;
+}
+extern "C" int nncf_peer_signal(void* flag_ptr, unsigned int value, void* stream) {
+  NNCF_CHECK_ARG(flag_ptr, "nncf_peer_signal: null flag");
+  peer_signal_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<unsigned int*>(flag_ptr), value);
+  NNCF_LAUNCH_OK();
+  return NNCF_OK;
+}
+extern "C" int nncf_peer_wait(const void* flag_ptr, unsigned int value, void* stream) {
+  NNCF_CHECK_ARG(flag_ptr, "nncf_peer_wait: null flag");
+  peer_wait_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(static_cast<const unsigned int*>(flag_ptr), value);
   NNCF_LAUNCH_OK();
   return NNCF_OK;
 }

@@ -34,6 +34,12 @@
 
 namespace nncf {
 
+// developer ablations (tools/score_bench.cu builds one binary per bit; the library is always built with 0):
+//   1 no epilogue math   2 no Y tile copies   4 no MMA2   8 no MMA1   16 no loss   32 no table update in the drain   64 no L2 prefetch
+#ifndef NNCF_ABLATE
+#define NNCF_ABLATE 0
+#endif
+
 constexpr int kScoreEpiWarps = 8;
 constexpr int kScoreThreads = 64 + 32 * kScoreEpiWarps + 64;   // 12 warps: registers are allocated in groups of 4 warps
 
@@ -54,6 +60,15 @@ struct ScoreTcArgs {
   // sum there) per owned row, issued from the staged fp32 block in shared memory.  Legal because every row of this step
   // was gathered by the PREVIOUS kernel, so nothing in this kernel reads the tables.
   int fuse_sgd;
+  // activity regulariser folded into the drain (ref: utils/utilities.py:129-135): the user-side CTAs add
+  // reg_scale * X (reg_scale = 2 u_reg / B) to their gradient block from the bf16 X block in shared memory, so the
+  // reference's default u_reg = 1e-6 keeps the two-launch step.  0 = off.
+  float reg_scale;
+  // split sweep: `split` CTAs share one owner block, each sweeps 1/split of the tiles and ADDS its partial gradient block
+  // (bulk reductions into the table rows in fused mode, red.global.add.v4 into the zeroed dX blocks otherwise).  A batch of
+  // 512 is only 8 CTAs: at R = 1 (the reference's sequential loop) the sweep is the critical path of the step.
+  int split;
+  int drain_vec;   // fused drain with vector reductions instead of bulk reductions (small grids), see the drain
   // fused mode has no finalize launch: the last side-0 CTA of a replica publishes the replica's loss and re-arms the
   // accumulators (loss_count[R] arrival counters, zero between steps)
   unsigned int* loss_count;
@@ -109,8 +124,12 @@ struct ScoreTcCfg {
   static constexpr int kMinBlocks = NSUB <= 2 ? 2 : 1;   // resident CTAs per SM
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry); two CTAs of
   // dp = 128 need 2 x (112 KiB + 256 B + 1 KiB reserved) <= 228 KiB
-  static constexpr size_t kSmemBytes =
-      (size_t)NSUB * kSubBytes + (size_t)kStages * NSUB * kYBytes + 256 /*barriers*/;
+  // layout: [barriers, 1 KiB][X block][Y stages]; at the drain the fp32 staging block [128][DP + 4] overlays the Y stages
+  // only, so the bf16 X block stays readable (the activity regulariser adds reg_scale * x there)
+  static constexpr size_t kBarBytes = 1024;
+  static constexpr size_t kYAllBytes = (size_t)kStages * NSUB * kYBytes;
+  static constexpr size_t kStageBytes = (size_t)128 * (DP + 4) * 4;
+  static constexpr size_t kSmemBytes = kBarBytes + (size_t)NSUB * kSubBytes + (kYAllBytes > kStageBytes ? kYAllBytes : kStageBytes);
 };
 
 __device__ __forceinline__ float tanh_approx(float x) {
@@ -276,9 +295,9 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   constexpr bool kPairwise = LOSS >= NNCF_LOSS_LOG_LOSS;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (smem_u32(smem) & 1023u) __trap();           // SWIZZLE_128B operands need 1024-byte aligned tiles
-  uint8_t* sX = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* sX = smem + C::kBarBytes;
   uint8_t* sY = sX + NSUB * kSubBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sY + C::kStages * NSUB * C::kYBytes);
   uint64_t* x_full = bars + 0;
   uint64_t* y_full = bars + 1;      // [4]
   uint64_t* y_empty = bars + 5;     // [4]
@@ -289,7 +308,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   float* loss_slots = reinterpret_cast<float*>(bars + 20);   // [8] per-epilogue-warp loss sums, handed to warp 0 (see below)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int ob = blockIdx.x, side = blockIdx.y, r = blockIdx.z;
+  const int nblk_grid = a.rows_pad >> 7;
+  const int ob = blockIdx.x % nblk_grid, sp = blockIdx.x / nblk_grid, side = blockIdx.y, r = blockIdx.z;
   pdl_launch_dependents();                         // the next kernel may start its prologue (it waits for us before reading)
   if (a.tl && tid == 0) atomicMin(&a.tl[3], global_timer_ns());
   if (GROUP) pdl_wait();                           // n_unique comes from a preceding kernel
@@ -297,7 +317,10 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   const int n_owner = side == 0 ? a.B : ncols;     // valid rows on the owner side
   const int n_other = side == 0 ? ncols : a.B;     // valid rows on the swept side
   if (ob * 128 >= n_owner) return;                 // whole CTA exits together (no barrier touched yet)
-  const int nt = (n_other + TN - 1) / TN;
+  const int nt_all = (n_other + TN - 1) / TN;
+  const int t_begin = (nt_all * sp) / a.split;        // this CTA sweeps tiles [t_begin, t_begin + nt)
+  const int nt = (nt_all * (sp + 1)) / a.split - t_begin;
+  if (nt <= 0) return;                             // (the host never asks for more splits than tiles)
   const int nblk = a.rows_pad >> 7;
   const int64_t base = (int64_t)r * a.rows_pad;
   const uint8_t* gX = (side == 0 ? a.Uimg : a.Vimg) + ((int64_t)r * nblk + ob) * NSUB * kSubBytes;
@@ -334,8 +357,9 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
       }
       int ready_blk = -1;                                // self-gather: blocks of the swept side known to be in the image
-      for (int t = 0; t < nt; ++t) {
-        const int st = t % C::kStages;
+      for (int it = 0; it < nt; ++it) {
+        const int t = t_begin + it;
+        const int st = it % C::kStages;
         if (a.self_gather && ((t * TN) >> 7) > ready_blk) {
           ready_blk = (t * TN) >> 7;
           const int* flag = a.gather_flags + (r * 2 + (1 - side)) * nblk + ready_blk;
@@ -343,7 +367,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           while (ld_acquire_gpu(flag) != a.gather_seq) { __nanosleep(20); if (++spins > 20000000u) __trap(); }
           fence_proxy_async_global();                    // the rows were written by generic stores; the bulk copy reads them
         }
-        mbar_wait(&y_empty[st], ((t / C::kStages) & 1) ^ 1);
+        mbar_wait(&y_empty[st], ((it / C::kStages) & 1) ^ 1);
+        if (NNCF_ABLATE & 2) { mbar_arrive(&y_full[st]); continue; }
         mbar_expect_tx(&y_full[st], NSUB * C::kYBytes);
         // rows [t TN, (t+1) TN) of the swept side: a contiguous piece of each [128 x 64] sub-tile of block (t TN) / 128
         const uint8_t* src = gY + (size_t)((t * TN) >> 7) * NSUB * kSubBytes + (size_t)((t * TN) & 127) * 128;
@@ -364,7 +389,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           // last arriving CTA of the replica publishes the loss and re-arms the accumulators.  One acq_rel atomic on the
           // counter orders my loss contribution before it and everybody's contributions before the read below
           // (instead of __threadfence() = MEMBAR.SC.GPU on either side of a relaxed atomic)
-          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) *
+          // (split CTAs whose tile range is empty left before the barriers: min(split, tiles) of them arrive per owner block)
+          const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * static_cast<unsigned int>(a.split < nt_all ? a.split : nt_all) *
                                       ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
           unsigned int arrived;
           asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(a.loss_count + r) : "memory");
@@ -398,7 +424,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           const uint64_t yd = ydesc0 + static_cast<uint64_t>((st * NSUB * C::kYBytes) >> 4);
           const uint32_t dcol = tmem_u + sb * TN;
 #pragma unroll
-          for (int k = 0; k < DP / 16; ++k)
+          for (int k = 0; k < ((NNCF_ABLATE & 8) ? 0 : DP / 16); ++k)
             umma_bf16(dcol, xdesc0 + static_cast<uint64_t>(((k >> 2) * kSubBytes + (k & 3) * 32) >> 4),
                       yd + static_cast<uint64_t>(((k >> 2) * C::kYBytes + (k & 3) * 32) >> 4), idesc_s, k > 0);
           umma_commit(&s_full[sb]);
@@ -419,7 +445,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           const uint64_t yd = ydesc0_mn + static_cast<uint64_t>((st * NSUB * C::kYBytes) >> 4);
           const uint32_t acol0 = tmem_u + sb * TN;
 #pragma unroll
-          for (int k = 0; k < TN / 16; ++k) {   // K = the TN swept rows of this tile, 16 per MMA = 8 TMEM columns of G'
+          for (int k = 0; k < ((NNCF_ABLATE & 4) ? 0 : TN / 16); ++k) {   // K = the TN swept rows of this tile, 16 per MMA = 8 TMEM columns of G'
             // K rows 16k.. were written by epilogue column-half (16k) / CW at column offset ((16k) % CW) / 2 of its own range
             umma_bf16_ts(tmem_u + C::kColDX, acol0 + ((16 * k) / CW) * CW + ((16 * k) % CW) / 2,
                          yd + static_cast<uint64_t>((k * 2048) >> 4), idesc_dx, (t > 0) || (k > 0));
@@ -499,10 +525,11 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       }
     }
 
-    for (int t = 0; t < nt; ++t) {
-      const int sb = t & 1;
-      mbar_wait(&s_full[sb], (t >> 1) & 1);
-      if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(16 + t);
+    for (int it = 0; it < nt; ++it) {
+      const int t = t_begin + it;                       // tile position in the sweep; `it` indexes the pipeline state
+      const int sb = it & 1;
+      mbar_wait(&s_full[sb], (it >> 1) & 1);
+      if (warp == 2 && lane == 0 && it < 8) NNCF_STAMP(16 + it);
       tc_fence_after();
       float v[NV][32];
 #pragma unroll
@@ -542,13 +569,17 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // for neg_shared skip-gram the two sides share it by the parity of the TN x TN block the scores sit in (every block is
       // seen once by each side); blocks that touch a ragged edge stay with side 0, whose general path handles them
       bool loss_here = (side == 0);
-      if (kBalanceLoss) {
+      if (NNCF_ABLATE & 16) loss_here = false;
+      else if (kBalanceLoss) {
         const bool take1 = (((o / TN) + t) & 1) && ((o / TN) * TN + TN <= n_owner);   // parity-1 block, my row block is full
         loss_here = (side == 0) ? !take1 : take1;
       }
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
-        if (general) {
+        if (NNCF_ABLATE & 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[j][i] = pack_bf16x2(v[j][2 * i], v[j][2 * i + 1]);
+        } else if (general) {
           if (side == 0) epi_chunk<LOSS, false, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
           else epi_chunk<LOSS, true, GROUP, true>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         } else if (kFastSg) {
@@ -584,7 +615,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&g_full[sb]);
-      if (warp == 2 && lane == 0 && t < 8) NNCF_STAMP(24 + t);
+      if (warp == 2 && lane == 0 && it < 8) NNCF_STAMP(24 + it);
     }
     // (the loss hand-off comes BEFORE the drain: its values are final once the tile loop has ended, and its two gpu-scope
     //  fences would otherwise sit behind ~20 MB of bulk reductions: 19 % of this kernel's stall samples were there)
@@ -599,6 +630,23 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // the drain + update is only 2.6 us.  The warps now leave their sums in shared memory, arrive on a named barrier
       // without waiting, and the idle producer warp does the hand-off while they drain.
       if (row_ok) lsum += ec.w_neg * ec.inv_b * lraw;      // fast-path elements: all negatives, weight w_neg / B
+      if (a.reg_scale != 0.0f && side == 0 && t_begin == 0 && row_ok) {
+        // activity regulariser, loss term: u_reg * sum_d mean_b x[b,d]^2 = (reg_scale / 2) * sum over my half row of x^2
+        // (ref: utils/utilities.py:129-135), x from the bf16 X block; its gradient is added at the drain
+        float ss = 0.0f;
+#pragma unroll
+        for (int q8 = 0; q8 < DP / 16; ++q8) {
+          const int c = h * (DP / 2) + 8 * q8;
+          const uint4 w = *reinterpret_cast<const uint4*>(sX + (c >> 6) * kSubBytes + sw128_offset(ol, c & 63));
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lo = __uint_as_float(ws[e] << 16), hi = __uint_as_float(ws[e] & 0xFFFF0000u);
+            ss = fmaf(lo, lo, fmaf(hi, hi, ss));
+          }
+        }
+        lsum = fmaf(0.5f * a.reg_scale, ss, lsum);
+      }
       lsum = warp_sum(lsum);
       if (lane == 0) loss_slots[ew] = lsum;
       __syncwarp();
@@ -613,16 +661,33 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // TMEM rows live in lanes, so a direct store would scatter 32 rows per instruction (measured: 4.4k cycles).
       // Transpose through shared memory (the Y/G buffers are idle now) and write whole rows, coalesced.
       constexpr int LD = DP + 4;                                  // padded row: STS.128 at the 4-wavefront minimum
-      float* stage = reinterpret_cast<float*>(smem);             // X / Y / G are all idle once dx_full has fired
+      float* stage = reinterpret_cast<float*>(sY);               // the Y stages are idle once dx_full has fired; X stays intact
+      // activity regulariser (user side): + reg_scale * x, x from the bf16 X block (4 LDS.128 per 32 columns of my row)
+      const bool with_reg = (a.reg_scale != 0.0f) && side == 0 && t_begin == 0;     // (ONE of the split CTAs adds it: the one that sweeps tile 0)
+      const float reg_s = with_reg ? a.reg_scale * (a.fuse_sgd ? a.neg_lr : 1.0f) : 0.0f;
 #pragma unroll 1
       for (int c0 = h * (DP / 2); c0 < (h + 1) * (DP / 2); c0 += 32) {
         float v[32];
         tmem_ld32(tmem + lane_addr + C::kColDX + c0, v);
         tmem_ld_wait();
 #pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] *= ec.g_scale;
+        if (with_reg) {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            const int c = c0 + 8 * q8;
+            const uint4 w = *reinterpret_cast<const uint4*>(sX + (c >> 6) * kSubBytes + sw128_offset(ol, c & 63));
+            const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * q8 + 2 * e] = fmaf(reg_s, __uint_as_float(ws[e] << 16), v[8 * q8 + 2 * e]);
+              v[8 * q8 + 2 * e + 1] = fmaf(reg_s, __uint_as_float(ws[e] & 0xFFFF0000u), v[8 * q8 + 2 * e + 1]);
+            }
+          }
+        }
+#pragma unroll
         for (int u = 0; u < 32; u += 4)
-          *reinterpret_cast<float4*>(stage + ol * LD + c0 + u) =
-              make_float4(v[u] * ec.g_scale, v[u + 1] * ec.g_scale, v[u + 2] * ec.g_scale, v[u + 3] * ec.g_scale);
+          *reinterpret_cast<float4*>(stage + ol * LD + c0 + u) = make_float4(v[u], v[u + 1], v[u + 2], v[u + 3]);
       }
       if (a.fuse_sgd) fence_proxy_async();                                     // staged rows are read by the TMA engine
       if (a.self_gather && tid == 64) {
@@ -637,61 +702,52 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         const ShardPtrs& sh = side == 0 ? a.shards_u : a.shards_v;
         float* table = side == 0 ? a.table_u : a.table_v;
         const int32_t* ids = (side == 0 ? a.ids_u + r * a.ids_stride_u : a.ids_v + r * a.ids_stride_v) + ob * 128;
-#ifndef NNCF_DRAIN_MODE
-#define NNCF_DRAIN_MODE 0
-#endif
-#if NNCF_DRAIN_MODE == 0
-        // one bulk reduction (TMA engine, performed at the L2) per owned row
-        const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
-        if (row < 128 && ob * 128 + row < n_owner) {
-          const int64_t id = ids[row];
-          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
-          bulk_reduce_add_f32_s2g(trow, stage + row * LD, static_cast<uint32_t>(a.d) * 4u);
-          bulk_commit_group();
-          bulk_wait_group_read0();                                 // shared memory must outlive the engine's reads
-        }
-#elif NNCF_DRAIN_MODE == 2
-        // two bulk reductions per row (half a row per epilogue thread)
-        const int et = tid - 64, row = et >> 1, hf = et & 1;
-        const uint32_t hb = (static_cast<uint32_t>(a.d) * 2u + 15u) & ~15u;          // bytes of the first half (16-byte multiple)
-        if (ob * 128 + row < n_owner) {
-          const int64_t id = ids[row];
-          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
-          const uint32_t off = hf ? hb : 0u, len = hf ? static_cast<uint32_t>(a.d) * 4u - hb : hb;
-          if (len) bulk_reduce_add_f32_s2g(reinterpret_cast<uint8_t*>(trow) + off, reinterpret_cast<uint8_t*>(stage + row * LD) + off, len);
-          bulk_commit_group();
-          bulk_wait_group_read0();
-        }
-#else
-        // vector reductions from the staged rows: a warp instruction covers one whole row (coalesced 128 B lines)
-        const int nrow = min(128, n_owner - ob * 128);
-        int64_t myid = 0;
-        if (lane < 16 && ew + 8 * lane < nrow) myid = ids[ew + 8 * lane];
+        if (!a.drain_vec) {
+          // one bulk reduction (TMA engine, performed at the L2) per owned row
+          const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
+          if (!(NNCF_ABLATE & 32) && row < 128 && ob * 128 + row < n_owner) {
+            const int64_t id = ids[row];
+            float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
+            bulk_reduce_add_f32_s2g(trow, stage + row * LD, static_cast<uint32_t>(a.d) * 4u);
+            bulk_commit_group();
+            bulk_wait_group_read0();                                 // shared memory must outlive the engine's reads
+          }
+        } else {
+          // alternative (NNCF_DRAIN_VEC=1): vector reductions from the staged rows, a warp instruction covers one whole row
+          // (coalesced 128 B lines), fire and forget.  Measured: no faster than the bulk form at R = 37 (the L2 reduction
+          // throughput bounds both) and slower at R = 1 (10.0 vs 8.9 us per step)
+          const int nrow = min(128, n_owner - ob * 128);
+          int64_t myid = 0;
+          if (lane < 16 && ew + 8 * lane < nrow) myid = ids[ew + 8 * lane];
 #pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
-          const int row = ew + 8 * k;
-          const int64_t id = __shfl_sync(0xffffffffu, myid, k);
-          if (row >= nrow) break;
-          float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
-          for (int c = 4 * lane; c < a.d; c += 128) {
-            const float4 g4 = *reinterpret_cast<const float4*>(stage + row * LD + c);
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(trow + c), "f"(g4.x), "f"(g4.y), "f"(g4.z), "f"(g4.w) : "memory");
+          for (int k = 0; k < 16; ++k) {
+            const int row = ew + 8 * k;
+            const int64_t id = __shfl_sync(0xffffffffu, myid, k);
+            if (row >= nrow) break;
+            float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
+            for (int c = 4 * lane; c < a.d; c += 128) {
+              const float4 g4 = *reinterpret_cast<const float4*>(stage + row * LD + c);
+              red_add_v4(trow + c, g4.x, g4.y, g4.z, g4.w);
+            }
           }
         }
-#endif
       } else {
         float4* dst = reinterpret_cast<float4*>((side == 0 ? a.dU : a.dV) + (base + (int64_t)ob * 128) * DP);
         for (int row = ew; row < 128; row += kScoreEpiWarps) {
           if (ob * 128 + row >= n_owner) break;
           const float4* src = reinterpret_cast<const float4*>(stage + row * LD);
-          for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
+          if (a.split > 1) {            // partial blocks of the split CTAs sum in the (zeroed) gradient block
+            for (int c = lane; c < DP / 4; c += 32) { const float4 g4 = src[c]; red_add_v4(reinterpret_cast<float*>(dst + row * (DP / 4) + c), g4.x, g4.y, g4.z, g4.w); }
+          } else {
+            for (int c = lane; c < DP / 4; c += 32) dst[row * (DP / 4) + c] = src[c];
+          }
         }
       }
     }
     if (warp == 2 && lane == 0) NNCF_STAMP(5);
     tc_fence_before();
   }
-  else if (a.next_ids_u) {
+  else if (a.next_ids_u && !(NNCF_ABLATE & 64)) {
     // ------------------------------------------------------------------------------ spare warps: L2 prefetch
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const int ncta = gridDim.x * gridDim.y * gridDim.z;
@@ -734,7 +790,7 @@ int launch_score_tc_one(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) 
                                    (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  NNCF_CUDA(launch_pdl(score_grad_tc_kernel<NSUB, LOSS, GROUP>, dim3(nblk, 2, R), dim3(kScoreThreads), C::kSmemBytes, st, a));
+  NNCF_CUDA(launch_pdl(score_grad_tc_kernel<NSUB, LOSS, GROUP>, dim3(nblk * a.split, 2, R), dim3(kScoreThreads), C::kSmemBytes, st, a));
   count_launch();
   return 0;
 }

@@ -1065,12 +1065,14 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // reduction (TMA engine) per row, and publishes the loss, so the step is two launches (NNCF_FUSE_SGD=0 disables it).
   // (A first version issued red.global.add.v4 from the epilogue warps: +9.7 us in the kernel for the 11 us it saved.)
   static const bool fuse_env = [] { const char* e = getenv("NNCF_FUSE_SGD"); return !e || atoi(e) != 0; }();
-  const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
+  // (the activity regulariser rides along: loss term and gradient are added by the user-side CTAs of the score kernel)
+  const bool fuse_sgd = fuse_env && bf16 && c.optimizer == NNCF_OPT_SGD && !c.norm_u && !c.norm_v && !pairwise &&
                         (d % 4 == 0) && !dense_items && !want_row_grads && !bias;
   // lazy Adam with nothing to post-process: the score kernel publishes the loss itself (as in the fused SGD mode) and
   // writes the finished gradient blocks, the Adam kernels read them: no finalize launch
-  const bool adam_plain = bf16 && c.optimizer == NNCF_OPT_LAZY_ADAM && !c.norm_u && !c.norm_v && !pairwise && c.u_reg == 0.0f &&
+  const bool adam_plain = bf16 && c.optimizer == NNCF_OPT_LAZY_ADAM && !c.norm_u && !c.norm_v && !pairwise &&
                           (d % 4 == 0) && !dense_items && !want_row_grads && !bias && t->n_shards <= 1;
+  const bool drain_reg = (fuse_sgd || adam_plain) && c.u_reg != 0.0f;    // regulariser gradient added by the score kernel's drain
   // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
   // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
   t->loss_published = true;   // by the last finalize launch, or by the score kernel itself in fused mode
@@ -1096,7 +1098,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   GatherArgs gu{};
   gu.table = tb->user_table; gu.ids = uid; gu.ids_stride = B; gu.count = B; gu.rows_pad = rp; gu.d = d; gu.dp = dp;
   gu.normalize = c.norm_u; gu.write_img = bf16; gu.zero_grad = bf16 ? 0 : 1;
-  gu.write_xf = (!bf16 || c.norm_u || c.norm_v || pairwise || c.u_reg != 0.0f) ? 1 : 0; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
+  gu.write_xf = (!bf16 || c.norm_u || c.norm_v || pairwise || (c.u_reg != 0.0f && !drain_reg)) ? 1 : 0; gu.Xf = t->Uf; gu.inv = t->invU; gu.img = t->Uimg; gu.dX = t->dU;
   gu.corr = t->corrU;
   unsigned long long* tl = nullptr;
   if (t->timeline) {
@@ -1117,6 +1119,18 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     for (int i = 0; i < t->n_shards; ++i) { gu.shards.p[i] = t->ushards[i]; gv.shards.p[i] = t->ishards[i]; }
   }
   const bool vec = (d % 4 == 0) && !bias;   // 16-byte aligned rows: 128-bit loads / vector reductions (the scalar kernels carry the bias-column logic)
+  // split sweep (score_tc.cuh): when a step is too small to fill the device (R = 1: 8 CTAs), `split` CTAs share an owner block
+  // and add their partial gradient blocks.  NNCF_SPLIT overrides (developer switch).
+  const int active_ctas = ceil_div(B, 128) * 2 * R;
+  int split = 1;
+  if (bf16 && vec && !dense_items && t->n_shards <= 1) {
+    const int tn = 64, nt_min = ceil_div(B, tn);     // (group: fewer unique items than B leave some split CTAs without tiles; they exit at once)
+    // (measured at R = 1, B = 512: 12.7 / 10.2 / 9.0 / 10.5 us per step for split 1 / 2 / 4 / 8)
+    while (split * 2 <= 4 && split * 2 <= nt_min && active_ctas * split * 2 <= t->resident_ctas) split *= 2;
+    const int split_env = [] { const char* e = getenv("NNCF_SPLIT"); return e ? atoi(e) : 0; }();   // (read per step: the tests switch it)
+    if (split_env >= 1 && split_env <= nt_min) split = split_env;
+  }
+  if (split > 1 && !fuse_sgd) gu.zero_grad = 1;    // partial blocks are summed with red.global.add
   // self-gather (opt-in, NNCF_SELF_GATHER=1): the score kernel's CTAs gather their own rows (no gather launch, no hand-off).
   // Needs the fused drain (nothing else reads the staging buffers), one local table, dp <= 128 and the whole grid resident
   // at once: CTAs wait for each other's image blocks, and no drain may start before the last gather has ended.
@@ -1124,8 +1138,8 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // uniform ids).  The separate gather kernel has 1,184 CTAs x 8 warps x 4 rows in flight and its launch overlaps the score
   // kernel's prologue through programmatic dependent launch; 8 warps x 8 rows per CTA behind the prologue do not beat it.
   const bool self_env = [] { const char* e = getenv("NNCF_SELF_GATHER"); return e && atoi(e) != 0; }();   // (read per step: the tests switch it)
-  const int active_ctas = ceil_div(B, 128) * 2 * R;
-  const bool self_gather = self_env && fuse_sgd && vec && !group && !sharded && dp <= 128 && !t->timeline &&
+  if (split > 1 && !fuse_sgd) gv.zero_grad = 1;
+  const bool self_gather = self_env && fuse_sgd && vec && !group && !sharded && dp <= 128 && !t->timeline && split == 1 &&
                            active_ctas <= t->resident_ctas;
   // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
   // reads what its predecessor wrote, so only launch latency and prologues overlap
@@ -1148,7 +1162,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
                                                               bf16 ? 1 : 0, t->spos);
     NNCF_LAUNCH_OK();
   }
-  if (c.u_reg != 0.0f) {
+  if (c.u_reg != 0.0f && !drain_reg) {  // (the fused step adds the regulariser's loss and gradient in the score kernel)
     reg_loss_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss, d_emb);
     NNCF_LAUNCH_OK();
   }
@@ -1165,6 +1179,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.spos = t->spos; ta.inverse = sa.inverse; ta.ncols_dev = sa.ncols_dev; ta.loss = t->loss; ta.rows_pad = rp;
     ta.B = B; ta.scheme = c.scheme; ta.loss_kind = c.loss; ta.lambda = c.neg_loss_weight; ta.gamma = c.loss_gamma;
     ta.loss_count = (fuse_sgd || adam_plain) ? t->loss_count : nullptr; ta.loss_out = (fuse_sgd || adam_plain) ? loss_out_step : nullptr;
+    {   // drain form of the fused update: bulk reductions; NNCF_DRAIN_VEC=1 selects vector reductions (developer switch)
+      const char* e = getenv("NNCF_DRAIN_VEC");
+      ta.drain_vec = e ? atoi(e) : 0;     // measured at R = 1, split 4: 8.9 us per step with bulk reductions, 10.0 with vector reductions
+    }
+    ta.split = split; ta.reg_scale = drain_reg ? 2.0f * c.u_reg / static_cast<float>(B) : 0.0f;
     ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;

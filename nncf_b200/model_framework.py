@@ -170,8 +170,9 @@ class SharedState(object):
         else:
             assert False, '[ERROR] Model name {} unknown'.format(model_name)
         self.norm_u = bool(conf.emb_normalization)
-        # reference quirk: the 'mf' branch never l2-normalises the item embedding (models/model_framework.py:85-88)
-        self.norm_v = bool(conf.emb_normalization) and model_name != 'mf'
+        # reference quirk: the item-side l2_normalize sits inside the content-model `else:` branch
+        # (models/model_framework.py:85-111), so neither 'mf' nor 'pretrained' items are normalised
+        self.norm_v = bool(conf.emb_normalization) and model_name not in ('mf', 'pretrained')
         self.adam = None
         if self.opt_kind == 'lazy_adam':
             z = torch.zeros_like
@@ -186,7 +187,10 @@ class SharedState(object):
             c = self.conf
             self._steps[scheme] = FusedStep(StepSpec(
                 scheme=scheme, loss=c.loss, precision=c.precision, batch_size_p=c.batch_size_p,
-                num_negatives=c.num_negatives, dim=self.dim, norm_u=self.norm_u, norm_v=self.norm_v,
+                num_negatives=c.num_negatives, dim=self.dim,
+                # reference quirk: the sampled_neg_shared view scores U_emb_front = Emb_U(uid_front) WITHOUT l2_normalize
+                # (models/model_framework.py:64-65,138-141); the item side is normalised as everywhere else
+                norm_u=self.norm_u and scheme != 'sampled_neg_shared', norm_v=self.norm_v,
                 optimizer=self.opt_kind, replicas=(c.replicas if self.item_table is not None else 1),
                 neg_loss_weight=float(c.neg_loss_weight), loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg),
                 learn_rate=float(self.lr), interaction_bias=self.bias))
@@ -314,7 +318,12 @@ class PairsView(_View):
                 dim=st.dim, norm_u=st.norm_u, norm_v=st.norm_v, optimizer='none', neg_loss_weight=float(c.neg_loss_weight),
                 loss_gamma=float(c.loss_gamma), u_reg=float(c.u_reg), interaction_bias=st.bias))
             st._user_updater = SparseUpdater(st.opt_kind, st.lr)
-        out = st._steps[key].run(st.user_table, compact.detach().contiguous(), uid, inv, 1, want_grads=True)
+        # y_true per row for the pointwise losses (ref: utils/objectives.py:59-70 weights by it): presample's shuffles and
+        # GroupSampler's ragged batches do not keep the positives in rows [0, B)
+        resp = None
+        if y is not None and y[0] is not None and c.loss in ('skip-gram', 'mse'):
+            resp = _dev_i32(y[0], st.device)
+        out = st._steps[key].run(st.user_table, compact.detach().contiguous(), uid, inv, 1, want_grads=True, responses=resp)
         st._user_updater.begin_step()
         st._user_updater.apply(st.user_table, uid, out['grad_user_rows'], *(st.adam[:2] if st.adam else (None, None)))
         g = torch.zeros_like(compact)

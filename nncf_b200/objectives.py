@@ -147,9 +147,13 @@ class Evaluator(object):
         scores = ops.score_pairs(U, V, uid, cid)
         if predict_only:
             return list(zip(t[:, 0].tolist(), t[:, 2].tolist(), scores.cpu().numpy().tolist()))
-        assert topk == -1, 'given@k is implemented for k = -1 (full list), the setting main.py uses (given@-1)'
+        assert topk == -1 or topk >= 1, '[ERROR] eval_topk {} must be -1 or > 0 when eval_scheme=given'.format(topk)
         users, counts = np.unique(t[:, 0], return_counts=True)
         indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         out = ops.eval_given(scores, torch.from_numpy(t[:, 2].astype(np.int32)).to(dev),
-                             torch.from_numpy(indptr).to(dev)).cpu().numpy().astype(np.float64)
-        return {'map@%d' % topk: round(float(np.mean(out[:, 0])), 16), 'auc': round(float(np.nanmean(out[:, 1])), 16)}
+                             torch.from_numpy(indptr).to(dev), topk).cpu().numpy().astype(np.float64)
+        # ref utils/objectives.py:286-294: unweighted means over users, rounded to 16 dp
+        return {'map@%d' % topk: round(float(np.mean(out[:, 0])), 16),
+                'recall@%d' % topk: round(float(np.mean(out[:, 2])), 16),
+                'precision@%d' % topk: round(float(np.mean(out[:, 3])), 16),
+                'auc': round(float(np.nanmean(out[:, 1])), 16)}

@@ -427,12 +427,13 @@ def score_pairs(user_table: torch.Tensor, item_table: torch.Tensor, uid: torch.T
     return out
 
 
-def eval_given(scores: torch.Tensor, truth: torch.Tensor, indptr: torch.Tensor) -> torch.Tensor:
+def eval_given(scores: torch.Tensor, truth: torch.Tensor, indptr: torch.Tensor, topk: int = -1) -> torch.Tensor:
+    """per user group (AP@k, AUC, recall@k, precision@k); topk = -1 ranks the whole list (given@-1)"""
     _need_cuda(scores, truth, indptr)
     ng = indptr.numel() - 1
-    out = torch.empty((ng, 2), dtype=torch.float32, device=scores.device)
+    out = torch.empty((ng, 4), dtype=torch.float32, device=scores.device)
     check(lib.nncf_eval_given(_ptr(scores.contiguous()), _ptr(_i32(truth)), _ptr(indptr.to(torch.int64).contiguous()), ng,
-                              _ptr(out), _stream()))
+                              int(topk), _ptr(out), _stream()))
     return out
 
 

@@ -6,16 +6,20 @@
   remote rows directly over NVLink (include/nncf_b200.h, section 3b) — no all-to-all staging buffers.
 
 * `StratifiedTrainer`: the schedule that scales.  The step moves ~2 KB of embedding rows per positive link; at the
-  single-GPU rate (7e8 links/s) that is 1.4 TB/s of random row traffic per GPU, more than NVLink 5 carries (0.9 TB/s per
+  single-GPU rate (9e8 links/s) that is 1.8 TB/s of random row traffic per GPU, more than NVLink 5 carries (0.9 TB/s per
   direction), so ANY scheme that fetches rows from their owners per step is NVLink-bound (measured with the peer-memory
   mode: 5.3e8 links/s on 2 GPUs against 7.2e8 on one).  Stratified SGD (Gemulla et al., KDD'11, "DSGD") removes the
-  per-step exchange: links are partitioned into N x N blocks by (user % N, item % N); rank r owns user shard r for good
-  and, in sub-epoch t, holds item shard (r + t) % N and trains ONLY on block (r, (r + t) % N), so every row it touches
-  is local and the single-GPU kernels run unchanged; between sub-epochs the item shards (and their optimizer state)
-  rotate one rank down the ring (one NCCL send/recv of n_items / N rows per rank).  The blocks trained concurrently are
-  disjoint in users AND items, so a sub-epoch equals a sequential pass over its N blocks in any order (checked against
-  the oracle on 2 GPUs, tools/multi_gpu_check.py).  Declared difference to a single-GPU epoch: a batch's shared
-  negatives come from the item shard of its block (a random 1/N of the items under id % N).
+  per-step exchange: rank r owns user shard r (user % N) for good; the items are cut into M = 2N strata (item % M) and
+  links into N x M blocks.  In phase p rank r trains ONLY on block (r, (2r + p) % M), so every row it touches is local
+  and the single-GPU kernels run unchanged.  The rotation is PIPELINED: while rank r trains stratum (2r + p) it also
+  holds the stratum it will train next, (2r + p + 1), which rank r + 1 finished one phase earlier and pushes into r's
+  memory DURING phase p (copy engines over NVLink peer mappings, `nncf_peer_copy`, on a side stream; arrival and
+  buffer-free credits are flag words in peer memory, `nncf_peer_signal` / `nncf_peer_wait`, so neither the host nor
+  the compute stream ever waits for a transfer that has had a whole phase to complete).  Three buffers per rank rotate
+  through the roles train / incoming / outgoing.  The strata trained concurrently are disjoint in users AND items, so a
+  phase equals a sequential pass over its N blocks in any order (checked against the oracle: tests/test_gpu_multi.py
+  runs the 2-rank schedule on ONE device, tools/multi_gpu_check.py on two).  Declared difference to a single-GPU epoch: a
+  batch's shared negatives come from the stratum of its block (a random 1/M of the items under id % M).
 
 The reference is single-process / single-device (no collective anywhere); everything here is the
 B200-native extension and is exercised on CPU with the gloo backend for the host-side logic (tests/test_parallel_cpu.py).
@@ -54,6 +58,37 @@ def shard_rows(n_rows: int, rank: int, world: int) -> int:
 def held_item_shard(rank: int, sub_epoch: int, world: int) -> int:
     """item shard held (and trained on) by `rank` during sub-epoch `sub_epoch` of the stratified schedule"""
     return (rank + sub_epoch) % world
+
+
+def n_item_strata(world: int) -> int:
+    """item strata of the pipelined stratified schedule: two per rank (one trained, one in flight)"""
+    return 2 * world if world > 1 else 1
+
+
+def stratum_of(rank: int, phase: int, world: int) -> int:
+    """item stratum trained by `rank` in phase `phase` (phases count on across epochs)"""
+    return (2 * rank + phase) % n_item_strata(world)
+
+
+def slot_of(phase: int) -> int:
+    """which of a rank's three stratum buffers is trained in `phase`; (phase + 1) % 3 is being filled for the next phase,
+    (phase - 1) % 3 is being sent to rank - 1 (the same on every rank, so sender and receiver agree without talking)"""
+    return phase % 3
+
+
+def partition_links_by_stratum(train, rank: int, world: int):
+    """Rows of `train` (int [n, 3]) owned by `rank` (user % world == rank) split by item stratum (item % M, M = 2 world).
+    Returns M int32 arrays [n_s, 3] with LOCAL ids (user // world, item // M); original order kept inside a block."""
+    train = np.asarray(train)
+    m = n_item_strata(world)
+    mine = train[train[:, 0] % world == rank]
+    out = []
+    for s in range(m):
+        b = mine[mine[:, 1] % m == s].astype(np.int32, copy=True)
+        b[:, 0] //= world
+        b[:, 1] //= m
+        out.append(b)
+    return out
 
 
 def partition_links_by_block(train, rank: int, world: int):
@@ -218,34 +253,74 @@ class ShardedTrainer:
             m.close()
 
 
-class StratifiedTrainer:
-    """Stratified (DSGD-style) multi-GPU training: rank r keeps user shard r, item shards rotate round the ring between
-    sub-epochs, every step touches local rows only (see the module docstring).  Works with sparse SGD and lazy Adam
-    (the optimizer state of the item shard travels with it)."""
+class LocalPeerGroup:
+    """In-process stand-in for the CUDA-IPC exchange: every 'rank' is an object of ONE process on ONE device and publishes
+    its arena pointer here (plain device pointers are valid for every rank).  Used by the single-device schedule test;
+    the kernels, copies and flag protocol are exactly the multi-process ones."""
 
-    def __init__(self, spec, n_users: int, n_items: int, rank: int, world: int, seed: int = 7):
+    def __init__(self, world: int):
+        self.world = world
+        self.ptrs = [0] * world
+        self.keep = [None] * world
+
+
+class _Arena:
+    """one peer-visible allocation per rank: 3 stratum slots x (items [, adam m, adam v]) + 2 flag words"""
+
+    def __init__(self, nbytes: int, rank: int, world: int, group):
+        import torch
+        self.rank, self.world = rank, world
+        if group is None:
+            self.mem = PeerMemory(nbytes, rank, world)
+            self.local_ptr, self.ptrs = self.mem.local_ptr, self.mem.ptrs
+        else:
+            self.mem = None
+            buf = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+            group.keep[rank] = buf
+            group.ptrs[rank] = buf.data_ptr()
+            self.local_ptr, self.ptrs = buf.data_ptr(), group.ptrs          # (the list fills in as the other ranks are built)
+
+    def close(self):
+        if self.mem is not None:
+            self.mem.close()
+
+
+class StratifiedTrainer:
+    """Stratified (DSGD-style) multi-GPU training with a pipelined stratum rotation (see the module docstring): rank r
+    keeps user shard r; the items live in M = 2 world strata; in phase p rank r trains stratum (2r + p) % M out of one of
+    three local buffers while the stratum of phase p + 1 arrives from rank r + 1 and the one of phase p - 1 leaves for
+    rank r - 1 on the copy engines.  Sparse SGD and lazy Adam (the optimizer state of a stratum travels with it).
+    `group`: None = one process per GPU (CUDA IPC through torch.distributed); a LocalPeerGroup = all ranks in this process."""
+
+    def __init__(self, spec, n_users: int, n_items: int, rank: int, world: int, seed: int = 7, group=None):
         import torch
         from .ops import FusedStep
         self.spec, self.rank, self.world = spec, rank, world
         self.n_users, self.n_items = n_users, n_items
+        self.m = n_item_strata(world)
         self.rows_u = shard_rows(n_users, rank, world)
-        self.rows_i_max = shard_rows(n_items, 0, world)                 # shard 0 is the largest
+        self.rows_s_max = shard_rows(n_items, 0, self.m)                 # stratum 0 is the largest
         dev = torch.device("cuda")
         d = spec.dim
-        # shard s of a table is initialised from (seed, s), independent of the rank that builds it
         self.users = self._init_shard(self.rows_u, d, seed + 1000 * rank, dev)
-        self.sub_epoch = 0
-        held = held_item_shard(rank, 0, world)
-        self.items = torch.zeros((self.rows_i_max, d), dtype=torch.float32, device=dev)
-        n_held = shard_rows(n_items, held, world)
-        self.items[:n_held] = self._init_shard(n_held, d, seed + 1 + 1000 * held, dev)
-        self._moving = [self.items]
-        self.adam = None
-        if spec.optimizer == "lazy_adam":
-            z = torch.zeros_like
-            self.adam = [z(self.users), z(self.users), z(self.items), z(self.items)]
-            self._moving += [self.adam[2], self.adam[3]]
-        self._spare = [torch.empty_like(t) for t in self._moving]
+        self.n_mov = 3 if spec.optimizer == "lazy_adam" else 1           # tensors that travel with a stratum
+        self.t_bytes = max(self.rows_s_max, 1) * d * 4
+        n_slots = 3 if world > 1 else 1
+        self.off_flags = n_slots * self.n_mov * self.t_bytes
+        self.arena = _Arena(self.off_flags + 256, rank, world, group)
+        self.slots = [[torch.as_tensor(_CudaBuffer(self.arena.local_ptr + (k * self.n_mov + j) * self.t_bytes,
+                                                   (max(self.rows_s_max, 1), d)), device="cuda")
+                       for j in range(self.n_mov)] for k in range(n_slots)]
+        for k in range(min(2, n_slots)):                                 # phase 0: stratum 2r in slot 0, 2r + 1 ready in slot 1
+            st = stratum_of(rank, k, world)
+            n_st = shard_rows(n_items, st, self.m)
+            self.slots[k][0].zero_()
+            self.slots[k][0][:n_st] = self._init_shard(n_st, d, seed + 1 + 1000 * st, dev)[:n_st]
+            for j in range(1, self.n_mov):
+                self.slots[k][j].zero_()
+        self.user_adam = [torch.zeros_like(self.users), torch.zeros_like(self.users)] if self.n_mov == 3 else None
+        self.phase = 0
+        self.xfer = torch.cuda.Stream() if world > 1 else None
         self.step = FusedStep(spec)
 
     @staticmethod
@@ -254,38 +329,87 @@ class StratifiedTrainer:
         g = torch.Generator(device="cuda").manual_seed(seed)
         return (torch.rand((max(rows, 1), d), device=dev, generator=g) - 0.5) * 0.1      # Keras-1 'uniform'
 
+    # ---- what the current phase trains on
     @property
     def held(self) -> int:
-        return held_item_shard(self.rank, self.sub_epoch, self.world)
+        return stratum_of(self.rank, self.phase, self.world)
+
+    @property
+    def items(self):
+        return self.slots[slot_of(self.phase) if self.world > 1 else 0][0]
+
+    @property
+    def adam(self):
+        if self.user_adam is None:
+            return None
+        sl = self.slots[slot_of(self.phase) if self.world > 1 else 0]
+        return [self.user_adam[0], self.user_adam[1], sl[1], sl[2]]
 
     def run_block(self, user_ids_local, item_ids_local, n_steps, loss_out=None):
-        """n_steps steps on links of block (rank, held): LOCAL ids (id // world) of the two shards"""
+        """n_steps steps on links of block (rank, held): LOCAL ids (user // world, item // M)"""
         return self.step.run(self.users, self.items, user_ids_local, item_ids_local, n_steps, adam_state=self.adam,
                              loss_out=loss_out)
 
     def run_block_host(self, user_ids_host, item_ids_host, n_steps, loss_out_host=None):
         return self.step.run_host(self.users, self.items, user_ids_host, item_ids_host, n_steps, loss_out_host)
 
-    def rotate(self):
-        """end of a sub-epoch: my item shard (and its optimizer state) goes to rank - 1, rank + 1's comes to me"""
-        self._moving, self._spare = ring_rotate(self._moving, self._spare, self.rank, self.world)
-        self.items = self._moving[0]
-        if self.adam is not None:
-            self.adam[2], self.adam[3] = self._moving[1], self._moving[2]
-        self.sub_epoch += 1
+    # ---- the pipelined rotation
+    def _flag(self, rank: int, which: int) -> int:
+        """address of flag word `which` (0 = arrived, 1 = credit) in `rank`'s arena"""
+        return self.arena.ptrs[rank % self.world] + self.off_flags + 4 * which
+
+    def advance(self):
+        """End of a phase.  Enqueues, without any host wait: (side stream) push the stratum just trained into rank - 1's
+        incoming buffer once that buffer is free, then raise rank - 1's `arrived` and rank + 1's `credit`; (compute stream)
+        wait until the stratum of the new phase has arrived - it has had the whole previous phase to do so."""
+        import torch
+        from ._lib import check, lib
+        self.phase += 1
+        if self.world == 1:
+            return
+        p = self.phase
+        cur = torch.cuda.current_stream()
+        done = torch.cuda.Event()
+        done.record(cur)                                     # phase p - 1 has been trained
+        self.xfer.wait_event(done)
+        xs = C.c_void_p(self.xfer.cuda_stream)
+        if p >= 2:                                           # rank - 1 has finished SENDING the buffer I am about to overwrite
+            check(lib.nncf_peer_wait(C.c_void_p(self._flag(self.rank, 1)), p - 1, xs))
+        src_slot, dst_slot = slot_of(p - 1), slot_of(p + 1)
+        left = self.arena.ptrs[(self.rank - 1) % self.world]
+        for j in range(self.n_mov):
+            check(lib.nncf_peer_copy(C.c_void_p(left + (dst_slot * self.n_mov + j) * self.t_bytes),
+                                     C.c_void_p(self.arena.local_ptr + (src_slot * self.n_mov + j) * self.t_bytes),
+                                     self.t_bytes, xs))
+        check(lib.nncf_peer_signal(C.c_void_p(self._flag(self.rank - 1, 0)), p, xs))     # rank - 1: stratum of phase p + 1 is there
+        check(lib.nncf_peer_signal(C.c_void_p(self._flag(self.rank + 1, 1)), p, xs))     # rank + 1: my slot (p - 1) % 3 is free again
+        if p >= 2:                                           # phase p trains what rank + 1 pushed during phase p - 1
+            check(lib.nncf_peer_wait(C.c_void_p(self._flag(self.rank, 0)), p - 1, C.c_void_p(cur.cuda_stream)))
+
+    rotate = advance                                         # (name used by bench.py and the round-1 callers)
+
+    def drain(self):
+        """blocks the host until this rank's transfers have completed (end of training / before reading the buffers)"""
+        import torch
+        torch.cuda.current_stream().synchronize()
+        if self.xfer is not None:
+            self.xfer.synchronize()
 
     def train_epoch(self, blocks, rows_per_step=None):
-        """One stratified epoch: `blocks[v]` = (user_ids_local, item_ids_local) CUDA int32 arrays of block (rank, v).
-        Returns the list of per-step loss tensors.  Every rank calls it (the rotations pair up)."""
+        """One stratified epoch = M phases: `blocks[s]` = (user_ids_local, item_ids_local) CUDA int32 arrays of block
+        (rank, s).  Returns the per-phase loss tensors.  Every rank calls it (the transfers pair up)."""
         per = (rows_per_step or self.spec.replicas * self.spec.batch_size_p)
         losses = []
-        for _ in range(self.world):
+        for _ in range(self.m):
             u, c = blocks[self.held]
             n_steps = u.numel() // per
             if n_steps > 0:
                 losses.append(self.run_block(u, c, n_steps)["loss"])
-            self.rotate()
+            self.advance()
         return losses
 
     def close(self):
+        self.drain()
         self.step = None
+        self.slots = None
+        self.arena.close()

@@ -703,13 +703,14 @@ def given_eval(user_emb, item_emb, pairs, topk=-1):
     unweighted means rounded to 16 dp (:286-294)."""
     pairs = np.asarray(pairs)
     pred = np.sum(user_emb[pairs[:, 0]] * item_emb[pairs[:, 1]], axis=1)
-    ap, auc = [], []
+    ap, rc, pr, auc = [], [], [], []
     for u in np.unique(pairs[:, 0]):
         sel = pairs[:, 0] == u
         f = eval_multiple_original if topk == -1 else eval_multiple
-        a, _, _ = f(pairs[sel, 2], pred[sel], topk)
-        ap.append(a); auc.append(auc_score(pairs[sel, 2], pred[sel]))
-    return {"map": round(float(np.mean(ap)), 16), "auc": round(float(np.mean(auc)), 16)}
+        a, r, p = f(pairs[sel, 2], pred[sel], topk)
+        ap.append(a); rc.append(r); pr.append(p); auc.append(auc_score(pairs[sel, 2], pred[sel]))
+    return {"map": round(float(np.mean(ap)), 16), "recall": round(float(np.mean(rc)), 16),
+            "precision": round(float(np.mean(pr)), 16), "auc": round(float(np.mean(auc)), 16)}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -740,6 +741,72 @@ def baseline_neg_shared_sgd_step(EU, EV, uid, cid, neg_loss_weight, lr):
     np.add.at(EU, uid, -lr * dU)
     np.add.at(EV, cid, -lr * dV)
     return float(loss) / B
+
+
+def baseline_neg_shared_step(EU, EV, uid, cid, loss, neg_loss_weight, gamma, lr, u_reg=0.0, norm=False, replicas=1):
+    """The reference's CPU step for any of the four neg_shared losses (float32, sparse SGD in place), `replicas` batches
+    of B = len(uid) / replicas links computed against ONE snapshot of the tables with their updates summed - what bench.py's
+    GPU arm calls a step (replicas = 1 is the reference's sequential loop).  Per batch: gather, one sgemm for S
+    (interaction_dot.py:100-103), loss + dL/dS element-wise (utils/objectives.py:78-117), two sgemms for dU / dV,
+    l2-normalise forward / backward when `norm` (model_framework.py:62-63,109-111), activity regulariser on the raw user
+    rows (utils/utilities.py:129-135).  Returns the mean loss of the batches."""
+    f32 = np.float32
+    n = uid.shape[0]
+    B = n // replicas
+    upd = []
+    total = 0.0
+    for r in range(replicas):
+        u, c = uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B]
+        U_raw = EU[u]; V_raw = EV[c]
+        if norm:
+            iu = (1.0 / np.sqrt(np.maximum(np.sum(U_raw * U_raw, axis=1, keepdims=True), 1e-12))).astype(f32)
+            iv = (1.0 / np.sqrt(np.maximum(np.sum(V_raw * V_raw, axis=1, keepdims=True), 1e-12))).astype(f32)
+            U, V = U_raw * iu, V_raw * iv
+        else:
+            U, V = U_raw, V_raw
+        S = U @ V.T
+        diag = np.arange(B)
+        if loss == "skip-gram":
+            w = f32(neg_loss_weight / (B - 1.0))
+            sg = 1.0 / (1.0 + np.exp(-S))
+            ls = np.log1p(np.exp(-np.abs(S))) + np.maximum(S, 0)      # softplus(S) = -log sigmoid(-S)
+            L = (w * (ls.sum() - ls[diag, diag].sum()) + (ls[diag, diag] - S[diag, diag]).sum()) / B
+            G = sg * w
+            G[diag, diag] = sg[diag, diag] - 1.0
+            G /= f32(B)
+        elif loss == "mse":
+            w = f32(neg_loss_weight / (B - 1.0))
+            T = S.copy(); T[diag, diag] -= 1.0
+            W = np.full_like(S, w); W[diag, diag] = 1.0
+            L = float(np.sum(W * T * T)) / B
+            G = (2.0 * W * T / f32(B)).astype(f32)
+        else:
+            D = S[diag, diag][None, :] - S                            # (B,) - (B,B): D[i,j] = S[j,j] - S[i,j]  (:92,:97)
+            if loss == "log-loss":
+                x = -f32(gamma) * D
+                L = float(np.mean(np.log1p(np.exp(-np.abs(x))) + np.maximum(x, 0)))
+                A = (-f32(gamma) / (1.0 + np.exp(-x)) / f32(B * B)).astype(f32)
+            else:                                                     # max-margin (:91-94)
+                M = np.full_like(S, f32(gamma)); M[diag, diag] = 0.0
+                T = M - D
+                L = float(np.mean(np.maximum(T, 0.0)))
+                A = (-(T > 0).astype(f32) / f32(B * B))
+            G = -A
+            G[diag, diag] += A.sum(axis=0)
+        dU = G @ V
+        dV = G.T @ U
+        if norm:
+            dU = (dU - U * np.sum(dU * U, axis=1, keepdims=True)) * iu
+            dV = (dV - V * np.sum(dV * V, axis=1, keepdims=True)) * iv
+        if u_reg:
+            L += float(u_reg * np.sum(np.mean(U_raw * U_raw, axis=0)))
+            dU = dU + f32(2.0 * u_reg / B) * U_raw
+        total += float(L)
+        upd.append((u, c, dU, dV))
+    for u, c, dU, dV in upd:                                          # every batch saw the same snapshot
+        np.add.at(EU, u, (-lr * dU).astype(f32))
+        np.add.at(EV, c, (-lr * dV).astype(f32))
+    return total / replicas
 
 
 def baseline_whole_eval_block(U, V, k):

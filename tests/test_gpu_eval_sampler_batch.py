@@ -112,7 +112,8 @@ def test_topk_large_property_check():
         assert float(s_all[mask].max()) <= float(kth) + 1e-4
 
 
-def test_given_eval_matches_oracle():
+@pytest.mark.parametrize("topk", [-1, 5, 50])
+def test_given_eval_matches_oracle(topk):
     from nncf_b200.ops import score_pairs, eval_given
     rng = np.random.RandomState(3)
     nu, ni, d = 50, 80, 50
@@ -124,15 +125,17 @@ def test_given_eval_matches_oracle():
         t = (rng.uniform(size=m) < 0.3).astype(np.int64); t[0] = 1; t[1] = 0
         pairs += [(u, i, tt) for i, tt in zip(its, t)]
     pairs = np.array(pairs, dtype=np.int64)
-    ref = O.given_eval(U.astype(np.float64), V.astype(np.float64), pairs, -1)
+    ref = O.given_eval(U.astype(np.float64), V.astype(np.float64), pairs, topk)   # k = 50 > every list: ranked whole
     tU, tV = torch.from_numpy(U).cuda(), torch.from_numpy(V).cuda()
     sc = score_pairs(tU, tV, torch.from_numpy(pairs[:, 0]).cuda(), torch.from_numpy(pairs[:, 1]).cuda())
     np.testing.assert_allclose(sc.cpu().numpy(), np.sum(U[pairs[:, 0]] * V[pairs[:, 1]], axis=1), rtol=1e-5, atol=1e-5)
     counts = np.bincount(pairs[:, 0], minlength=nu)
     indptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-    out = eval_given(sc, torch.from_numpy(pairs[:, 2]).cuda(), torch.from_numpy(indptr).cuda()).cpu().numpy()
+    out = eval_given(sc, torch.from_numpy(pairs[:, 2]).cuda(), torch.from_numpy(indptr).cuda(), topk).cpu().numpy()
     assert abs(out[:, 0].mean() - ref["map"]) < 1e-5
     assert abs(out[:, 1].mean() - ref["auc"]) < 1e-5
+    assert abs(out[:, 2].mean() - ref["recall"]) < 1e-5
+    assert abs(out[:, 3].mean() - ref["precision"]) < 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ sampler

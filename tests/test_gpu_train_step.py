@@ -465,3 +465,35 @@ def test_interaction_bias_matches_oracle(scheme, loss, norm, bias, precision):
         assert np.all(tU.cpu().numpy()[:, d] == 0)
     if bias == "user":
         assert np.all(tV.cpu().numpy()[:, d + 1] == 0)
+
+
+@pytest.mark.parametrize("split", ["1", "2", "4", "8"])
+@pytest.mark.parametrize("optimizer,u_reg", [("sgd", 0.0), ("sgd", 1.0), ("lazy_adam", 1.0)])   # u_reg = 1: the regulariser's gradient is as large as the loss's
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
+def test_split_sweep_and_folded_regulariser(scheme, optimizer, u_reg, split, monkeypatch):
+    """Small steps (R = 1, the reference's sequential loop) split every owner block's sweep over several CTAs that ADD their
+    partial gradient blocks (bulk reductions into the table in the fused SGD mode, red.global.add into the zeroed blocks for
+    lazy Adam); the activity regulariser (ref: utils/utilities.py:129-135) is folded into the two-launch step: loss term
+    in the gather, gradient in the drain.  Any split must reproduce the oracle: loss, table update / Adam first moment."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    monkeypatch.setenv("NNCF_SPLIT", split)
+    B, d, nu, ni, lr = 512, 128, 700, 260, 0.05
+    EU, EV = _tables(nu, ni, d, seed=31)
+    rng = np.random.RandomState(17)
+    uid = rng.randint(0, nu, size=B).astype(np.int32)
+    cid = rng.randint(0, ni, size=B).astype(np.int32)
+    ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid, cid, scheme, "skip-gram", 128.0, 10.0, u_reg=u_reg)
+    spec = StepSpec(scheme=scheme, loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer=optimizer,
+                    learn_rate=lr, neg_loss_weight=128.0, loss_gamma=10.0, u_reg=u_reg)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    st = [torch.zeros_like(tU), torch.zeros_like(tU), torch.zeros_like(tV), torch.zeros_like(tV)] if optimizer == "lazy_adam" else None
+    out = FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), 1, adam_state=st)
+    torch.cuda.synchronize()
+    assert abs(float(out["loss"][0]) - ref["loss"]) <= 1e-2 * abs(ref["loss"])
+    if optimizer == "sgd":
+        assert _rel(tU.cpu().numpy() - EU, -lr * ref["dEU"]) <= 1e-2
+        assert _rel(tV.cpu().numpy() - EV, -lr * ref["dEV"]) <= 1e-2
+    else:
+        # first Adam step: m = (1 - beta1) * g on the touched rows (duplicates summed)
+        assert _rel(st[0].cpu().numpy(), 0.1 * ref["dEU"]) <= 1e-2
+        assert _rel(st[2].cpu().numpy(), 0.1 * ref["dEV"]) <= 1e-2

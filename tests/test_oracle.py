@@ -293,3 +293,24 @@ def test_golden_fixtures():
     r = O.evaluate_mat(g["ev_truth"], g["ev_pred"], 10)
     assert r["map"] == pytest.approx(float(g["ev_map"]), rel=1e-12)
     assert r["recall"] == pytest.approx(float(g["ev_recall"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("loss", ["skip-gram", "mse", "log-loss", "max-margin"])
+@pytest.mark.parametrize("norm", [False, True])
+def test_cpu_baseline_step_equals_checker(loss, norm):
+    """bench.py's CPU arm (float32, sparse, in place, R batches on one snapshot) against the fp64 checker step_matmul"""
+    rng = np.random.RandomState(5)
+    nu, ni, B, d, R, lr = 90, 70, 24, 16, 3, 0.1
+    EU = rng.uniform(-0.5, 0.5, size=(nu, d)).astype(np.float32); EV = rng.uniform(-0.5, 0.5, size=(ni, d)).astype(np.float32)
+    uid = rng.randint(0, nu, size=R * B); cid = rng.randint(0, ni, size=R * B)
+    lam, gamma = (8.0, 10.0) if loss == "mse" else (128.0, 0.1 if loss == "max-margin" else 10.0)
+    dU = np.zeros((nu, d)); dV = np.zeros((ni, d)); L = 0.0
+    for r in range(R):
+        ref = O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B],
+                            "neg_shared", loss, lam, gamma, u_reg=1e-2, norm_u=norm, norm_v=norm)
+        dU += ref["dEU"]; dV += ref["dEV"]; L += ref["loss"] / R
+    U1, V1 = EU.copy(), EV.copy()
+    got = O.baseline_neg_shared_step(U1, V1, uid, cid, loss, lam, gamma, lr, u_reg=1e-2, norm=norm, replicas=R)
+    assert abs(got - L) <= 1e-4 * abs(L)
+    np.testing.assert_allclose(U1 - EU, -lr * dU, rtol=2e-3, atol=2e-6)
+    np.testing.assert_allclose(V1 - EV, -lr * dV, rtol=2e-3, atol=2e-6)

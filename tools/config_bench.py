@@ -1,10 +1,11 @@
-"""Times one training configuration (device-resident ids): python tools/config_bench.py scheme loss B d R steps [norm] [adam]"""
+"""Times one training configuration (device-resident ids): python tools/config_bench.py scheme loss B d R steps [norm] [adam] [ureg]"""
 import sys, torch
 sys.path.insert(0, '.')
 from nncf_b200.ops import FusedStep, StepSpec
 scheme, loss, B, d, R, steps = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]), int(sys.argv[6])
 norm = "norm" in sys.argv[7:]
 adam = "adam" in sys.argv[7:]
+u_reg = 1e-6 if "ureg" in sys.argv[7:] else 0.0          # the reference's default activity regulariser
 nu = ni = 1_000_000
 g = torch.Generator(device="cuda").manual_seed(0)
 EU = (torch.rand((nu, d), device="cuda", generator=g) - 0.5) * 0.1
@@ -14,7 +15,7 @@ uid = torch.randint(0, nu, (n,), device="cuda", generator=g, dtype=torch.int32)
 cid = torch.randint(0, ni if scheme != "group_neg_shared" else 20000, (n,), device="cuda", generator=g, dtype=torch.int32)
 lam, gamma = (8.0 if loss == "mse" else 128.0), (0.1 if loss == "max-margin" else 10.0)
 st = FusedStep(StepSpec(scheme=scheme, loss=loss, precision="bf16", batch_size_p=B, dim=d, norm_u=norm, norm_v=norm, optimizer=("lazy_adam" if adam else "sgd"),
-                        learn_rate=(0.001 if adam else 0.01), replicas=R, neg_loss_weight=lam, loss_gamma=gamma))
+                        learn_rate=(0.001 if adam else 0.01), replicas=R, neg_loss_weight=lam, loss_gamma=gamma, u_reg=u_reg))
 state = [torch.zeros_like(EU), torch.zeros_like(EU), torch.zeros_like(EV), torch.zeros_like(EV)] if adam else None
 st.run(EU, EV, uid, cid, 5, adam_state=state)
 torch.cuda.synchronize()

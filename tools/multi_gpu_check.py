@@ -3,8 +3,9 @@
 Checks the row-sharded training step (peer-memory gather + remote red.add + device barriers) against the CPU oracle:
 after one synchronous step in which every rank contributes its own batch, the GLOBAL tables must equal
 table_before - lr * sum_over_ranks(dE_rank), every gradient taken on the same snapshot.
-Then the stratified (DSGD) schedule: one epoch with rotating item shards must equal the oracle's SEQUENTIAL pass over the
-same blocks (the blocks of a sub-epoch are disjoint in users and items, so their order does not matter)."""
+Then the stratified (DSGD) schedule with its pipelined stratum rotation (peer copies on side streams + flag hand-offs over
+CUDA IPC): two epochs must equal the oracle's SEQUENTIAL pass over the same blocks (the blocks of a phase are disjoint in
+users and items, so their order does not matter)."""
 import os
 import sys
 
@@ -15,8 +16,8 @@ import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import nncf_oracle as O   # noqa: E402  (test tool: the oracle is the checker)
 from nncf_b200.ops import StepSpec    # noqa: E402
-from nncf_b200.parallel import (ShardedTrainer, StratifiedTrainer, held_item_shard, partition_links_by_block, shard_rows,  # noqa: E402
-                                sharded_whole_eval)
+from nncf_b200.parallel import (ShardedTrainer, StratifiedTrainer, n_item_strata, partition_links_by_stratum, shard_rows,  # noqa: E402
+                                sharded_whole_eval, stratum_of)
 
 
 def main():
@@ -62,33 +63,41 @@ def main():
         assert np.all(np.isfinite(out["loss"].cpu().numpy()))
         dist.barrier()
         tr.close()
-    # ---- stratified schedule against the sequential oracle
+    # ---- stratified schedule (pipelined rotation) against the sequential oracle
     for opt in ("sgd", "lazy_adam"):
-        nu, ni, B, d, lr = 1003, 777, 128, 64, 0.05
+        nu, ni, B, d, lr, epochs = 1003, 777, 128, 64, 0.05, 2
+        m = n_item_strata(world)
         spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="fp32", batch_size_p=B, dim=d, optimizer=opt,
                         learn_rate=lr, replicas=1)
         st = StratifiedTrainer(spec, nu, ni, rank, world, seed=11)
+        dist.barrier()
         EU = np.zeros((nu, d)); EV = np.zeros((ni, d))
         for s_ in range(world):                                # every rank can rebuild every shard's initial values
-            EU[s_::world] = StratifiedTrainer._init_shard(shard_rows(nu, s_, world), d, 11 + 1000 * s_, "cuda")[:shard_rows(nu, s_, world)].cpu().numpy()
-            EV[s_::world] = StratifiedTrainer._init_shard(shard_rows(ni, s_, world), d, 12 + 1000 * s_, "cuda")[:shard_rows(ni, s_, world)].cpu().numpy()
+            n = shard_rows(nu, s_, world)
+            EU[s_::world] = StratifiedTrainer._init_shard(n, d, 11 + 1000 * s_, "cuda")[:n].cpu().numpy()
+        for s_ in range(m):
+            n = shard_rows(ni, s_, m)
+            EV[s_::m] = StratifiedTrainer._init_shard(n, d, 12 + 1000 * s_, "cuda")[:n].cpu().numpy()
         g = np.random.RandomState(77)
-        train = np.stack([g.randint(0, nu, 6000), g.randint(0, ni, 6000), np.ones(6000, dtype=np.int64)], 1)
-        blocks = partition_links_by_block(train, rank, world)
+        train = np.stack([g.randint(0, nu, 12000), g.randint(0, ni, 12000), np.ones(12000, dtype=np.int64)], 1)
+        blocks = partition_links_by_stratum(train, rank, world)
         dev_blocks = [(torch.from_numpy(np.ascontiguousarray(b[:, 0])).cuda(), torch.from_numpy(np.ascontiguousarray(b[:, 1])).cuda()) for b in blocks]
-        st.train_epoch(dev_blocks)
+        for _ in range(epochs):
+            st.train_epoch(dev_blocks)
+        st.drain()
+        dist.barrier()
         torch.cuda.synchronize()
-        assert st.held == rank                                  # item shards are home again
-        # oracle: sequential pass over the same blocks
+        assert st.held == stratum_of(rank, 0, world)            # the strata are home again
+        # oracle: sequential pass over the same blocks, phase-major
         mU = np.zeros_like(EU); vU = np.zeros_like(EU); mV = np.zeros_like(EV); vV = np.zeros_like(EV)
         t_adam = {}
-        for t in range(world):
+        for p in range(epochs * m):
             for r in range(world):
-                v = held_item_shard(r, t, world)
-                b = partition_links_by_block(train, r, world)[v]
+                v = stratum_of(r, p, world)
+                b = partition_links_by_stratum(train, r, world)[v]
                 for k0 in range(0, (len(b) // B) * B, B):
                     u = b[k0:k0 + B, 0].astype(np.int64) * world + r
-                    c = b[k0:k0 + B, 1].astype(np.int64) * world + v
+                    c = b[k0:k0 + B, 1].astype(np.int64) * m + v
                     ref = O.step_matmul(EU, EV, u, c, "neg_shared", "skip-gram", 128.0, 10.0)
                     if opt == "sgd":
                         EU -= lr * ref["dEU"]; EV -= lr * ref["dEV"]
@@ -97,13 +106,18 @@ def main():
                         EU, mU, vU = O.lazy_adam_sparse(EU, mU, vU, u, ref["dEU"], lr, t_adam[r])
                         EV, mV, vV = O.lazy_adam_sparse(EV, mV, vV, c, ref["dEV"], lr, t_adam[r])
         mineU = st.users[:shard_rows(nu, rank, world)].cpu().numpy().astype(np.float64)
-        mineV = st.items[:shard_rows(ni, rank, world)].cpu().numpy().astype(np.float64)
         eu = np.max(np.abs(mineU - EU[rank::world])) / np.max(np.abs(EU))
-        ev = np.max(np.abs(mineV - EV[rank::world])) / np.max(np.abs(EV))
+        ev = 0.0
+        for k in (0, 1):                                        # the stratum held for the current phase and the one that arrived for the next
+            s_ = stratum_of(rank, st.phase + k, world)
+            n = shard_rows(ni, s_, m)
+            mine = st.slots[(st.phase + k) % 3][0][:n].cpu().numpy().astype(np.float64)
+            ev = max(ev, np.max(np.abs(mine - EV[s_::m])) / np.max(np.abs(EV)))
         good = eu <= 1e-3 and ev <= 1e-3
         ok &= good
-        print("rank %d stratified %s: rel err users %.2e items %.2e -> %s" % (rank, opt, eu, ev, "OK" if good else "FAIL"), flush=True)
+        print("rank %d stratified (pipelined) %s: rel err users %.2e items %.2e -> %s" % (rank, opt, eu, ev, "OK" if good else "FAIL"), flush=True)
         dist.barrier()
+        st.close()
     # user-sharded whole@k: global metrics must equal the single-process value
     rng = np.random.RandomState(3)
     nU, nI, k = 500, 2000, 20

@@ -29,12 +29,12 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&dU, nel * 4)); CK(cudaMalloc(&dV, nel * 4));
   CK(cudaMalloc(&cU, R * rp * 4)); CK(cudaMalloc(&cV, R * rp * 4)); CK(cudaMalloc(&sp, R * rp * 4));
   CK(cudaMalloc(&loss, R * 8)); CK(cudaMemset(loss, 0, R * 8));
-  size_t ndbg = (size_t)nblk * 2 * R * 64;
+  size_t ndbg = (size_t)nblk * 8 * 2 * R * 64;
   CK(cudaMalloc(&dbg, ndbg * 8)); CK(cudaMemset(dbg, 0, ndbg * 8));
   ScoreTcArgs a{};
   a.Uimg = U; a.Vimg = V; a.dU = dU; a.dV = dV; a.corrU = cU; a.corrV = cV; a.spos = sp; a.loss = loss;
   a.rows_pad = rp; a.B = B; a.scheme = NNCF_SCHEME_NEG_SHARED; a.loss_kind = NNCF_LOSS_SKIP_GRAM; a.lambda = 128.f; a.gamma = 10.f;
-  a.dbg = dbg;
+  a.dbg = dbg; a.split = argc > 6 ? atoi(argv[6]) : 1;
   if (fuse) {
     const int NR = 1000000;
     float *tu, *tv; int *iu, *iv; unsigned int* lc;
@@ -61,12 +61,12 @@ int main(int argc, char** argv) {
     printf("resident CTAs per SM: %d (dyn smem %zu B, static %zu B, regs %d, maxdyn %d, carveout %d)\n", nb, (size_t)C::kSmemBytes, fa.sharedSizeBytes, fa.numRegs, fa.maxDynamicSharedSizeBytes, fa.preferredShmemCarveout);
     for (size_t sz = 100 * 1024; sz <= C::kSmemBytes; sz += 1024) { int q = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, score_grad_tc_kernel<NSUB, 0, false>, kScoreThreads, sz); if (q < 2) { printf("  occupancy drops to %d at dyn smem %zu\n", q, sz); break; } } }
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int it = 0; it < 3; ++it) score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
+  for (int it = 0; it < 3; ++it) score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk * a.split, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
   CK(cudaDeviceSynchronize());
   cudaEventRecord(e0);
   for (int it = 0; it < 20; ++it) {
     if (touch) touch_images<<<1184, 256>>>((uint4*)U, (uint4*)V, img / 16, it);
-    score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
+    score_grad_tc_kernel<NSUB, 0, false><<<dim3(nblk * a.split, 2, R), kScoreThreads, C::kSmemBytes>>>(a);
   }
   cudaEventRecord(e1);
   CK(cudaDeviceSynchronize());
