@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""bench.py — positive links/sec of the neg_shared training loop on the C3 workload (synthetic 1M users x 1M items,
-100M power-law links, dim 128, skip-gram, batch_size_p 512), plus whole@k users/sec as an extra.
+"""bench.py — positive links/sec of the neg_shared training loop (BASELINE.json's metric) on synthetic power-law data.
 
-  python bench.py --gpus N --steps K --warmup W            # this framework (CUDA path through the C-ABI)
-  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (NumPy transcription)
+  python bench.py --gpus N --steps K --warmup W                    # this framework (CUDA path through the C-ABI)
+  python bench.py --impl reference --steps K --warmup W            # the reference's CPU path (NumPy transcription)
+  python bench.py --workload c5 ...                                # BASELINE config 5 instead of config 3 (default c3)
 
-One "step" = one pass of the hot path over one device batch = R replicas x batch_size_p positive links
-(R independent neg_shared batches computed against one table snapshot: synchronous data-parallel virtual workers;
-R = 1 is the reference's strictly sequential loop and is reported alongside as `sequential`).
-Prints ONE JSON line on rank 0.
+Workloads (BASELINE.json configs):
+  c3  synthetic 1M users x 1M items, 100M power-law links, dim 128, neg_shared skip-gram, batch_size_p 512, u_reg 1e-6
+  c5  synthetic neg_shared max-margin, batch 16,384, dim 256, l2-normalised rows (tensor-core-bound score contraction)
+
+One "step" = one pass of the hot path over one device batch = R replicas x batch_size_p positive links: R independent
+neg_shared batches computed against ONE snapshot of the tables, their sparse updates summed (synchronous data-parallel
+virtual workers on one GPU).  BOTH arms run exactly this step (the CPU arm computes its R batches one after the other
+against the snapshot); R = 1 is the reference's strictly sequential loop and is reported beside the headline in
+`config.reference_semantics` / `sequential`.  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
@@ -23,13 +28,25 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "C3: synthetic 1M users x 1M items, 100M power-law links, dim 128, neg_shared skip-gram, batch_size_p 512"
-N_USERS = N_ITEMS = 1_000_000
-N_LINKS = 100_000_000
-DIM = 128
-BATCH = 512
-LAMBDA = 128.0
-LR = 0.01
+WORKLOADS = {
+    "c3": dict(name="C3: synthetic 1M users x 1M items, 100M power-law links, dim 128, neg_shared skip-gram, batch_size_p 512",
+               n_users=1_000_000, n_items=1_000_000, links=100_000_000, dim=128, batch=512, loss="skip-gram", lam=128.0,
+               gamma=10.0, lr=0.01, norm=False, replicas=37, u_reg=1e-6, cpu_steps=150),
+    "c5": dict(name="C5: synthetic neg_shared max-margin, batch 16384, dim 256, l2-normalised rows, 1M users x 1M items",
+               n_users=1_000_000, n_items=1_000_000, links=20_000_000, dim=256, batch=16384, loss="max-margin", lam=128.0,
+               gamma=0.1, lr=0.01, norm=True, replicas=1, u_reg=1e-6, cpu_steps=8),
+}
+METRIC = "positive links/sec train (neg_shared)"
+
+
+def workload_config(w, replicas):
+    """`config` of the JSON line: the same dict in both arms (what is measured), arm-specific facts live in `arm`"""
+    return {"workload": w["name"], "batch_size_p": w["batch"], "dim": w["dim"], "loss": w["loss"], "replicas_per_step": replicas,
+            "links_per_step_per_gpu": replicas * w["batch"], "optimizer": "sparse SGD", "u_reg": w["u_reg"],
+            "l2_normalised_rows": w["norm"],
+            "semantics": "each step = R independent neg_shared batches against one table snapshot, updates summed; "
+                         "R = 1 is the reference's sequential loop (reported in `sequential`)",
+            "l2": "inputs larger than L2: >= 1 GB of embedding tables, random power-law rows, batches never repeat within a pass"}
 
 
 def _peaks():
@@ -41,130 +58,134 @@ def _peaks():
         return {"hbm": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "src": "fallback"}
 
 
+def powerlaw_ids_np(n_ids, n_draws, exponent, perm_seed, draw_rng, offset=10.0):
+    """ids ~ p(rank) ∝ (rank + offset)^-exponent over a seeded random permutation of the id space (BASELINE.md §3);
+    NumPy only: the reference arm must not import the product package"""
+    p = np.power(np.arange(n_ids, dtype=np.float64) + offset, -exponent)
+    cdf = np.cumsum(p)
+    cdf /= cdf[-1]
+    ranks = np.minimum(np.searchsorted(cdf, draw_rng.random_sample(n_draws), side="right"), n_ids - 1)
+    return np.random.RandomState(perm_seed).permutation(n_ids)[ranks]
+
+
 # ----------------------------------------------------------------------------------------------------------------
-# synthetic data
+# synthetic data on the device (BASELINE.md §3)
 # ----------------------------------------------------------------------------------------------------------------
-def synth_links_device(n_links, n_users, n_items, seed, torch):
-    """int32 [n_links, 3] rows (user, item, 1) on the device: items ~ (rank+10)^-1.0, users ~ (rank+10)^-0.8 over
-    seeded permutations of the id spaces; duplicates kept (the reference never dedupes)."""
+def _draw_powerlaw(torch, g, n_ids, expo, perm_seed, n, offset):
+    p = torch.pow(torch.arange(n_ids, device="cuda", dtype=torch.float64) + offset, -expo)
+    cdf = torch.cumsum(p, 0)
+    cdf = cdf / cdf[-1]
+    r = torch.searchsorted(cdf, torch.rand(n, device="cuda", generator=g, dtype=torch.float64), right=True)
+    r.clamp_(max=n_ids - 1)
+    perm = torch.randperm(n_ids, device="cuda", generator=torch.Generator(device="cuda").manual_seed(perm_seed))
+    return perm[r].to(torch.int32)
+
+
+def synth_ids_device(n_links, n_users, n_items, seed, torch, user_offset=10.0, item_offset=10.0):
+    """(uid, cid) int32 [n_links]: items ~ (rank + 10)^-1.0, users ~ (rank + 10)^-0.8 over seeded permutations of the id
+    spaces; duplicates kept (the reference never dedupes).  For a stratified block the id spaces are the LOCAL rows of a
+    user shard / item stratum, which are (about) a power law again with the offset divided by the number of shards."""
     g = torch.Generator(device="cuda").manual_seed(seed)
-
-    def draw(n_ids, expo, perm_seed, n):
-        p = torch.pow(torch.arange(n_ids, device="cuda", dtype=torch.float64) + 10.0, -expo)
-        cdf = torch.cumsum(p, 0)
-        cdf = cdf / cdf[-1]
-        r = torch.searchsorted(cdf, torch.rand(n, device="cuda", generator=g, dtype=torch.float64), right=True)
-        r.clamp_(max=n_ids - 1)
-        perm = torch.randperm(n_ids, device="cuda", generator=torch.Generator(device="cuda").manual_seed(perm_seed))
-        return perm[r].to(torch.int32)
-
-    out = torch.empty((n_links, 3), dtype=torch.int32, device="cuda")
-    chunk = 20_000_000
-    for s in range(0, n_links, chunk):
-        n = min(chunk, n_links - s)
-        out[s:s + n, 0] = draw(n_users, 0.8, 124, n)
-        out[s:s + n, 1] = draw(n_items, 1.0, 123, n)
-    out[:, 2] = 1
-    return out
-
-
-def synth_block_device(n_links, n_users_local, n_items_local, world, seed, torch):
-    """links of ONE stratified block with LOCAL ids: the rank's shard of a power-law id space is itself (about) a power
-    law over its local rows, p(j) ∝ (j + 10 / N)^-a (the ids of shard s are every N-th rank of a random permutation)"""
-    g = torch.Generator(device="cuda").manual_seed(seed)
-
-    def draw(n_ids, expo, perm_seed, n):
-        p = torch.pow(torch.arange(n_ids, device="cuda", dtype=torch.float64) + 10.0 / world, -expo)
-        cdf = torch.cumsum(p, 0)
-        cdf = cdf / cdf[-1]
-        r = torch.searchsorted(cdf, torch.rand(n, device="cuda", generator=g, dtype=torch.float64), right=True)
-        r.clamp_(max=n_ids - 1)
-        perm = torch.randperm(n_ids, device="cuda", generator=torch.Generator(device="cuda").manual_seed(perm_seed))
-        return perm[r].to(torch.int32)
-
     uid = torch.empty(n_links, dtype=torch.int32, device="cuda")
     cid = torch.empty(n_links, dtype=torch.int32, device="cuda")
     chunk = 20_000_000
     for s in range(0, n_links, chunk):
         n = min(chunk, n_links - s)
-        uid[s:s + n] = draw(n_users_local, 0.8, 124, n)
-        cid[s:s + n] = draw(n_items_local, 1.0, 123, n)
+        uid[s:s + n] = _draw_powerlaw(torch, g, n_users, 0.8, 124, n, user_offset)
+        cid[s:s + n] = _draw_powerlaw(torch, g, n_items, 1.0, 123, n, item_offset)
     return uid, cid
 
 
-class ClockSampler(threading.Thread):
-    """samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+# ----------------------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe): NVML directly, one synchronous sample on either side of the timed region (a 0.4 ms
+# region is shorter than any polling interval) plus a polling thread for the longer ones
+# ----------------------------------------------------------------------------------------------------------------
+class Clocks:
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index = index
-        self.rows = []
-        self.stop_flag = False
-
-    def run(self):
-        # NVML directly (nvidia_ml_py): a sample costs ~0.1 ms, so even a 50 ms timed region gets dozens of samples;
-        # rows have the layout of the nvidia-smi query below, which is the fallback
+        self.index, self.rows, self.h, self.nv, self.max_mhz = index, [], None, None, None
+        self._stop, self._thread = False, None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            bits = [("hw_slowdown", getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8)),
-                    ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40)),
-                    ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20)),
-                    ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4))]
-            reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
-            while not self.stop_flag:
-                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
-                r = reasons_fn(h)
-                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
-                self.rows.append([str(sm), str(mx), "%.1f" % pw] + ["Active" if (r & b) else "Not Active" for _, b in bits])
-                time.sleep(0.002)
-            return
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = [getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8), getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                         getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)]
+            self.reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
         except Exception:
-            pass
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
+            self.nv = None
+
+    def sample(self):
+        if self.nv is not None:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                nv = self.nv
+                r = self.reasons_fn(self.h)
+                self.rows.append((float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)), nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0,
+                                  [bool(r & b) for b in self.bits]))
+                return
             except Exception:
                 pass
-            time.sleep(0.05)
+        try:   # fallback: nvidia-smi (slow, ~50 ms)
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+            self.max_mhz = float(o[1])
+            self.rows.append((float(o[0]), float(o[2]), [x.strip() == "Active" for x in o[3:7]]))
+        except Exception:
+            pass
+
+    def start(self):
+        self._stop = False
+
+        def poll():
+            while not self._stop:
+                self.sample()
+                time.sleep(0.001)
+        self._thread = threading.Thread(target=poll, daemon=True)
+        self._thread.start()
+
+    def stop(self):
+        self._stop = True
+        if self._thread is not None:
+            self._thread.join(timeout=2)
 
     def summary(self):
         if not self.rows:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in self.rows if len(r) >= 7)]
-        pw = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows), "power_w_max": max(pw) if pw else None}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unsampled"]}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = [n for i, n in enumerate(self.NAMES) if any(r[2][i] for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.rows),
+                "power_w_max": max(r[1] for r in self.rows)}
 
 
 # ----------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's path, NumPy transcription (oracle/), all host threads BLAS can use
+# CPU arm: the reference's path, NumPy transcription (oracle/), all host threads BLAS can use.  Same step as the GPU arm.
 # ----------------------------------------------------------------------------------------------------------------
-def cpu_links_per_sec(n_steps, warmup, n_rows=N_USERS):
+def cpu_links_per_sec(w, replicas, n_steps, warmup):
     from oracle import nncf_oracle as O
     rng = np.random.RandomState(7)
-    EU = rng.uniform(-0.05, 0.05, size=(n_rows, DIM)).astype(np.float32)
-    EV = rng.uniform(-0.05, 0.05, size=(n_rows, DIM)).astype(np.float32)
-    from nncf_b200.data_utils import powerlaw_ids
-    n = (n_steps + warmup) * BATCH
-    uid = powerlaw_ids(n_rows, n, 0.8, 124, rng).astype(np.int64)
-    cid = powerlaw_ids(n_rows, n, 1.0, 123, rng).astype(np.int64)
+    n_rows, d, B = w["n_users"], w["dim"], w["batch"]
+    EU = rng.uniform(-0.05, 0.05, size=(n_rows, d)).astype(np.float32)
+    EV = rng.uniform(-0.05, 0.05, size=(n_rows, d)).astype(np.float32)
+    per = replicas * B
+    n = (n_steps + warmup) * per
+    uid = powerlaw_ids_np(n_rows, n, 0.8, 124, rng).astype(np.int64)
+    cid = powerlaw_ids_np(n_rows, n, 1.0, 123, rng).astype(np.int64)
+
+    def step(s):
+        return O.baseline_neg_shared_step(EU, EV, uid[s * per:(s + 1) * per], cid[s * per:(s + 1) * per], w["loss"], w["lam"],
+                                          w["gamma"], w["lr"], u_reg=w["u_reg"], norm=w["norm"], replicas=replicas)
     for s in range(warmup):
-        O.baseline_neg_shared_sgd_step(EU, EV, uid[s * BATCH:(s + 1) * BATCH], cid[s * BATCH:(s + 1) * BATCH], LAMBDA, LR)
+        step(s)
     t0 = time.perf_counter()
     for s in range(warmup, warmup + n_steps):
-        O.baseline_neg_shared_sgd_step(EU, EV, uid[s * BATCH:(s + 1) * BATCH], cid[s * BATCH:(s + 1) * BATCH], LAMBDA, LR)
+        loss = step(s)
     dt = time.perf_counter() - t0
-    return n_steps * BATCH / dt, dt
+    assert np.isfinite(loss)
+    return n_steps * per / dt, dt
 
 
 _OUT = sys.stdout
@@ -174,19 +195,21 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20000))
-    v, dt = cpu_links_per_sec(steps, max(3, min(args.warmup, 50)))
+    w = WORKLOADS[args.workload]
+    R = args.replicas or w["replicas"]
+    steps = max(1, min(args.steps, 2000))
+    warm = max(1, min(args.warmup, 20))
+    v, dt = cpu_links_per_sec(w, R, steps, warm)
     cores = os.cpu_count()
     line = {
-        "impl": "reference", "metric": "positive links/sec train (neg_shared)", "value": v, "unit": "links/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup, "ms_per_step": dt / steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_size_p": BATCH, "dim": DIM, "optimizer": "sparse SGD",
-                   "note": "reference CPU path: Keras 1.2.2 / TF 1.0 / py2 cannot be installed offline -> NumPy "
-                           "transcription of the same step (oracle/nncf_oracle.py baseline_neg_shared_sgd_step), one "
-                           "batch of 512 links per step, strictly sequential"},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "links/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(w, R),
+        "arm": {"what": "reference CPU path: Keras 1.2.2 / TF 1.0 / py2 cannot be installed offline -> NumPy transcription of the "
+                        "same step (oracle/nncf_oracle.py baseline_neg_shared_step: BLAS sgemm + element-wise loss + np.add.at), "
+                        "the R batches of a step computed one after the other against the snapshot", "blas_threads": cores},
         "cpu_baseline": {"value": v, "unit": "links/s", "cores": cores, "kind": "port",
-                         "sample": "%d sequential neg_shared steps of 512 links on 1M x 128 fp32 tables" % steps},
+                         "sample": "%d steps of %d x %d links on %d x %d fp32 tables" % (steps, R, w["batch"], w["n_users"], w["dim"])},
         "e2e": {"value": v, "unit": "links/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -197,12 +220,23 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------------------------------------------
+def _time_steps(torch, fn):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from nncf_b200 import ops
     from nncf_b200.ops import FusedStep, StepSpec
 
+    w = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,53 +244,58 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     peaks = _peaks()
-    R, B, d = args.replicas, BATCH, DIM
+    R, B, d = (args.replicas or w["replicas"]), w["batch"], w["dim"]
+    NU, NI = w["n_users"], w["n_items"]
     links_per_step = R * B
+    n_links = args.links or w["links"]
 
-    # ---- resident state.  N = 1: the two 1M x 128 tables live on the GPU.  N > 1 (weak scaling: per-GPU work fixed, every
-    #      rank trains on its own links of the SAME global 1M x 1M problem):
-    #        stratified (default): DSGD schedule, tables sharded by row, rank r owns user shard r and the item shards rotate
-    #          round the ring between sub-epochs; every step touches local rows only (nncf_b200/parallel.py)
+    def make_spec(replicas=R, optimizer="sgd", lr=w["lr"], batch=B):
+        return StepSpec(scheme="neg_shared", loss=w["loss"], precision="bf16", batch_size_p=batch, dim=d, optimizer=optimizer,
+                        learn_rate=lr, replicas=replicas, neg_loss_weight=w["lam"], loss_gamma=w["gamma"], u_reg=w["u_reg"],
+                        norm_u=w["norm"], norm_v=w["norm"])
+
+    # ---- resident state.  N = 1: the two tables live on the GPU.  N > 1 (weak scaling: per-GPU work fixed, every rank trains
+    #      on its own links of the SAME global problem):
+    #        stratified (default): DSGD schedule with a pipelined stratum rotation (nncf_b200/parallel.py): rank r owns user
+    #          shard r, the items live in 2N strata, every step touches local rows only, the stratum of the next phase
+    #          arrives over NVLink (copy engines, peer mappings) while the current one is trained
     #        peer: rows read and updated in the owners' shards over NVLink peer memory inside the step kernels
-    #      Links are shuffled once on the device; np.random.shuffle semantics are exercised by the parity tests, the
-    #      order itself is not part of the timed hot path.
+    #      Links are shuffled once on the device; np.random.shuffle semantics are exercised by the parity tests, the order
+    #      itself is not part of the timed hot path.
     g = torch.Generator(device="cuda").manual_seed(7 + rank)
-    spec = StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="sgd",
-                    learn_rate=LR, replicas=R, neg_loss_weight=LAMBDA)
+    spec = make_spec()
     sharded = strat = None
-    n_links = args.links
     loss_buf = torch.empty(max(args.steps, args.warmup, 1) * R, dtype=torch.float32, device="cuda")
     pos = {"step": 0, "rot": 0}
     if world > 1 and args.parallelism == "stratified":
         from nncf_b200.parallel import StratifiedTrainer, shard_rows
-        strat = StratifiedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
+        strat = StratifiedTrainer(spec, NU, NI, rank, world, seed=7)
         step = strat.step
-        links_per_block = n_links // world
-        blocks = [synth_block_device(links_per_block, strat.rows_u, shard_rows(N_ITEMS, v, world), world,
-                                     2017 + rank * world + v, torch) for v in range(world)]
-        steps_per_pass = links_per_block // links_per_step          # steps until the item shards rotate
+        m = strat.m
+        links_per_block = n_links // m
+        blocks = [synth_ids_device(links_per_block, strat.rows_u, shard_rows(NI, s, m), 2017 + rank * m + s, torch,
+                                   user_offset=10.0 / world, item_offset=10.0 / m) for s in range(m)]
+        steps_per_pass = links_per_block // links_per_step          # steps of a phase
         assert steps_per_pass >= 1
-        tables = lambda: (strat.users, strat.items)                 # noqa: E731  (the item tensor changes at every rotation)
+        tables = lambda: (strat.users, strat.items)                 # noqa: E731  (the item buffer changes with the phase)
         ids_now = lambda: blocks[strat.held]                        # noqa: E731
 
         def end_of_pass():
-            strat.rotate()
+            strat.advance()
             pos["rot"] += 1
     else:
         if world > 1:
             from nncf_b200.parallel import ShardedTrainer
-            sharded = ShardedTrainer(spec, N_USERS, N_ITEMS, rank, world, seed=7)
+            sharded = ShardedTrainer(make_spec(), NU, NI, rank, world, seed=7)
             step, EU, EV = sharded.step, sharded.users.local, sharded.items.local
         else:
-            EU = (torch.rand((N_USERS, d), device="cuda", generator=g) - 0.5) * 0.1
-            EV = (torch.rand((N_ITEMS, d), device="cuda", generator=g) - 0.5) * 0.1
+            EU = (torch.rand((NU, d), device="cuda", generator=g) - 0.5) * 0.1
+            EV = (torch.rand((NI, d), device="cuda", generator=g) - 0.5) * 0.1
             step = FusedStep(spec)
-        train = synth_links_device(n_links, N_USERS, N_ITEMS, 2017 + rank, torch)
+        uid_all, cid_all = synth_ids_device(n_links, NU, NI, 2017 + rank, torch)
         perm = torch.randperm(n_links, device="cuda", generator=g)
-        train = ops.permute_rows(train, perm)
-        uid_all = train[:, 0].contiguous()
-        cid_all = train[:, 1].contiguous()
-        del train, perm
+        uid_all, cid_all = uid_all[perm].contiguous(), cid_all[perm].contiguous()
+        del perm
         steps_per_pass = n_links // links_per_step
         assert steps_per_pass >= 1
         tables = lambda: (EU, EV)                                   # noqa: E731
@@ -265,16 +304,18 @@ def run_ours(args):
         def end_of_pass():
             pass
 
-    def run_steps(k, start_step=None):
-        """k consecutive steps from the current position (wraps around the link array / moves to the next stratified
-        block, rotating the item shards, when a pass is exhausted)"""
+    def run_steps(k):
+        """k consecutive steps from the current position (wraps around the link array / moves on to the next stratified
+        phase when a pass is exhausted)"""
         done = 0
+        nbuf = loss_buf.numel() // R
         while done < k:
-            n = min(k - done, steps_per_pass - pos["step"])
+            n = min(k - done, steps_per_pass - pos["step"], nbuf - done % nbuf)
             off = pos["step"] * links_per_step
             u, c = ids_now()
             tu, tv = tables()
-            step.run(tu, tv, u[off:], c[off:], n, loss_out=loss_buf[done * R:])
+            step.run(tu, tv, u[off:], c[off:], n, loss_out=loss_buf[(done % nbuf) * R:],
+                     adam_state=(strat.adam if strat is not None else None))
             done += n
             pos["step"] += n
             if pos["step"] == steps_per_pass:
@@ -282,6 +323,9 @@ def run_ours(args):
                 end_of_pass()
 
     def barrier():
+        torch.cuda.synchronize()
+        if strat is not None:
+            strat.drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -294,66 +338,86 @@ def run_ours(args):
         return x
 
     # ---- value: device-resident throughput ------------------------------------------------------------------
-    run_steps(args.warmup, 0)
+    # priming (untimed, not one of the W warm-up steps): ~40 ms of the same steps bring the SM clocks up from idle and
+    # fill the L2-prefetch / programmatic-launch chain, so that a short driver run (K = 20) times the steady state
+    prime = min(max(200, int(0.04 / (links_per_step * 1.2e-9))), steps_per_pass, 2000)
+    run_steps(prime)
     if strat is not None:
-        end_of_pass()            # untimed: the first send/recv sets up the NCCL peer-to-peer channels (~0.3 s)
+        end_of_pass()            # untimed: the first transfer opens the peer mappings' copy path
         pos["step"] = 0
         run_steps(min(20, steps_per_pass))
+    run_steps(args.warmup)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    clocks = Clocks(local_rank)
+    clocks.sample()
+    clocks.start()
     launches0 = ops.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     rot0 = pos["rot"]
+    # ~0.1 ms of device-side sleep in front of the first event: the host prepares and enqueues the window's first launches
+    # while it runs, so the device-timed region holds the K steps back to back and no host start-up gap
+    torch.cuda._sleep(200_000)
     e0.record()
-    run_steps(args.steps, args.warmup)
-    if strat is not None and pos["rot"] - rot0 < -(-args.steps // steps_per_pass):
-        # the timed window must carry its share of rotations even when it ends inside a block (rounded UP)
+    if strat is not None:
+        # the timed window carries its share of phase changes, rounded UP: it OPENS with one (the stratum trained so far
+        # leaves for rank - 1 while the window's steps run) and only closes when that transfer has completed as well
         pos["step"] = 0
         end_of_pass()
+    run_steps(args.steps)
+    if strat is not None:
+        torch.cuda.current_stream().wait_stream(strat.xfer)
     e1.record()
+    torch.cuda.synchronize()
+    clocks.sample()
+    clocks.stop()
     barrier()
     rotations = pos["rot"] - rot0
     launches = ops.launch_count() - launches0
-    sampler.stop_flag = True
     ms = max_over_ranks(e0.elapsed_time(e1))
-    sampler.join(timeout=2)
-    final_loss = float(loss_buf[(args.steps - 1) * R:(args.steps) * R].mean().item())
+    final_loss = float(loss_buf[((args.steps - 1) % (loss_buf.numel() // R)) * R:][:R].mean().item())
     assert np.isfinite(final_loss), "training diverged"
     value = world * args.steps * links_per_step / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel: CUDA events around the score+gradient kernel, on its stream (every rank
-    #      runs the same number of profiled steps so that the device barriers of the sharded mode pair up)
+    # ---- per-kernel times: CUDA events around the kernels of a step, on their stream (every rank runs the same number of
+    #      profiled steps so that the device barriers of the peer mode pair up)
     step.set_profile(True)
-    nprof = min(200, steps_per_pass)
-    pos["step"] = 0
-    run_steps(nprof)
+    nprof = min(200, steps_per_pass - pos["step"]) if strat is not None else min(200, steps_per_pass)
+    if strat is None:
+        pos["step"] = 0
+    run_steps(max(nprof, 1))
     torch.cuda.synchronize()
     phase_ms, psteps = step.get_profile()
     step.set_profile(False)
     gather_ms, score_ms, final_ms = [x / max(psteps, 1) for x in phase_ms]
+    barrier()
 
     # ---- e2e: the public host-fed call (FusedStep.run_host -> nncf_train_steps_host): link ids in pinned HOST memory,
     #      every step copies its own ids H2D (overlapping the previous step's kernels) and its R losses D2H; wall clock
     #      around the call, which returns only when every step and copy has completed.  `per_call` is the same work issued
     #      as one blocking train_on_batch-style call per step (H2D, step, loss.cpu()) from Python.
-    e2e_steps = max(1, min(args.steps, 1000, steps_per_pass - 5))
+    if strat is not None and steps_per_pass - pos["step"] < 12:
+        pos["step"] = 0
+    room = steps_per_pass - pos["step"] - 5
+    e2e_steps = max(1, min(args.steps, 1000, room))
     h_uid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
     h_cid = torch.empty((e2e_steps + 5, links_per_step), dtype=torch.int32).pin_memory()
-    uid_all, cid_all = ids_now()
-    EU, EV = tables()
-    h_uid.copy_(uid_all[:h_uid.numel()].view(h_uid.shape).cpu())
-    h_cid.copy_(cid_all[:h_cid.numel()].view(h_cid.shape).cpu())
+    u_now, c_now = ids_now()
+    off = pos["step"] * links_per_step
+    EUc, EVc = tables()
+    h_uid.copy_(u_now[off:off + h_uid.numel()].view(h_uid.shape).cpu())
+    h_cid.copy_(c_now[off:off + h_cid.numel()].view(h_cid.shape).cpu())
     h_loss = torch.empty((e2e_steps + 5) * R, dtype=torch.float32).pin_memory()
-    step.run_host(EU, EV, h_uid, h_cid, 5, h_loss)
+    step.run_host(EUc, EVc, h_uid, h_cid, 5, h_loss)
     barrier()
     t0 = time.perf_counter()
-    step.run_host(EU, EV, h_uid[5:], h_cid[5:], e2e_steps, h_loss)
+    step.run_host(EUc, EVc, h_uid[5:], h_cid[5:], e2e_steps, h_loss)
     if strat is not None:
-        # e2e carries the rotations of its window too (rounded up to one), synchronised like the step calls
+        # e2e carries a phase change too (rounded up to one): the transfer runs beside nothing here, fully exposed
         end_of_pass()
-        torch.cuda.synchronize()
-        EU, EV = tables()
+        pos["step"] = 0
+        strat.drain()
+        EUc, EVc = tables()
+        u_now, c_now = ids_now()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * e2e_steps * links_per_step / e2e_s
     assert np.isfinite(float(h_loss[:e2e_steps * R].mean())), "e2e training diverged"
@@ -364,7 +428,7 @@ def run_ours(args):
     def e2e_step(i):
         d_uid.copy_(h_uid[i], non_blocking=True)
         d_cid.copy_(h_cid[i], non_blocking=True)
-        out = step.run(EU, EV, d_uid, d_cid, 1)
+        out = step.run(EUc, EVc, d_uid, d_cid, 1, adam_state=(strat.adam if strat is not None else None))
         return out["loss"].cpu()            # D2H + sync: the python-float loss Keras' train_on_batch returns
 
     per_call_steps = min(e2e_steps, 300)
@@ -379,170 +443,88 @@ def run_ours(args):
     per_call_value = world * per_call_steps * links_per_step / per_call_s
     barrier()
 
-    # ---- extra: whole@k users/sec, users sharded over the ranks (C4 shape: every rank scores its own users against all
-    #      2M items, k = 50; no data-path collective, the metric sums would be all-reduced).  Time = max over ranks.
+    # ---- extra: whole@k users/sec on the C4 shape, users sharded over the ranks: every rank scores ITS 1.25M users (the
+    #      per-GPU shard of 10M users over 8 GPUs) against all 2M items for k = 10 / 50 / 100, reduces them to AP / recall /
+    #      precision@k against CSR truth (nncf_eval_metrics) and the four metric sums are all-reduced — all inside the timed
+    #      region.  No data-path collective.  Time = max over ranks.
     extra = {}
     if not args.no_eval:
-        n_eval_users, n_eval_items, k = args.eval_users, 2_000_000, 50
-        ge = torch.Generator(device="cuda").manual_seed(99)
-        Ve = torch.randn((n_eval_items, d), device="cuda", generator=ge) / d ** 0.5            # replicated item table
-        Ue = torch.randn((n_eval_users, d), device="cuda", generator=g) / d ** 0.5             # this rank's user shard
-        ops.eval_topk(Ue[:1024], Ve, k, "bf16")
-        barrier()
-        e0.record()
-        ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
-        e1.record()
-        barrier()
-        ems = max_over_ranks(e0.elapsed_time(e1))
-        etf = 2.0 * world * n_eval_users * n_eval_items * d / (ems * 1e-3) / 1e12
-        extra = {"whole_at_k": {"users_per_sec": world * n_eval_users / (ems * 1e-3), "k": k, "users": world * n_eval_users,
-                                "items": n_eval_items, "dim": d, "ms": ems, "sharding": "users over %d GPU(s)" % world,
-                                "roofline": {"bound": "tensor", "achieved": etf, "peak": world * peaks["bf16_burst"],
-                                             "unit": "TFLOP/s", "frac": etf / (world * peaks["bf16_burst"])}}}
-        # the other two k of the C4 configuration (same users, same 2M items), one timed call each
-        by_k = {}
-        for kk in (10, 100):
-            ops.eval_topk(Ue[:1024], Ve, kk, "bf16")
-            barrier()
-            e0.record()
-            ops.eval_topk(Ue, Ve, kk, "bf16")
-            e1.record()
-            barrier()
-            kms = max_over_ranks(e0.elapsed_time(e1))
-            by_k[str(kk)] = {"users_per_sec": world * n_eval_users / (kms * 1e-3), "ms": kms,
-                             "tflops": 2.0 * world * n_eval_users * n_eval_items * d / (kms * 1e-3) / 1e12}
-        extra["whole_at_k"]["other_k"] = by_k
-        del Ue, Ve, ids
+        extra["whole_at_k"] = bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_over_ranks)
 
     if rank != 0:
         if sharded is not None:
             dist.barrier()
             sharded.close()
+        if strat is not None:
+            dist.barrier()
+            strat.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
         return
 
+    step_s = ms / args.steps * 1e-3
+    step_bytes = links_per_step * (8 + 16 * d)
+    flops = 6.0 * B * B * d * R
+    score_tf = flops / (score_ms * 1e-3) / 1e12
+    tensor_bound = args.workload == "c5"
     traffic = None
-    try:   # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same R, B, d)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
-        if R == 37:
+    try:   # DRAM bytes per launch of the score kernel from the committed `ncu --set full` capture (same R, B, d)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
+        if tj.get("replicas") == R and tj.get("batch") == B and tj.get("dim") == d:
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
     except Exception:
         pass
-    flops = 6.0 * B * B * d * R
-    achieved_tf = flops / (score_ms * 1e-3) / 1e12
-    step_bytes = links_per_step * (8 + 16 * d)
-    step_s = ms / args.steps * 1e-3
-    roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<2,skip-gram,neg_shared>", "achieved": achieved_tf,
-                "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": achieved_tf / peaks["bf16_burst"], "traffic": traffic,
-                "peak_source": peaks["src"], "ms_per_launch": score_ms, "flops_per_launch": flops,
-                "note": "algorithmic 6*B^2*d*R flops per launch; the one-sided kernel executes 8*B^2*dp*R (S is recomputed "
-                        "by the item side); its epilogue is MUFU-bound (DESIGN.md 3.1)",
-                "phases_ms": {"gather_prepare": gather_ms, "score_grad": score_ms, "finalize_update": final_ms},
-                "step_hbm": {"algorithmic_bytes_per_step": step_bytes, "achieved_gbs": step_bytes / step_s / 1e9,
-                             "peak_gbs": peaks["hbm"], "frac": step_bytes / step_s / 1e9 / peaks["hbm"]}}
+    if tensor_bound:
+        roofline = {"bound": "tensor", "kernel": "score_grad_tc_kernel<%d,%s,neg_shared>" % (d // 64, w["loss"]), "achieved": score_tf,
+                    "peak": peaks["bf16_burst"], "unit": "TFLOP/s", "frac": score_tf / peaks["bf16_burst"], "traffic": traffic,
+                    "peak_source": peaks["src"], "ms_per_launch": score_ms, "flops_per_launch": flops,
+                    "note": "algorithmic 6*B^2*d*R flops per launch; the one-sided kernel executes 8*B^2*dp*R (S is recomputed by "
+                            "the item side)"}
+    else:
+        # C3 is HBM-bound by SURVEY 8(d): 8 + 16 d algorithmic bytes per link (ids, two row gathers, two row updates).  The
+        # step is two programmatic-dependent launches that together move those bytes, so the roofline is taken over the
+        # step: bytes of a step / step time from the timed region's own CUDA events; the per-kernel split follows.
+        ach = step_bytes / step_s / 1e9
+        roofline = {"bound": "hbm", "kernel": "fused step = gather_rows_vec_kernel + score_grad_tc_kernel<2,skip-gram,neg_shared> "
+                                              "(sparse update in its drain), chained by programmatic dependent launch",
+                    "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": traffic,
+                    "peak_source": peaks["src"], "algorithmic_bytes_per_step": step_bytes, "ms_per_step": ms / args.steps,
+                    "score_kernel": {"ms_per_launch": score_ms, "tflops_algorithmic": score_tf, "flops_per_launch": flops,
+                                     "frac_of_bf16_burst": score_tf / peaks["bf16_burst"],
+                                     "update_bytes_per_launch": links_per_step * 8 * d},
+                    "gather_kernel": {"ms_per_launch": gather_ms, "bytes_per_launch": links_per_step * (8 + 8 * d),
+                                      "note": "serialised by the profiling events; 4.4 us inside the real chain (profiles/)"},
+                    "note": "kernel times are CUDA events around each launch with the dependent-launch overlap switched off, so "
+                            "they sum to more than the step"}
+    roofline["phases_ms"] = {"gather_prepare": gather_ms, "score_grad": score_ms, "finalize_update": final_ms}
 
-    seq_info, cpu = None, None
+    seq_info, cpu, ref_sem = None, None, None
     if world == 1:
-        # ---- sequential reference semantics (R = 1) ----------------------------------------------------------
-        seq = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
-                                 optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA))
-        nseq = min(2000, n_links // B)
-        seq.run(EU, EV, uid_all, cid_all, 50)
-        torch.cuda.synchronize()
-        e0.record()
-        seq.run(EU, EV, uid_all, cid_all, nseq)
-        e1.record()
-        torch.cuda.synchronize()
-        seq_info = {"value": nseq * B / (e0.elapsed_time(e1) * 1e-3), "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq}
-        # ---- the reference's optimizer family: sparse (lazy) Adam on the gathered rows, same R / B / d ------------
-        try:
-            adam = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=B, dim=d,
-                                      optimizer="lazy_adam", learn_rate=0.001, replicas=R, neg_loss_weight=LAMBDA))
-            state = [torch.zeros_like(EU), torch.zeros_like(EU), torch.zeros_like(EV), torch.zeros_like(EV)]
-            nad = min(600, n_links // (R * B))
-            adam.run(EU, EV, uid_all, cid_all, 30, adam_state=state)
-            torch.cuda.synchronize()
-            e0.record()
-            adam.run(EU, EV, uid_all, cid_all, nad, adam_state=state)
-            e1.record()
-            torch.cuda.synchronize()
-            ams = e0.elapsed_time(e1) / nad
-            seq_info["lazy_adam"] = {"value": R * B / (ams * 1e-3), "unit": "links/s", "replicas_per_gpu": R, "ms_per_step": ams,
-                                     "hbm_frac": R * B * (8 + 48 * d) / (ams * 1e-3) / 1e9 / peaks["hbm"],
-                                     "note": "lazy Adam (utils/optimizer.py _apply_sparse rule), algorithmic 8 + 48 d bytes per link"}
-            del state, adam
-        except Exception as ex:      # an extra must never cost the headline line
-            seq_info["lazy_adam"] = {"error": str(ex)[:200]}
-        # ---- the other batch sizes SURVEY.md 8 names for C3 (same tables, same links; fewer replicas so that a step still
-        #      fills the 148 SMs once) and the tensor-bound C5 shape are reported beside the headline -----------------------
-        sweep = {}
-        for Bx, Rx in ((4096, 5), (8192, 2)):
-            try:
-                sx = FusedStep(StepSpec(scheme="neg_shared", loss="skip-gram", precision="bf16", batch_size_p=Bx, dim=d,
-                                        optimizer="sgd", learn_rate=LR, replicas=Rx, neg_loss_weight=LAMBDA))
-                nx = min(300, n_links // (Rx * Bx) - 12)
-                sx.run(EU, EV, uid_all, cid_all, 10)
-                torch.cuda.synchronize()
-                e0.record()
-                sx.run(EU, EV, uid_all, cid_all, nx)
-                e1.record()
-                torch.cuda.synchronize()
-                xms = e0.elapsed_time(e1) / nx
-                sweep[str(Bx)] = {"value": Rx * Bx / (xms * 1e-3), "unit": "links/s", "replicas_per_gpu": Rx, "ms_per_step": xms,
-                                  "tflops_algorithmic": 6.0 * Bx * Bx * d * Rx / (xms * 1e-3) / 1e12}
-                del sx
-            except Exception as ex:
-                sweep[str(Bx)] = {"error": str(ex)[:200]}
-        seq_info["batch_size_sweep"] = sweep
-        # ---- BASELINE config 5: neg_shared max-margin, batch 16,384, dim 256, l2-normalised rows (tensor-bound contraction)
-        try:
-            g5 = torch.Generator(device="cuda").manual_seed(55)
-            U5 = (torch.rand((1_000_000, 256), device="cuda", generator=g5) - 0.5) * 0.1
-            V5 = (torch.rand((1_000_000, 256), device="cuda", generator=g5) - 0.5) * 0.1
-            n5 = 40
-            u5 = torch.randint(0, 1_000_000, ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
-            c5 = torch.randint(0, 1_000_000, ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
-            s5 = FusedStep(StepSpec(scheme="neg_shared", loss="max-margin", precision="bf16", batch_size_p=16384, dim=256, norm_u=True,
-                                    norm_v=True, optimizer="sgd", learn_rate=LR, replicas=1, neg_loss_weight=LAMBDA, loss_gamma=0.1))
-            s5.run(U5, V5, u5, c5, 5)
-            torch.cuda.synchronize()
-            e0.record()
-            s5.run(U5, V5, u5[5 * 16384:], c5[5 * 16384:], n5)
-            e1.record()
-            torch.cuda.synchronize()
-            ms5 = e0.elapsed_time(e1) / n5
-            tf5 = 6.0 * 16384 * 16384 * 256 / (ms5 * 1e-3) / 1e12
-            seq_info["c5_max_margin_b16384_d256"] = {"value": 16384 / (ms5 * 1e-3), "unit": "links/s", "ms_per_step": ms5,
-                                                     "roofline": {"bound": "tensor", "achieved": tf5, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                                                                  "frac": tf5 / peaks["bf16_burst"],
-                                                                  "note": "algorithmic 6 B^2 d; the one-sided kernel executes 8 B^2 d"}}
-            del U5, V5, u5, c5, s5
-        except Exception as ex:
-            seq_info["c5_max_margin_b16384_d256"] = {"error": str(ex)[:200]}
-        # ---- cpu baseline: bounded sample on the box's host cores (rank 0, N = 1 only) ------------------------
-        cpu_v, cpu_dt = cpu_links_per_sec(args.cpu_steps, 5)
+        seq_info, ref_sem = bench_variants(torch, ops, FusedStep, make_spec, w, args, EU, EV, uid_all, cid_all, n_links, peaks)
+        cpu_steps = args.cpu_steps or w["cpu_steps"]
+        cpu_v, cpu_dt = cpu_links_per_sec(w, R, cpu_steps, 2)
         cpu = {"value": cpu_v, "unit": "links/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": "%d sequential neg_shared steps of 512 links (%.1f s) on 1M x 128 fp32 tables, NumPy/BLAS" % (args.cpu_steps, cpu_dt)}
+               "sample": "%d steps of %d x %d links (%.1f s) on %d x %d fp32 tables, NumPy/BLAS, same step as the GPU arm"
+                         % (cpu_steps, R, B, cpu_dt, NU, d)}
 
+    cfg = workload_config(w, R)
+    if ref_sem is not None:
+        cfg["reference_semantics"] = ref_sem
     line = {
-        "metric": "positive links/sec train (neg_shared)", "value": value, "unit": "links/s", "n_gpus": world,
+        "metric": METRIC, "value": value, "unit": "links/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch_size_p": B, "dim": d, "replicas_per_gpu": R, "links_per_step_per_gpu": links_per_step,
-                   "links_resident_per_gpu": n_links, "optimizer": "sparse SGD (atomic scatter-add)",
-                   "precision": "bf16 operands, fp32 accumulate (tcgen05)",
-                   "parallelism": "1 GPU" if world == 1 else (
-                       "stratified SGD (DSGD) over %d GPUs: tables row-sharded (owner = id mod N), rank r owns user shard r, item "
-                       "shards rotate round the ring (NCCL send/recv) between sub-epochs of %d steps, every step touches local "
-                       "rows only; %d rotation(s) inside the timed region" % (world, steps_per_pass, rotations)
-                       if strat is not None else
-                       "tables row-sharded over %d GPUs (owner = id mod N), rows read and updated over NVLink peer memory "
-                       "inside the step kernels, 2 device barriers per step" % world),
-                   "semantics": "each step = R independent neg_shared batches per GPU against one table snapshot (synchronous "
-                                "data-parallel virtual workers); R=1 (the reference's sequential loop) is reported in `sequential`",
-                   "l2": "inputs larger than L2: 1.02 GB of embedding tables, random rows, batches never repeat within a pass"},
+        "config": cfg,
+        "arm": {"links_resident_per_gpu": n_links, "precision": "bf16 operands, fp32 accumulate (tcgen05)", "priming_steps": prime,
+                "parallelism": "1 GPU" if world == 1 else (
+                    "stratified SGD (DSGD) over %d GPUs: rank r owns user shard r (id mod N), items in %d strata (id mod 2N); a phase "
+                    "is %d steps on local rows only; the next phase's stratum arrives over NVLink peer copies (copy engines, side "
+                    "stream, flag hand-offs) while the current one is trained; %d phase change(s) with their transfers inside the "
+                    "timed region" % (world, 2 * world, steps_per_pass, rotations)
+                    if strat is not None else
+                    "tables row-sharded over %d GPUs (owner = id mod N), rows read and updated over NVLink peer memory "
+                    "inside the step kernels, 2 device barriers per step" % world)},
         "sequential": seq_info,
         "final_loss": final_loss,
         "roofline": roofline,
@@ -555,7 +537,7 @@ def run_ours(args):
                         "pinned host memory (overlapping the previous step's kernels) and its R losses are copied back; "
                         "wall clock around the call, which returns after the last copy"},
         "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
+        "clocks": clocks.summary(),
         "extra": extra,
     }
     _OUT.write(json.dumps(line) + "\n")
@@ -563,9 +545,125 @@ def run_ours(args):
     if sharded is not None:
         dist.barrier()
         sharded.close()
+    if strat is not None:
+        dist.barrier()
+        strat.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_variants(torch, ops, FusedStep, make_spec, w, args, EU, EV, uid_all, cid_all, n_links, peaks):
+    """N = 1 only: the same workload at reference semantics (R = 1), with the reference's optimizer family (lazy Adam, the
+    Conf default), the other batch sizes SURVEY 8 names, and the other BASELINE training config as a short extra."""
+    B, d, R = w["batch"], w["dim"], (args.replicas or w["replicas"])
+
+    def timed(stepper, n_warm, n, per, state=None):
+        stepper.run(EU, EV, uid_all, cid_all, n_warm, adam_state=state)
+        ms = _time_steps(torch, lambda: stepper.run(EU, EV, uid_all[n_warm * per:], cid_all[n_warm * per:], n, adam_state=state))
+        return ms / n
+
+    out = {}
+    # ---- sequential reference semantics (R = 1), sparse SGD + the default regulariser
+    nseq = min(3000, n_links // B - 60)
+    ms1 = timed(FusedStep(make_spec(replicas=1)), 50, nseq, B)
+    out.update({"value": B / (ms1 * 1e-3), "unit": "links/s", "replicas_per_gpu": 1, "steps": nseq, "ms_per_step": ms1})
+    ref_sem = {"sgd_R1": {"links_per_s": B / (ms1 * 1e-3), "us_per_step": ms1 * 1e3}}
+    # ---- the drop-in default path: lazy Adam (utils/optimizer.py _apply_sparse rule), u_reg 1e-6, at R = 1 and at R
+    for RR, key in ((1, "lazy_adam_R1"), (R, "lazy_adam_R%d" % R)):
+        try:
+            st = [torch.zeros_like(EU), torch.zeros_like(EU), torch.zeros_like(EV), torch.zeros_like(EV)]
+            nad = min(2000 if RR == 1 else 600, n_links // (RR * B) - 40)
+            msa = timed(FusedStep(make_spec(replicas=RR, optimizer="lazy_adam", lr=0.001)), 30, nad, RR * B, st)
+            ref_sem[key] = {"links_per_s": RR * B / (msa * 1e-3), "us_per_step": msa * 1e3,
+                            "hbm_frac": RR * B * (8 + 48 * d) / (msa * 1e-3) / 1e9 / peaks["hbm"]}
+            del st
+        except Exception as ex:      # an extra must never cost the headline line
+            ref_sem[key] = {"error": str(ex)[:200]}
+    ref_sem["note"] = ("same workload; R = 1 is the reference's sequential loop (models/train_neg_shared.py:40-58); lazy Adam + u_reg "
+                       "1e-6 + R = 1 are the Conf defaults main.py runs with; hbm_frac at 8 + 48 d algorithmic bytes per link")
+    out["lazy_adam"] = ref_sem.get("lazy_adam_R%d" % R)
+    if args.workload != "c3":
+        return out, ref_sem
+    # ---- the other batch sizes SURVEY.md 8 names for C3 (same tables, same links; fewer replicas so that a step still
+    #      fills the 148 SMs once)
+    sweep = {}
+    for Bx, Rx in ((4096, 5), (8192, 2)):
+        try:
+            nx = min(300, n_links // (Rx * Bx) - 12)
+            xms = timed(FusedStep(make_spec(replicas=Rx, batch=Bx)), 10, nx, Rx * Bx)
+            sweep[str(Bx)] = {"value": Rx * Bx / (xms * 1e-3), "unit": "links/s", "replicas_per_gpu": Rx, "ms_per_step": xms,
+                              "tflops_algorithmic": 6.0 * Bx * Bx * d * Rx / (xms * 1e-3) / 1e12}
+        except Exception as ex:
+            sweep[str(Bx)] = {"error": str(ex)[:200]}
+    out["batch_size_sweep"] = sweep
+    # ---- BASELINE config 5 as a short extra (its own bench line: --workload c5)
+    try:
+        w5 = WORKLOADS["c5"]
+        g5 = torch.Generator(device="cuda").manual_seed(55)
+        U5 = (torch.rand((w5["n_users"], 256), device="cuda", generator=g5) - 0.5) * 0.1
+        V5 = (torch.rand((w5["n_items"], 256), device="cuda", generator=g5) - 0.5) * 0.1
+        n5 = 40
+        u5 = torch.randint(0, w5["n_users"], ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
+        c5 = torch.randint(0, w5["n_items"], ((n5 + 5) * 16384,), device="cuda", generator=g5, dtype=torch.int32)
+        from nncf_b200.ops import StepSpec
+        s5 = FusedStep(StepSpec(scheme="neg_shared", loss="max-margin", precision="bf16", batch_size_p=16384, dim=256, norm_u=True,
+                                norm_v=True, optimizer="sgd", learn_rate=w5["lr"], replicas=1, neg_loss_weight=w5["lam"],
+                                loss_gamma=w5["gamma"], u_reg=w5["u_reg"]))
+        s5.run(U5, V5, u5, c5, 5)
+        ms5 = _time_steps(torch, lambda: s5.run(U5, V5, u5[5 * 16384:], c5[5 * 16384:], n5)) / n5
+        tf5 = 6.0 * 16384 * 16384 * 256 / (ms5 * 1e-3) / 1e12
+        out["c5_max_margin_b16384_d256"] = {"value": 16384 / (ms5 * 1e-3), "unit": "links/s", "ms_per_step": ms5,
+                                            "roofline": {"bound": "tensor", "achieved": tf5, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                                                         "frac": tf5 / peaks["bf16_burst"],
+                                                         "note": "algorithmic 6 B^2 d over the whole step; the one-sided kernel executes 8 B^2 d"}}
+        del U5, V5, u5, c5, s5
+    except Exception as ex:
+        out["c5_max_margin_b16384_d256"] = {"error": str(ex)[:200]}
+    return out, ref_sem
+
+
+def bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_over_ranks):
+    d = 128
+    n_users, n_items = args.eval_users, 2_000_000
+    ge = torch.Generator(device="cuda").manual_seed(99)
+    Ve = torch.randn((n_items, d), device="cuda", generator=ge) / d ** 0.5                       # replicated item table (seed 11-style)
+    gu = torch.Generator(device="cuda").manual_seed(1000 + rank)
+    Ue = torch.randn((n_users, d), device="cuda", generator=gu) / d ** 0.5                       # this rank's user shard
+    # CSR truth: 1 + Poisson(4) test items per user drawn from the item power law (BASELINE.md §3), sorted + unique per user
+    cnt = (1 + torch.poisson(torch.full((n_users,), 4.0, device="cuda"), generator=gu)).to(torch.int64)
+    owner = torch.repeat_interleave(torch.arange(n_users, device="cuda"), cnt)
+    cols = _draw_powerlaw(torch, gu, n_items, 1.0, 123, int(owner.numel()), 10.0).to(torch.int64)
+    key = torch.unique(owner * n_items + cols)                                                   # sorted by (user, column)
+    owner, cols = key // n_items, (key % n_items).to(torch.int32)
+    indptr = torch.zeros(n_users + 1, dtype=torch.int64, device="cuda")
+    indptr[1:] = torch.cumsum(torch.bincount(owner, minlength=n_users), 0)
+    del key, owner, cnt
+    res = {}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for k in (50, 10, 100):
+        ops.eval_topk(Ue[:2048], Ve, k, "bf16")
+        barrier()
+        e0.record()
+        ids, _ = ops.eval_topk(Ue, Ve, k, "bf16")
+        _, sums = ops.eval_metrics(ids, indptr, cols)
+        if world > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        e1.record()
+        barrier()
+        kms = max_over_ranks(e0.elapsed_time(e1))
+        s = sums.cpu().numpy()
+        tf = 2.0 * world * n_users * n_items * d / (kms * 1e-3) / 1e12
+        res[str(k)] = {"users_per_sec": world * n_users / (kms * 1e-3), "ms": kms, "tflops": tf, "frac_of_bf16_burst": tf / (world * peaks["bf16_burst"]),
+                       "recall": float(s[1] / max(s[3], 1.0)), "map": float(s[0] / max(s[3], 1.0)), "users_kept": int(s[3])}
+        del ids
+    r50 = res["50"]
+    return {"users_per_sec": r50["users_per_sec"], "k": 50, "users": world * n_users, "items": n_items, "dim": d, "ms": r50["ms"],
+            "sharding": "users over %d GPU(s), %d per GPU (the C4 shard: 10M users over 8 GPUs)" % (world, n_users),
+            "timed": "nncf_eval_topk + nncf_eval_metrics + all-reduce of the 4 metric sums",
+            "roofline": {"bound": "tensor", "achieved": r50["tflops"], "peak": world * peaks["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": r50["frac_of_bf16_burst"]},
+            "by_k": res}
 
 
 def main():
@@ -574,13 +672,16 @@ def main():
     ap.add_argument("--steps", type=int, default=3000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas", type=int, default=37)  # 37 x 8 CTAs = 2 full waves of 148 SMs
-    ap.add_argument("--links", type=int, default=N_LINKS)
-    ap.add_argument("--cpu-steps", type=int, default=3000)
-    ap.add_argument("--eval-users", type=int, default=75776)   # 4 full waves of 148 CTAs x 128 users
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--replicas", type=int, default=0)   # 0 = the workload's default (c3: 37 x 8 CTAs = 2 per SM on 148 SMs)
+    ap.add_argument("--links", type=int, default=0)      # 0 = the workload's default
+    ap.add_argument("--cpu-steps", type=int, default=0)
+    ap.add_argument("--eval-users", type=int, default=1_250_000)   # the C4 per-GPU shard: 10M users over 8 GPUs
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--parallelism", default="stratified", choices=["stratified", "peer"])   # N > 1 only
     args = ap.parse_args()
+    if args.workload == "c5" and args.steps == 3000:
+        args.steps, args.warmup = 60, 5
     # stdout carries ONE JSON line and nothing else: libraries that print to the process's stdout (NCCL's "NCCL version ..."
     # banner under torchrun, for one) are sent to stderr for the whole run, the line goes to the saved descriptor
     global _OUT

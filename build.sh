@@ -7,7 +7,7 @@ mkdir -p build
 OBJS=""
 for f in $SRC; do
   o=build/$(basename ${f%.cu}).o
-  if [ ! -f $o ] || [ $f -nt $o ] || [ nncf_b200/csrc/common.cuh -nt $o ] || [ nncf_b200/csrc/sm100.cuh -nt $o ] || [ nncf_b200/csrc/score_tc.cuh -nt $o ] || [ nncf_b200/csrc/row_kernels.cuh -nt $o ] || [ nncf_b200/csrc/sns_kernels.cuh -nt $o ] || [ nncf_b200/csrc/alias.cuh -nt $o ] || [ include/nncf_b200.h -nt $o ]; then
+  if [ ! -f $o ] || [ $f -nt $o ] || [ nncf_b200/csrc/common.cuh -nt $o ] || [ nncf_b200/csrc/sm100.cuh -nt $o ] || [ nncf_b200/csrc/score_tc.cuh -nt $o ] || [ nncf_b200/csrc/row_kernels.cuh -nt $o ] || [ nncf_b200/csrc/sns_kernels.cuh -nt $o ] || [ nncf_b200/csrc/pairs_kernels.cuh -nt $o ] || [ nncf_b200/csrc/alias.cuh -nt $o ] || [ include/nncf_b200.h -nt $o ]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -c $f -o $o &
   fi
   OBJS="$OBJS $o"

@@ -184,6 +184,9 @@ typedef struct {
                                      (1 = positive; -1 / 0 = negative), the y_true of ref utils/objectives.py:59-70.
                                      NULL = rows [0, B) of every batch are the positives (the reference's layout for
                                      train_original / train_group_sample); presample's shuffled batches need it. */
+  const int32_t* next_user_ids_dev;  /* optional hint: ids of the step that FOLLOWS this call's last step (the caller's next */
+  const int32_t* next_item_ids_dev;  /* call), [R * rows] each; their rows are pulled into L2 while the last step computes.
+                                     A hint only: never dereferenced for results, stale or NULL values are harmless. */
 } nncf_step_io;
 
 int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_dev,

@@ -58,6 +58,7 @@ class StepIO(C.Structure):
         ("loss_out_dev", C.c_void_p), ("grad_user_rows_dev", C.c_void_p), ("grad_item_rows_dev", C.c_void_p),
         ("unique_ids_dev", C.c_void_p), ("inverse_dev", C.c_void_p), ("n_unique_dev", C.c_void_p),
         ("item_rows_dev", C.c_void_p), ("response_dev", C.c_void_p),
+        ("next_user_ids_dev", C.c_void_p), ("next_item_ids_dev", C.c_void_p),
     ]
 
 

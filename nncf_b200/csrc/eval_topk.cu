@@ -1394,6 +1394,15 @@ static int make_plan(int64_t n_users, int64_t n_items, int dim, int topk, int pr
           for (int t = kEval3MaxStages; t >= want; --t) if (eval3_smem_bytes(p->nsub, t, cap) <= 232448) { st = t; break; }
           if (st) { best_st = st; best_cap = cap; }
         }
+      // large k (k = 100 of the C4 configuration): the row buffers need not be a multiple of 32 keys - a row compacts when
+      // fewer than 32 slots are free and keeps at most cap - 48 >= k keys - so the smallest buffer that leaves two item
+      // stages keeps the pair kernel in play (k = 100, d = 128: 152 keys per row, 2 stages)
+      for (int want = 3; want >= 2 && !best_st; --want)
+        for (int cap = p->KP + 24; cap >= (topk + 48 + 7) / 8 * 8 && !best_st; cap -= 8) {
+          int st = 0;
+          for (int t = kEval3MaxStages; t >= want; --t) if (eval3_smem_bytes(p->nsub, t, cap) <= 232448) { st = t; break; }
+          if (st) { best_st = st; best_cap = cap; }
+        }
       { const char* e = getenv("NNCF_EVAL_NST3"); if (e && best_st) { const int v = atoi(e); if (v >= 2 && v <= best_st) best_st = v; } }   // developer override
       if (best_st) {
         p->v3 = 1; p->cap = best_cap; p->nstages2 = best_st; p->nstages = best_st; p->cl = 2;

@@ -80,7 +80,9 @@ struct ScoreTcArgs {
   int64_t n_rows_u, n_rows_v;                 // table sizes (ids are clamped: a hint must never fault)
   int d;                                      // true embedding dim (table row stride), d % 4 == 0 when fused
   float neg_lr;
-  float* table_u; float* table_v;
+  float* table_u; float* table_v;             // what the fused drain adds into: the embedding tables (sparse SGD) or the
+                                              // per-table gradient accumulators of the folded lazy Adam (neg_lr = 1)
+  const float* pf_table_u; const float* pf_table_v;   // tables whose rows the spare warps prefetch for the next step
   const int32_t* ids_u; const int32_t* ids_v; // table row of each owner row: ids_x[r * stride_x + row]
   int64_t ids_stride_u, ids_stride_v;
   ShardPtrs shards_u, shards_v;
@@ -753,7 +755,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     const int ncta = gridDim.x * gridDim.y * gridDim.z;
     const bool vside = warp == 2 + kScoreEpiWarps + 1;
     const int32_t* ids = vside ? a.next_ids_v : a.next_ids_u;
-    const float* table = vside ? a.table_v : a.table_u;
+    const float* table = vside ? a.pf_table_v : a.pf_table_u;
     const int64_t nrows = vside ? a.n_rows_v : a.n_rows_u;
     const uint32_t row_bytes = static_cast<uint32_t>(a.d) * 4u;
     for (int i = cta * 32 + lane; i < a.next_count; i += ncta * 32) {

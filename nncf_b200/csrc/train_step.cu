@@ -611,6 +611,73 @@ adam_apply_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int d, int dp, flo
     if (lane == 0) s.owner[ids[k]] = 0x7fffffff;          // re-arm (was adam_reset_kernel)
   }
 }
+// ---- folded form (the plain matmul step: nothing to post-process): the score kernel's drain has ALREADY summed every
+// position's gradient row into a per-table accumulation table keyed by id (bulk reductions at the L2, the same mechanism
+// as the fused sparse SGD update; duplicates - also across replicas - sum there), so the owner / combine launches and the
+// [R][rows][d] gradient staging disappear: gather, score, this kernel.  The first position of an id to swap the step's
+// tag into claim[id] applies the _apply_sparse rule (ref: utils/optimizer.py:108-134) to the row and re-zeroes its
+// accumulator; the other positions of the same id do nothing.
+struct AdamAccSide {
+  const int32_t* ids; int64_t ids_stride; int count; const int32_t* count_dev;
+  int32_t* claim; float* acc; float* table; float* m; float* v;
+};
+template <int NV>
+__global__ void __launch_bounds__(256)
+adam_apply_accum_kernel(AdamAccSide s0, AdamAccSide s1, int tag, int d, float lr_t, float beta1, float beta2, float eps) {
+  pdl_launch_dependents();
+  const AdamAccSide& s = blockIdx.z ? s1 : s0;
+  if (!s.ids) return;
+  constexpr int kRows = 4;                              // rows in flight per warp (id -> claim -> rows: dependent accesses)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = (blockIdx.x * 8 + warp) * kRows, r = blockIdx.y;
+  // link ids are inputs of the step: fetched before waiting for the score kernel (the group scheme's compact ids are not)
+  int64_t myid = -1;
+  const bool early = s.count_dev == nullptr;
+  if (early && lane < kRows && row0 + lane < s.count) myid = s.ids[r * s.ids_stride + row0 + lane];
+  pdl_wait();
+  const int cnt = s.count_dev ? s.count_dev[r] : s.count;
+  if (row0 >= cnt) return;
+  if (!early && lane < kRows && row0 + lane < cnt) myid = s.ids[r * s.ids_stride + row0 + lane];
+  if (myid >= 0 && atomicExch(&s.claim[myid], tag) == tag) myid = -1;      // somebody else applies this id
+  float4 g[kRows][NV], mm[kRows][NV], vv[kRows][NV], pp[kRows][NV];
+  int64_t ids[kRows];
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    ids[k] = __shfl_sync(0xffffffffu, myid, k);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (lane + 32 * v);
+      if (ids[k] >= 0 && c < d) {
+        const int64_t o = ids[k] * d + c;
+        g[k][v] = *reinterpret_cast<const float4*>(s.acc + o);
+        mm[k][v] = *reinterpret_cast<const float4*>(s.m + o);
+        vv[k][v] = *reinterpret_cast<const float4*>(s.v + o);
+        pp[k][v] = *reinterpret_cast<const float4*>(s.table + o);
+      }
+    }
+  }
+  const float c1 = 1.0f - beta1, c2 = 1.0f - beta2;
+#pragma unroll
+  for (int k = 0; k < kRows; ++k) {
+    if (ids[k] < 0) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c = 4 * (lane + 32 * v);
+      if (c < d) {
+        float4 G = g[k][v], M = mm[k][v], V = vv[k][v], P = pp[k][v];
+        M.x = beta1 * M.x + c1 * G.x; M.y = beta1 * M.y + c1 * G.y; M.z = beta1 * M.z + c1 * G.z; M.w = beta1 * M.w + c1 * G.w;
+        V.x = beta2 * V.x + c2 * G.x * G.x; V.y = beta2 * V.y + c2 * G.y * G.y; V.z = beta2 * V.z + c2 * G.z * G.z; V.w = beta2 * V.w + c2 * G.w * G.w;
+        P.x -= lr_t * M.x / (sqrtf(V.x) + eps); P.y -= lr_t * M.y / (sqrtf(V.y) + eps);
+        P.z -= lr_t * M.z / (sqrtf(V.z) + eps); P.w -= lr_t * M.w / (sqrtf(V.w) + eps);
+        const int64_t o = ids[k] * d + c;
+        *reinterpret_cast<float4*>(s.m + o) = M;
+        *reinterpret_cast<float4*>(s.v + o) = V;
+        *reinterpret_cast<float4*>(s.table + o) = P;
+        *reinterpret_cast<float4*>(s.acc + o) = make_float4(0.f, 0.f, 0.f, 0.f);     // re-armed for the next step
+      }
+    }
+  }
+}
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
@@ -752,6 +819,10 @@ rows_sgd_kernel(const float* __restrict__ rows, const int32_t* __restrict__ ids,
   for (int c = lane; c < d; c += 32) atomicAdd(t + c, -lr * g[c]);
 }
 
+}  // namespace nncf
+#include "pairs_kernels.cuh"
+namespace nncf {
+
 __global__ void loss_out_kernel(const double* __restrict__ loss, int R, float* out) {
   const int r = threadIdx.x;
   if (r < R) out[r] = static_cast<float>(loss[r]);
@@ -806,6 +877,10 @@ struct nncf_trainer {
   int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
   int32_t *ownerU = nullptr, *ownerV = nullptr;
   int64_t ownerU_n = 0, ownerV_n = 0;
+  // folded lazy Adam: per-table gradient accumulators [rows][d] (zero between steps) and claim words [rows]
+  float *accU = nullptr, *accV = nullptr;
+  int32_t *claimU = nullptr, *claimV = nullptr;
+  int64_t accU_rows = 0, accV_rows = 0;
   float *ps = nullptr;   // PAIRS scores
   float *dVn = nullptr;  // sampled_neg_shared: [R][k][d] accumulated dL/d(vhat_neg)
   bool tc_attr_set = false;
@@ -935,7 +1010,7 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
                   t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn,
-                  t->gather_flags, t->gather_count};
+                  t->gather_flags, t->gather_count, t->accU, t->accV, t->claimU, t->claimV};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
@@ -1011,6 +1086,19 @@ static int ensure_owner(int32_t** owner, int64_t* have, int64_t need, cudaStream
   return 0;
 }
 
+static int ensure_accum(float** acc, int32_t** claim, int64_t* have, int64_t rows, int d, cudaStream_t st) {
+  if (*have >= rows) return 0;
+  if (*acc) cudaFree(*acc);
+  if (*claim) cudaFree(*claim);
+  *acc = nullptr; *claim = nullptr; *have = 0;
+  NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(acc), (size_t)rows * d * sizeof(float)));
+  NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(claim), (size_t)rows * sizeof(int32_t)));
+  NNCF_CUDA(cudaMemsetAsync(*acc, 0, (size_t)rows * d * sizeof(float), st));
+  NNCF_CUDA(cudaMemsetAsync(*claim, 0, (size_t)rows * sizeof(int32_t), st));
+  *have = rows;
+  return 0;
+}
+
 static int run_adam2(nncf_trainer* t, const AdamSide& su, const AdamSide& sv, int rows_stride, int d, int dp, float lr_t,
                      cudaStream_t st) {
   const int R = t->cfg.replicas;
@@ -1073,6 +1161,15 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool adam_plain = bf16 && c.optimizer == NNCF_OPT_LAZY_ADAM && !c.norm_u && !c.norm_v && !pairwise &&
                           (d % 4 == 0) && !dense_items && !want_row_grads && !bias && t->n_shards <= 1;
   const bool drain_reg = (fuse_sgd || adam_plain) && c.u_reg != 0.0f;    // regulariser gradient added by the score kernel's drain
+  // folded lazy Adam (NNCF_ADAM_FOLD=0 keeps the owner / combine / apply form): the drain sums the gradient rows into
+  // per-table accumulators keyed by id, one apply launch follows (see adam_apply_accum_kernel)
+  const bool adam_fold = adam_plain && [] { const char* e = getenv("NNCF_ADAM_FOLD"); return !e || atoi(e) != 0; }();
+  if (adam_fold) {
+    NNCF_CHECK_ARG(tb->user_m && tb->user_v && tb->item_m && tb->item_v, "lazy Adam needs m / v tables");
+    if (ensure_accum(&t->accU, &t->claimU, &t->accU_rows, tb->n_users, d, st)) return NNCF_ECUDA;
+    if (ensure_accum(&t->accV, &t->claimV, &t->accV_rows, tb->n_items, d, st)) return NNCF_ECUDA;
+  }
+  const bool drain_adds = fuse_sgd || adam_fold;     // the drain reduces into a table: no gradient staging blocks
   // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
   // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
   t->loss_published = true;   // by the last finalize launch, or by the score kernel itself in fused mode
@@ -1130,7 +1227,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     const int split_env = [] { const char* e = getenv("NNCF_SPLIT"); return e ? atoi(e) : 0; }();   // (read per step: the tests switch it)
     if (split_env >= 1 && split_env <= nt_min) split = split_env;
   }
-  if (split > 1 && !fuse_sgd) gu.zero_grad = 1;    // partial blocks are summed with red.global.add
+  if (split > 1 && !drain_adds) gu.zero_grad = 1;    // partial blocks are summed with red.global.add
   // self-gather (opt-in, NNCF_SELF_GATHER=1): the score kernel's CTAs gather their own rows (no gather launch, no hand-off).
   // Needs the fused drain (nothing else reads the staging buffers), one local table, dp <= 128 and the whole grid resident
   // at once: CTAs wait for each other's image blocks, and no drain may start before the last gather has ended.
@@ -1138,7 +1235,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   // uniform ids).  The separate gather kernel has 1,184 CTAs x 8 warps x 4 rows in flight and its launch overlaps the score
   // kernel's prologue through programmatic dependent launch; 8 warps x 8 rows per CTA behind the prologue do not beat it.
   const bool self_env = [] { const char* e = getenv("NNCF_SELF_GATHER"); return e && atoi(e) != 0; }();   // (read per step: the tests switch it)
-  if (split > 1 && !fuse_sgd) gv.zero_grad = 1;
+  if (split > 1 && !drain_adds) gv.zero_grad = 1;
   const bool self_gather = self_env && fuse_sgd && vec && !group && !sharded && dp <= 128 && !t->timeline && split == 1 &&
                            active_ctas <= t->resident_ctas;
   // gather / score / finalize are launched with programmatic dependent launch: each calls griddepcontrol.wait before it
@@ -1184,7 +1281,9 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       ta.drain_vec = e ? atoi(e) : 0;     // measured at R = 1, split 4: 8.9 us per step with bulk reductions, 10.0 with vector reductions
     }
     ta.split = split; ta.reg_scale = drain_reg ? 2.0f * c.u_reg / static_cast<float>(B) : 0.0f;
-    ta.fuse_sgd = fuse_sgd ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
+    ta.fuse_sgd = drain_adds ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
+    ta.pf_table_u = tb->user_table; ta.pf_table_v = tb->item_table;
+    if (adam_fold) { ta.table_u = t->accU; ta.table_v = t->accV; ta.neg_lr = 1.0f; }
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
     ta.tl = tl;
@@ -1278,7 +1377,18 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       NNCF_CHECK_ARG(tb->item_m && tb->item_v, "lazy Adam needs item_m / item_v");
       if (ensure_owner(&t->ownerV, &t->ownerV_n, tb->n_items, st)) return NNCF_ECUDA;
     }
-    if (vec) {
+    if (adam_fold) {
+      AdamAccSide su{uid, B, B, nullptr, t->claimU, t->accU, tb->user_table, tb->user_m, tb->user_v};
+      AdamAccSide sv{item_ids, item_stride, B, group ? t->nuniq : nullptr, t->claimV, t->accV, tb->item_table, tb->item_m, tb->item_v};
+      const int tag = static_cast<int>(t->adam_t & 0x7fffffff);          // (claim words start at 0, adam_t at 1)
+      if (dp <= 128)
+        NNCF_CUDA(launch_pdl(adam_apply_accum_kernel<1>, dim3(ceil_div(B, 32), R, 2), dim3(256), 0, st, su, sv, tag, d, lr_t,
+                             c.beta1, c.beta2, c.epsilon));
+      else
+        NNCF_CUDA(launch_pdl(adam_apply_accum_kernel<2>, dim3(ceil_div(B, 32), R, 2), dim3(256), 0, st, su, sv, tag, d, lr_t,
+                             c.beta1, c.beta2, c.epsilon));
+      count_launch();
+    } else if (vec) {
       // both tables per launch, 3 launches (owner, combine, apply + re-arm), 128-bit accesses, programmatic dependent launch
       AdamSide su{uid, B, B, nullptr, t->ownerU, t->dU, tb->user_table, tb->user_m, tb->user_v};
       AdamSide sv{};
@@ -1325,12 +1435,17 @@ static int step_pairs(nncf_trainer* t, const nncf_tables* tb, const int32_t* uid
     pa.d_emb = bias ? d - 2 : 0;
     pa.fu0 = bias ? d - 1 : -1; pa.fu1 = (bias && !(bias & 1)) ? d - 2 : -1;
     pa.fv0 = bias ? d - 2 : -1; pa.fv1 = (bias && !(bias & 2)) ? d - 1 : -1; }
-  dim3 g8(ceil_div(n, 8), R);
+  dim3 g8(ceil_div(n, 8), R), g32(ceil_div(n, 8 * kPairsPerWarp), R);
+  const bool vec = (d % 4 == 0) && !c.interaction_bias && d <= 256;     // 16-byte aligned rows, no bias columns: pairs_kernels.cuh
   NNCF_PROFILE_MARK(t, 0, st);
-  pairs_score_kernel<<<g8, 256, 0, st>>>(pa);
+  if (vec && d <= 128) pairs_score_vec_kernel<1><<<g32, 256, 0, st>>>(pa);
+  else if (vec) pairs_score_vec_kernel<2><<<g32, 256, 0, st>>>(pa);
+  else pairs_score_kernel<<<g8, 256, 0, st>>>(pa);
   NNCF_LAUNCH_OK();
   NNCF_PROFILE_MARK(t, 1, st);
-  pairs_grad_kernel<<<g8, 256, 0, st>>>(pa);
+  if (vec && d <= 128) pairs_grad_vec_kernel<1><<<g32, 256, 0, st>>>(pa);
+  else if (vec) pairs_grad_vec_kernel<2><<<g32, 256, 0, st>>>(pa);
+  else pairs_grad_kernel<<<g8, 256, 0, st>>>(pa);
   NNCF_LAUNCH_OK();
   NNCF_PROFILE_MARK(t, 2, st);
   if (int rc = apply_row_grads(t, tb, uid, cid, n, st)) return rc;
@@ -1344,10 +1459,23 @@ static int apply_row_grads(nncf_trainer* t, const nncf_tables* tb, const int32_t
   const int R = c.replicas, d = c.dim;
   dim3 g8(ceil_div(n, 8), R);
   if (c.optimizer == NNCF_OPT_SGD) {
-    rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
-    NNCF_LAUNCH_OK();
-    rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dV, cid, n, n, d, c.learn_rate, tb->item_table);
-    NNCF_LAUNCH_OK();
+    const dim3 g32(ceil_div(n, 8 * kPairsPerWarp), R);
+    if (d % 4 == 0 && d <= 128) {
+      rows_sgd_vec_kernel<1><<<g32, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
+      NNCF_LAUNCH_OK();
+      rows_sgd_vec_kernel<1><<<g32, 256, 0, st>>>(t->dV, cid, n, n, d, c.learn_rate, tb->item_table);
+      NNCF_LAUNCH_OK();
+    } else if (d % 4 == 0 && d <= 256) {
+      rows_sgd_vec_kernel<2><<<g32, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
+      NNCF_LAUNCH_OK();
+      rows_sgd_vec_kernel<2><<<g32, 256, 0, st>>>(t->dV, cid, n, n, d, c.learn_rate, tb->item_table);
+      NNCF_LAUNCH_OK();
+    } else {
+      rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dU, uid, n, n, d, c.learn_rate, tb->user_table);
+      NNCF_LAUNCH_OK();
+      rows_sgd_kernel<<<g8, 256, 0, st>>>(t->dV, cid, n, n, d, c.learn_rate, tb->item_table);
+      NNCF_LAUNCH_OK();
+    }
   } else if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
     NNCF_CHECK_ARG(tb->user_m && tb->user_v && tb->item_m && tb->item_v, "lazy Adam needs m / v tables");
     t->adam_t += 1;
@@ -1420,8 +1548,8 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
       rc = step_sns(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, st);
     else
       rc = step_matmul(t, tables, user_ids_dev + s * per_step, item_ids_dev + s * per_step, io, last, loss_out_step,
-                       last ? t->hint_next_uid : user_ids_dev + (s + 1) * per_step,
-                       last ? t->hint_next_cid : item_ids_dev + (s + 1) * per_step, st);
+                       last ? (t->hint_next_uid ? t->hint_next_uid : (io ? io->next_user_ids_dev : nullptr)) : user_ids_dev + (s + 1) * per_step,
+                       last ? (t->hint_next_cid ? t->hint_next_cid : (io ? io->next_item_ids_dev : nullptr)) : item_ids_dev + (s + 1) * per_step, st);
     if (rc) return rc;
     if (t->profile) {
       NNCF_CUDA(cudaEventSynchronize(t->ev[3]));

@@ -247,7 +247,7 @@ class FusedStep:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:                    # (module globals are gone when this runs at interpreter exit)
             lib.nncf_trainer_destroy(h)
             self._h = None
 
@@ -311,6 +311,11 @@ class FusedStep:
             responses = responses.contiguous()
             keep.append(responses)
             io.response_dev = responses.data_ptr()
+        if sp.scheme in ("neg_shared", "group_neg_shared") and item_table is not None and user_ids.numel() >= need + sp.replicas * self.rows \
+                and item_ids.numel() >= need + sp.replicas * self.rows and user_ids.is_contiguous() and item_ids.is_contiguous():
+            # the caller's id arrays go on beyond this call: the rows of its next step are an L2 prefetch hint for the last one
+            io.next_user_ids_dev = user_ids.data_ptr() + 4 * need
+            io.next_item_ids_dev = item_ids.data_ptr() + 4 * need
         if item_rows is not None:
             item_rows = item_rows.contiguous()
             keep.append(item_rows)

@@ -16,7 +16,7 @@ def _int_embeddings(n, d, seed):
 
 @pytest.mark.parametrize("gen", ["3", "2", "1"])
 @pytest.mark.parametrize("nu,ni,d,k", [(300, 2500, 50, 50), (700, 9000, 128, 10), (385, 4100, 96, 32), (260, 1500, 200, 40),
-                                       (1100, 20000, 128, 64), (130, 1000, 128, 100)])
+                                       (1100, 20000, 128, 64), (130, 1000, 128, 100), (600, 40000, 128, 100)])
 def test_topk_generations_bit_exact(gen, nu, ni, d, k, monkeypatch):
     """the three tensor-core generations of whole@k (CTA pair with readers / selectors = default, one CTA per 128 users,
     streaming exact sets) on tie-heavy integer embeddings: odd numbers of user blocks (a padded pair), ragged item tiles,

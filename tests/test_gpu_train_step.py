@@ -18,6 +18,31 @@ def _rel(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
 
 
+def _rel_rows(a, b, floor=0.1):
+    """row-wise check: for every row whose reference magnitude is at least `floor` of the tensor's largest, the row's
+    max-abs error over the row's own max-abs reference value (a small row next to a large one cannot hide behind it)"""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    mag = np.max(np.abs(b), axis=1)
+    sel = mag >= floor * max(mag.max(), 1e-30)
+    if not np.any(sel):
+        return 0.0
+    return float(np.max(np.max(np.abs(a - b)[sel], axis=1) / mag[sel]))
+
+
+def _margin_T(ref, scheme, gamma, cid):
+    """M - D of the max-margin losses on the oracle's scores (utils/objectives.py:91-94 / :194-197): an element's gradient
+    is the indicator [T > 0], so only elements with |T| within the operand rounding of 0 can come out differently in bf16"""
+    S = ref["S"]
+    if scheme == "neg_shared":
+        D = np.diagonal(S)[None, :] - S
+        M = gamma * (1.0 - np.eye(S.shape[0]))
+    else:
+        _, cid_x = O.unique_first_occurrence(cid)
+        D = S[np.arange(S.shape[0]), cid_x][:, None] - S
+        M = gamma
+    return M - D
+
+
 def _tables(nu, ni, d, seed, scale=0.5):
     rng = np.random.RandomState(seed)
     EU = rng.uniform(-scale, scale, size=(nu, d)).astype(np.float32)
@@ -66,10 +91,17 @@ def test_matmul_schemes_loss_and_grads(scheme, loss, precision, B, d, norm):
     tol = TOL[precision]
     loss_gpu = float(out["loss"][0].item())
     assert abs(loss_gpu - ref["loss"]) <= tol * max(abs(ref["loss"]), 1e-6), (loss_gpu, ref["loss"])
+    flips_allowed = None
     if loss == "max-margin" and precision == "bf16" and norm:
         # indicator gradient + l2-normalised operands (not bf16-representable): a score within bf16 rounding of the margin
-        # flips its indicator, which moves the gradient by a whole 1/(B*n) unit; the loss (continuous) keeps 1e-2
-        tol = 3e-2
+        # flips its indicator, which moves the gradient of ITS user row and ITS item row (and the positive's) by a whole
+        # 1/(B*n) unit; the loss (continuous) keeps 1e-2.  Instead of a wider tolerance for the whole tensor: count the
+        # elements whose margin term is within the rounding of its two scores (unit rows in bf16: each score is good to
+        # ~2^-10, so 2^-9 for the pair) of zero, and allow at most that many ROWS (x3: row, column, positive) to miss
+        # 1e-2 - by no more than 3e-2.
+        T = _margin_T(ref, scheme, gamma, cid)
+        flips_allowed = int(np.sum(np.abs(T) < 2.0 ** -9))
+        assert flips_allowed <= 0.02 * T.size, flips_allowed          # the test data keep the near-margin set small
     gu = out["grad_user_rows"].cpu().numpy()
     gv = out["grad_item_rows"].cpu().numpy()
     dEU = _scatter(nu, uid, gu)
@@ -82,8 +114,15 @@ def test_matmul_schemes_loss_and_grads(scheme, loss, precision, B, d, norm):
         np.testing.assert_array_equal(out["unique_ids"].cpu().numpy()[:n_u], cid_u)     # integer work: bit-exact
         np.testing.assert_array_equal(out["inverse"].cpu().numpy(), cid_x)
         dEV = _scatter(ni, cid_u, gv[:n_u])
-    assert _rel(dEU, ref["dEU"]) <= tol, ("dEU", _rel(dEU, ref["dEU"]))
-    assert _rel(dEV, ref["dEV"]) <= tol, ("dEV", _rel(dEV, ref["dEV"]))
+    for name, got, want in (("dEU", dEU, ref["dEU"]), ("dEV", dEV, ref["dEV"])):
+        if flips_allowed is None:
+            assert _rel(got, want) <= tol, (name, _rel(got, want))
+            # and row by row, for the rows that carry at least a tenth of the largest gradient
+            assert _rel_rows(got, want) <= 3 * tol, (name, "rows", _rel_rows(got, want))
+        else:
+            row_err = np.max(np.abs(got - want), axis=1) / np.max(np.abs(want))
+            assert np.max(row_err) <= 3e-2, (name, float(np.max(row_err)))
+            assert int(np.sum(row_err > tol)) <= 3 * flips_allowed, (name, int(np.sum(row_err > tol)), flips_allowed)
     # optimizer='none' must leave the tables untouched
     np.testing.assert_array_equal(tU.cpu().numpy(), EU)
     np.testing.assert_array_equal(tV.cpu().numpy(), EV)
@@ -459,6 +498,15 @@ def test_interaction_bias_matches_oracle(scheme, loss, norm, bias, precision):
             assert bias_grad_ok(gU[:, d], ref["dubias"])
         if bias in ("item", "both"):
             assert bias_grad_ok(gV[:, d + 1], ref["dcbias"])
+    else:
+        # max-margin + bf16 + l2-normalised rows: indicator gradients; rows may miss 1e-2 only where an element's margin term
+        # sits within the operand rounding of zero (counted on the oracle's scores), and then by at most 3e-2
+        T = _margin_T(ref, scheme, gamma, cid)
+        flips_allowed = int(np.sum(np.abs(T) < 2.0 ** -9))
+        for got, want in ((gU[:, :d], ref["dEU"]), (gV[:, :d], ref["dEV"])):
+            row_err = np.max(np.abs(got - want), axis=1) / np.max(np.abs(want))
+            assert np.max(row_err) <= 3e-2, float(np.max(row_err))
+            assert int(np.sum(row_err > tol)) <= 3 * flips_allowed, (int(np.sum(row_err > tol)), flips_allowed)
     # the constant columns never move; an unused bias column stays zero
     assert np.array_equal(tU.cpu().numpy()[:, d + 1], np.ones(nu, np.float32)) and np.array_equal(tV.cpu().numpy()[:, d], np.ones(ni, np.float32))
     if bias == "item":
@@ -497,3 +545,47 @@ def test_split_sweep_and_folded_regulariser(scheme, optimizer, u_reg, split, mon
         # first Adam step: m = (1 - beta1) * g on the touched rows (duplicates summed)
         assert _rel(st[0].cpu().numpy(), 0.1 * ref["dEU"]) <= 1e-2
         assert _rel(st[2].cpu().numpy(), 0.1 * ref["dEV"]) <= 1e-2
+
+
+@pytest.mark.parametrize("fold", ["1", "0"])
+@pytest.mark.parametrize("scheme", ["neg_shared", "group_neg_shared"])
+def test_lazy_adam_folded_matches_oracle_over_steps(scheme, fold, monkeypatch):
+    """bf16 lazy Adam, three dependent steps of R = 3 replicas with many duplicate ids (inside a batch, across replicas,
+    across steps): the folded form (the score kernel's drain sums gradient rows into per-table accumulators keyed by id,
+    one apply launch claims each id once) and the owner / combine / apply form against the oracle's _apply_sparse rule
+    with duplicates summed (ref: utils/optimizer.py:108-134)."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    monkeypatch.setenv("NNCF_ADAM_FOLD", fold)
+    B, d, nu, ni, lr, R, steps = 256, 64, 300, 90, 0.01, 3, 3
+    EU, EV = _tables(nu, ni, d, seed=21)
+    rng = np.random.RandomState(8)
+    uid = rng.randint(0, nu, size=steps * R * B).astype(np.int32)
+    cid = rng.randint(0, ni, size=steps * R * B).astype(np.int32)
+    U, V = EU.astype(np.float64), EV.astype(np.float64)
+    mU, vU, mV, vV = np.zeros_like(U), np.zeros_like(U), np.zeros_like(V), np.zeros_like(V)
+    for t in range(steps):
+        dU = np.zeros_like(U); dV = np.zeros_like(V)
+        us, cs = [], []
+        for r in range(R):
+            sl = slice((t * R + r) * B, (t * R + r + 1) * B)
+            ref = O.step_matmul(U, V, uid[sl], cid[sl], scheme, "skip-gram", 128.0, 10.0, u_reg=1e-3)
+            dU += ref["dEU"]; dV += ref["dEV"]; us.append(uid[sl]); cs.append(cid[sl])
+        U, mU, vU = O.lazy_adam_sparse(U, mU, vU, np.concatenate(us), dU, lr, t + 1)
+        V, mV, vV = O.lazy_adam_sparse(V, mV, vV, np.concatenate(cs), dV, lr, t + 1)
+    spec = StepSpec(scheme=scheme, loss="skip-gram", precision="bf16", batch_size_p=B, dim=d, optimizer="lazy_adam", learn_rate=lr,
+                    replicas=R, neg_loss_weight=128.0, loss_gamma=10.0, u_reg=1e-3)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    st = [torch.zeros_like(tU), torch.zeros_like(tU), torch.zeros_like(tV), torch.zeros_like(tV)]
+    out = FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), steps, adam_state=st)
+    torch.cuda.synchronize()
+    assert np.all(np.isfinite(out["loss"].cpu().numpy()))
+    # Adam's first steps move every touched coordinate by ~lr whatever the gradient's size: compare the tables absolutely
+    # (3 steps x lr = 0.03 of travel; bf16 gradients may flip a near-zero coordinate's direction for one step)
+    assert np.mean(np.abs(tU.cpu().numpy() - U)) <= 2e-4 and np.max(np.abs(tU.cpu().numpy() - U)) <= 2.5 * lr
+    assert np.mean(np.abs(tV.cpu().numpy() - V)) <= 2e-4 and np.max(np.abs(tV.cpu().numpy() - V)) <= 2.5 * lr
+    assert _rel(st[0].cpu().numpy(), mU) <= 2e-2 and _rel(st[2].cpu().numpy(), mV) <= 2e-2
+    assert _rel(st[1].cpu().numpy(), vU) <= 3e-2 and _rel(st[3].cpu().numpy(), vV) <= 3e-2
+    # untouched rows did not move
+    untouched = np.setdiff1d(np.arange(nu), uid)
+    if untouched.size:
+        np.testing.assert_array_equal(tU.cpu().numpy()[untouched], EU[untouched])

@@ -329,14 +329,22 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "6", "--warmup", "3"],
+    # (also: the reference arm must not map the product library; bench.py prints the modules it loaded on request)
+    probe = ("import runpy, sys; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '3', '--warmup', '1', '--replicas', '2'];\n"
+             "runpy.run_path('bench.py', run_name='__main__')\n"
+             "bad = [m for m in sys.modules if m == 'nncf_b200' or m.startswith('nncf_b200.')]\n"
+             "sys.stderr.write('PRODUCT_MODULES=%r\\n' % bad)\n")
+    q = subprocess.run([sys.executable, "-c", probe], capture_output=True, text=True, timeout=600, cwd=root)
+    assert q.returncode == 0 and "PRODUCT_MODULES=[]" in q.stderr, q.stderr[-800:]
+    p = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert p.returncode == 0, p.stderr[-500:]
     lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, p.stdout[:500]
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["unit"] == "links/s" and j["higher_is_better"] is True
-    assert j["steps"] == 6 and j["warmup"] == 3 and j["n_gpus"] == 1 and j["value"] > 0
+    assert j["steps"] == 3 and j["warmup"] == 1 and j["n_gpus"] == 1 and j["value"] > 0
+    assert j["config"]["replicas_per_step"] == 37 and j["config"]["u_reg"] == 1e-6      # the same step as the GPU arm
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
     assert j["config"]["workload"].startswith("C3")
