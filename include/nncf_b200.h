@@ -203,6 +203,10 @@ int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const in
  * synchronises after every step, so never enable it inside a throughput measurement).
  * phase_ms_out[3] = accumulated ms of { gather/prepare, score+gradient kernel, finalize/optimizer }. */
 int nncf_trainer_set_profile(nncf_trainer_t* t, int enable);
+/* Device step clock for CUDA-graph capture: with it enabled the lazy-Adam step count and the bias-corrected rate
+ * lr_t (ref: utils/optimizer.py:109-111) are kept in device memory and advanced by a kernel of the step itself, so a
+ * captured step stays correct when the graph is replayed (a host-side count would be frozen into the graph). */
+int nncf_trainer_set_device_clock(nncf_trainer_t* t, int enable);
 int nncf_trainer_get_profile(nncf_trainer_t* t, double* phase_ms_out, int64_t* steps_out);
 /* tf.unique on device (first-occurrence order), exposed because group_neg_shared towers need it before
  * they can produce item_rows_dev.   ref: models/model_framework.py:45-48 */
@@ -263,6 +267,23 @@ int nncf_meanpool_fwd(const float* word_table_dev, int word_dim, const int32_t* 
 /* grad_word_table[content[item_ids[n], l], :] += grad_out[n, :] / L   (atomic scatter-add) */
 int nncf_meanpool_bwd(float* grad_word_table_dev, int word_dim, const int32_t* content_dev, int content_len,
                       const int32_t* item_ids_dev, int n_items, const float* grad_out_dev, void* stream);
+/* The same two with the number of valid slots in DEVICE memory (slots [*n_valid, n_slots) read no id: the forward writes
+ * zero rows, the backward skips them): the unique-item count of tf.unique never has to reach the host, so a training
+ * step of the content model can be captured and replayed as a CUDA graph. */
+int nncf_meanpool_fwd_n(const float* word_table_dev, int word_dim, const int32_t* content_dev, int content_len,
+                        const int32_t* item_ids_dev, int n_slots, const int32_t* n_valid_dev, float* out_dev, void* stream);
+int nncf_meanpool_bwd_n(float* grad_word_table_dev, int word_dim, const int32_t* content_dev, int content_len,
+                        const int32_t* item_ids_dev, int n_slots, const int32_t* n_valid_dev, const float* grad_out_dev, void* stream);
+/* Tail of the content towers on the block of unique items: BatchNorm over the first *n_valid rows (batch statistics,
+ * Keras defaults; running statistics updated in place; ref: modules/content/mean_pool.py:90-97) followed by the
+ * activation (0 linear, 1 relu, 2 tanh), and its backward.  h / y / xhat / dy / dh are [rows, dim] row-major, rows beyond
+ * *n_valid come out as zeros; rstd / dgamma / dbeta are [dim].  use_bn = 0: activation only. */
+int nncf_tower_bn_act_fwd(const float* h_dev, int rows, int dim, const int32_t* n_valid_dev, int use_bn, int activation,
+                          const float* gamma_dev, const float* beta_dev, float eps, float momentum, float* running_mean_dev,
+                          float* running_var_dev, float* y_dev, float* xhat_dev, float* rstd_dev, void* stream);
+int nncf_tower_bn_act_bwd(const float* dy_dev, const float* y_dev, const float* xhat_dev, const float* rstd_dev, int rows, int dim,
+                          const int32_t* n_valid_dev, int use_bn, int activation, const float* gamma_dev, float* dh_dev,
+                          float* dgamma_dev, float* dbeta_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * (5) Evaluation.   ref: utils/objectives.py:296-321 (test_eval_mat: all users x candidate items),

@@ -486,7 +486,8 @@ adam_combine_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int cou
 __global__ void __launch_bounds__(256)
 adam_apply_kernel(const int32_t* __restrict__ ids, int64_t ids_stride, int count, const int32_t* __restrict__ count_dev,
                   int rows_pad, int d, int dp, int32_t* owner, const float* __restrict__ dX, float* table, float* m,
-                  float* v, float lr_t, float beta1, float beta2, float eps) {
+                  float* v, float lr_t, float beta1, float beta2, float eps, const float* lr_dev) {
+  if (lr_dev) lr_t = *lr_dev;                     // device step clock (CUDA-graph replay): see adam_tick_kernel
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
   const int cnt = count_dev ? count_dev[r] : count;
@@ -557,9 +558,11 @@ adam_combine_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int dp) {
 }
 template <int NV>
 __global__ void __launch_bounds__(256)
-adam_apply_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int d, int dp, float lr_t, float beta1, float beta2, float eps) {
+adam_apply_vec_kernel(AdamSide s0, AdamSide s1, int rows_pad, int d, int dp, float lr_t, float beta1, float beta2, float eps,
+                      const float* lr_dev) {
   pdl_launch_dependents();
   pdl_wait();
+  if (lr_dev) lr_t = *lr_dev;
   const AdamSide& s = blockIdx.z ? s1 : s0;
   if (!s.ids) return;
   constexpr int kRows = 4;                              // rows in flight per warp (id -> owner -> rows: dependent loads)
@@ -623,7 +626,8 @@ struct AdamAccSide {
 };
 template <int NV>
 __global__ void __launch_bounds__(256)
-adam_apply_accum_kernel(AdamAccSide s0, AdamAccSide s1, int tag, int d, float lr_t, float beta1, float beta2, float eps) {
+adam_apply_accum_kernel(AdamAccSide s0, AdamAccSide s1, int tag, int d, float lr_t, float beta1, float beta2, float eps,
+                        const float* lr_dev) {
   pdl_launch_dependents();
   const AdamAccSide& s = blockIdx.z ? s1 : s0;
   if (!s.ids) return;
@@ -635,6 +639,7 @@ adam_apply_accum_kernel(AdamAccSide s0, AdamAccSide s1, int tag, int d, float lr
   const bool early = s.count_dev == nullptr;
   if (early && lane < kRows && row0 + lane < s.count) myid = s.ids[r * s.ids_stride + row0 + lane];
   pdl_wait();
+  if (lr_dev) lr_t = *lr_dev;
   const int cnt = s.count_dev ? s.count_dev[r] : s.count;
   if (row0 >= cnt) return;
   if (!early && lane < kRows && row0 + lane < cnt) myid = s.ids[r * s.ids_stride + row0 + lane];
@@ -677,6 +682,14 @@ adam_apply_accum_kernel(AdamAccSide s0, AdamAccSide s1, int tag, int d, float lr
       }
     }
   }
+}
+// Device step clock: when a training step is captured into a CUDA graph and replayed, a step count kept on the host (and the
+// bias-corrected rate lr_t derived from it, passed by value) would be frozen into the graph.  With the clock enabled
+// (nncf_trainer_set_device_clock) this one-thread kernel advances the count in device memory and leaves
+// lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t) (ref: utils/optimizer.py:109-111) where the apply kernels read it.
+__global__ void adam_tick_kernel(long long* step, float* lr_out, double lr, double beta1, double beta2) {
+  const long long t = ++(*step);
+  *lr_out = static_cast<float>(lr * sqrt(1.0 - pow(beta2, static_cast<double>(t))) / (1.0 - pow(beta1, static_cast<double>(t))));
 }
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t v) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -878,6 +891,8 @@ struct nncf_trainer {
   int32_t *ownerU = nullptr, *ownerV = nullptr;
   int64_t ownerU_n = 0, ownerV_n = 0;
   // folded lazy Adam: per-table gradient accumulators [rows][d] (zero between steps) and claim words [rows]
+  long long* step_dev = nullptr;        // device step clock (see adam_tick_kernel); lr_dev != nullptr = enabled
+  float* lr_dev = nullptr;
   float *accU = nullptr, *accV = nullptr;
   int32_t *claimU = nullptr, *claimV = nullptr;
   int64_t accU_rows = 0, accV_rows = 0;
@@ -1010,7 +1025,7 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
                   t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn,
-                  t->gather_flags, t->gather_count, t->accU, t->accV, t->claimU, t->claimV};
+                  t->gather_flags, t->gather_count, t->accU, t->accV, t->claimU, t->claimV, t->step_dev, t->lr_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
@@ -1046,6 +1061,24 @@ extern "C" int nncf_trainer_set_shards(nncf_trainer_t* t, int n_shards, int rank
   t->n_shards = n_shards;
   t->rank = rank;
   t->epoch = 0;
+  return NNCF_OK;
+}
+
+extern "C" int nncf_trainer_set_device_clock(nncf_trainer_t* t, int enable) {
+  NNCF_CHECK_ARG(t, "nncf_trainer_set_device_clock: null trainer");
+  if (enable && !t->lr_dev) {
+    NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->step_dev), sizeof(long long)));
+    NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->lr_dev), sizeof(float)));
+    const long long t0 = t->adam_t;                  // continue from the host count
+    NNCF_CUDA(cudaMemcpy(t->step_dev, &t0, sizeof(long long), cudaMemcpyHostToDevice));
+    NNCF_CUDA(cudaMemset(t->lr_dev, 0, sizeof(float)));
+  } else if (!enable && t->lr_dev) {
+    long long td = 0;
+    NNCF_CUDA(cudaMemcpy(&td, t->step_dev, sizeof(long long), cudaMemcpyDeviceToHost));
+    t->adam_t = td;
+    cudaFree(t->step_dev); cudaFree(t->lr_dev);
+    t->step_dev = nullptr; t->lr_dev = nullptr;
+  }
   return NNCF_OK;
 }
 
@@ -1107,11 +1140,11 @@ static int run_adam2(nncf_trainer* t, const AdamSide& su, const AdamSide& sv, in
   if (dp <= 128) {
     NNCF_CUDA(launch_pdl(adam_combine_vec_kernel<1>, dim3(ceil_div(count, 8), R, 2), dim3(256), 0, st, su, sv, rows_stride, dp));
     NNCF_CUDA(launch_pdl(adam_apply_vec_kernel<1>, dim3(ceil_div(count, 32), R, 2), dim3(256), 0, st, su, sv, rows_stride, d, dp, lr_t,
-                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon));
+                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon, t->lr_dev));
   } else {
     NNCF_CUDA(launch_pdl(adam_combine_vec_kernel<2>, dim3(ceil_div(count, 8), R, 2), dim3(256), 0, st, su, sv, rows_stride, dp));
     NNCF_CUDA(launch_pdl(adam_apply_vec_kernel<2>, dim3(ceil_div(count, 32), R, 2), dim3(256), 0, st, su, sv, rows_stride, d, dp, lr_t,
-                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon));
+                         t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon, t->lr_dev));
   }
   return 0;
 }
@@ -1126,7 +1159,7 @@ static int run_adam(nncf_trainer* t, const int32_t* ids, int64_t ids_stride, int
   adam_combine_kernel<<<g8, 256, 0, st>>>(ids, ids_stride, count, count_dev, rows_stride, dp, owner, dX);
   NNCF_LAUNCH_OK();
   adam_apply_kernel<<<g8, 256, 0, st>>>(ids, ids_stride, count, count_dev, rows_stride, d, dp, owner, dX, table, m, v,
-                                        lr_t, t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon);
+                                        lr_t, t->cfg.beta1, t->cfg.beta2, t->cfg.epsilon, t->lr_dev);
   NNCF_LAUNCH_OK();
   adam_reset_kernel<<<g1, 256, 0, st>>>(ids, ids_stride, count, count_dev, owner);
   NNCF_LAUNCH_OK();
@@ -1163,7 +1196,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   const bool drain_reg = (fuse_sgd || adam_plain) && c.u_reg != 0.0f;    // regulariser gradient added by the score kernel's drain
   // folded lazy Adam (NNCF_ADAM_FOLD=0 keeps the owner / combine / apply form): the drain sums the gradient rows into
   // per-table accumulators keyed by id, one apply launch follows (see adam_apply_accum_kernel)
-  const bool adam_fold = adam_plain && [] { const char* e = getenv("NNCF_ADAM_FOLD"); return !e || atoi(e) != 0; }();
+  const bool adam_fold = adam_plain && !t->lr_dev && [] { const char* e = getenv("NNCF_ADAM_FOLD"); return !e || atoi(e) != 0; }();
   if (adam_fold) {
     NNCF_CHECK_ARG(tb->user_m && tb->user_v && tb->item_m && tb->item_v, "lazy Adam needs m / v tables");
     if (ensure_accum(&t->accU, &t->claimU, &t->accU_rows, tb->n_users, d, st)) return NNCF_ECUDA;
@@ -1222,8 +1255,17 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   int split = 1;
   if (bf16 && vec && !dense_items && t->n_shards <= 1) {
     const int tn = 64, nt_min = ceil_div(B, tn);     // (group: fewer unique items than B leave some split CTAs without tiles; they exit at once)
-    // (measured at R = 1, B = 512: 12.7 / 10.2 / 9.0 / 10.5 us per step for split 1 / 2 / 4 / 8)
-    while (split * 2 <= 4 && split * 2 <= nt_min && active_ctas * split * 2 <= t->resident_ctas) split *= 2;
+    // Cost model in units of one tile: a CTA takes (tiles / split + c0) with c0 ~ 4 tiles of prologue + drain, the grid runs
+    // in ceil(CTAs / resident) waves.  It reproduces the measurements: R = 1, B = 512 (8 CTAs, 8 tiles): 12.7 / 10.2 /
+    // 9.0 / 10.5 us per step for split 1 / 2 / 4 / 8; and it removes wave quantisation where a step is a fractional number
+    // of waves: C5 (256 CTAs of 256 tiles on 148 one-CTA SMs = 1.73 waves) and B = 4,096 x 5 replicas (320 CTAs on 296 slots).
+    const int resident = dp <= 128 ? t->resident_ctas : t->resident_ctas / 2;     // dp = 256 kernels: one CTA per SM
+    double best = 1e30;
+    for (int sp = 1; sp <= 4 && sp <= nt_min; sp *= 2) {                         // (8-way measured slower than 4-way: 8x the partial updates)
+      const double waves = ceil_div((int64_t)active_ctas * sp, resident);
+      const double cost = waves * (static_cast<double>(nt_min) / sp + 4.0);
+      if (cost < best * 0.97) { best = cost; split = sp; }                         // (needs a 3 % predicted gain to split further)
+    }
     const int split_env = [] { const char* e = getenv("NNCF_SPLIT"); return e ? atoi(e) : 0; }();   // (read per step: the tests switch it)
     if (split_env >= 1 && split_env <= nt_min) split = split_env;
   }
@@ -1370,6 +1412,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
     NNCF_CHECK_ARG(tb->user_m && tb->user_v, "lazy Adam needs user_m / user_v");
     t->adam_t += 1;
+    if (t->lr_dev) {                                   // device step clock: the count and lr_t live in device memory
+      adam_tick_kernel<<<1, 1, 0, st>>>(t->step_dev, t->lr_dev, (double)c.learn_rate, (double)c.beta1, (double)c.beta2);
+      NNCF_LAUNCH_OK();
+    }
     const double b1t = pow((double)c.beta1, (double)t->adam_t), b2t = pow((double)c.beta2, (double)t->adam_t);
     const float lr_t = (float)(c.learn_rate * sqrt(1.0 - b2t) / (1.0 - b1t));   // optimizer.py:109-111
     if (ensure_owner(&t->ownerU, &t->ownerU_n, tb->n_users, st)) return NNCF_ECUDA;
@@ -1383,10 +1429,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       const int tag = static_cast<int>(t->adam_t & 0x7fffffff);          // (claim words start at 0, adam_t at 1)
       if (dp <= 128)
         NNCF_CUDA(launch_pdl(adam_apply_accum_kernel<1>, dim3(ceil_div(B, 32), R, 2), dim3(256), 0, st, su, sv, tag, d, lr_t,
-                             c.beta1, c.beta2, c.epsilon));
+                             c.beta1, c.beta2, c.epsilon, t->lr_dev));
       else
         NNCF_CUDA(launch_pdl(adam_apply_accum_kernel<2>, dim3(ceil_div(B, 32), R, 2), dim3(256), 0, st, su, sv, tag, d, lr_t,
-                             c.beta1, c.beta2, c.epsilon));
+                             c.beta1, c.beta2, c.epsilon, t->lr_dev));
       count_launch();
     } else if (vec) {
       // both tables per launch, 3 launches (owner, combine, apply + re-arm), 128-bit accesses, programmatic dependent launch
@@ -1479,6 +1525,10 @@ static int apply_row_grads(nncf_trainer* t, const nncf_tables* tb, const int32_t
   } else if (c.optimizer == NNCF_OPT_LAZY_ADAM) {
     NNCF_CHECK_ARG(tb->user_m && tb->user_v && tb->item_m && tb->item_v, "lazy Adam needs m / v tables");
     t->adam_t += 1;
+    if (t->lr_dev) {                                   // device step clock: the count and lr_t live in device memory
+      adam_tick_kernel<<<1, 1, 0, st>>>(t->step_dev, t->lr_dev, (double)c.learn_rate, (double)c.beta1, (double)c.beta2);
+      NNCF_LAUNCH_OK();
+    }
     const double b1t = pow((double)c.beta1, (double)t->adam_t), b2t = pow((double)c.beta2, (double)t->adam_t);
     const float lr_t = (float)(c.learn_rate * sqrt(1.0 - b2t) / (1.0 - b1t));
     if (ensure_owner(&t->ownerU, &t->ownerU_n, tb->n_users, st)) return NNCF_ECUDA;
@@ -1708,7 +1758,7 @@ extern "C" int nncf_updater_apply(nncf_updater_t* u, float* table_dev, float* m_
   adam_combine_kernel<<<g8, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, 0, dim, u->owner, grads_dev);
   NNCF_LAUNCH_OK();
   adam_apply_kernel<<<g8, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, 0, dim, dim, u->owner, grads_dev, table_dev, m_dev, v_dev,
-                                        lr_t, u->beta1, u->beta2, u->eps);
+                                        lr_t, u->beta1, u->beta2, u->eps, nullptr);
   NNCF_LAUNCH_OK();
   adam_reset_kernel<<<g1, 256, 0, st>>>(ids_dev, 0, cnt, nullptr, u->owner);
   NNCF_LAUNCH_OK();

@@ -50,7 +50,7 @@ class DeviceSampler:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.nncf_sampler_destroy(h)
             self._h = None
 
@@ -100,7 +100,7 @@ class DeviceGroupSampler:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.nncf_group_sampler_destroy(h)
             self._h = None
 
@@ -251,6 +251,10 @@ class FusedStep:
             lib.nncf_trainer_destroy(h)
             self._h = None
 
+    def set_device_clock(self, enable: bool) -> None:
+        """keep the lazy-Adam step count / lr_t on the device so that a captured step can be replayed as a CUDA graph"""
+        check(lib.nncf_trainer_set_device_clock(self._h, int(bool(enable))))
+
     def set_profile(self, enable: bool) -> None:
         check(lib.nncf_trainer_set_profile(self._h, int(bool(enable))))
 
@@ -370,6 +374,63 @@ def meanpool_bwd(grad_word_table: torch.Tensor, content: torch.Tensor, item_ids:
                                 _ptr(item_ids), n, _ptr(grad_out), _stream()))
 
 
+def meanpool_fwd_n(word_table: torch.Tensor, content: torch.Tensor, item_ids: torch.Tensor, n_valid: torch.Tensor) -> torch.Tensor:
+    """mean-pool of `item_ids.numel()` slots of which only the first *n_valid (device int32) exist; the rest come out as zero rows"""
+    _need_cuda(word_table, content, item_ids, n_valid)
+    n = item_ids.numel()
+    out = torch.empty((n, word_table.shape[1]), dtype=torch.float32, device=word_table.device)
+    check(lib.nncf_meanpool_fwd_n(_ptr(word_table), word_table.shape[1], _ptr(content), content.shape[1], _ptr(item_ids), n,
+                                  _ptr(n_valid), _ptr(out), _stream()))
+    return out
+
+
+def meanpool_bwd_n(grad_word_table: torch.Tensor, content: torch.Tensor, item_ids: torch.Tensor, n_valid: torch.Tensor,
+                   grad_out: torch.Tensor) -> None:
+    _need_cuda(grad_word_table, content, item_ids, n_valid, grad_out)
+    grad_out = grad_out.contiguous()
+    check(lib.nncf_meanpool_bwd_n(_ptr(grad_word_table), grad_word_table.shape[1], _ptr(content), content.shape[1],
+                                  _ptr(item_ids), item_ids.numel(), _ptr(n_valid), _ptr(grad_out), _stream()))
+
+
+_ACTS = {"linear": 0, "relu": 1, "tanh": 2}
+
+
+def tower_bn_act_fwd(h: torch.Tensor, n_valid: torch.Tensor, bn, activation: str):
+    """BatchNorm over the first *n_valid rows of h (bn: a torch BatchNorm1d whose parameters / running statistics are used
+    and updated, or None) + activation.  Returns (y, xhat, rstd) - what tower_bn_act_bwd needs."""
+    _need_cuda(h, n_valid)
+    h = h.contiguous()
+    rows, d = h.shape
+    y, xhat = torch.empty_like(h), torch.empty_like(h)
+    rstd = torch.empty(d, dtype=torch.float32, device=h.device)
+    if bn is not None:
+        check(lib.nncf_tower_bn_act_fwd(_ptr(h), rows, d, _ptr(n_valid), 1, _ACTS[activation], _ptr(bn.weight), _ptr(bn.bias),
+                                        float(bn.eps), float(bn.momentum), _ptr(bn.running_mean), _ptr(bn.running_var),
+                                        _ptr(y), _ptr(xhat), _ptr(rstd), _stream()))
+    else:
+        check(lib.nncf_tower_bn_act_fwd(_ptr(h), rows, d, _ptr(n_valid), 0, _ACTS[activation], None, None, 0.0, 0.0, None, None,
+                                        _ptr(y), _ptr(xhat), _ptr(rstd), _stream()))
+    return y, xhat, rstd
+
+
+def tower_bn_act_bwd(dy: torch.Tensor, y: torch.Tensor, xhat: torch.Tensor, rstd: torch.Tensor, n_valid: torch.Tensor, bn,
+                     activation: str):
+    """Returns (dh, dgamma, dbeta); dgamma / dbeta are None without BatchNorm."""
+    _need_cuda(dy, y, xhat, rstd, n_valid)
+    dy = dy.contiguous()
+    rows, d = dy.shape
+    dh = torch.empty_like(dy)
+    if bn is not None:
+        dg = torch.empty(d, dtype=torch.float32, device=dy.device)
+        db = torch.empty(d, dtype=torch.float32, device=dy.device)
+        check(lib.nncf_tower_bn_act_bwd(_ptr(dy), _ptr(y), _ptr(xhat), _ptr(rstd), rows, d, _ptr(n_valid), 1, _ACTS[activation],
+                                        _ptr(bn.weight), _ptr(dh), _ptr(dg), _ptr(db), _stream()))
+        return dh, dg, db
+    check(lib.nncf_tower_bn_act_bwd(_ptr(dy), _ptr(y), _ptr(xhat), _ptr(rstd), rows, d, _ptr(n_valid), 0, _ACTS[activation], None,
+                                    _ptr(dh), None, None, _stream()))
+    return dh, None, None
+
+
 class MeanPoolFunction(torch.autograd.Function):
     """Segmented gather-mean over word rows with a dense-gradient backward (scatter-add kernel)."""
 
@@ -464,7 +525,7 @@ class SparseUpdater:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h:
+        if h and lib is not None:
             lib.nncf_updater_destroy(h)
             self._h = None
 

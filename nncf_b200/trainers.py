@@ -71,6 +71,8 @@ class TrainerBase(object):
             else:
                 losses = model.train_on_batches(uid, cid, n_steps)
             return float(losses.double().sum().item()), n_steps * R
+        if responses is None and hasattr(model, 'train_tower_batches'):
+            return model.train_tower_batches(uid, cid, rows_per_batch)         # content towers: no host sync per batch
         cost = 0.0
         for b in range(n_batches):
             s = slice(b * rows_per_batch, (b + 1) * rows_per_batch)

@@ -157,3 +157,42 @@ def test_pretrained_item_vectors_models_run(model, transform, capsys):
     else:
         assert isinstance(st.tower, PretrainCombinedTower)
         assert np.allclose(st.tower.c_pretrain.cpu().numpy(), C)
+
+
+@pytest.mark.parametrize("scheme,loss", [("neg_shared", "skip-gram"), ("group_neg_shared", "log-loss")])
+def test_meanpool_graph_step_equals_eager_tower_step(scheme, loss, monkeypatch):
+    """basic_embedding: the CUDA-graph step (masked BatchNorm over the n_u unique items, explicit backward, device-side step
+    clock, no host sync per batch) against the eager autograd step on the same batches from the same initial state: user
+    table, every tower parameter, BatchNorm running statistics and the epoch's loss must agree."""
+    from nncf_b200.conf import Conf
+    from nncf_b200.data_utils import get_data
+    from nncf_b200.model_framework import get_model
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NNCF_TOWER_GRAPH", mode)
+        conf = Conf('synthetic_small', {'loss': loss, 'batch_size_p': 128, 'user_dim': 32, 'item_dim': 32, 'word_dim': 32,
+                                        'learn_rate': 0.01, 'seed': 3})
+        np.random.seed(0)
+        torch.manual_seed(0)                                 # (the tower's Dense layer is initialised from torch's global stream)
+        dh = get_data('synthetic_small', conf, reverse_samping=True)
+        md = get_model(conf, dh, 'basic_embedding')
+        view = md['model_neg_shared' if scheme == 'neg_shared' else 'model_group_neg_shared']
+        train = torch.from_numpy(np.ascontiguousarray(dh.data['train'][:128 * 7], dtype=np.int32)).cuda()
+        cost, nb = view.train_tower_batches(train[:, 0].contiguous(), train[:, 1].contiguous(), 128)
+        torch.cuda.synchronize()
+        st = md['_state']
+        st.tower.eval()
+        with torch.no_grad():
+            emb = st.tower(torch.arange(64, device="cuda", dtype=torch.int32)).clone()
+        # (the Dense bias feeds a BatchNorm, which removes it: its gradient is pure rounding noise that Adam turns into +-lr
+        #  steps, so its VALUE is not comparable between two runs - nor does it matter: the tower's output is)
+        res[mode] = (cost, nb, st.user_table.clone(), [p.detach().clone() for n_, p in st.tower.named_parameters() if n_ != 'dense.bias'],
+                     st.tower.bn.running_mean.clone(), st.tower.bn.running_var.clone(), emb)
+    a, b = res["1"], res["0"]
+    assert a[1] == b[1] == 7
+    assert abs(a[0] - b[0]) <= 1e-4 * abs(b[0]), (a[0], b[0])
+    assert torch.allclose(a[2], b[2], rtol=1e-4, atol=2e-5)
+    for pa, pb in zip(a[3], b[3]):
+        assert torch.allclose(pa, pb, rtol=1e-3, atol=5e-5), float((pa - pb).abs().max())
+    assert torch.allclose(a[5], b[5], rtol=1e-3, atol=1e-6)
+    assert torch.allclose(a[6], b[6], rtol=1e-3, atol=1e-4), float((a[6] - b[6]).abs().max())      # the tower's embeddings (test phase)

@@ -308,3 +308,60 @@ def test_topk_c4_item_count_property_check(k):
         assert torch.allclose(sc[u], ref.values, rtol=1e-4, atol=1e-5)
         same = (ids[u].long() == ref.indices)
         assert bool(same.all()) or float((sc[u][~same] - ref.values[~same]).abs().max()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ content-tower tail
+@pytest.mark.parametrize("use_bn", [True, False])
+@pytest.mark.parametrize("act", ["relu", "tanh", "linear"])
+@pytest.mark.parametrize("rows,n,d", [(512, 377, 50), (128, 128, 32), (64, 3, 70)])
+def test_tower_bn_act_kernels_match_torch_batchnorm(rows, n, d, act, use_bn):
+    """BatchNorm over the first n rows (count in device memory) + activation, forward and backward, against torch's
+    BatchNorm1d (training mode, Keras-1 defaults eps 1e-3 / momentum 0.99 -> torch momentum 0.01) under autograd."""
+    from nncf_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(rows + d)
+    h = torch.randn((rows, d), device="cuda", generator=g) * 0.7 + 0.3
+    dy = torch.randn((rows, d), device="cuda", generator=g)
+    nv = torch.tensor([n], dtype=torch.int32, device="cuda")
+    bn = torch.nn.BatchNorm1d(d, eps=1e-3, momentum=0.01).cuda() if use_bn else None
+    ref_bn = torch.nn.BatchNorm1d(d, eps=1e-3, momentum=0.01).cuda() if use_bn else None
+    if use_bn:
+        with torch.no_grad():
+            bn.weight.uniform_(0.5, 1.5); bn.bias.uniform_(-0.3, 0.3)
+            ref_bn.weight.copy_(bn.weight); ref_bn.bias.copy_(bn.bias)
+    hr = h[:n].clone().requires_grad_(True)
+    z = ref_bn(hr) if use_bn else hr
+    yr = torch.relu(z) if act == "relu" else (torch.tanh(z) if act == "tanh" else z)
+    yr.backward(dy[:n])
+    with torch.no_grad():
+        y, xhat, rstd = ops.tower_bn_act_fwd(h, nv, bn, act)
+        dh, dg, db = ops.tower_bn_act_bwd(dy, y, xhat, rstd, nv, bn, act)
+    torch.cuda.synchronize()
+    assert torch.allclose(y[:n], yr, rtol=1e-4, atol=1e-5)
+    assert float(y[n:].abs().max()) == 0.0 if n < rows else True
+    assert torch.allclose(dh[:n], hr.grad, rtol=1e-3, atol=2e-5), float((dh[:n] - hr.grad).abs().max())
+    assert float(dh[n:].abs().max()) == 0.0 if n < rows else True
+    if use_bn:
+        assert torch.allclose(dg, ref_bn.weight.grad, rtol=1e-3, atol=2e-5) and torch.allclose(db, ref_bn.bias.grad, rtol=1e-3, atol=2e-5)
+        assert torch.allclose(bn.running_mean, ref_bn.running_mean, rtol=1e-5, atol=1e-7)
+        assert torch.allclose(bn.running_var, ref_bn.running_var, rtol=1e-5, atol=1e-7)
+
+
+def test_meanpool_device_count_variant_matches_plain():
+    from nncf_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    V, dw, L, n_slots, n = 900, 50, 37, 96, 61
+    W = torch.randn((V, dw), device="cuda", generator=g)
+    content = torch.randint(0, V, (300, L), device="cuda", generator=g, dtype=torch.int32)
+    content[:, :5] = 0                                                   # 0-left-padded, as the reference's content matrix
+    ids = torch.randint(0, 300, (n_slots,), device="cuda", generator=g, dtype=torch.int32)
+    ids[n:] = 2_000_000_000                                              # slots beyond the count must never be dereferenced
+    nv = torch.tensor([n], dtype=torch.int32, device="cuda")
+    out = ops.meanpool_fwd_n(W, content, ids, nv)
+    ref = ops.meanpool_fwd(W, content, ids[:n].contiguous(), n)
+    assert torch.equal(out[:n], ref) and float(out[n:].abs().max()) == 0.0
+    gy = torch.randn((n_slots, dw), device="cuda", generator=g)
+    dW1, dW2 = torch.zeros_like(W), torch.zeros_like(W)
+    ops.meanpool_bwd_n(dW1, content, ids, nv, gy)
+    ops.meanpool_bwd(dW2, content, ids[:n].contiguous(), n, gy[:n].contiguous())
+    torch.cuda.synchronize()
+    assert torch.allclose(dW1, dW2, rtol=1e-5, atol=1e-6)

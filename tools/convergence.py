@@ -45,6 +45,27 @@ def planted_links(n_users=5551, n_items=16980, n_links=204986, rank=16, temp=0.3
     return (users[n_test:].to(torch.int32), items[n_test:].to(torch.int32)), (users[:n_test], items[:n_test]), n_users, n_items
 
 
+def planted_links_big(n_users, n_items, n_links, rank=16, n_cand=64, temp=0.5, seed=2018):
+    """the same kind of planted preference data at a scale where a softmax over all items per link is too much: every link's
+    user ~ (rank + 10)^-0.8, then 64 candidate items ~ (rank + 10)^-1.0 and ONE of them drawn ∝ exp(<u*, v*> / (temp sqrt(rank)))"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    Us = torch.randn((n_users, rank), device="cuda", generator=g)
+    Vs = torch.randn((n_items, rank), device="cuda", generator=g)
+    pu = torch.pow(torch.arange(n_users, device="cuda", dtype=torch.float64) + 10.0, -0.8); cu = torch.cumsum(pu, 0); cu = cu / cu[-1]
+    pi = torch.pow(torch.arange(n_items, device="cuda", dtype=torch.float64) + 10.0, -1.0); ci = torch.cumsum(pi, 0); ci = ci / ci[-1]
+    perm_u = torch.randperm(n_users, device="cuda", generator=g); perm_i = torch.randperm(n_items, device="cuda", generator=g)
+    users = torch.empty(n_links, dtype=torch.int64, device="cuda"); items = torch.empty(n_links, dtype=torch.int64, device="cuda")
+    for s in range(0, n_links, 1_000_000):
+        n = min(1_000_000, n_links - s)
+        u = perm_u[torch.searchsorted(cu, torch.rand(n, device="cuda", generator=g, dtype=torch.float64)).clamp_(max=n_users - 1)]
+        cand = perm_i[torch.searchsorted(ci, torch.rand((n, n_cand), device="cuda", generator=g, dtype=torch.float64)).clamp_(max=n_items - 1)]
+        logits = torch.einsum("nr,ncr->nc", Us[u], Vs[cand]) / (temp * rank ** 0.5)
+        pick = torch.multinomial(torch.softmax(logits, dim=1), 1, generator=g)
+        users[s:s + n] = u; items[s:s + n] = cand.gather(1, pick)[:, 0]
+    n_test = n_links // 10
+    return (users[n_test:].to(torch.int32), items[n_test:].to(torch.int32)), (users[:n_test], items[:n_test]), n_users, n_items
+
+
 def csr_truth(users, items, n_users, n_items):
     key = torch.unique(users.to(torch.int64) * n_items + items.to(torch.int64))
     owner, cols = key // n_items, (key % n_items).to(torch.int32)
@@ -135,6 +156,31 @@ def run_stratified(train, truth, n_users, n_items, world, R, epochs, opt, lr, d,
     return hist
 
 
+def medium_scale(emit, args):
+    """the same comparison where the throughput modes are meant to run: 200k x 200k rows, 20M links (1/5 of C3 in rows and links):
+    a stratified block at N = 8 still holds 25k users x 12.5k items, a step of 37 batches touches ~10 % of the rows"""
+    d, B, E = 64, 512, 8
+    nu = ni = 200_000
+    train, test, nu, ni = planted_links_big(nu, ni, 20_000_000)
+    truth = csr_truth(test[0], test[1], nu, ni)
+    emit("## medium scale: %d users x %d items, %d train / %d held-out links, d = %d, B = %d, %d epochs, recall@50 per epoch" % (
+        nu, ni, train[0].numel(), test[0].numel(), d, B, E))
+    emit("")
+    emit("| mode | " + " | ".join("ep%d" % (e + 1) for e in range(E)) + " | MAP@50 last | loss last | recall last vs R=1 |")
+    emit("|---|" + "---|" * (E + 3))
+    for opt, lr1, variants in (("lazy_adam", 0.01, ((1, 0.01), (37, 0.01), (37, 0.0608), (37, 0.2))), ("sgd", 1.0, ((1, 1.0), (8, 1.0), (37, 1.0)))):
+        base = None
+        for R, lr in variants:
+            h = run_single(train, truth, nu, ni, R, E, opt, lr, d, B, 1)
+            if R == 1:
+                base = h[-1][1]
+            emit("| %s lr %.3g, 1 GPU, R = %d | " % (opt, lr, R) + " | ".join("%.4f" % x[1] for x in h) + " | %.4f | %.3f | %+.1f %% |" % (h[-1][2], h[-1][0], 100 * (h[-1][1] / base - 1)))
+        for R, lr in ((1, lr1), (37, lr1 if opt == "sgd" else 0.0608)):
+            h = run_stratified(train, truth, nu, ni, 8, R, E, opt, lr, d, B, 1)
+            emit("| %s lr %.3g, stratified N = 8 (16 strata), R = %d | " % (opt, lr, R) + " | ".join("%.4f" % x[1] for x in h) + " | %.4f | %.3f | %+.1f %% |" % (h[-1][2], h[-1][0], 100 * (h[-1][1] / base - 1)))
+    emit("")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--epochs", type=int, default=40)
@@ -142,6 +188,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--sgd-lr", type=float, default=1.0)
     ap.add_argument("--sweep-sgd", action="store_true", help="only: SGD learning-rate sweep at R = 1")
+    ap.add_argument("--medium", action="store_true", help="also: 200k x 200k rows, 20M links, 8 epochs (early training only; not converged)")
     args = ap.parse_args()
     d, B, E = 64, 512, args.epochs
     train, test, nu, ni = planted_links()
@@ -227,6 +274,8 @@ def main():
                 h = run_stratified(train, truth, nu, ni, world, R, E, "sgd", sgd_lr, d, B, 1)
                 row("stratified N = %d (%d strata), R = %d" % (world, 2 * world, R), [h], base)
         emit("")
+    if args.medium:
+        medium_scale(emit, args)
     emit("(wall time %.0f s)" % (time.time() - t0))
     if args.out:
         with open(args.out, "w") as f:
