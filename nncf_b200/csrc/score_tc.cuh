@@ -69,6 +69,7 @@ struct ScoreTcArgs {
   // 512 is only 8 CTAs: at R = 1 (the reference's sequential loop) the sweep is the critical path of the step.
   int split;
   int drain_vec;   // fused drain with vector reductions instead of bulk reductions (small grids), see the drain
+  int dedup;       // fused drain: rows of a warp's 32 that share an id are summed in shared memory first (crowded ids)
   // fused mode has no finalize launch: the last side-0 CTA of a replica publishes the replica's loss and re-arms the
   // accumulators (loss_count[R] arrival counters, zero between steps)
   unsigned int* loss_count;
@@ -91,6 +92,17 @@ struct ScoreTcArgs {
   // and into the global image, where the CTAs of the other side read them as their Y tiles once the block's flag
   // carries this step's sequence number.  The tables are read and updated inside one kernel now, so no drain may
   // start before every CTA has finished reading: gather_count (monotonic) must reach gather_target first.
+  // G' exchange ("two-sided", neg_shared with a pointwise loss, dp <= 128, B % 128 == 0, no split): only the user-side CTAs
+  // run the score / loss / gradient epilogue.  Besides feeding G' to their own MMA2 through tensor memory they store every
+  // G' tile (bf16) into gx_buf as the 128B-swizzled tile image [128 user rows][128 B = 64 item columns] of an MN-major A
+  // operand, and raise gx_flags[(r, a, b)] = gx_seq once both 64-column halves of item block b are written.  The item-side
+  // CTA of block b has no epilogue loop: its producer warp waits for the flag of each user block a, copies the G' image
+  // and user block a's rows (both with the bulk-copy engine), and its MMA warp accumulates dV_b += G'(a, b)^T U_a - every
+  // sigmoid is computed ONCE, the item side is a plain contraction.  All flags of a step carry the step's sequence number.
+  int gx;
+  int gx_seq;
+  uint8_t* gx_buf;                            // [R][nblk a][nblk b][2 halves][16 KiB]
+  int* gx_flags;                              // [R][nblk a][nblk b]
   int self_gather;
   int gather_seq;                             // this step's sequence number (> 0, increasing)
   int* gather_flags;                          // [R][2][rows_pad / 128]
@@ -112,16 +124,31 @@ struct ScoreTcCfg {
   // swept rows per tile = columns of one S' tile.  dp = 256 used 128-row tiles with 2 stages of 64 KiB: a stage is held
   // from MMA1 through the epilogue to MMA2, so the next-but-one tile's copy (64 KiB, ~2k cycles) could only start after
   // MMA2 and was fully exposed (tensor pipe ~50 % busy at C5).  64-row tiles: 32 KiB stages, four of them in flight.
-  static constexpr int TN = NSUB <= 2 ? 64 : NNCF_SCORE_TN4;
-  static constexpr int CW = TN / 2;                   // S' columns per epilogue warp
+#ifndef NNCF_SCORE_TEAMS
+#define NNCF_SCORE_TEAMS 0
+#endif
+  // "teams" (compile-time option, measured and NOT used): 32-row tiles, FOUR S' buffers of 32 columns, the two groups of four
+  // epilogue warps take alternate tiles instead of the two column halves of every tile.  The idea: the tile loop is a
+  // dependent chain per S' buffer (S' ready -> TMEM load -> G' -> TMEM store -> barrier -> MMA2 -> MMA1 of the tile that
+  // reuses the buffer -> commit: ~600 cycles with everything but the synchronisation switched off, tools/score_bench.cu
+  // ablation 63), tensor memory fixes the columns in flight (128 next to the accumulator) but not their granularity, so four
+  // shorter chains should fill the bubbles of two long ones.  Measured (tools/gpu_r2_v.sh, parity green): C3 22.9 vs 21.0 us
+  // per step, B = 4,096: 130.6 vs 104.8 us.  The loop is not waiting for round trips, it is MUFU-bound: one MUFU.TANH per
+  // score = 8.2k cycles per SM sub-partition and step against a measured 12.2k for the loop, and N = 32 MMAs only double the
+  // issue work of the MMA warp.  What halves the MUFU work is computing every sigmoid once: the G' exchange below.
+  static constexpr bool kTeams = (NSUB <= 2) && NNCF_SCORE_TEAMS;
+  static constexpr int TN = kTeams ? 32 : (NSUB <= 2 ? 64 : NNCF_SCORE_TN4);
+  static constexpr int CW = kTeams ? 32 : TN / 2;     // S' columns per epilogue warp
+  static constexpr int kBufs = kTeams ? 4 : 2;        // S' buffers in tensor memory
   static constexpr int kYBytes = TN * 128;            // one [TN rows x 64 bf16] piece of a Y tile (8 or 16 KiB)
 #ifndef NNCF_SCORE_STAGES
 #define NNCF_SCORE_STAGES 4
 #endif
   // Two resident CTAs of a tcgen05 kernel have (228 KiB - 2 x (1 KiB reserved + 1 KiB tcgen05 block)) / 2 = 112 KiB of
   // dynamic shared memory each (measured with tools/occ_probe.cu), barriers included.
-  static constexpr int kStages = (NSUB <= 2 || TN == 64) ? NNCF_SCORE_STAGES : 2;   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
-  static constexpr int kColDX = 2 * TN;               // S' is double buffered in TMEM columns [0, 2 TN)
+  static constexpr int kStages = kTeams ? 2 * NNCF_SCORE_STAGES : ((NSUB <= 2 || TN == 64) ? NNCF_SCORE_STAGES : 2);   // Y tiles in flight (the bulk-copy latency is ~2k cycles)
+  static_assert(kStages <= 8, "barrier block: eight Y stages");
+  static constexpr int kColDX = kBufs * TN;           // the S' buffers take TMEM columns [0, kBufs TN)
   static constexpr int kTmemCols = (kColDX + DP) <= 256 ? 256 : 512;
   static constexpr int kMinBlocks = NSUB <= 2 ? 2 : 1;   // resident CTAs per SM
   // no alignment slack: the dynamic shared window starts 1024-byte aligned (checked at kernel entry); two CTAs of
@@ -286,9 +313,10 @@ __device__ __forceinline__ void epi_chunk(const EpiConst& c, float (&v)[32], int
   for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
 }
 
-template <int NSUB, int LOSS, bool GROUP>
+template <int NSUB, int LOSS, bool GROUP, bool GX = false>
 __global__ void __launch_bounds__(kScoreThreads, ScoreTcCfg<NSUB>::kMinBlocks)
 score_grad_tc_kernel(ScoreTcArgs a) {
+  static_assert(!GX || (!GROUP && LOSS < NNCF_LOSS_LOG_LOSS && NSUB <= 2 && !ScoreTcCfg<NSUB>::kTeams), "G' exchange: neg_shared, pointwise loss, dp <= 128");
   using C = ScoreTcCfg<NSUB>;
   constexpr int DP = C::DP;
   constexpr int TN = C::TN;
@@ -301,13 +329,16 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   uint8_t* sX = smem + C::kBarBytes;
   uint8_t* sY = sX + NSUB * kSubBytes;
   uint64_t* x_full = bars + 0;
-  uint64_t* y_full = bars + 1;      // [4]
-  uint64_t* y_empty = bars + 5;     // [4]
-  uint64_t* s_full = bars + 9;      // [2]  S'(t) is in TMEM buffer t & 1
-  uint64_t* g_full = bars + 11;     // [2]  G'(t) has replaced it
-  uint64_t* dx_full = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* loss_slots = reinterpret_cast<float*>(bars + 20);   // [8] per-epilogue-warp loss sums, handed to warp 0 (see below)
+  uint64_t* y_full = bars + 1;      // [kStages <= 8]
+  uint64_t* y_empty = bars + 9;     // [kStages <= 8]
+  uint64_t* s_full = bars + 17;     // [kBufs <= 4]  S'(t) is in TMEM buffer t % kBufs
+  uint64_t* g_full = bars + 21;     // [kBufs <= 4]  G'(t) has replaced it
+  uint64_t* dx_full = bars + 25;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* loss_slots = reinterpret_cast<float*>(bars + 28);   // [8] per-epilogue-warp loss sums, handed to warp 0 (see below)
+  uint32_t* gx_cnt = reinterpret_cast<uint32_t*>(bars + 32);   // G' exchange: epilogue warps that have stored their part of a tile (monotonic)
+  constexpr int kBufs = C::kBufs;
+  constexpr int kGArrive = C::kTeams ? kScoreEpiWarps / 2 : kScoreEpiWarps;   // epilogue warps that write one G' tile
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nblk_grid = a.rows_pad >> 7;
@@ -325,14 +356,24 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   if (nt <= 0) return;                             // (the host never asks for more splits than tiles)
   const int nblk = a.rows_pad >> 7;
   const int64_t base = (int64_t)r * a.rows_pad;
+  // G' exchange: side-1 CTAs only contract (gx1); side-0 CTAs sweep the item tiles starting at their own diagonal block
+  // (rot), so that the item block every item-side CTA waits for next comes from a different user-side CTA each time
+  const bool gx1 = GX && side == 1;
+  constexpr int kTilesPerBlk = 128 / C::TN;
+  const int rot = (GX && side == 0) ? (ob * kTilesPerBlk) % nt : 0;
+  constexpr bool bal_loss = (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) && !GX;   // the two sides share the loss code (see the epilogue)
+  constexpr int kGxStages = NSUB >= 2 ? 3 : 2;                              // item side: stages of [G' 2 x 8 KiB][U rows NSUB x 8 KiB] = 64 user rows
+  constexpr uint32_t kGxStageBytes = 2 * 8192 + NSUB * 8192;
+  static_assert(kGxStages * kGxStageBytes <= NSUB * kSubBytes + (C::kYAllBytes > C::kStageBytes ? C::kYAllBytes : C::kStageBytes), "G' exchange stages overlay the X block and the Y stages");
   const uint8_t* gX = (side == 0 ? a.Uimg : a.Vimg) + ((int64_t)r * nblk + ob) * NSUB * kSubBytes;
   const uint8_t* gY = (side == 0 ? a.Vimg : a.Uimg) + (int64_t)r * nblk * NSUB * kSubBytes;
 
   if (tid == 0) {
     mbar_init(x_full, 1);
-    for (int s = 0; s < 4; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&g_full[s], kScoreEpiWarps); }
+    for (int s = 0; s < C::kStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
+    for (int s = 0; s < kBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&g_full[s], kGArrive); }
     mbar_init(dx_full, 1);
+    *gx_cnt = 0u;
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C::kTmemCols);
@@ -353,14 +394,36 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ producer
-    if (lane == 0) {
+    if (lane == 0 && gx1) {
+      // item side of the G' exchange: for the user blocks in the order their CTAs finish my item block, wait for the flag,
+      // then copy the G' image (A operand, K = user rows) and the user rows (B operand) in two stages of 64 user rows
+      int i = 0;
+      for (int j = 0; j < nblk; ++j) {
+        const int ua = (ob - j + nblk) % nblk;
+        const int64_t pair = ((int64_t)r * nblk + ua) * nblk + ob;
+        const int* flag = a.gx_flags + pair;
+        uint32_t spins = 0;
+        while (ld_acquire_gpu(flag) != a.gx_seq) { __nanosleep(32); if (++spins > 40000000u) __trap(); }
+        fence_proxy_async_global();                      // G' was written with generic stores; the bulk copy reads it
+        const uint8_t* gsrc = a.gx_buf + pair * 2 * kSubBytes;
+        const uint8_t* usrc = a.Uimg + ((int64_t)r * nblk + ua) * NSUB * kSubBytes;
+        for (int kh = 0; kh < 2; ++kh, ++i) {
+          const int st = i % kGxStages;
+          mbar_wait(&y_empty[st], ((i / kGxStages) & 1) ^ 1);
+          mbar_expect_tx(&y_full[st], kGxStageBytes);
+          uint8_t* dst = sX + st * kGxStageBytes;
+          for (int m = 0; m < 2; ++m) bulk_g2s(dst + m * 8192, gsrc + (size_t)m * kSubBytes + kh * 8192, 8192, &y_full[st]);
+          for (int s2 = 0; s2 < NSUB; ++s2) bulk_g2s(dst + 16384 + s2 * 8192, usrc + (size_t)s2 * kSubBytes + kh * 8192, 8192, &y_full[st]);
+        }
+      }
+    } else if (lane == 0) {
       if (!a.self_gather) {
         mbar_expect_tx(x_full, NSUB * kSubBytes);
         for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
       }
       int ready_blk = -1;                                // self-gather: blocks of the swept side known to be in the image
       for (int it = 0; it < nt; ++it) {
-        const int t = t_begin + it;
+        const int t = t_begin + (GX ? (it + rot) % nt : it);
         const int st = it % C::kStages;
         if (a.self_gather && ((t * TN) >> 7) > ready_blk) {
           ready_blk = (t * TN) >> 7;
@@ -378,7 +441,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           bulk_g2s(sY + (st * NSUB + s) * C::kYBytes, src + (size_t)s * kSubBytes, C::kYBytes, &y_full[st]);
       }
     }
-    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {
+    if (side == 0 || bal_loss) {
       // loss hand-off for the whole CTA (the epilogue warps have moved on to the drain)
       __syncwarp();                                      // lane 0 comes out of the producer loop: the barrier below is .aligned
       asm volatile("bar.sync 2, %0;" ::"n"(32 * kScoreEpiWarps + 32) : "memory");
@@ -393,7 +456,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           // (instead of __threadfence() = MEMBAR.SC.GPU on either side of a relaxed atomic)
           // (split CTAs whose tile range is empty left before the barriers: min(split, tiles) of them arrive per owner block)
           const unsigned int expect = static_cast<unsigned int>((n_owner + 127) >> 7) * static_cast<unsigned int>(a.split < nt_all ? a.split : nt_all) *
-                                      ((LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) ? 2u : 1u);
+                                      (bal_loss ? 2u : 1u);
           unsigned int arrived;
           asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(arrived) : "l"(a.loss_count + r) : "memory");
           if (arrived + 1u == expect) {
@@ -411,7 +474,29 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     // registers, one UIADD3.64 per MMA); one elected lane issues.  Under `if (lane == 0)` ptxas rebuilt every descriptor
     // and moved the addresses through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence: ~160 cycles per MMA, against 32-64
     // cycles of tensor work.
-    {
+    if (gx1) {
+      // item side of the G' exchange: dV_b += G'(a, b)^T U_a, both operands MN-major (rows = user rows = K), 64 user rows per stage
+      const uint32_t idesc3 = make_idesc_bf16(128, DP, 1, 1);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      const uint64_t gdesc0 = make_smem_desc(smem_u32(sX), 8192, 1024);              // A: [64 user rows][2 x 64 item columns]
+      const uint64_t udesc0 = make_smem_desc(smem_u32(sX) + 16384, 8192, 1024);      // B: [64 user rows][NSUB x 64 columns of d]
+      for (int i = 0; i < 2 * nblk; ++i) {
+        const int st = i % kGxStages;
+        mbar_wait(&y_full[st], (i / kGxStages) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t off = static_cast<uint64_t>((st * kGxStageBytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_u + C::kColDX, gdesc0 + off + static_cast<uint64_t>((k * 2048) >> 4),
+                      udesc0 + off + static_cast<uint64_t>((k * 2048) >> 4), idesc3, (i > 0) || (k > 0));
+          umma_commit(&y_empty[st]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(dx_full);
+      __syncwarp();
+    } else {
       const uint32_t idesc_s = make_idesc_bf16(128, TN, 0, 0);
       const uint32_t idesc_dx = make_idesc_bf16(128, DP, 0, 1);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -419,9 +504,9 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       const uint64_t ydesc0 = make_smem_desc(smem_u32(sY), 16, 1024);            // K-major view of a Y stage (MMA1)
       const uint64_t ydesc0_mn = make_smem_desc(smem_u32(sY), C::kYBytes, 1024); // MN-major view of the same bytes (MMA2)
       auto issue_mma1 = [&](int t) {
-        const int st = t % C::kStages, sb = t & 1;
+        const int st = t % C::kStages, sb = t % kBufs;
         mbar_wait(&y_full[st], (t / C::kStages) & 1);
-        // buffer sb was last read by MMA2(t - 2), issued earlier by this warp: the tensor pipe runs in issue order
+        // buffer sb was last read by MMA2(t - kBufs), issued earlier by this warp: the tensor pipe runs in issue order
         if (elect_one()) {
           const uint64_t yd = ydesc0 + static_cast<uint64_t>((st * NSUB * C::kYBytes) >> 4);
           const uint32_t dcol = tmem_u + sb * TN;
@@ -435,12 +520,13 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       };
       mbar_wait(x_full, 0);
       if (lane == 0) NNCF_STAMP(1);
-      issue_mma1(0);
+      constexpr int kAhead = kBufs - 1;         // MMA1 runs this many tiles ahead of MMA2
+      for (int p = 0; p < kAhead && p < nt; ++p) issue_mma1(p);
       if (lane == 0) NNCF_STAMP(2);
       for (int t = 0; t < nt; ++t) {
-        const int st = t % C::kStages, sb = t & 1;
-        if (t + 1 < nt) issue_mma1(t + 1);
-        mbar_wait(&g_full[sb], (t >> 1) & 1);
+        const int st = t % C::kStages, sb = t % kBufs;
+        if (t + kAhead < nt) issue_mma1(t + kAhead);
+        mbar_wait(&g_full[sb], (t / kBufs) & 1);
         if (lane == 0 && t < 8) NNCF_STAMP(8 + t);
         tc_fence_after();
         if (elect_one()) {
@@ -527,17 +613,20 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       }
     }
 
-    for (int it = 0; it < nt; ++it) {
-      const int t = t_begin + it;                       // tile position in the sweep; `it` indexes the pipeline state
-      const int sb = it & 1;
-      mbar_wait(&s_full[sb], (it >> 1) & 1);
+    // teams: this warp's group of four takes tiles h, h + 2, ...; otherwise every warp takes its column half of every tile
+    constexpr int kItStep = C::kTeams ? 2 : 1;
+    const int hcol = C::kTeams ? 0 : h * CW;            // my first column inside a tile
+    for (int it = C::kTeams ? h : 0; it < (gx1 ? 0 : nt); it += kItStep) {
+      const int t = t_begin + (GX ? (it + rot) % nt : it);   // tile position in the sweep; `it` indexes the pipeline state
+      const int sb = it % kBufs;
+      mbar_wait(&s_full[sb], (it / kBufs) & 1);
       if (warp == 2 && lane == 0 && it < 8) NNCF_STAMP(16 + it);
       tc_fence_after();
       float v[NV][32];
 #pragma unroll
-      for (int j = 0; j < NV; ++j) tmem_ld32(tmem + lane_addr + sb * TN + h * CW + 32 * j, v[j]);
+      for (int j = 0; j < NV; ++j) tmem_ld32(tmem + lane_addr + sb * TN + hcol + 32 * j, v[j]);
       tmem_ld_wait();
-      const int x0 = t * TN + h * CW;                   // swept index of my first column
+      const int x0 = t * TN + hcol;                     // swept index of my first column
       // fast path: a full tile that cannot contain a positive (neg_shared: only the diagonal tiles have them)
       constexpr bool kFastSg = (LOSS == NNCF_LOSS_SKIP_GRAM);
       constexpr bool kBalanceLoss = kFastSg && !GROUP;
@@ -572,7 +661,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // seen once by each side); blocks that touch a ragged edge stay with side 0, whose general path handles them
       bool loss_here = (side == 0);
       if (NNCF_ABLATE & 16) loss_here = false;
-      else if (kBalanceLoss) {
+      else if (kBalanceLoss && !GX) {
         const bool take1 = (((o / TN) + t) & 1) && ((o / TN) * TN + TN <= n_owner);   // parity-1 block, my row block is full
         loss_here = (side == 0) ? !take1 : take1;
       }
@@ -610,13 +699,29 @@ score_grad_tc_kernel(ScoreTcArgs a) {
             pk[j][i] = (pw == 16 * j + i) ? patched : pk[j][i];
           }
       }
+      if (GX) {
+        // G' exchange: my 32 (= CW) item columns of row ol go into the image the item-side CTA of this item block copies
+        // as an MN-major A operand: row = user row, 16-byte chunk c of the 128-byte row at position c ^ (row & 7)
+        const int tb = t * TN;
+        uint8_t* gdst = a.gx_buf + ((((int64_t)r * nblk + ob) * nblk + (tb >> 7)) * 2 + ((tb >> 6) & 1)) * kSubBytes + ol * 128;
+#pragma unroll
+        for (int j = 0; j < NV; ++j)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int c = (((tb + hcol + 32 * j) & 63) >> 3) + i;
+            *reinterpret_cast<uint4*>(gdst + ((c ^ (ol & 7)) << 4)) = make_uint4(pk[j][4 * i], pk[j][4 * i + 1], pk[j][4 * i + 2], pk[j][4 * i + 3]);
+          }
+      }
       // G' goes back into TMEM over the first half of my own S' columns (two bf16 per column): the A operand of MMA2
 #pragma unroll
-      for (int j = 0; j < NV; ++j) tmem_st16(tmem + lane_addr + sb * TN + h * CW + 16 * j, pk[j]);
+      for (int j = 0; j < NV; ++j) tmem_st16(tmem + lane_addr + sb * TN + hcol + 16 * j, pk[j]);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&g_full[sb]);
+      if (lane == 0) {
+        mbar_arrive(&g_full[sb]);
+        if (GX) red_release_cta_smem_add(gx_cnt, 1u);   // (after the __syncwarp: covers the whole warp's G' stores)
+      }
       if (warp == 2 && lane == 0 && it < 8) NNCF_STAMP(24 + it);
     }
     // (the loss hand-off comes BEFORE the drain: its values are final once the tile loop has ended, and its two gpu-scope
@@ -626,7 +731,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       if (side == 0 && GROUP) atomicAdd(a.corrU + base + o, asum);
       if (side == 1 && !GROUP) atomicAdd(a.corrV + base + o, asum);
     }
-    if (side == 0 || (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP)) {   // (balanced loss: both sides hold a share)
+    if (side == 0 || bal_loss) {   // (balanced loss: both sides hold a share)
       // The replica's loss is summed with a gpu-scope atomic, a fence and an arrival counter (the last arriver publishes):
       // ~4 us when the epilogue warps did it themselves in front of (or behind) the drain - the in-kernel timeline showed
       // the drain + update is only 2.6 us.  The warps now leave their sums in shared memory, arrive on a named barrier
@@ -707,8 +812,34 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         if (!a.drain_vec) {
           // one bulk reduction (TMA engine, performed at the L2) per owned row
           const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
-          if (!(NNCF_ABLATE & 32) && row < 128 && ob * 128 + row < n_owner) {
-            const int64_t id = ids[row];
+          int64_t id = (row < 128 && ob * 128 + row < n_owner) ? ids[row] : -1;
+          if (a.dedup && row < 128) {
+            // Crowded ids (a stratified block at N = 8 spreads 18,944 links over 62,500 item rows: its hottest row takes
+            // ~10 % of them) make thousands of 512-byte reductions queue on the same L2 lines: the score kernel went from
+            // 21.9 us (N = 1) to 29.6 us (N = 8).  Rows of a warp's 32 that share an id are summed in shared memory first
+            // and leave as ONE reduction: one MATCH per warp, no block barrier, nothing to do when there are no duplicates.
+            // (Folding over the whole 128-row block with two block barriers cost 3.5 us per step and gained 2.6 at N = 8.)
+            const unsigned same = __match_any_sync(0xffffffffu, static_cast<int32_t>(id));
+            const int leader = __ffs(same) - 1;
+            unsigned dup = __ballot_sync(0xffffffffu, id >= 0 && leader != lane);
+            while (dup) {                                                          // warp-cooperative: lanes along the row
+              const int L = __ffs(dup) - 1;
+              dup &= dup - 1;
+              const int src = (row & ~31) + L, dst = (row & ~31) + __shfl_sync(0xffffffffu, leader, L);
+              for (int c = 4 * lane; c < a.d; c += 128) {
+                const float4 g4 = *reinterpret_cast<const float4*>(stage + src * LD + c);
+                float4* q = reinterpret_cast<float4*>(stage + dst * LD + c);
+                float4 t4 = *q;
+                t4.x += g4.x; t4.y += g4.y; t4.z += g4.z; t4.w += g4.w;
+                *q = t4;
+              }
+              __syncwarp();
+            }
+            if (id >= 0 && leader != lane) id = -1;                                // folded into the warp's first occurrence
+            fence_proxy_async();                                                   // the sums are read by the TMA engine
+            __syncwarp();
+          }
+          if (!(NNCF_ABLATE & 32) && id >= 0) {
             float* trow = sh.n > 1 ? sh.p[id % sh.n] + (id / sh.n) * a.d : table + id * a.d;
             bulk_reduce_add_f32_s2g(trow, stage + row * LD, static_cast<uint32_t>(a.d) * 4u);
             bulk_commit_group();
@@ -749,7 +880,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     if (warp == 2 && lane == 0) NNCF_STAMP(5);
     tc_fence_before();
   }
-  else if (a.next_ids_u && !(NNCF_ABLATE & 64)) {
+  else {
+   if (a.next_ids_u && !(NNCF_ABLATE & 64)) {
     // ------------------------------------------------------------------------------ spare warps: L2 prefetch
     const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     const int ncta = gridDim.x * gridDim.y * gridDim.z;
@@ -763,6 +895,18 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       id = id < 0 ? 0 : (id >= nrows ? nrows - 1 : id);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(table + id * a.d), "r"(row_bytes) : "memory");
     }
+   }
+   if (GX && side == 0 && warp == 2 + kScoreEpiWarps && lane == 0) {
+    // G' exchange: publish every item block of my G' rows once all epilogue warps have stored both of its tiles.  The
+    // warps' stores are ordered before their release-add on the counter, my acquire-load of the counter before the
+    // gpu-scope release store of the flag (cumulative), so whoever acquires the flag sees the image.
+    for (int j = 0; j < nblk; ++j) {
+      const uint32_t need = static_cast<uint32_t>(kScoreEpiWarps * kTilesPerBlk * (j + 1));
+      uint32_t spins = 0;
+      while (ld_acquire_cta_smem_u32(gx_cnt) < need) { __nanosleep(32); if (++spins > 40000000u) __trap(); }
+      st_release_gpu(a.gx_flags + ((int64_t)r * nblk + ob) * nblk + (ob + j) % nblk, a.gx_seq);
+    }
+   }
   }
   __syncthreads();
   if (warp == 1) {
@@ -780,26 +924,34 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 }
 
 // host-side dispatch over <LOSS, GROUP> for one NSUB (instantiated by score_tc_nsub*.cu)
-template <int NSUB, int LOSS, bool GROUP>
+template <int NSUB, int LOSS, bool GROUP, bool GX = false>
 int launch_score_tc_one(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) {
   using C = ScoreTcCfg<NSUB>;
   static bool attr_set = false;
   if (!attr_set) {
-    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)C::kSmemBytes));
     // two resident CTAs per SM need the full shared-memory carve-out
-    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    NNCF_CUDA(cudaFuncSetAttribute(score_grad_tc_kernel<NSUB, LOSS, GROUP, GX>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    (int)cudaSharedmemCarveoutMaxShared));
     attr_set = true;
   }
-  NNCF_CUDA(launch_pdl(score_grad_tc_kernel<NSUB, LOSS, GROUP>, dim3(nblk * a.split, 2, R), dim3(kScoreThreads), C::kSmemBytes, st, a));
+  NNCF_CUDA(launch_pdl(score_grad_tc_kernel<NSUB, LOSS, GROUP, GX>, dim3(nblk * a.split, 2, R), dim3(kScoreThreads), C::kSmemBytes, st, a));
   count_launch();
   return 0;
+}
+
+// G' exchange instantiations exist for dp <= 128 and the pointwise losses of neg_shared (the host asks for nothing else)
+template <int NSUB, int LOSS>
+int launch_score_tc_gx(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) {
+  if constexpr (NSUB <= 2 && !ScoreTcCfg<NSUB>::kTeams) return launch_score_tc_one<NSUB, LOSS, false, true>(a, nblk, R, st);
+  else { (void)a; (void)nblk; (void)R; (void)st; ::nncf::set_error("G' exchange: dp <= 128 only"); return NNCF_EUNSUPPORTED; }
 }
 
 template <int NSUB>
 int launch_score_tc_all(const ScoreTcArgs& a, int nblk, int R, cudaStream_t st) {
   const bool g = a.scheme == NNCF_SCHEME_GROUP_NEG_SHARED;
+  if (a.gx) return a.loss_kind == NNCF_LOSS_SKIP_GRAM ? launch_score_tc_gx<NSUB, 0>(a, nblk, R, st) : launch_score_tc_gx<NSUB, 1>(a, nblk, R, st);
   switch (a.loss_kind) {
     case NNCF_LOSS_SKIP_GRAM: return g ? launch_score_tc_one<NSUB, 0, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 0, false>(a, nblk, R, st);
     case NNCF_LOSS_MSE: return g ? launch_score_tc_one<NSUB, 1, true>(a, nblk, R, st) : launch_score_tc_one<NSUB, 1, false>(a, nblk, R, st);

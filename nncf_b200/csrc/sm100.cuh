@@ -273,6 +273,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// monotonic counter in shared memory between warps of one CTA (release add / acquire load at CTA scope)
+__device__ __forceinline__ void red_release_cta_smem_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
 // orders this thread's earlier generic-proxy observations of global memory before its later async-proxy (bulk copy) reads
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 

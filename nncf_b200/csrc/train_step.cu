@@ -14,6 +14,7 @@
 //
 // ref: models/model_framework.py:40-65,85-143; modules/interaction/interaction_dot.py:92-107;
 //      utils/objectives.py:35-220; utils/utilities.py:122-135; utils/optimizer.py:108-147.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -886,6 +887,9 @@ struct nncf_trainer {
   int* gather_flags = nullptr;          // self-gather mode (score_tc.cuh): [R][2][rows_pad / 128] step sequence numbers
   unsigned long long* gather_count = nullptr;
   int gather_seq = 0;
+  uint8_t* gx_buf = nullptr;            // G' exchange (score_tc.cuh): [R][nblk][nblk][32 KiB] bf16 gradient tiles, allocated at the first eligible step
+  int* gx_flags = nullptr;              // [R][nblk][nblk] step sequence numbers
+  int gx_seq = 0;
   int resident_ctas = 0;                // CTAs of the score kernel that fit on the device at once
   int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
   int32_t *ownerU = nullptr, *ownerV = nullptr;
@@ -907,12 +911,16 @@ struct nncf_trainer {
   float* ishards[16] = {nullptr};
   void* flags[16] = {nullptr};
   unsigned int epoch = 0;
-  // host-fed mode (nncf_train_steps_host): staging ring for ids / losses, copy streams, hand-off events
-  static constexpr int kHostBufs = 4;
-  int32_t* h_ids[kHostBufs] = {nullptr, nullptr, nullptr, nullptr};   // [2][R * rows] device staging (uid then cid)
-  float* h_loss[kHostBufs] = {nullptr, nullptr, nullptr, nullptr};    // [R] device
+  // host-fed mode (nncf_train_steps_host): a ring of chunk buffers (ids and losses of up to host_chunk steps each), copy
+  // streams, hand-off events
+  static constexpr int kHostBufs = 3;
+  static constexpr int kHostChunkMax = 16;
+  int host_chunk = 0;                                                  // steps per chunk buffer (fixed at the first call)
+  int32_t* h_ids[kHostBufs] = {nullptr, nullptr, nullptr};             // [2][host_chunk * R * rows] device staging (uids then cids)
+  float* h_loss[kHostBufs] = {nullptr, nullptr, nullptr};              // [host_chunk][R] device
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-  cudaEvent_t ev_ready[kHostBufs] = {}, ev_done[kHostBufs] = {}, ev_read[kHostBufs] = {};
+  cudaEvent_t ev_ready[kHostBufs] = {}, ev_read[kHostBufs] = {};
+  cudaEvent_t ev_step[kHostBufs * kHostChunkMax] = {};                 // step finished (its loss may leave; a chunk's last one frees the ids)
   // developer timeline (env NNCF_TIMELINE=<file>): per step 16 stamp slots written by the kernels themselves,
   // dumped as text when the trainer is destroyed (tools/timeline.py reads it)
   unsigned long long* timeline = nullptr;
@@ -1025,16 +1033,16 @@ extern "C" int nncf_trainer_destroy(nncf_trainer_t* t) {
   }
   void* ptrs[] = {t->Uf, t->Vf, t->invU, t->invV, t->dU, t->dV, t->corrU, t->corrV, t->spos, t->Uimg, t->Vimg,
                   t->loss, t->loss_count, t->uniq, t->inverse, t->nuniq, t->ownerU, t->ownerV, t->ps, t->dVn,
-                  t->gather_flags, t->gather_count, t->accU, t->accV, t->claimU, t->claimV, t->step_dev, t->lr_dev};
+                  t->gather_flags, t->gather_count, t->gx_buf, t->gx_flags, t->accU, t->accV, t->claimU, t->claimV, t->step_dev, t->lr_dev};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int i = 0; i < 4; ++i) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
   for (int i = 0; i < nncf_trainer::kHostBufs; ++i) {
     if (t->h_ids[i]) cudaFree(t->h_ids[i]);
     if (t->h_loss[i]) cudaFree(t->h_loss[i]);
     if (t->ev_ready[i]) cudaEventDestroy(t->ev_ready[i]);
-    if (t->ev_done[i]) cudaEventDestroy(t->ev_done[i]);
     if (t->ev_read[i]) cudaEventDestroy(t->ev_read[i]);
   }
+  for (cudaEvent_t e : t->ev_step) if (e) cudaEventDestroy(e);
   if (t->s_h2d) cudaStreamDestroy(t->s_h2d);
   if (t->s_d2h) cudaStreamDestroy(t->s_d2h);
   delete t;
@@ -1322,6 +1330,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       const char* e = getenv("NNCF_DRAIN_VEC");
       ta.drain_vec = e ? atoi(e) : 0;     // measured at R = 1, split 4: 8.9 us per step with bulk reductions, 10.0 with vector reductions
     }
+    {   // duplicate folding in the fused drain (one MATCH per warp: on by default; NNCF_DEDUP=0 switches it off)
+      const char* e = getenv("NNCF_DEDUP");
+      ta.dedup = e ? atoi(e) : (drain_adds ? 1 : 0);
+    }
     ta.split = split; ta.reg_scale = drain_reg ? 2.0f * c.u_reg / static_cast<float>(B) : 0.0f;
     ta.fuse_sgd = drain_adds ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
     ta.pf_table_u = tb->user_table; ta.pf_table_v = tb->item_table;
@@ -1329,6 +1341,23 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
     ta.tl = tl;
+    // G' exchange (two-sided: every sigmoid computed once, the item side a plain contraction), opt-in with NNCF_GX=1:
+    // neg_shared with a pointwise loss, full 128-row blocks, no split sweep.  Not under a device step clock (= the caller
+    // captures steps into a CUDA graph: the sequence number is a kernel argument).  Measured slower than the one-sided
+    // kernel (C3: 32.7 vs 22.8 us per step, tools/gpu_r2_w.sh; see score_tc.cuh), kept with its parity tests.
+    {
+      const bool gx_env = [] { const char* e = getenv("NNCF_GX"); return e && atoi(e) != 0; }();    // (read per step: the tests switch it)
+      const bool gx_ok = gx_env && !group && !pairwise && dp <= 128 && (B % 128 == 0) && split == 1 && !self_gather &&
+                         !dense_items && vec && !t->lr_dev && !NNCF_SCORE_TEAMS;
+      if (gx_ok) {
+        const size_t nb = (size_t)rp / 128;
+        if (!t->gx_buf) {
+          NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->gx_buf), (size_t)R * nb * nb * 2 * kSubBytes));
+          if (int rc3 = dev_alloc(&t->gx_flags, (size_t)R * nb * nb)) return rc3;
+        }
+        ta.gx = 1; ta.gx_seq = ++t->gx_seq; ta.gx_buf = t->gx_buf; ta.gx_flags = t->gx_flags;
+      }
+    }
     if (self_gather) {
       ta.self_gather = 1; ta.gather_seq = ++t->gather_seq; ta.gather_flags = t->gather_flags; ta.gather_count = t->gather_count;
       ta.gather_target = static_cast<unsigned long long>(t->gather_seq) * static_cast<unsigned long long>(active_ctas);
@@ -1620,9 +1649,14 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
 
 // Host-fed training loop: the link ids of every batch live in HOST memory, as the reference's `train` array does (it
 // slices a NumPy array per batch and feeds it through feed_dict, ref: models/train_neg_shared.py:46-50), and every
-// batch's loss goes back to the host (what train_on_batch returns).  Step s's ids travel on a copy stream into a ring of
-// device staging buffers while step s-1's kernels run; the losses return on a second copy stream.  Nothing is skipped:
-// every step does its H2D and D2H; the host is only synchronised once, at the end.
+// batch's loss goes back to the host (what train_on_batch returns).  The ids travel on a copy stream into a ring of
+// device chunk buffers while earlier steps compute; every step's losses return on a second copy stream as soon as the
+// step has finished.  Nothing is skipped: every step's ids are copied H2D, every step's losses D2H; the host is only
+// synchronised once, at the end.
+// The loop is bound by the host's CUDA calls once a step is ~20 us (12 calls per step in the first version = 26 us): ids
+// now travel in chunks of several steps (two copies per chunk instead of per step; the first chunk is one step, so the
+// pipeline starts after one step's worth of ids), which leaves 5 calls per step: two launches, an event, and the loss copy
+// with its wait.
 extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
                                      const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream) {
   NNCF_CHECK_ARG(t && tables && user_ids_host && item_ids_host, "nncf_train_steps_host: null argument");
@@ -1633,47 +1667,65 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
   const int R = t->cfg.replicas;
   const int64_t per_step = (int64_t)R * t->rows;
   if (!t->s_h2d) {
+    // chunk length: up to 16 steps or ~1 MB of ids per side, whichever is smaller (NNCF_HOST_CHUNK overrides)
+    int ch = static_cast<int>(std::min<int64_t>(nncf_trainer::kHostChunkMax, std::max<int64_t>(1, (1 << 18) / per_step)));
+    if (const char* e = getenv("NNCF_HOST_CHUNK")) ch = std::min(nncf_trainer::kHostChunkMax, std::max(1, atoi(e)));
+    t->host_chunk = ch;
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
     for (int i = 0; i < NB; ++i) {
-      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_ids[i]), 2 * per_step * sizeof(int32_t)));
-      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_loss[i]), R * sizeof(float)));
+      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_ids[i]), 2 * ch * per_step * sizeof(int32_t)));
+      NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_loss[i]), (size_t)ch * R * sizeof(float)));
       NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_ready[i], cudaEventDisableTiming));
-      NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_done[i], cudaEventDisableTiming));
       NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_read[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < NB * ch; ++i) NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_step[i], cudaEventDisableTiming));
   }
-  nncf_step_io io{};
-  auto enqueue_ids = [&](int64_t s) -> int {
-    const int b = static_cast<int>(s % NB);
-    // ids of step s -> staging buffer b (free once step s - NB has finished with it)
-    if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_done[b], 0));
-    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b], user_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
-    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b] + per_step, item_ids_host + s * per_step, per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
+  const int CH = t->host_chunk;
+  const int64_t cid_off = (int64_t)CH * per_step;                      // the cids of a chunk buffer start here
+  // chunk k covers steps [first(k), first(k) + len(k)): chunk 0 is ONE step, the others CH steps
+  auto first = [&](int64_t k) -> int64_t { return k == 0 ? 0 : 1 + (k - 1) * CH; };
+  auto len = [&](int64_t k) -> int64_t { return std::min<int64_t>(k == 0 ? 1 : CH, n_steps - first(k)); };
+  const int64_t n_chunks = n_steps == 0 ? 0 : 1 + (n_steps - 1 + CH - 1) / CH;
+  auto enqueue_ids = [&](int64_t k) -> int {
+    const int b = static_cast<int>(k % NB);
+    const int64_t s0 = first(k), n = len(k);
+    // chunk buffer b is free once the last step of chunk k - NB has finished
+    if (k >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_step[b * CH + (len(k - NB) - 1)], 0));
+    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b], user_ids_host + s0 * per_step, n * per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
+    NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b] + cid_off, item_ids_host + s0 * per_step, n * per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
     NNCF_CUDA(cudaEventRecord(t->ev_ready[b], t->s_h2d));
     return NNCF_OK;
   };
-  if (n_steps > 0) if (int rc = enqueue_ids(0)) return rc;
-  for (int64_t s = 0; s < n_steps; ++s) {
-    const int b = static_cast<int>(s % NB), bn = static_cast<int>((s + 1) % NB);
-    // the copy of step s + 1's ids is in flight while step s computes; its staging buffer doubles as the L2 prefetch
-    // hint of step s (a hint: if the copy has not landed yet the kernel prefetches stale rows, never faults)
-    if (s + 1 < n_steps) if (int rc = enqueue_ids(s + 1)) return rc;
+  nncf_step_io io{};
+  if (n_chunks > 0) if (int rc = enqueue_ids(0)) return rc;
+  if (n_chunks > 1) if (int rc = enqueue_ids(1)) return rc;
+  for (int64_t k = 0; k < n_chunks; ++k) {
+    const int b = static_cast<int>(k % NB), bn = static_cast<int>((k + 1) % NB);
+    // two chunks of ids are in flight ahead of the one that computes
+    if (k + 2 < n_chunks) if (int rc = enqueue_ids(k + 2)) return rc;
     NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_ready[b], 0));
-    if (s >= NB) NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_read[b], 0));       // loss slot b has been read back
-    io.loss_out_dev = t->h_loss[b];
-    t->hint_next_uid = (s + 1 < n_steps) ? t->h_ids[bn] : nullptr;
-    t->hint_next_cid = (s + 1 < n_steps) ? t->h_ids[bn] + per_step : nullptr;
-    const int rc = nncf_train_steps(t, tables, t->h_ids[b], t->h_ids[b] + per_step, 1, &io, st);
-    t->hint_next_uid = t->hint_next_cid = nullptr;
-    if (rc) return rc;
-    NNCF_CUDA(cudaEventRecord(t->ev_done[b], st));
-    // loss of step s -> host
-    if (loss_out_host) {
-      NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, t->ev_done[b], 0));
-      NNCF_CUDA(cudaMemcpyAsync(loss_out_host + s * R, t->h_loss[b], R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));
+    if (k >= NB && loss_out_host) NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_read[b], 0));   // the loss slots of buffer b have been read back
+    const int64_t n = len(k);
+    for (int64_t j = 0; j < n; ++j) {
+      const int32_t* uid = t->h_ids[b] + j * per_step;
+      io.loss_out_dev = t->h_loss[b] + j * R;
+      // L2 prefetch hint: the ids of the next step (a hint: if the next chunk has not landed yet the kernel prefetches
+      // stale rows, never faults)
+      const bool more = (j + 1 < n) || (k + 1 < n_chunks);
+      t->hint_next_uid = !more ? nullptr : (j + 1 < n ? uid + per_step : t->h_ids[bn]);
+      t->hint_next_cid = !more ? nullptr : (j + 1 < n ? uid + cid_off + per_step : t->h_ids[bn] + cid_off);
+      const int rc = nncf_train_steps(t, tables, uid, uid + cid_off, 1, &io, st);
+      t->hint_next_uid = t->hint_next_cid = nullptr;
+      if (rc) return rc;
+      cudaEvent_t done = t->ev_step[b * CH + j];
+      NNCF_CUDA(cudaEventRecord(done, st));
+      if (loss_out_host) {                                             // loss of this step -> host
+        NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, done, 0));
+        NNCF_CUDA(cudaMemcpyAsync(loss_out_host + (first(k) + j) * R, t->h_loss[b] + j * R, R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));
+      }
     }
-    NNCF_CUDA(cudaEventRecord(t->ev_read[b], t->s_d2h));
+    if (loss_out_host) NNCF_CUDA(cudaEventRecord(t->ev_read[b], t->s_d2h));
   }
   NNCF_CUDA(cudaStreamSynchronize(st));
   NNCF_CUDA(cudaStreamSynchronize(t->s_d2h));

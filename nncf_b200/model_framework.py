@@ -56,6 +56,12 @@ class MeanPoolTower(torch.nn.Module):
         self.dense = torch.nn.Linear(dw, d)
         self.use_bn = not getattr(conf, 'no_BN', False)
         self.bn = torch.nn.BatchNorm1d(d, eps=1e-3, momentum=0.01) if self.use_bn else None
+        if self.use_bn:
+            # A Dense bias that feeds a BatchNorm has NO gradient (the batch mean removes it); what autograd returns is the
+            # rounding error of a zero sum, which Adam's normalisation turns into random +-lr steps per batch - harmless in
+            # training mode, but the test phase normalises with running statistics that lag ~100 batches behind the random
+            # walk.  The gradient is set to its exact value, zero.  (Declared difference: the reference lets TF do the walk.)
+            self.dense.bias.register_hook(torch.zeros_like)
         self.dropout_rate = float(conf.word_emb_dropout_rate)
         self.content = content            # int32 [items, L] on device
         self.actv = conf.item_dense_transform['dense_hidden_actv']
@@ -276,7 +282,7 @@ class MeanPoolGraphStep(object):
         if t.bn is not None:
             t.bn.weight.grad, t.bn.bias.grad = dgamma, dbeta
         t.dense.weight.grad = dh1.t() @ h0
-        t.dense.bias.grad = dh1.sum(0)
+        t.dense.bias.grad = dh1.sum(0) if t.bn is None else torch.zeros_like(bd)     # (exactly zero in front of a BatchNorm, see MeanPoolTower)
         dh0 = dh1 @ Wd
         dW = torch.zeros_like(W)
         ops.meanpool_bwd_n(dW, t.content, uq, nuq, dh0)
@@ -296,6 +302,8 @@ class MeanPoolGraphStep(object):
             with torch.no_grad():
                 self._body()                                            # warm-up (real steps): optimizer state, workspaces, attributes
         else:
+            import gc
+            gc.collect()                                                # (a CUDAGraph freed by the collector DURING a capture invalidates the capture)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.no_grad(), torch.cuda.graph(g):

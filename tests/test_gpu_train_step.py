@@ -589,3 +589,57 @@ def test_lazy_adam_folded_matches_oracle_over_steps(scheme, fold, monkeypatch):
     untouched = np.setdiff1d(np.arange(nu), uid)
     if untouched.size:
         np.testing.assert_array_equal(tU.cpu().numpy()[untouched], EU[untouched])
+
+
+@pytest.mark.parametrize("gx", ["1", "0"])
+@pytest.mark.parametrize("loss", ["skip-gram", "mse"])
+@pytest.mark.parametrize("B,d,replicas,norm", [(128, 64, 1, False), (256, 128, 2, True), (512, 128, 3, False), (640, 100, 2, False),
+                                              (1024, 128, 2, False), (512, 32, 40, False)])
+def test_g_exchange_two_sided_matches_oracle(loss, B, d, replicas, norm, gx, monkeypatch):
+    """G' exchange (score_tc.cuh): the user-side CTAs compute every sigmoid once and hand the bf16 gradient tiles to the
+    item-side CTAs, which only contract (dV_b += G'(a, b)^T U_a).  Both modes (NNCF_GX=0: the item side recomputes S^T)
+    against the oracle: loss and both gradients of every replica with optimizer='none', then the fused sparse-SGD step
+    (table deltas summed over the replicas) over two consecutive steps on one handle (the flags carry a sequence number)."""
+    monkeypatch.setenv("NNCF_GX", gx)
+    from nncf_b200.ops import FusedStep, StepSpec
+    nu, ni, lr = 700, 260, 0.05
+    EU, EV = _tables(nu, ni, d, seed=B + d + replicas)
+    rng = np.random.RandomState(B + 1)
+    uid = rng.randint(0, nu, size=B * replicas).astype(np.int32)
+    cid = rng.randint(0, ni, size=B * replicas).astype(np.int32)
+    lam, gamma = _params(loss)
+    refs = [O.step_matmul(EU.astype(np.float64), EV.astype(np.float64), uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B],
+                          "neg_shared", loss, lam, gamma, norm_u=norm, norm_v=norm) for r in range(replicas)]
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    d_uid, d_cid = torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda()
+    if replicas == 1:
+        spec = StepSpec(scheme="neg_shared", loss=loss, precision="bf16", batch_size_p=B, dim=d, norm_u=norm, norm_v=norm,
+                        optimizer="none", neg_loss_weight=lam, loss_gamma=gamma)
+        out = FusedStep(spec).run(tU, tV, d_uid, d_cid, 1, want_grads=True)
+        torch.cuda.synchronize()
+        assert abs(float(out["loss"][0]) - refs[0]["loss"]) <= 1e-2 * abs(refs[0]["loss"])
+        for name, got, want in (("dEU", _scatter(nu, uid, out["grad_user_rows"].cpu().numpy()), refs[0]["dEU"]),
+                                ("dEV", _scatter(ni, cid, out["grad_item_rows"].cpu().numpy()), refs[0]["dEV"])):
+            assert _rel(got, want) <= 1e-2, (name, _rel(got, want))
+            assert _rel_rows(got, want) <= 3e-2, (name, "rows", _rel_rows(got, want))
+    if norm:
+        return                                   # (the fused drain is the un-normalised pointwise step)
+    spec = StepSpec(scheme="neg_shared", loss=loss, precision="bf16", batch_size_p=B, dim=d, optimizer="sgd", learn_rate=lr,
+                    replicas=replicas, neg_loss_weight=lam, loss_gamma=gamma)
+    step = FusedStep(spec)
+    out = step.run(tU, tV, d_uid, d_cid, 1)
+    torch.cuda.synchronize()
+    assert np.allclose(out["loss"].cpu().numpy(), [r["loss"] for r in refs], rtol=1e-2)
+    dU, dV = sum(r["dEU"] for r in refs), sum(r["dEV"] for r in refs)
+    U1, V1 = tU.cpu().numpy().astype(np.float64), tV.cpu().numpy().astype(np.float64)
+    assert _rel(U1 - EU, -lr * dU) <= 1e-2, _rel(U1 - EU, -lr * dU)
+    assert _rel(V1 - EV, -lr * dV) <= 1e-2, _rel(V1 - EV, -lr * dV)
+    assert _rel_rows(V1 - EV, -lr * dV) <= 3e-2
+    # second step on the same handle, from the updated tables
+    refs2 = [O.step_matmul(U1, V1, uid[r * B:(r + 1) * B], cid[r * B:(r + 1) * B], "neg_shared", loss, lam, gamma) for r in range(replicas)]
+    out2 = step.run(tU, tV, d_uid, d_cid, 1)
+    torch.cuda.synchronize()
+    assert np.allclose(out2["loss"].cpu().numpy(), [r["loss"] for r in refs2], rtol=1e-2)
+    dU2, dV2 = sum(r["dEU"] for r in refs2), sum(r["dEV"] for r in refs2)
+    assert _rel(tU.cpu().numpy() - U1, -lr * dU2) <= 1e-2
+    assert _rel(tV.cpu().numpy() - V1, -lr * dV2) <= 1e-2
