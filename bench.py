@@ -463,6 +463,11 @@ def run_ours(args):
     extra = {}
     if not args.no_eval:
         extra["whole_at_k"] = bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_over_ranks)
+    if not args.no_eval and world == 1 and args.workload == "c3":
+        try:
+            extra["content_tower"] = bench_content_tower(torch, ops, peaks)
+        except Exception as ex:                                   # an extra must never take the bench line down
+            extra["content_tower"] = {"error": repr(ex)}
 
     if rank != 0:
         if sharded is not None:
@@ -546,9 +551,12 @@ def run_ours(args):
                 "d2h_bytes_per_step": 4 * R, "steps": e2e_steps,
                 "per_call": {"value": per_call_value, "unit": "links/s", "steps": per_call_steps,
                              "note": "one blocking train_on_batch-style Python call per step (H2D, step, loss.cpu())"},
-                "note": "FusedStep.run_host / nncf_train_steps_host: per step and per GPU, that step's ids are copied from "
-                        "pinned host memory (overlapping the previous step's kernels) and its R losses are copied back; "
-                        "wall clock around the call, which returns after the last copy"},
+                "note": "FusedStep.run_host / nncf_train_steps_host: per GPU, every step's ids are copied H2D from pinned host "
+                        "memory (cudaMemcpyAsync in chunks of 1, 2, 4, ... up to 16 steps, overlapping the kernels of earlier steps) and "
+                        "every step's R losses are copied D2H into the pinned host loss array on a second copy stream as "
+                        "soon as the step has finished; wall clock around the call, which returns "
+                        "after the last step and transfer; N > 1: the window opens with one stratum phase change and "
+                        "waits for it"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "extra": extra,
@@ -634,6 +642,55 @@ def bench_variants(torch, ops, FusedStep, make_spec, w, args, EU, EV, uid_all, c
     except Exception as ex:
         out["c5_max_margin_b16384_d256"] = {"error": str(ex)[:200]}
     return out, ref_sem
+
+
+def bench_content_tower(torch, ops, peaks):
+    """C1 / C2 (BASELINE.json configs[0:2]): the CiteULike-shaped content model (basic_embedding: mean of word vectors ->
+    Dense -> BatchNorm -> relu; 5,551 users x 16,980 items, ~205k links, B = 512, d = dw = 50, L = 300, vocabulary 8,000,
+    synthetic text) through the trainer's own path (MatmulView.train_tower_batches: one replayed CUDA graph per batch),
+    one epoch each of neg_shared + skip-gram (C1) and group_neg_shared + log-loss (C2); wall clock, device synchronised at
+    both ends.  The mean-pool kernels alone are timed with CUDA events on the shape of a batch (B unique items) and
+    reported against their algorithmic bytes L (4 + 4 dw) per unique item each way."""
+    import numpy as _np
+    from nncf_b200.conf import Conf
+    from nncf_b200.data_utils import get_data
+    from nncf_b200.model_framework import get_model
+    out = {}
+    for key, scheme, loss in (("c1_neg_shared_skip_gram", "neg_shared", "skip-gram"), ("c2_group_neg_shared_log_loss", "group_neg_shared", "log-loss")):
+        conf = Conf('synthetic_citeulike', {'loss': loss})
+        _np.random.seed(0)
+        dh = get_data('synthetic_citeulike', conf, reverse_samping=True)
+        md = get_model(conf, dh, 'basic_embedding')
+        view = md['model_neg_shared' if scheme == 'neg_shared' else 'model_group_neg_shared']
+        train = torch.from_numpy(_np.ascontiguousarray(dh.data['train'], dtype=_np.int32)).cuda()
+        B = conf.batch_size_p
+        nb = train.shape[0] // B
+        u, c = train[:nb * B, 0].contiguous(), train[:nb * B, 1].contiguous()
+        view.train_tower_batches(u[:B * 8], c[:B * 8], B)          # warm-up + graph capture
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        cost, it = view.train_tower_batches(u, c, B)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        out[key] = {"links_per_sec": it * B / dt, "us_per_step": dt / it * 1e6, "steps": it, "batch_size_p": B, "mean_loss": cost / it,
+                    "optimizer": "lazy Adam (user table) + Adam (tower)", "path": "MatmulView.train_tower_batches, CUDA graph per batch"}
+        if "meanpool" not in out:
+            st = md['_state']
+            W, content = st.tower.word_embedding.detach(), st.tower.content
+            L, dw = int(content.shape[1]), int(W.shape[1])
+            ids = torch.randperm(content.shape[0], device="cuda")[:B].to(torch.int32)
+            g = torch.randn((B, dw), device="cuda")
+            dW = torch.zeros_like(W)
+            alg = B * L * (4 + 4 * dw)
+            res = {"algorithmic_bytes": alg, "shape": "n_u = %d unique items, L = %d, dw = %d (word table %d rows: L2-resident)" % (B, L, dw, W.shape[0])}
+            for name, fn in (("fwd", lambda: ops.meanpool_fwd(W, content, ids, B)), ("bwd", lambda: ops.meanpool_bwd(dW, content, ids, B, g))):
+                for _ in range(5):
+                    fn()
+                ms = _time_steps(torch, lambda: [fn() for _ in range(50)]) / 50
+                res[name] = {"us": ms * 1e3, "gbs_algorithmic": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peaks["hbm"]}
+            out["meanpool"] = res
+        del md, view, dh
+    return out
 
 
 def bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_over_ranks):

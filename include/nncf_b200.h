@@ -194,9 +194,10 @@ int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t
 /* Host-fed variant of nncf_train_steps: the ids of all n_steps x R batches live in HOST memory (pinned memory lets the
  * copies overlap the kernels), as the reference's `train` array does (ref: models/train_neg_shared.py:46-50 slices it per
  * batch and feeds it through feed_dict), and loss_out_host[n_steps * R] receives every batch's loss (what Keras'
- * train_on_batch returns, ref: models/train_neg_shared.py:50).  Per step: H2D copy of that step's ids on an internal
- * copy stream (overlapping the previous step's kernels), the step on `stream`, D2H copy of its losses.  Returns when
- * all steps and copies have completed.  Embedding-table models only. */
+ * train_on_batch returns, ref: models/train_neg_shared.py:50).  Every step's ids are copied H2D on an internal copy
+ * stream, in chunks of 1, 2, 4, ... up to 16 steps that overlap the kernels of earlier steps; the step runs on `stream`;
+ * its R losses are copied to loss_out_host on a second copy stream as soon as it has finished.
+ * Returns when all steps and copies have completed.  Embedding-table models only. */
 int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
                           const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream);
 /* Optional per-phase device timing with CUDA events on the launching stream (used by bench.py's roofline leg; it

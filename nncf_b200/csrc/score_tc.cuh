@@ -92,17 +92,21 @@ struct ScoreTcArgs {
   // and into the global image, where the CTAs of the other side read them as their Y tiles once the block's flag
   // carries this step's sequence number.  The tables are read and updated inside one kernel now, so no drain may
   // start before every CTA has finished reading: gather_count (monotonic) must reach gather_target first.
-  // G' exchange ("two-sided", neg_shared with a pointwise loss, dp <= 128, B % 128 == 0, no split): only the user-side CTAs
-  // run the score / loss / gradient epilogue.  Besides feeding G' to their own MMA2 through tensor memory they store every
-  // G' tile (bf16) into gx_buf as the 128B-swizzled tile image [128 user rows][128 B = 64 item columns] of an MN-major A
-  // operand, and raise gx_flags[(r, a, b)] = gx_seq once both 64-column halves of item block b are written.  The item-side
-  // CTA of block b has no epilogue loop: its producer warp waits for the flag of each user block a, copies the G' image
-  // and user block a's rows (both with the bulk-copy engine), and its MMA warp accumulates dV_b += G'(a, b)^T U_a - every
-  // sigmoid is computed ONCE, the item side is a plain contraction.  All flags of a step carry the step's sequence number.
+  // G' exchange ("two-sided": every score, sigmoid and loss term is computed ONCE; neg_shared with a pointwise loss,
+  // dp <= 128, B % 256 == 0, no split).  The 128 x 128 block (user block a, item block b) is computed by the user-side CTA
+  // of a when a + b is even and by the item-side CTA of b when it is odd, so EVERY CTA runs the score / loss / gradient
+  // epilogue on half of its sweep (its "own" blocks: MMA1 -> epilogue -> MMA2 as before).  It also stores each own G' tile
+  // (bf16) into gx_buf as the 128B-swizzled tile image [128 of my rows][128 B = 64 swept columns] - an MN-major A operand
+  // for the CTA on the other side of the block - and raises gx_flags[(r, side, my block, swept block)] = gx_seq once both
+  // 64-column halves are written.  The other half of its gradient comes from those images: after its own tiles the
+  // producer warp waits for the flag of each "foreign" block, copies the image and the swept block's rows with the
+  // bulk-copy engine, and the MMA warp accumulates dX += G'^T Y - a plain contraction, no epilogue.  Own blocks are swept
+  // and foreign blocks consumed in the same rotating order, so a CTA's i-th foreign block is its producer's i-th own
+  // block.  All flags of a step carry the step's sequence number.
   int gx;
   int gx_seq;
-  uint8_t* gx_buf;                            // [R][nblk a][nblk b][2 halves][16 KiB]
-  int* gx_flags;                              // [R][nblk a][nblk b]
+  uint8_t* gx_buf;                            // [R][2 sides][nblk mine][nblk swept][2 halves][16 KiB]
+  int* gx_flags;                              // [R][2 sides][nblk mine][nblk swept]
   int self_gather;
   int gather_seq;                             // this step's sequence number (> 0, increasing)
   int* gather_flags;                          // [R][2][rows_pad / 128]
@@ -356,15 +360,21 @@ score_grad_tc_kernel(ScoreTcArgs a) {
   if (nt <= 0) return;                             // (the host never asks for more splits than tiles)
   const int nblk = a.rows_pad >> 7;
   const int64_t base = (int64_t)r * a.rows_pad;
-  // G' exchange: side-1 CTAs only contract (gx1); side-0 CTAs sweep the item tiles starting at their own diagonal block
-  // (rot), so that the item block every item-side CTA waits for next comes from a different user-side CTA each time
-  const bool gx1 = GX && side == 1;
+  // G' exchange: my i-th own block is swept block (ob + side + 2 i) % nblk, my i-th foreign block (ob + side - 1 - 2 i) % nblk
+  // (nblk is even); nt_loop = tiles this CTA runs through MMA1 / epilogue / MMA2
   constexpr int kTilesPerBlk = 128 / C::TN;
-  const int rot = (GX && side == 0) ? (ob * kTilesPerBlk) % nt : 0;
-  constexpr bool bal_loss = (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) && !GX;   // the two sides share the loss code (see the epilogue)
-  constexpr int kGxStages = NSUB >= 2 ? 3 : 2;                              // item side: stages of [G' 2 x 8 KiB][U rows NSUB x 8 KiB] = 64 user rows
-  constexpr uint32_t kGxStageBytes = 2 * 8192 + NSUB * 8192;
-  static_assert(kGxStages * kGxStageBytes <= NSUB * kSubBytes + (C::kYAllBytes > C::kStageBytes ? C::kYAllBytes : C::kStageBytes), "G' exchange stages overlay the X block and the Y stages");
+  const int nt_loop = GX ? nt / 2 : nt;
+  auto gx_tile = [&](int it) -> int {                    // sweep position of my it-th own tile
+    return ((ob + side + 2 * (it / kTilesPerBlk)) % nblk) * kTilesPerBlk + it % kTilesPerBlk;
+  };
+  constexpr bool bal_loss = (LOSS == NNCF_LOSS_SKIP_GRAM && !GROUP) || GX;  // both sides hold a share of the loss (see the epilogue)
+  constexpr int kGxStages = 2;                           // foreign blocks arrive in stages of kGxRows rows: [G' 2 x kGxPiece][rows NSUB x kGxPiece]
+  constexpr int kGxRows = NSUB >= 2 ? 64 : 32;           // (dp = 64: the Y stages it overlays are 32 KiB)
+  constexpr uint32_t kGxPiece = kGxRows * 128;           // kGxRows rows of one [128 x 64] sub-tile: contiguous in the tile image
+  constexpr uint32_t kGxStageBytes = (2 + NSUB) * kGxPiece;
+  static_assert(!GX || kGxStages * kGxStageBytes <= C::kYAllBytes, "G' exchange stages overlay the Y stages (the X block stays: the regulariser reads it)");
+  uint64_t* gx_full = bars + 34;    // [2]
+  uint64_t* gx_empty = bars + 36;   // [2]
   const uint8_t* gX = (side == 0 ? a.Uimg : a.Vimg) + ((int64_t)r * nblk + ob) * NSUB * kSubBytes;
   const uint8_t* gY = (side == 0 ? a.Vimg : a.Uimg) + (int64_t)r * nblk * NSUB * kSubBytes;
 
@@ -373,6 +383,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     for (int s = 0; s < C::kStages; ++s) { mbar_init(&y_full[s], 1); mbar_init(&y_empty[s], 1); }
     for (int s = 0; s < kBufs; ++s) { mbar_init(&s_full[s], 1); mbar_init(&g_full[s], kGArrive); }
     mbar_init(dx_full, 1);
+    for (int s = 0; s < kGxStages; ++s) { mbar_init(&gx_full[s], 1); mbar_init(&gx_empty[s], 1); }
     *gx_cnt = 0u;
     mbar_fence_init();
   }
@@ -394,36 +405,14 @@ score_grad_tc_kernel(ScoreTcArgs a) {
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------ producer
-    if (lane == 0 && gx1) {
-      // item side of the G' exchange: for the user blocks in the order their CTAs finish my item block, wait for the flag,
-      // then copy the G' image (A operand, K = user rows) and the user rows (B operand) in two stages of 64 user rows
-      int i = 0;
-      for (int j = 0; j < nblk; ++j) {
-        const int ua = (ob - j + nblk) % nblk;
-        const int64_t pair = ((int64_t)r * nblk + ua) * nblk + ob;
-        const int* flag = a.gx_flags + pair;
-        uint32_t spins = 0;
-        while (ld_acquire_gpu(flag) != a.gx_seq) { __nanosleep(32); if (++spins > 40000000u) __trap(); }
-        fence_proxy_async_global();                      // G' was written with generic stores; the bulk copy reads it
-        const uint8_t* gsrc = a.gx_buf + pair * 2 * kSubBytes;
-        const uint8_t* usrc = a.Uimg + ((int64_t)r * nblk + ua) * NSUB * kSubBytes;
-        for (int kh = 0; kh < 2; ++kh, ++i) {
-          const int st = i % kGxStages;
-          mbar_wait(&y_empty[st], ((i / kGxStages) & 1) ^ 1);
-          mbar_expect_tx(&y_full[st], kGxStageBytes);
-          uint8_t* dst = sX + st * kGxStageBytes;
-          for (int m = 0; m < 2; ++m) bulk_g2s(dst + m * 8192, gsrc + (size_t)m * kSubBytes + kh * 8192, 8192, &y_full[st]);
-          for (int s2 = 0; s2 < NSUB; ++s2) bulk_g2s(dst + 16384 + s2 * 8192, usrc + (size_t)s2 * kSubBytes + kh * 8192, 8192, &y_full[st]);
-        }
-      }
-    } else if (lane == 0) {
+    if (lane == 0) {
       if (!a.self_gather) {
         mbar_expect_tx(x_full, NSUB * kSubBytes);
         for (int s = 0; s < NSUB; ++s) bulk_g2s(sX + s * kSubBytes, gX + (size_t)s * kSubBytes, kSubBytes, x_full);
       }
       int ready_blk = -1;                                // self-gather: blocks of the swept side known to be in the image
-      for (int it = 0; it < nt; ++it) {
-        const int t = t_begin + (GX ? (it + rot) % nt : it);
+      for (int it = 0; it < nt_loop; ++it) {
+        const int t = GX ? gx_tile(it) : t_begin + it;
         const int st = it % C::kStages;
         if (a.self_gather && ((t * TN) >> 7) > ready_blk) {
           ready_blk = (t * TN) >> 7;
@@ -439,6 +428,31 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         const uint8_t* src = gY + (size_t)((t * TN) >> 7) * NSUB * kSubBytes + (size_t)((t * TN) & 127) * 128;
         for (int s = 0; s < NSUB; ++s)
           bulk_g2s(sY + (st * NSUB + s) * C::kYBytes, src + (size_t)s * kSubBytes, C::kYBytes, &y_full[st]);
+      }
+      if (GX) {
+        // foreign blocks: the Y stages are free once the MMA2 of my last own tiles has read them (the waits a tile
+        // nt_loop + j would do); then, per foreign block, the flag of the CTA that computed it, and two stages of 64 rows:
+        // its G' image (A operand, K = its rows) and its rows (B operand)
+        for (int j = 0; j < C::kStages; ++j) mbar_wait(&y_empty[(nt_loop + j) % C::kStages], (((nt_loop + j) / C::kStages) & 1) ^ 1);
+        int i = 0;
+        for (int f = 0; f < nblk / 2; ++f) {
+          const int fb = ((ob + side - 1 - 2 * f) % nblk + nblk) % nblk;
+          const int64_t pair = (((int64_t)r * 2 + (1 - side)) * nblk + fb) * nblk + ob;
+          const int* flag = a.gx_flags + pair;
+          uint32_t spins = 0;
+          while (ld_acquire_gpu(flag) != a.gx_seq) { __nanosleep(32); if (++spins > 40000000u) __trap(); }
+          fence_proxy_async_global();                    // G' was written with generic stores; the bulk copy reads it
+          const uint8_t* gsrc = a.gx_buf + pair * 2 * kSubBytes;
+          const uint8_t* ysrc = gY + (size_t)fb * NSUB * kSubBytes;
+          for (int kh = 0; kh < 128 / kGxRows; ++kh, ++i) {
+            const int st = i % kGxStages;
+            mbar_wait(&gx_empty[st], ((i / kGxStages) & 1) ^ 1);
+            mbar_expect_tx(&gx_full[st], kGxStageBytes);
+            uint8_t* dst = sY + st * kGxStageBytes;
+            for (int m = 0; m < 2; ++m) bulk_g2s(dst + m * kGxPiece, gsrc + (size_t)m * kSubBytes + kh * kGxPiece, kGxPiece, &gx_full[st]);
+            for (int s2 = 0; s2 < NSUB; ++s2) bulk_g2s(dst + (2 + s2) * kGxPiece, ysrc + (size_t)s2 * kSubBytes + kh * kGxPiece, kGxPiece, &gx_full[st]);
+          }
+        }
       }
     }
     if (side == 0 || bal_loss) {
@@ -474,29 +488,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     // registers, one UIADD3.64 per MMA); one elected lane issues.  Under `if (lane == 0)` ptxas rebuilt every descriptor
     // and moved the addresses through an ELECT / R2UR.BROADCAST / BRA.U.ANY sequence: ~160 cycles per MMA, against 32-64
     // cycles of tensor work.
-    if (gx1) {
-      // item side of the G' exchange: dV_b += G'(a, b)^T U_a, both operands MN-major (rows = user rows = K), 64 user rows per stage
-      const uint32_t idesc3 = make_idesc_bf16(128, DP, 1, 1);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint64_t gdesc0 = make_smem_desc(smem_u32(sX), 8192, 1024);              // A: [64 user rows][2 x 64 item columns]
-      const uint64_t udesc0 = make_smem_desc(smem_u32(sX) + 16384, 8192, 1024);      // B: [64 user rows][NSUB x 64 columns of d]
-      for (int i = 0; i < 2 * nblk; ++i) {
-        const int st = i % kGxStages;
-        mbar_wait(&y_full[st], (i / kGxStages) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint64_t off = static_cast<uint64_t>((st * kGxStageBytes) >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_u + C::kColDX, gdesc0 + off + static_cast<uint64_t>((k * 2048) >> 4),
-                      udesc0 + off + static_cast<uint64_t>((k * 2048) >> 4), idesc3, (i > 0) || (k > 0));
-          umma_commit(&y_empty[st]);
-        }
-        __syncwarp();
-      }
-      if (elect_one()) umma_commit(dx_full);
-      __syncwarp();
-    } else {
+    {
       const uint32_t idesc_s = make_idesc_bf16(128, TN, 0, 0);
       const uint32_t idesc_dx = make_idesc_bf16(128, DP, 0, 1);
       const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -521,11 +513,11 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       mbar_wait(x_full, 0);
       if (lane == 0) NNCF_STAMP(1);
       constexpr int kAhead = kBufs - 1;         // MMA1 runs this many tiles ahead of MMA2
-      for (int p = 0; p < kAhead && p < nt; ++p) issue_mma1(p);
+      for (int p = 0; p < kAhead && p < nt_loop; ++p) issue_mma1(p);
       if (lane == 0) NNCF_STAMP(2);
-      for (int t = 0; t < nt; ++t) {
+      for (int t = 0; t < nt_loop; ++t) {
         const int st = t % C::kStages, sb = t % kBufs;
-        if (t + kAhead < nt) issue_mma1(t + kAhead);
+        if (t + kAhead < nt_loop) issue_mma1(t + kAhead);
         mbar_wait(&g_full[sb], (t / kBufs) & 1);
         if (lane == 0 && t < 8) NNCF_STAMP(8 + t);
         tc_fence_after();
@@ -541,6 +533,26 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           umma_commit(&y_empty[st]);
         }
         __syncwarp();
+      }
+      if (GX) {
+        // foreign blocks: dX += G'^T Y, both operands MN-major (rows = the other side's rows = K), 64 rows per stage
+        const uint32_t idesc3 = make_idesc_bf16(128, DP, 1, 1);
+        const uint64_t gdesc0 = make_smem_desc(smem_u32(sY), kGxPiece, 1024);                  // A: [kGxRows rows][2 x 64 of my rows]
+        const uint64_t ydesc3 = make_smem_desc(smem_u32(sY) + 2 * kGxPiece, kGxPiece, 1024);   // B: [kGxRows rows][NSUB x 64 columns of d]
+        for (int i = 0; i < (nblk / 2) * (128 / kGxRows); ++i) {
+          const int st = i % kGxStages;
+          mbar_wait(&gx_full[st], (i / kGxStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t off = static_cast<uint64_t>((st * kGxStageBytes) >> 4);
+#pragma unroll
+            for (int k = 0; k < kGxRows / 16; ++k)
+              umma_bf16(tmem_u + C::kColDX, gdesc0 + off + static_cast<uint64_t>((k * 2048) >> 4),
+                        ydesc3 + off + static_cast<uint64_t>((k * 2048) >> 4), idesc3, 1u);
+            umma_commit(&gx_empty[st]);
+          }
+          __syncwarp();
+        }
       }
       if (elect_one()) umma_commit(dx_full);    // (elect.sync picks the same lane for the same mask: all MMAs are its own)
       __syncwarp();
@@ -616,8 +628,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
     // teams: this warp's group of four takes tiles h, h + 2, ...; otherwise every warp takes its column half of every tile
     constexpr int kItStep = C::kTeams ? 2 : 1;
     const int hcol = C::kTeams ? 0 : h * CW;            // my first column inside a tile
-    for (int it = C::kTeams ? h : 0; it < (gx1 ? 0 : nt); it += kItStep) {
-      const int t = t_begin + (GX ? (it + rot) % nt : it);   // tile position in the sweep; `it` indexes the pipeline state
+    for (int it = C::kTeams ? h : 0; it < nt_loop; it += kItStep) {
+      const int t = GX ? gx_tile(it) : t_begin + it;    // tile position in the sweep; `it` indexes the pipeline state
       const int sb = it % kBufs;
       mbar_wait(&s_full[sb], (it / kBufs) & 1);
       if (warp == 2 && lane == 0 && it < 8) NNCF_STAMP(16 + it);
@@ -661,7 +673,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       // seen once by each side); blocks that touch a ragged edge stay with side 0, whose general path handles them
       bool loss_here = (side == 0);
       if (NNCF_ABLATE & 16) loss_here = false;
-      else if (kBalanceLoss && !GX) {
+      else if (GX) loss_here = true;                    // every block is computed once, by one side: that side adds its loss
+      else if (kBalanceLoss) {
         const bool take1 = (((o / TN) + t) & 1) && ((o / TN) * TN + TN <= n_owner);   // parity-1 block, my row block is full
         loss_here = (side == 0) ? !take1 : take1;
       }
@@ -680,7 +693,8 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           if (side == 0) epi_chunk_mm_fast<false, GROUP>(ec, v[j], x0 + 32 * j, row_ok, my_sp, spos_row, lsum, asum, pk[j]);
           else epi_chunk_mm_fast<true, GROUP>(ec, v[j], x0 + 32 * j, row_ok, my_sp, spos_row, lsum, asum, pk[j]);
         } else {
-          if (side == 0) epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
+          // (pointwise losses: the two variants differ only in who adds the loss; under the G' exchange whoever computes a block does)
+          if (side == 0 || GX) epi_chunk<LOSS, false, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
           else epi_chunk<LOSS, true, GROUP, false>(ec, v[j], x0 + 32 * j, n_other, row_ok, o, my_posc, my_sp, inv_row, spos_row, lsum, asum, pk[j]);
         }
       }
@@ -703,7 +717,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
         // G' exchange: my 32 (= CW) item columns of row ol go into the image the item-side CTA of this item block copies
         // as an MN-major A operand: row = user row, 16-byte chunk c of the 128-byte row at position c ^ (row & 7)
         const int tb = t * TN;
-        uint8_t* gdst = a.gx_buf + ((((int64_t)r * nblk + ob) * nblk + (tb >> 7)) * 2 + ((tb >> 6) & 1)) * kSubBytes + ol * 128;
+        uint8_t* gdst = a.gx_buf + (((((int64_t)r * 2 + side) * nblk + ob) * nblk + (tb >> 7)) * 2 + ((tb >> 6) & 1)) * kSubBytes + ol * 128;
 #pragma unroll
         for (int j = 0; j < NV; ++j)
 #pragma unroll
@@ -896,15 +910,15 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(table + id * a.d), "r"(row_bytes) : "memory");
     }
    }
-   if (GX && side == 0 && warp == 2 + kScoreEpiWarps && lane == 0) {
+   if (GX && warp == 2 + kScoreEpiWarps && lane == 0) {
     // G' exchange: publish every item block of my G' rows once all epilogue warps have stored both of its tiles.  The
     // warps' stores are ordered before their release-add on the counter, my acquire-load of the counter before the
     // gpu-scope release store of the flag (cumulative), so whoever acquires the flag sees the image.
-    for (int j = 0; j < nblk; ++j) {
+    for (int j = 0; j < nblk / 2; ++j) {
       const uint32_t need = static_cast<uint32_t>(kScoreEpiWarps * kTilesPerBlk * (j + 1));
       uint32_t spins = 0;
       while (ld_acquire_cta_smem_u32(gx_cnt) < need) { __nanosleep(32); if (++spins > 40000000u) __trap(); }
-      st_release_gpu(a.gx_flags + ((int64_t)r * nblk + ob) * nblk + (ob + j) % nblk, a.gx_seq);
+      st_release_gpu(a.gx_flags + (((int64_t)r * 2 + side) * nblk + ob) * nblk + (ob + side + 2 * j) % nblk, a.gx_seq);
     }
    }
   }

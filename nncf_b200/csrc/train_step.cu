@@ -887,8 +887,8 @@ struct nncf_trainer {
   int* gather_flags = nullptr;          // self-gather mode (score_tc.cuh): [R][2][rows_pad / 128] step sequence numbers
   unsigned long long* gather_count = nullptr;
   int gather_seq = 0;
-  uint8_t* gx_buf = nullptr;            // G' exchange (score_tc.cuh): [R][nblk][nblk][32 KiB] bf16 gradient tiles, allocated at the first eligible step
-  int* gx_flags = nullptr;              // [R][nblk][nblk] step sequence numbers
+  uint8_t* gx_buf = nullptr;            // G' exchange (score_tc.cuh): [R][2][nblk][nblk][32 KiB] bf16 gradient tiles, allocated at the first eligible step
+  int* gx_flags = nullptr;              // [R][2][nblk][nblk] step sequence numbers
   int gx_seq = 0;
   int resident_ctas = 0;                // CTAs of the score kernel that fit on the device at once
   int32_t *uniq = nullptr, *inverse = nullptr, *nuniq = nullptr;
@@ -1347,13 +1347,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     // kernel (C3: 32.7 vs 22.8 us per step, tools/gpu_r2_w.sh; see score_tc.cuh), kept with its parity tests.
     {
       const bool gx_env = [] { const char* e = getenv("NNCF_GX"); return e && atoi(e) != 0; }();    // (read per step: the tests switch it)
-      const bool gx_ok = gx_env && !group && !pairwise && dp <= 128 && (B % 128 == 0) && split == 1 && !self_gather &&
+      const bool gx_ok = gx_env && !group && !pairwise && dp <= 128 && (B % 256 == 0) && split == 1 && !self_gather &&
                          !dense_items && vec && !t->lr_dev && !NNCF_SCORE_TEAMS;
       if (gx_ok) {
         const size_t nb = (size_t)rp / 128;
         if (!t->gx_buf) {
-          NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->gx_buf), (size_t)R * nb * nb * 2 * kSubBytes));
-          if (int rc3 = dev_alloc(&t->gx_flags, (size_t)R * nb * nb)) return rc3;
+          NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->gx_buf), (size_t)R * 2 * nb * nb * 2 * kSubBytes));
+          if (int rc3 = dev_alloc(&t->gx_flags, (size_t)R * 2 * nb * nb)) return rc3;
         }
         ta.gx = 1; ta.gx_seq = ++t->gx_seq; ta.gx_buf = t->gx_buf; ta.gx_flags = t->gx_flags;
       }
@@ -1653,10 +1653,13 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
 // device chunk buffers while earlier steps compute; every step's losses return on a second copy stream as soon as the
 // step has finished.  Nothing is skipped: every step's ids are copied H2D, every step's losses D2H; the host is only
 // synchronised once, at the end.
-// The loop is bound by the host's CUDA calls once a step is ~20 us (12 calls per step in the first version = 26 us): ids
-// now travel in chunks of several steps (two copies per chunk instead of per step; the first chunk is one step, so the
-// pipeline starts after one step's worth of ids), which leaves 5 calls per step: two launches, an event, and the loss copy
-// with its wait.
+// Chunks: the first version copied per step and put two stream waits and an event between consecutive steps on the compute
+// stream, which also breaks the programmatic-dependent-launch overlap of step s + 1's gather with step s's drain: 26 us per
+// C3 step against 21.7 device-fed.  Ids now travel in chunks of 1, 2, 4, ... up to 16 steps (two copies per chunk; the ramp
+// lets a short run start after one step's worth of ids), the compute stream waits once per chunk, and per step there is one
+// event record + the loss copy on the side stream: 21.9 us per step (tools/host_fed_bench.py, 1,000 steps).  Measured and
+// dropped: the kernel storing its losses straight into pinned host memory (no copy, no event) - the PCIe write sits at the
+// end of the step's last CTA and the next step waits for it: 26-28 us per step.
 extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
                                      const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream) {
   NNCF_CHECK_ARG(t && tables && user_ids_host && item_ids_host, "nncf_train_steps_host: null argument");
@@ -1667,9 +1670,11 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
   const int R = t->cfg.replicas;
   const int64_t per_step = (int64_t)R * t->rows;
   if (!t->s_h2d) {
-    // chunk length: up to 16 steps or ~1 MB of ids per side, whichever is smaller (NNCF_HOST_CHUNK overrides)
-    int ch = static_cast<int>(std::min<int64_t>(nncf_trainer::kHostChunkMax, std::max<int64_t>(1, (1 << 18) / per_step)));
-    if (const char* e = getenv("NNCF_HOST_CHUNK")) ch = std::min(nncf_trainer::kHostChunkMax, std::max(1, atoi(e)));
+    // longest chunk: a power of two, up to 16 steps or ~2 MB of ids per side (NNCF_HOST_CHUNK overrides)
+    int64_t want = std::max<int64_t>(1, (1 << 19) / per_step);
+    if (const char* e = getenv("NNCF_HOST_CHUNK")) want = std::max(1, atoi(e));
+    int ch = 1;
+    while (ch * 2 <= want && ch * 2 <= nncf_trainer::kHostChunkMax) ch *= 2;
     t->host_chunk = ch;
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
@@ -1682,11 +1687,14 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
     for (int i = 0; i < NB * ch; ++i) NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_step[i], cudaEventDisableTiming));
   }
   const int CH = t->host_chunk;
+  int ramp = 0;                                                        // chunks 0 .. ramp - 1 have 1, 2, 4, ... steps, the rest CH
+  while ((1 << ramp) < CH) ++ramp;
+  const int64_t ramp_steps = ((int64_t)1 << ramp) - 1;
   const int64_t cid_off = (int64_t)CH * per_step;                      // the cids of a chunk buffer start here
-  // chunk k covers steps [first(k), first(k) + len(k)): chunk 0 is ONE step, the others CH steps
-  auto first = [&](int64_t k) -> int64_t { return k == 0 ? 0 : 1 + (k - 1) * CH; };
-  auto len = [&](int64_t k) -> int64_t { return std::min<int64_t>(k == 0 ? 1 : CH, n_steps - first(k)); };
-  const int64_t n_chunks = n_steps == 0 ? 0 : 1 + (n_steps - 1 + CH - 1) / CH;
+  auto first = [&](int64_t k) -> int64_t { return k <= ramp ? ((int64_t)1 << k) - 1 : ramp_steps + (k - ramp) * CH; };
+  auto len = [&](int64_t k) -> int64_t { return std::min<int64_t>(k < ramp ? (int64_t)1 << k : CH, n_steps - first(k)); };
+  const int64_t n_chunks = n_steps <= ramp_steps ? [&] { int64_t k = 0; while (first(k) < n_steps) ++k; return k; }()
+                                                 : ramp + (n_steps - ramp_steps + CH - 1) / CH;
   auto enqueue_ids = [&](int64_t k) -> int {
     const int b = static_cast<int>(k % NB);
     const int64_t s0 = first(k), n = len(k);
@@ -1719,7 +1727,7 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
       t->hint_next_uid = t->hint_next_cid = nullptr;
       if (rc) return rc;
       cudaEvent_t done = t->ev_step[b * CH + j];
-      NNCF_CUDA(cudaEventRecord(done, st));
+      if (loss_out_host || j + 1 == n) NNCF_CUDA(cudaEventRecord(done, st));   // (a chunk's last step also frees its id buffer)
       if (loss_out_host) {                                             // loss of this step -> host
         NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, done, 0));
         NNCF_CUDA(cudaMemcpyAsync(loss_out_host + (first(k) + j) * R, t->h_loss[b] + j * R, R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));

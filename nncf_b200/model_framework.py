@@ -153,8 +153,9 @@ class SharedState(object):
                 self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
             # Keras Adam(lr); capturable: its step count lives on the device, so the captured mean-pool step (below) and the
             # eager paths share one optimizer state
+            # fused: one multi-tensor kernel per step instead of ~a dozen (the captured step is launch-gap-bound)
             self.tower_opt = torch.optim.Adam([p for p in self.tower.parameters() if p.requires_grad], lr=self.lr,
-                                              eps=1e-8, capturable=True)
+                                              eps=1e-8, capturable=True, fused=True)
         elif model_name == 'pretrained':
             # ref: models/model_framework.py:69-84 + configs/pretrained_conf.py:57-65,77-105
             from .towers import FrozenItemTable, PretrainCombinedTower

@@ -282,11 +282,12 @@ def test_bad_arguments_raise():
         FusedStep(StepSpec(loss="hinge"))
 
 
-@pytest.mark.parametrize("replicas,n_steps", [(1, 9), (3, 6)])
+@pytest.mark.parametrize("replicas,n_steps", [(1, 9), (3, 6), (2, 60)])
 def test_host_fed_steps_match_device_fed(replicas, n_steps):
-    """nncf_train_steps_host (ids in host memory, one H2D + one D2H per step on copy streams, staging ring of 4) must
-    produce exactly what the device-fed loop produces on the same ids: same losses, same tables (fp32 path: the update
-    is order-independent only up to atomic ordering, so tables are compared at 1e-6)."""
+    """nncf_train_steps_host (ids in host memory, copied H2D in chunks of up to 16 steps into a ring of 3 chunk buffers,
+    every step's losses back to the host with a D2H copy per step, into pinned or pageable memory) must produce exactly what the device-fed loop produces on the same ids: same losses, same tables
+    (the update is order-independent only up to atomic ordering, so tables are compared at 1e-6).  60 steps = 5 chunks:
+    the ring wraps."""
     from nncf_b200.ops import FusedStep, StepSpec
     nu, ni, B, d = 500, 400, 128, 64
     EU, EV = _tables(nu, ni, d, seed=11)
@@ -305,9 +306,17 @@ def test_host_fed_steps_match_device_fed(replicas, n_steps):
     h_uid, h_cid = torch.from_numpy(uid).pin_memory(), torch.from_numpy(cid).pin_memory()
     loss_h = b.run_host(hU, hV, h_uid, h_cid, n_steps)
     assert not loss_h.is_cuda and loss_h.numel() == n_steps * replicas
-    assert np.allclose(loss_h.numpy(), out["loss"].cpu().numpy(), rtol=1e-5, atol=1e-6)
-    assert _rel(hU.cpu().numpy(), tU.cpu().numpy()) < 1e-6 and _rel(hV.cpu().numpy(), tV.cpu().numpy()) < 1e-6
-    # a second call reuses the staging ring; pageable host memory is accepted too
+    # (two runs of the same steps differ by the order of their float atomics; over 60 dependent steps that grows past 1e-6)
+    lt, tt = (1e-5, 1e-6) if n_steps <= 10 else (1e-4, 2e-5)
+    assert np.allclose(loss_h.numpy(), out["loss"].cpu().numpy(), rtol=lt, atol=1e-6)
+    assert _rel(hU.cpu().numpy(), tU.cpu().numpy()) < tt and _rel(hV.cpu().numpy(), tV.cpu().numpy()) < tt
+    # pageable loss array: must return the same numbers
+    c = FusedStep(spec)
+    cU, cV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    loss_p = c.run_host(cU, cV, h_uid, h_cid, n_steps, torch.zeros(n_steps * replicas, dtype=torch.float32))
+    assert np.allclose(loss_p.numpy(), loss_h.numpy(), rtol=lt, atol=1e-6)
+    assert _rel(cU.cpu().numpy(), hU.cpu().numpy()) < tt
+    # a second call reuses the staging ring; pageable id arrays are accepted too
     loss_h2 = b.run_host(hU, hV, torch.from_numpy(uid), torch.from_numpy(cid), 2)
     assert np.all(np.isfinite(loss_h2.numpy()[:2 * replicas]))
     with pytest.raises(AssertionError):
@@ -593,7 +602,7 @@ def test_lazy_adam_folded_matches_oracle_over_steps(scheme, fold, monkeypatch):
 
 @pytest.mark.parametrize("gx", ["1", "0"])
 @pytest.mark.parametrize("loss", ["skip-gram", "mse"])
-@pytest.mark.parametrize("B,d,replicas,norm", [(128, 64, 1, False), (256, 128, 2, True), (512, 128, 3, False), (640, 100, 2, False),
+@pytest.mark.parametrize("B,d,replicas,norm", [(128, 64, 1, False), (256, 128, 1, True), (256, 64, 2, False), (512, 128, 3, False), (640, 100, 2, False),
                                               (1024, 128, 2, False), (512, 32, 40, False)])
 def test_g_exchange_two_sided_matches_oracle(loss, B, d, replicas, norm, gx, monkeypatch):
     """G' exchange (score_tc.cuh): the user-side CTAs compute every sigmoid once and hand the bf16 gradient tiles to the
