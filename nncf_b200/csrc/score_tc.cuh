@@ -136,7 +136,7 @@ struct ScoreTcCfg {
   // dependent chain per S' buffer (S' ready -> TMEM load -> G' -> TMEM store -> barrier -> MMA2 -> MMA1 of the tile that
   // reuses the buffer -> commit: ~600 cycles with everything but the synchronisation switched off, tools/score_bench.cu
   // ablation 63), tensor memory fixes the columns in flight (128 next to the accumulator) but not their granularity, so four
-  // shorter chains should fill the bubbles of two long ones.  Measured (tools/gpu_r2_v.sh, parity green): C3 22.9 vs 21.0 us
+  // shorter chains should fill the bubbles of two long ones.  Measured (tools/gpu_experiments_r02.sh teams, parity green): C3 22.9 vs 21.0 us
   // per step, B = 4,096: 130.6 vs 104.8 us.  The loop is not waiting for round trips, it is MUFU-bound: one MUFU.TANH per
   // score = 8.2k cycles per SM sub-partition and step against a measured 12.2k for the loop, and N = 32 MMAs only double the
   // issue work of the MMA warp.  What halves the MUFU work is computing every sigmoid once: the G' exchange below.

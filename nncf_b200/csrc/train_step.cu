@@ -1341,10 +1341,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     ta.ids_u = uid; ta.ids_stride_u = B; ta.ids_v = item_ids; ta.ids_stride_v = item_stride;
     ta.shards_u = gu.shards; ta.shards_v = gv.shards;
     ta.tl = tl;
-    // G' exchange (two-sided: every sigmoid computed once, the item side a plain contraction), opt-in with NNCF_GX=1:
-    // neg_shared with a pointwise loss, full 128-row blocks, no split sweep.  Not under a device step clock (= the caller
-    // captures steps into a CUDA graph: the sequence number is a kernel argument).  Measured slower than the one-sided
-    // kernel (C3: 32.7 vs 22.8 us per step, tools/gpu_r2_w.sh; see score_tc.cuh), kept with its parity tests.
+    // G' exchange (two-sided: every block's scores, sigmoids and loss computed once, by one side; the other side contracts
+    // the exchanged bf16 tiles), opt-in with NNCF_GX=1: neg_shared with a pointwise loss, an even number of full 128-row
+    // blocks, no split sweep.  Not under a device step clock (= the caller captures steps into a CUDA graph: the sequence
+    // number is a kernel argument).  Measured slower than the one-sided kernel (C3: 25.2 vs 21.1 us per step,
+    // tools/gpu_experiments_r02.sh gx), kept with its parity tests.
     {
       const bool gx_env = [] { const char* e = getenv("NNCF_GX"); return e && atoi(e) != 0; }();    // (read per step: the tests switch it)
       const bool gx_ok = gx_env && !group && !pairwise && dp <= 128 && (B % 256 == 0) && split == 1 && !self_gather &&

@@ -211,7 +211,8 @@ def test_meanpool_graph_step_equals_eager_tower_step(scheme, loss, monkeypatch):
         assert ok, "tower parameter: " + msg
     assert torch.allclose(a[4], b[4], rtol=1e-3, atol=1e-4 if noisy else 1e-5), float((a[4] - b[4]).abs().max())
     assert torch.allclose(a[5], b[5], rtol=1e-3, atol=1e-6)
-    ok, msg = close(a[7], b[7], 1e-3, 1e-4, 0.1 if noisy else 0.0, 1e-3)
+    # (tower outputs are O(0.1 .. 1): the noisy scheme is held to 5e-4 absolute with 2 % counted outliers below 2e-3)
+    ok, msg = close(a[7], b[7], 1e-3, 5e-4 if noisy else 1e-4, 0.02 if noisy else 0.0, 2e-3)
     assert ok, "tower output, batch statistics: " + msg
-    ok, msg = close(a[6], b[6], 1e-3, 1e-4, 0.1 if noisy else 0.0, 1e-3)
+    ok, msg = close(a[6], b[6], 1e-3, 5e-4 if noisy else 1e-4, 0.02 if noisy else 0.0, 2e-3)
     assert ok, "tower output, test phase: " + msg
