@@ -93,8 +93,36 @@ meanpool_bwd_kernel(float* __restrict__ dW, int dw, const int32_t* __restrict__ 
   cnt = 0; cnt0 = 0;
 #pragma unroll
   for (int w = 0; w < 8; ++w) { cnt += cnts[w]; cnt0 += cnts0[w]; }
-  float g[NM];
   const float inv = 1.0f / static_cast<float>(cnt);
+  if ((dw & 1) == 0) {
+    // even word_dim: rows are 8-byte aligned, every lane adds PAIRS of columns with one red.global.add.v2.f32 (half the
+    // reduction instructions of the scalar form; the kernel is bound by the L2's reduction rate)
+    float2 g2[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) {
+      const int col = 2 * (lane + 32 * m);
+      g2[m] = (col < dw) ? make_float2(dout[(int64_t)it * dw + col] * inv, dout[(int64_t)it * dw + col + 1] * inv) : make_float2(0.f, 0.f);
+    }
+    auto add_row = [&](float* wr, float scale) {
+#pragma unroll
+      for (int m = 0; m < NM; ++m) {
+        const int col = 2 * (lane + 32 * m);
+        if (col < dw)
+          asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(wr + col), "f"(g2[m].x * scale), "f"(g2[m].y * scale) : "memory");
+      }
+    };
+    if (cnt0 > 0 && warp == 0) add_row(dW, static_cast<float>(cnt0));
+    for (int l0 = warp * 32; l0 < L; l0 += 256) {
+      const int32_t mine = (l0 + lane < L) ? __ldg(c + l0 + lane) : -1;
+      for (int t = 0; t < 32; ++t) {
+        const int32_t w = __shfl_sync(0xffffffffu, mine, t);
+        if (w <= 0) continue;
+        add_row(dW + (int64_t)w * dw, 1.0f);
+      }
+    }
+    return;
+  }
+  float g[NM];
 #pragma unroll
   for (int m = 0; m < NM; ++m) {
     const int col = lane + 32 * m;

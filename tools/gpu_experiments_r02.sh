@@ -6,9 +6,12 @@
 #   gx       symmetric G' exchange (two-sided score kernel) on / off
 #   hostfed  host-fed loop vs device-fed loop, per chunk length
 #   tower    graph-captured content-tower step vs the eager step: where the two end up (diagnostic), and the step time
+#   suite2   the whole GPU suite twice (flakiness check)
+#   tower_ncu  ncu launch list of the graph-captured content-tower step (which nodes the 190 us are)
 #   mufu     issue cost of the special-function and packed-math instructions (tools/mufu_bench.cu -> build/probe/mufu_bench)
 #   scale2   bench.py at N = 1 and N = 2 (needs gpurun --gpus 2), the driver's short window and a long one
 #   scale8   bench.py at N = 8 / 4 / 2 / 1 the way the driver launches it (needs gpurun --gpus 8), C5 at N = 8
+#   scale4   the same at N = 4 / 2 / 1 (gpurun --gpus 4)
 #   ncu_score   ncu --set full + source page of the score kernel
 mkdir -p gpurun_out
 CB="python tools/config_bench.py"
@@ -44,6 +47,22 @@ for what in "$@"; do
     tower)
       timeout 600 python tools/tower_graph_diag.py 2>&1 | tail -30 | tee gpurun_out/r02_tower_diag.txt
       for s in neg_shared group_neg_shared; do for g in 1 0; do timeout 300 python tools/tower_bench.py $s $g 2>&1 | tail -1; done; done | tee gpurun_out/r02_tower_bench.txt ;;
+    suite2)
+      for i in 1 2; do timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -4; done | tee gpurun_out/r02_suite2.txt ;;
+    tower_ncu)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 400 --csv --log-file gpurun_out/r02_tower_launches.csv python tools/tower_bench.py neg_shared 1 > gpurun_out/r02_tower_ncu.log 2>&1
+      python - <<PY
+import csv
+rows = [r for r in csv.reader(open("gpurun_out/r02_tower_launches.csv")) if len(r) > 5]
+hdr = rows[0]; ik, iv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+agg = {}
+for r in rows[1:]:
+    agg.setdefault(r[ik].split("(")[0][:90], []).append(float(r[iv].replace(",", "")))
+tot = sum(sum(v) for v in agg.values())
+print("launches %d, total %.1f us" % (len(rows) - 1, tot / 1e3))
+for n, v in sorted(agg.items(), key=lambda x: -sum(x[1])): print("%-92s %4d  avg %7.2f us  share %.3f" % (n, len(v), sum(v) / len(v) / 1e3, sum(v) / tot))
+PY
+      ;;
     mufu) ./build/probe/mufu_bench | tee gpurun_out/r02_mufu.txt ;;
     scale2)
       run 1 --steps 20 --warmup 5 --no-eval --cpu-steps 1 > gpurun_out/r02_scale_n1.json 2> gpurun_out/r02_scale_n1.err
@@ -77,6 +96,22 @@ for f in ("r02q_scale_n1", "r02q_scale_n2", "r02q_scale_n4", "r02q_scale_n8", "r
               ("eff=%.3f" % (j["value"] / (j["n_gpus"] * v1))) if v1 and "scale" in f else "", {k: round(v * 1e3, 1) for k, v in j["roofline"]["phases_ms"].items()}, j["clocks"].get("reasons"))
         w = j.get("extra", {}).get("whole_at_k")
         if w: print("   whole@k", {k: (round(v["users_per_sec"]), round(v["tflops"], 1)) for k, v in w["by_k"].items()})
+    except Exception as ex: print(f, "ERR", ex)
+PY
+      ;;
+    scale4)
+      for n in 4 2 1; do
+        run $n --steps 20 --warmup 5 --no-eval --cpu-steps 1 > gpurun_out/r02q_scale_n$n.json 2> gpurun_out/r02q_scale_n$n.err; echo "n$n rc=$?"
+      done
+      run 4 --steps 2000 --warmup 50 --no-eval > gpurun_out/r02q_scale_n4_long.json 2> gpurun_out/r02q_scale_n4_long.err; echo "n4 long rc=$?"
+      python - <<PY
+import json
+v1 = json.load(open("gpurun_out/r02q_scale_n1.json"))["value"]
+for f in ("r02q_scale_n1", "r02q_scale_n2", "r02q_scale_n4", "r02q_scale_n4_long"):
+    try:
+        j = json.load(open("gpurun_out/%s.json" % f))
+        print(f, "N=%d value=%.3e us/step=%.2f e2e=%.3e eff=%.3f" % (j["n_gpus"], j["value"], j["ms_per_step"] * 1e3, j["e2e"]["value"], j["value"] / (j["n_gpus"] * v1)),
+              {k: round(v * 1e3, 1) for k, v in j["roofline"]["phases_ms"].items()}, j["clocks"].get("reasons"))
     except Exception as ex: print(f, "ERR", ex)
 PY
       ;;
