@@ -286,6 +286,15 @@ int nncf_tower_bn_act_bwd(const float* dy_dev, const float* y_dev, const float* 
                           const int32_t* n_valid_dev, int use_bn, int activation, const float* gamma_dev, float* dh_dev,
                           float* dgamma_dev, float* dbeta_dev, void* stream);
 
+/* Dense Adam step on n_tensors parameter tensors (host arrays of device pointers; sizes in elements), Keras-1 form:
+ * lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t), p -= lr_t m / (sqrt(v) + eps) - what the reference's towers train with
+ * (ref: configs/basic_embedding_conf.py `optimizer = Adam(lr)`; utils/optimizer.py:108-147 restates the rule).  The step
+ * count t lives in *step_dev (int64, zero at the start) and is advanced by the call itself on the stream, lr_t_dev is one
+ * float of scratch: a call captured into a CUDA graph stays correct when replayed. */
+int nncf_dense_adam_step(int n_tensors, float* const* params_dev, const float* const* grads_dev, float* const* m_dev,
+                         float* const* v_dev, const int64_t* sizes, float lr, float beta1, float beta2, float eps,
+                         long long* step_dev, float* lr_t_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (5) Evaluation.   ref: utils/objectives.py:296-321 (test_eval_mat: all users x candidate items),
  *     utils/metrics_ranking.py:6-35 (eval_multiple), utils/objectives.py:333-370 (evaluate_mat),

@@ -24,7 +24,7 @@ EXPORTS = [
     "nncf_trainer_create", "nncf_trainer_destroy", "nncf_train_steps", "nncf_train_steps_host", "nncf_trainer_set_profile", "nncf_trainer_set_device_clock",
     "nncf_trainer_get_profile", "nncf_unique_first_occurrence", "nncf_gather_rows", "nncf_updater_create",
     "nncf_updater_destroy", "nncf_updater_begin_step", "nncf_updater_apply",
-    "nncf_meanpool_fwd", "nncf_meanpool_bwd", "nncf_meanpool_fwd_n", "nncf_meanpool_bwd_n", "nncf_tower_bn_act_fwd", "nncf_tower_bn_act_bwd",
+    "nncf_meanpool_fwd", "nncf_meanpool_bwd", "nncf_meanpool_fwd_n", "nncf_meanpool_bwd_n", "nncf_tower_bn_act_fwd", "nncf_tower_bn_act_bwd", "nncf_dense_adam_step",
     "nncf_peer_alloc", "nncf_peer_open", "nncf_peer_close", "nncf_peer_free", "nncf_peer_barrier", "nncf_peer_copy", "nncf_peer_signal", "nncf_peer_wait", "nncf_trainer_set_shards",
     "nncf_eval_topk_workspace_bytes", "nncf_eval_topk", "nncf_eval_metrics", "nncf_score_pairs", "nncf_eval_given",
 ]
@@ -117,6 +117,7 @@ def _load():
         "nncf_meanpool_bwd_n": (i32, [vp, i32, vp, i32, vp, i32, vp, vp, vp]),
         "nncf_tower_bn_act_fwd": (i32, [vp, i32, i32, vp, i32, i32, vp, vp, f32, f32, vp, vp, vp, vp, vp, vp]),
         "nncf_tower_bn_act_bwd": (i32, [vp, vp, vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp, vp]),
+        "nncf_dense_adam_step": (i32, [i32, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp]),
         "nncf_eval_topk_workspace_bytes": (sz, [i64, i64, i32, i32, i32]),
         "nncf_eval_topk": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, sz, vp]),
         "nncf_eval_metrics": (i32, [vp, i64, i32, vp, vp, vp, vp, vp]),

@@ -29,10 +29,11 @@ namespace nncf {
 // tf.unique (first occurrence order), one block per replica.   ref: models/model_framework.py:45-48
 // =================================================================================================
 constexpr int kUniqueThreads = 1024;
+constexpr int kUniqueHashMax = 2048;      // up to this many ids the first occurrences come from a shared-memory hash table
 
 __global__ void __launch_bounds__(kUniqueThreads)
 unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, int32_t* __restrict__ uniq_all,
-              int32_t* __restrict__ inv_all, int32_t* __restrict__ nuniq_all, int out_stride) {
+              int32_t* __restrict__ inv_all, int32_t* __restrict__ nuniq_all, int out_stride, int hash_slots) {
   extern __shared__ int32_t sm[];
   int32_t* s_ids = sm;            // [n]
   int32_t* s_first = sm + n;      // [n]
@@ -46,13 +47,45 @@ unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, in
   const int tid = threadIdx.x;
   for (int i = tid; i < n; i += blockDim.x) s_ids[i] = ids[i];
   if (tid == 0) s_carry = 0;
-  __syncthreads();
-  for (int i = tid; i < n; i += blockDim.x) {
-    const int32_t me = s_ids[i];
-    int f = i;
-    for (int j = 0; j < i; ++j)
-      if (s_ids[j] == me) { f = j; break; }
-    s_first[i] = f;
+  if (hash_slots > 0) {
+    // first occurrence of every id through an open-addressing table of (id << 32 | position) entries: insert with
+    // compare-and-swap into an empty slot or atomicMin into the id's slot (the smallest position wins: the result is
+    // exactly the quadratic scan's, in ~2 probes per id instead of up to n comparisons - 23 us -> ~3 us at n = 512)
+    unsigned long long* tab = reinterpret_cast<unsigned long long*>(sm + 3 * n + ((3 * n) & 1));       // 8-byte aligned
+    constexpr unsigned long long kEmpty = ~0ull;
+    const unsigned int mask = static_cast<unsigned int>(hash_slots - 1);
+    for (int i = tid; i < hash_slots; i += blockDim.x) tab[i] = kEmpty;
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned int key = static_cast<unsigned int>(s_ids[i]);
+      const unsigned long long packed = (static_cast<unsigned long long>(key) << 32) | static_cast<unsigned int>(i);
+      unsigned int slot = (key * 2654435761u) >> 7 & mask;
+      while (true) {
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[slot]);
+        if (cur == kEmpty) {
+          cur = atomicCAS(&tab[slot], kEmpty, packed);
+          if (cur == kEmpty) break;                                   // the slot is mine
+        }
+        if (static_cast<unsigned int>(cur >> 32) == key) { atomicMin(&tab[slot], packed); break; }
+        slot = (slot + 1) & mask;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const unsigned int key = static_cast<unsigned int>(s_ids[i]);
+      unsigned int slot = (key * 2654435761u) >> 7 & mask;
+      while (static_cast<unsigned int>(tab[slot] >> 32) != key) slot = (slot + 1) & mask;
+      s_first[i] = static_cast<int32_t>(tab[slot] & 0xFFFFFFFFull);
+    }
+  } else {
+    __syncthreads();
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int32_t me = s_ids[i];
+      int f = i;
+      for (int j = 0; j < i; ++j)
+        if (s_ids[j] == me) { f = j; break; }
+      s_first[i] = f;
+    }
   }
   __syncthreads();
   // exclusive scan of is_first flags, chunk by chunk
@@ -1106,13 +1139,28 @@ extern "C" int nncf_trainer_get_profile(nncf_trainer_t* t, double* phase_ms_out,
   return NNCF_OK;
 }
 
+// dynamic shared memory of unique_kernel for n ids: three int arrays, plus (n <= kUniqueHashMax) the hash table of the next
+// power of two >= 2 n 64-bit entries
+static size_t unique_smem_bytes(int n, int* hash_slots) {
+  size_t sm = (size_t)3 * n * sizeof(int32_t);
+  *hash_slots = 0;
+  if (n <= nncf::kUniqueHashMax) {
+    int slots = 64;
+    while (slots < 2 * n) slots *= 2;
+    *hash_slots = slots;
+    sm = ((size_t)3 * n + ((3 * n) & 1)) * sizeof(int32_t) + (size_t)slots * sizeof(unsigned long long);
+  }
+  return sm;
+}
+
 extern "C" int nncf_unique_first_occurrence(const int32_t* ids_dev, int n, int32_t* unique_ids_dev, int32_t* inverse_dev,
                                             int32_t* n_unique_dev, void* stream) {
   NNCF_CHECK_ARG(ids_dev && unique_ids_dev && inverse_dev && n_unique_dev, "nncf_unique_first_occurrence: null argument");
   NNCF_CHECK_ARG(n >= 1 && n <= 12288, "nncf_unique_first_occurrence: n must be in [1, 12288]");
-  const size_t sm = (size_t)3 * n * sizeof(int32_t);
+  int slots = 0;
+  const size_t sm = unique_smem_bytes(n, &slots);
   if (sm > 48 * 1024) NNCF_CUDA(cudaFuncSetAttribute(unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-  unique_kernel<<<1, kUniqueThreads, sm, (cudaStream_t)stream>>>(ids_dev, 0, n, unique_ids_dev, inverse_dev, n_unique_dev, 0);
+  unique_kernel<<<1, kUniqueThreads, sm, (cudaStream_t)stream>>>(ids_dev, 0, n, unique_ids_dev, inverse_dev, n_unique_dev, 0, slots);
   NNCF_LAUNCH_OK();
   return NNCF_OK;
 }
@@ -1223,10 +1271,11 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       NNCF_CUDA(cudaMemcpyAsync(t->inverse, io->inverse_dev, sizeof(int32_t) * B, cudaMemcpyDeviceToDevice, st));
       NNCF_CUDA(cudaMemcpyAsync(t->nuniq, io->n_unique_dev, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
     } else {
-      const size_t sm = (size_t)3 * B * sizeof(int32_t);
+      int slots = 0;
+      const size_t sm = unique_smem_bytes(B, &slots);
       if (sm > 48 * 1024)
         NNCF_CUDA(cudaFuncSetAttribute(unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      unique_kernel<<<R, kUniqueThreads, sm, st>>>(cid, B, B, t->uniq, t->inverse, t->nuniq, rp);
+      unique_kernel<<<R, kUniqueThreads, sm, st>>>(cid, B, B, t->uniq, t->inverse, t->nuniq, rp, slots);
       NNCF_LAUNCH_OK();
       item_ids = t->uniq;
       item_stride = rp;

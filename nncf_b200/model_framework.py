@@ -151,11 +151,9 @@ class SharedState(object):
                 self.tower = PretrainCombinedTower(self.tower, spec.C_pretrain, conf, tower_dim).to(dev)
             if self.bias:
                 self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
-            # Keras Adam(lr); capturable: its step count lives on the device, so the captured mean-pool step (below) and the
-            # eager paths share one optimizer state
-            # fused: one multi-tensor kernel per step instead of ~a dozen (the captured step is launch-gap-bound)
-            self.tower_opt = torch.optim.Adam([p for p in self.tower.parameters() if p.requires_grad], lr=self.lr,
-                                              eps=1e-8, capturable=True, fused=True)
+            # Keras Adam(lr) on the tower's dense parameters: one launch for all tensors, step count on the device, so the
+            # captured mean-pool step (below) and the eager paths share one optimizer state
+            self.tower_opt = ops.KerasAdam([p for p in self.tower.parameters() if p.requires_grad], lr=self.lr, eps=1e-8)
         elif model_name == 'pretrained':
             # ref: models/model_framework.py:69-84 + configs/pretrained_conf.py:57-65,77-105
             from .towers import FrozenItemTable, PretrainCombinedTower
@@ -177,7 +175,7 @@ class SharedState(object):
             if self.bias:
                 self.tower = BiasedTower(self.tower, spec.item_count, self.bias in ('item', 'both'))
             params = [p for p in self.tower.parameters() if p.requires_grad]
-            self.tower_opt = torch.optim.Adam(params, lr=self.lr, eps=1e-8) if params else None
+            self.tower_opt = ops.KerasAdam(params, lr=self.lr, eps=1e-8) if params else None
         else:
             assert False, '[ERROR] Model name {} unknown'.format(model_name)
         self.norm_u = bool(conf.emb_normalization)

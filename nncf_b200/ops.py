@@ -393,6 +393,42 @@ def meanpool_bwd_n(grad_word_table: torch.Tensor, content: torch.Tensor, item_id
                                   _ptr(item_ids), item_ids.numel(), _ptr(n_valid), _ptr(grad_out), _stream()))
 
 
+class KerasAdam(object):
+    """Adam for the towers' dense parameters in Keras-1 form (nncf_dense_adam_step: lr_t = lr sqrt(1 - b2^t) / (1 - b1^t),
+    p -= lr_t m / (sqrt(v) + eps); ref: configs/*_conf.py `optimizer = Adam(lr)`), one launch for all tensors (plus a
+    one-thread step-clock kernel), step count on the device: safe inside a captured CUDA graph.  Same two methods the
+    trainers use of a torch optimizer: zero_grad() and step().  Parameters without a gradient are skipped, like torch does."""
+
+    def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.params = [p for p in params]
+        assert all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() for p in self.params), "KerasAdam: contiguous fp32 CUDA parameters"
+        self.lr, self.beta1, self.beta2, self.eps = float(lr), float(beta1), float(beta2), float(eps)
+        self.m = [torch.zeros_like(p) for p in self.params]
+        self.v = [torch.zeros_like(p) for p in self.params]
+        dev = self.params[0].device if self.params else torch.device("cuda")
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.lr_t_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            if set_to_none:
+                p.grad = None
+            elif p.grad is not None:
+                p.grad.zero_()
+
+    def step(self):
+        idx = [i for i, p in enumerate(self.params) if p.grad is not None]
+        n = len(idx)
+        if n == 0:
+            return
+        grads = [self.params[i].grad.contiguous() for i in idx]
+        arr = lambda ptrs: (C.c_void_p * n)(*ptrs)                      # noqa: E731
+        sizes = (C.c_int64 * n)(*[self.params[i].numel() for i in idx])
+        check(lib.nncf_dense_adam_step(n, arr([self.params[i].data_ptr() for i in idx]), arr([g.data_ptr() for g in grads]),
+                                       arr([self.m[i].data_ptr() for i in idx]), arr([self.v[i].data_ptr() for i in idx]), sizes,
+                                       self.lr, self.beta1, self.beta2, self.eps, _ptr(self.step_dev), _ptr(self.lr_t_dev), _stream()))
+
+
 _ACTS = {"linear": 0, "relu": 1, "tanh": 2}
 
 

@@ -201,7 +201,10 @@ def test_meanpool_graph_step_equals_eager_tower_step(scheme, loss, monkeypatch):
 
     a, b = res["1"], res["0"]
     noisy = scheme == "group_neg_shared"
-    frac, cap = (3e-3, 5e-3) if noisy else (0.0, None)
+    # (cap: an element whose gradient is rounding noise takes +-lr Adam steps in either run: 7 steps of lr = 0.01 bound the gap)
+    # measured: ~0.4 % of the user table (elements whose gradient is rounding noise under the saturated log-loss) end up one
+    # Adam step (~lr) apart, in graph vs graph runs as well (tools/tower_graph_diag.py); 99 % must agree to 2e-5 + 1e-4 rel
+    frac, cap = (1e-2, 7e-2) if noisy else (0.0, None)
     assert a[1] == b[1] == 7
     assert abs(a[0] - b[0]) <= 1e-4 * abs(b[0]), (a[0], b[0])
     ok, msg = close(a[2], b[2], 1e-4, 2e-5, frac, cap)
@@ -216,3 +219,34 @@ def test_meanpool_graph_step_equals_eager_tower_step(scheme, loss, monkeypatch):
     assert ok, "tower output, batch statistics: " + msg
     ok, msg = close(a[6], b[6], 1e-3, 5e-4 if noisy else 1e-4, 0.02 if noisy else 0.0, 2e-3)
     assert ok, "tower output, test phase: " + msg
+
+
+def test_keras_adam_matches_formula():
+    """ops.KerasAdam (nncf_dense_adam_step) against the Keras-1 Adam formulas in NumPy fp64 over four steps on tensors of odd
+    sizes (one of them larger than a launch's grid stride), a parameter without gradient skipped."""
+    from nncf_b200.ops import KerasAdam
+    rng = np.random.RandomState(4)
+    shapes = [(7, 13), (50,), (8000, 50), (3,), (5_000_011,)]
+    P = [rng.normal(size=sh).astype(np.float32) for sh in shapes]
+    params = [torch.nn.Parameter(torch.from_numpy(p.copy()).cuda()) for p in P] + [torch.nn.Parameter(torch.ones(4, device="cuda"))]
+    opt = KerasAdam(params, lr=0.01, eps=1e-8)
+    ref = [p.astype(np.float64) for p in P]
+    M = [np.zeros_like(r) for r in ref]; V = [np.zeros_like(r) for r in ref]
+    b1, b2 = 0.9, 0.999
+    for t in range(1, 5):
+        G = [(rng.normal(size=sh) * (10.0 ** rng.randint(-6, 1))).astype(np.float32) for sh in shapes]
+        for p, g in zip(params, G):
+            p.grad = torch.from_numpy(g).cuda()
+        opt.step()
+        lr_t = 0.01 * np.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+        for i, g in enumerate(G):
+            M[i] = b1 * M[i] + (1 - b1) * g
+            V[i] = b2 * V[i] + (1 - b2) * g.astype(np.float64) ** 2
+            ref[i] -= lr_t * M[i] / (np.sqrt(V[i]) + 1e-8)
+        opt.zero_grad()
+        assert all(p.grad is None for p in params)
+    torch.cuda.synchronize()
+    assert int(opt.step_dev.item()) == 4
+    for p, r in zip(params, ref):
+        np.testing.assert_allclose(p.detach().cpu().numpy(), r, rtol=2e-5, atol=2e-6)
+    assert float(params[-1].detach().abs().max()) == 1.0            # no gradient: untouched

@@ -257,7 +257,8 @@ def test_permute_rows_and_assemble_pairs_bit_exact():
 def test_unique_first_occurrence_bit_exact():
     from nncf_b200.ops import unique_first_occurrence
     rng = np.random.RandomState(1)
-    for n, hi in [(1, 5), (512, 40), (512, 100000), (3000, 700)]:
+    # (n <= 2,048: shared-memory hash table; above: the quadratic scan.  hi = 2: a table of two long chains; 2**31 - 1: ids with the top bits set)
+    for n, hi in [(1, 5), (2, 1), (512, 40), (512, 100000), (511, 2), (2048, 1500), (2048, 2 ** 31 - 1), (2049, 900), (3000, 700)]:
         ids = rng.randint(0, hi, size=n).astype(np.int32)
         uq, inv, cnt = unique_first_occurrence(torch.from_numpy(ids).cuda())
         eu, ex = O.unique_first_occurrence(ids)
