@@ -195,8 +195,8 @@ int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, const int32_t
  * copies overlap the kernels), as the reference's `train` array does (ref: models/train_neg_shared.py:46-50 slices it per
  * batch and feeds it through feed_dict), and loss_out_host[n_steps * R] receives every batch's loss (what Keras'
  * train_on_batch returns, ref: models/train_neg_shared.py:50).  Every step's ids are copied H2D on an internal copy
- * stream, in chunks of 1, 2, 4, ... up to 16 steps that overlap the kernels of earlier steps; the step runs on `stream`;
- * its R losses are copied to loss_out_host on a second copy stream as soon as it has finished.
+ * stream, in chunks of 1, 4, 16, 16, ... steps that overlap the kernels of earlier steps; the steps run on `stream`; the
+ * R losses of every step of a chunk are copied to loss_out_host on a second copy stream as soon as the chunk has finished.
  * Returns when all steps and copies have completed.  Embedding-table models only. */
 int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
                           const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream);

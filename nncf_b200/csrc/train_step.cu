@@ -16,8 +16,10 @@
 //      utils/objectives.py:35-220; utils/utilities.py:122-135; utils/optimizer.py:108-147.
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <vector>
 #include "common.cuh"
 #include "sm100.cuh"
@@ -953,7 +955,7 @@ struct nncf_trainer {
   float* h_loss[kHostBufs] = {nullptr, nullptr, nullptr};              // [host_chunk][R] device
   cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t ev_ready[kHostBufs] = {}, ev_read[kHostBufs] = {};
-  cudaEvent_t ev_step[kHostBufs * kHostChunkMax] = {};                 // step finished (its loss may leave; a chunk's last one frees the ids)
+  cudaEvent_t ev_step[kHostBufs] = {};                                 // chunk finished (its losses may leave, its id buffer is free)
   // developer timeline (env NNCF_TIMELINE=<file>): per step 16 stamp slots written by the kernels themselves,
   // dumped as text when the trainer is destroyed (tools/timeline.py reads it)
   unsigned long long* timeline = nullptr;
@@ -1700,16 +1702,18 @@ extern "C" int nncf_train_steps(nncf_trainer_t* t, const nncf_tables* tables, co
 // Host-fed training loop: the link ids of every batch live in HOST memory, as the reference's `train` array does (it
 // slices a NumPy array per batch and feeds it through feed_dict, ref: models/train_neg_shared.py:46-50), and every
 // batch's loss goes back to the host (what train_on_batch returns).  The ids travel on a copy stream into a ring of
-// device chunk buffers while earlier steps compute; every step's losses return on a second copy stream as soon as the
-// step has finished.  Nothing is skipped: every step's ids are copied H2D, every step's losses D2H; the host is only
+// device chunk buffers while earlier steps compute; the losses of a chunk's steps return on a second copy stream as soon as
+// the chunk has finished.  Nothing is skipped: every step's ids are copied H2D, every step's losses D2H; the host is only
 // synchronised once, at the end.
-// Chunks: the first version copied per step and put two stream waits and an event between consecutive steps on the compute
-// stream, which also breaks the programmatic-dependent-launch overlap of step s + 1's gather with step s's drain: 26 us per
-// C3 step against 21.7 device-fed.  Ids now travel in chunks of 1, 2, 4, ... up to 16 steps (two copies per chunk; the ramp
-// lets a short run start after one step's worth of ids), the compute stream waits once per chunk, and per step there is one
-// event record + the loss copy on the side stream: 21.9 us per step (tools/host_fed_bench.py, 1,000 steps).  Measured and
-// dropped: the kernel storing its losses straight into pinned host memory (no copy, no event) - the PCIe write sits at the
-// end of the step's last CTA and the next step waits for it: 26-28 us per step.
+// The loop is bound by the HOST's CUDA calls (3-5 us each on the boxes this was measured on; tools/host_fed_trace.py shows
+// the device idling at every point where the host has more than a launch pair to issue between two steps).  The first
+// version made 12 calls per step - and its two stream waits + event between consecutive steps also broke the
+// programmatic-dependent-launch overlap of step s + 1's gather with step s's drain: 26 us per C3 step against 21.7
+// device-fed.  Now ids AND losses travel in chunks of 1, 4, 16, 16, ... steps (the short first chunk lets the call start
+// after one step's worth of ids): two H2D copies, one D2H copy, three events and two waits per CHUNK, and per step nothing
+// but the step's own two launches.  The ids of chunk k + 2 are enqueued right AFTER chunk k's launches, never in front of
+// them.  Measured and dropped: the kernel storing its losses straight into pinned host memory (no copy at all) - the PCIe
+// write sits at the end of the step's last CTA and the next step waits for it: 26-28 us per step.
 extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* tables, const int32_t* user_ids_host,
                                      const int32_t* item_ids_host, int64_t n_steps, float* loss_out_host, void* stream) {
   NNCF_CHECK_ARG(t && tables && user_ids_host && item_ids_host, "nncf_train_steps_host: null argument");
@@ -1720,11 +1724,11 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
   const int R = t->cfg.replicas;
   const int64_t per_step = (int64_t)R * t->rows;
   if (!t->s_h2d) {
-    // longest chunk: a power of two, up to 16 steps or ~2 MB of ids per side (NNCF_HOST_CHUNK overrides)
+    // longest chunk: a power of four, up to 16 steps or ~2 MB of ids per side (NNCF_HOST_CHUNK overrides)
     int64_t want = std::max<int64_t>(1, (1 << 19) / per_step);
     if (const char* e = getenv("NNCF_HOST_CHUNK")) want = std::max(1, atoi(e));
     int ch = 1;
-    while (ch * 2 <= want && ch * 2 <= nncf_trainer::kHostChunkMax) ch *= 2;
+    while (ch * 4 <= want && ch * 4 <= nncf_trainer::kHostChunkMax) ch *= 4;
     t->host_chunk = ch;
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_h2d, cudaStreamNonBlocking));
     NNCF_CUDA(cudaStreamCreateWithFlags(&t->s_d2h, cudaStreamNonBlocking));
@@ -1733,35 +1737,37 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
       NNCF_CUDA(cudaMalloc(reinterpret_cast<void**>(&t->h_loss[i]), (size_t)ch * R * sizeof(float)));
       NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_ready[i], cudaEventDisableTiming));
       NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_read[i], cudaEventDisableTiming));
+      NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_step[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < NB * ch; ++i) NNCF_CUDA(cudaEventCreateWithFlags(&t->ev_step[i], cudaEventDisableTiming));
   }
   const int CH = t->host_chunk;
-  int ramp = 0;                                                        // chunks 0 .. ramp - 1 have 1, 2, 4, ... steps, the rest CH
-  while ((1 << ramp) < CH) ++ramp;
-  const int64_t ramp_steps = ((int64_t)1 << ramp) - 1;
+  int ramp = 0;                                                        // chunks 0 .. ramp - 1 have 1, 4, 16, ... steps, the rest CH
+  while (((int64_t)1 << (2 * ramp)) < CH) ++ramp;
+  auto pow4 = [](int64_t k) -> int64_t { return (int64_t)1 << (2 * k); };
+  const int64_t ramp_steps = (pow4(ramp) - 1) / 3;                     // 1 + 4 + ... + 4^(ramp - 1)
   const int64_t cid_off = (int64_t)CH * per_step;                      // the cids of a chunk buffer start here
-  auto first = [&](int64_t k) -> int64_t { return k <= ramp ? ((int64_t)1 << k) - 1 : ramp_steps + (k - ramp) * CH; };
-  auto len = [&](int64_t k) -> int64_t { return std::min<int64_t>(k < ramp ? (int64_t)1 << k : CH, n_steps - first(k)); };
+  auto first = [&](int64_t k) -> int64_t { return k <= ramp ? (pow4(k) - 1) / 3 : ramp_steps + (k - ramp) * CH; };
+  auto len = [&](int64_t k) -> int64_t { return std::min<int64_t>(k < ramp ? pow4(k) : CH, n_steps - first(k)); };
   const int64_t n_chunks = n_steps <= ramp_steps ? [&] { int64_t k = 0; while (first(k) < n_steps) ++k; return k; }()
                                                  : ramp + (n_steps - ramp_steps + CH - 1) / CH;
   auto enqueue_ids = [&](int64_t k) -> int {
     const int b = static_cast<int>(k % NB);
     const int64_t s0 = first(k), n = len(k);
-    // chunk buffer b is free once the last step of chunk k - NB has finished
-    if (k >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_step[b * CH + (len(k - NB) - 1)], 0));
+    if (k >= NB) NNCF_CUDA(cudaStreamWaitEvent(t->s_h2d, t->ev_step[b], 0));   // chunk k - NB has finished with buffer b
     NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b], user_ids_host + s0 * per_step, n * per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
     NNCF_CUDA(cudaMemcpyAsync(t->h_ids[b] + cid_off, item_ids_host + s0 * per_step, n * per_step * sizeof(int32_t), cudaMemcpyHostToDevice, t->s_h2d));
     NNCF_CUDA(cudaEventRecord(t->ev_ready[b], t->s_h2d));
     return NNCF_OK;
   };
+  // developer trace (NNCF_HOST_TRACE=1): host-side wall clock of the call's phases on stderr
+  static const bool trace = [] { const char* e = getenv("NNCF_HOST_TRACE"); return e && atoi(e) != 0; }();
+  auto now_us = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
+  const double t_in = trace ? now_us() : 0.0;
   nncf_step_io io{};
   if (n_chunks > 0) if (int rc = enqueue_ids(0)) return rc;
-  if (n_chunks > 1) if (int rc = enqueue_ids(1)) return rc;
+  if (n_chunks > 1) if (int rc = enqueue_ids(1)) return rc;          // (behind chunk 0's one step it would land after that step has ended)
   for (int64_t k = 0; k < n_chunks; ++k) {
     const int b = static_cast<int>(k % NB), bn = static_cast<int>((k + 1) % NB);
-    // two chunks of ids are in flight ahead of the one that computes
-    if (k + 2 < n_chunks) if (int rc = enqueue_ids(k + 2)) return rc;
     NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_ready[b], 0));
     if (k >= NB && loss_out_host) NNCF_CUDA(cudaStreamWaitEvent(st, t->ev_read[b], 0));   // the loss slots of buffer b have been read back
     const int64_t n = len(k);
@@ -1776,17 +1782,23 @@ extern "C" int nncf_train_steps_host(nncf_trainer_t* t, const nncf_tables* table
       const int rc = nncf_train_steps(t, tables, uid, uid + cid_off, 1, &io, st);
       t->hint_next_uid = t->hint_next_cid = nullptr;
       if (rc) return rc;
-      cudaEvent_t done = t->ev_step[b * CH + j];
-      if (loss_out_host || j + 1 == n) NNCF_CUDA(cudaEventRecord(done, st));   // (a chunk's last step also frees its id buffer)
-      if (loss_out_host) {                                             // loss of this step -> host
-        NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, done, 0));
-        NNCF_CUDA(cudaMemcpyAsync(loss_out_host + (first(k) + j) * R, t->h_loss[b] + j * R, R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));
-      }
     }
-    if (loss_out_host) NNCF_CUDA(cudaEventRecord(t->ev_read[b], t->s_d2h));
+    NNCF_CUDA(cudaEventRecord(t->ev_step[b], st));                     // chunk k has finished: its losses may leave, its id buffer is free
+    if (loss_out_host) {                                               // the chunk's n x R losses -> host
+      NNCF_CUDA(cudaStreamWaitEvent(t->s_d2h, t->ev_step[b], 0));
+      NNCF_CUDA(cudaMemcpyAsync(loss_out_host + first(k) * R, t->h_loss[b], n * R * sizeof(float), cudaMemcpyDeviceToHost, t->s_d2h));
+      NNCF_CUDA(cudaEventRecord(t->ev_read[b], t->s_d2h));
+    }
+    // ids of the chunks ahead: two in flight, enqueued BEHIND this chunk's launches (the device never waits for the host
+    // to finish copy calls before it gets a step to run)
+    if (k + 2 < n_chunks) if (int rc = enqueue_ids(k + 2)) return rc;
   }
+  const double t_enq = trace ? now_us() : 0.0;
   NNCF_CUDA(cudaStreamSynchronize(st));
+  const double t_sync = trace ? now_us() : 0.0;
   NNCF_CUDA(cudaStreamSynchronize(t->s_d2h));
+  if (trace) fprintf(stderr, "[nncf_train_steps_host] %lld steps, %lld chunks (max %d): enqueue %.1f us, compute-stream sync +%.1f us, loss-stream sync +%.1f us\n",
+                     (long long)n_steps, (long long)n_chunks, CH, t_enq - t_in, t_sync - t_enq, now_us() - t_sync);
   return NNCF_OK;
 }
 

@@ -243,8 +243,8 @@ class MeanPoolGraphStep(object):
         B = conf.batch_size_p
         dev = st.device
         self.B = B
-        self.uid = torch.zeros(B, dtype=torch.int32, device=dev)
-        self.cid = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.ids = torch.zeros((2, B), dtype=torch.int32, device=dev)    # the graph reads its batch here: one copy per step
+        self.uid, self.cid = self.ids[0], self.ids[1]
         self.arange = torch.arange(B, device=dev, dtype=torch.int32)
         self.loss_sum = torch.zeros((), dtype=torch.float64, device=dev)
         self.graph = None
@@ -281,7 +281,7 @@ class MeanPoolGraphStep(object):
         if t.bn is not None:
             t.bn.weight.grad, t.bn.bias.grad = dgamma, dbeta
         t.dense.weight.grad = dh1.t() @ h0
-        t.dense.bias.grad = dh1.sum(0) if t.bn is None else torch.zeros_like(bd)     # (exactly zero in front of a BatchNorm, see MeanPoolTower)
+        t.dense.bias.grad = dh1.sum(0) if t.bn is None else None     # (exactly zero in front of a BatchNorm, see MeanPoolTower: Adam skips it)
         dh0 = dh1 @ Wd
         dW = torch.zeros_like(W)
         ops.meanpool_bwd_n(dW, t.content, uq, nuq, dh0)
@@ -289,10 +289,14 @@ class MeanPoolGraphStep(object):
         st.tower_opt.step()
         self.loss_sum += out['loss'][0].double()
 
-    def run(self, uid, cid):
-        """one step on the B ids of `uid` / `cid` (device int32); returns nothing - see take_loss()"""
-        self.uid.copy_(uid, non_blocking=True)
-        self.cid.copy_(cid, non_blocking=True)
+    def run(self, uid, cid=None):
+        """one step on the B ids of `uid` / `cid` (device int32), or on a [2, B] tensor holding both; returns nothing - see
+        take_loss()"""
+        if cid is None:
+            self.ids.copy_(uid, non_blocking=True)
+        else:
+            self.uid.copy_(uid, non_blocking=True)
+            self.cid.copy_(cid, non_blocking=True)
         self.state.tower.train()
         self.calls += 1
         if self.graph is not None:
@@ -363,9 +367,10 @@ class MatmulView(_View):
         if key not in st._steps:
             st._steps[key] = MeanPoolGraphStep(st, self.scheme)
         gs = st._steps[key]
+        both = torch.stack([user_ids[:nb * rows_per_batch].view(nb, rows_per_batch),
+                            item_ids[:nb * rows_per_batch].view(nb, rows_per_batch)], dim=1)     # [nb, 2, B]: one copy per batch
         for b in range(nb):
-            s = slice(b * rows_per_batch, (b + 1) * rows_per_batch)
-            gs.run(user_ids[s], item_ids[s])
+            gs.run(both[b])
         return gs.take_loss(), nb
 
     def _train_with_tower(self, uid, cid):

@@ -334,8 +334,8 @@ class FusedStep:
     def run_host(self, user_table: torch.Tensor, item_table: torch.Tensor, user_ids_host: torch.Tensor,
                  item_ids_host: torch.Tensor, n_steps: int, loss_out_host: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Host-fed loop (nncf_train_steps_host): ids are HOST int32 tensors (pinned memory lets the copies overlap the
-        kernels), every step's ids are copied H2D (in chunks of a few steps) and every step's losses go back to the host
-        (a D2H copy per step on a second stream); returns the host
+        kernels), every step's ids are copied H2D and every step's losses D2H, both in chunks of 1, 4, 16, 16, ... steps
+        on two copy streams beside the compute stream; returns the host
         loss tensor [n_steps * R] after everything has completed.   ref: models/train_neg_shared.py:46-50"""
         sp = self.spec
         _need_cuda(user_table, item_table)

@@ -284,9 +284,9 @@ def test_bad_arguments_raise():
 
 @pytest.mark.parametrize("replicas,n_steps", [(1, 9), (3, 6), (2, 60)])
 def test_host_fed_steps_match_device_fed(replicas, n_steps):
-    """nncf_train_steps_host (ids in host memory, copied H2D in chunks of up to 16 steps into a ring of 3 chunk buffers,
-    every step's losses back to the host with a D2H copy per step, into pinned or pageable memory) must produce exactly what the device-fed loop produces on the same ids: same losses, same tables
-    (the update is order-independent only up to atomic ordering, so tables are compared at 1e-6).  60 steps = 5 chunks:
+    """nncf_train_steps_host (ids in host memory, copied H2D in chunks of 1, 4, 16, 16, ... steps into a ring of 3 chunk
+    buffers, every step's losses back to the host chunk by chunk, into pinned or pageable memory) must produce exactly what the device-fed loop produces on the same ids: same losses, same tables
+    (the update is order-independent only up to atomic ordering, so tables are compared at 1e-6).  60 steps = 6 chunks:
     the ring wraps."""
     from nncf_b200.ops import FusedStep, StepSpec
     nu, ni, B, d = 500, 400, 128, 64

@@ -29,7 +29,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "one":
         " ".join("%.2f" % x for x in res)), flush=True)
 else:
     for steps in (20, 1000):
-        for chunk in ("1", "4", "16", ""):
+        for chunk in ("1", "4", ""):
             env = dict(os.environ)
             if chunk: env["NNCF_HOST_CHUNK"] = chunk
             subprocess.run([sys.executable, __file__, "one", str(steps)], env=env, timeout=300)
