@@ -78,13 +78,10 @@ for f in ("r02_scale_n1", "r02_scale_n2", "r02_scale_n2_long"):
 PY
       ;;
     scale8)
-      for n in 8 4 2 1; do
-        ev="--no-eval"; [ $n -eq 8 ] && ev=""
-        run $n --steps 20 --warmup 5 $ev --cpu-steps 1 > gpurun_out/r02q_scale_n$n.json 2> gpurun_out/r02q_scale_n$n.err; echo "n$n rc=$?"
-      done
+      run 8 --steps 20 --warmup 5 --cpu-steps 1 > gpurun_out/r02q_scale_n8.json 2> gpurun_out/r02q_scale_n8.err; echo "n8 rc=$?"
+      run 1 --steps 20 --warmup 5 --no-eval --cpu-steps 1 > gpurun_out/r02q_scale_n1.json 2> gpurun_out/r02q_scale_n1.err; echo "n1 rc=$?"
       run 8 --steps 2000 --warmup 50 --no-eval > gpurun_out/r02q_scale_n8_long.json 2> gpurun_out/r02q_scale_n8_long.err; echo "n8 long rc=$?"
       run 8 --workload c5 --steps 20 --warmup 5 --no-eval > gpurun_out/r02q_c5_n8.json 2> gpurun_out/r02q_c5_n8.err; echo "c5 n8 rc=$?"
-      run 1 --workload c5 --steps 20 --warmup 5 --no-eval --cpu-steps 1 > gpurun_out/r02q_c5_n1.json 2> gpurun_out/r02q_c5_n1.err; echo "c5 n1 rc=$?"
       python - <<PY
 import json
 v1 = None
