@@ -12,6 +12,7 @@
 #   scale2   bench.py at N = 1 and N = 2 (needs gpurun --gpus 2), the driver's short window and a long one
 #   scale8   bench.py at N = 8 / 4 / 2 / 1 the way the driver launches it (needs gpurun --gpus 8), C5 at N = 8
 #   scale4   the same at N = 4 / 2 / 1 (gpurun --gpus 4)
+#   ncu_c5   ncu --set full of the C5 step's gather and finalize kernels (B = 16,384, d = 256, l2-normalised rows, max-margin)
 #   ncu_score   ncu --set full + source page of the score kernel
 mkdir -p gpurun_out
 CB="python tools/config_bench.py"
@@ -112,6 +113,19 @@ for f in ("r02q_scale_n1", "r02q_scale_n2", "r02q_scale_n4", "r02q_scale_n4_long
     except Exception as ex: print(f, "ERR", ex)
 PY
       ;;
+    ncu_c5)
+      for k in gather_rows_vec finalize_vec pos_score; do
+        timeout 600 ncu --set full --clock-control none -k regex:$k -s 6 -c 1 -o gpurun_out/r02_c5_$k $CB neg_shared max-margin 16384 256 1 20 ureg norm > gpurun_out/r02_c5_$k.log 2>&1
+        ncu -i gpurun_out/r02_c5_$k.ncu-rep --page raw --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin)); h,u,v=rows[0],rows[1],rows[2]
+for k in ['Kernel Name','gpu__time_duration.sum','launch__grid_size','launch__registers_per_thread','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','lts__t_sector_hit_rate.pct','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active']:
+    if k in h: print('%-64s %s %s' % (k, v[h.index(k)][:80], u[h.index(k)]))
+"
+        rm -f gpurun_out/r02_c5_$k.ncu-rep
+      done | tee gpurun_out/r02_c5_ncu.txt
+      for sp in 0 1 2 4; do echo "== NNCF_SPLIT=$sp (0 = the host's choice)"; NNCF_SPLIT=$sp timeout 120 $CB neg_shared max-margin 16384 256 1 200 ureg norm 2>&1 | tail -1; done | tee -a gpurun_out/r02_c5_ncu.txt
+      echo "== u_reg = 0"; timeout 120 $CB neg_shared max-margin 16384 256 1 200 norm 2>&1 | tail -1 ;;
     ncu_score)
       ZIPF=10,10 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'score_grad_tc' -s 40 -c 1 -o gpurun_out/r02_score $CB neg_shared skip-gram 512 128 37 60 ureg > gpurun_out/r02_score.log 2>&1
       ncu -i gpurun_out/r02_score.ncu-rep --page source --csv > gpurun_out/r02_score_source.csv 2>/dev/null
