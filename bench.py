@@ -744,6 +744,7 @@ def bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_ov
         s = sums.cpu().numpy()
         tf = 2.0 * world * n_users * n_items * d / (kms * 1e-3) / 1e12
         res[str(k)] = {"users_per_sec": world * n_users / (kms * 1e-3), "ms": kms, "tflops": tf, "frac_of_bf16_burst": tf / (world * peaks["bf16_burst"]),
+                       "frac_of_bf16_sustained": tf / (world * peaks["bf16_sustained"]),
                        "recall": float(s[1] / max(s[3], 1.0)), "map": float(s[0] / max(s[3], 1.0)), "users_kept": int(s[3])}
         del ids
     r50 = res["50"]
@@ -751,7 +752,10 @@ def bench_whole_at_k(torch, dist, ops, args, world, rank, peaks, barrier, max_ov
             "sharding": "users over %d GPU(s), %d per GPU (the C4 shard: 10M users over 8 GPUs)" % (world, n_users),
             "timed": "nncf_eval_topk + nncf_eval_metrics + all-reduce of the 4 metric sums",
             "roofline": {"bound": "tensor", "achieved": r50["tflops"], "peak": world * peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": r50["frac_of_bf16_burst"]},
+                         "frac": r50["frac_of_bf16_burst"], "peak_sustained": world * peaks["bf16_sustained"],
+                         "frac_of_sustained": r50["frac_of_bf16_sustained"],
+                         "note": "a 0.7 s kernel under the power cap: MEASURED_PEAKS' sustained cuBLAS figure is the denominator that "
+                                 "applies to a kernel this long; `frac` keeps the burst figure"},
             "by_k": res}
 
 
