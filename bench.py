@@ -705,7 +705,13 @@ def bench_content_tower(torch, ops, peaks):
             for name, fn in (("fwd", lambda: ops.meanpool_fwd_n(W, content, ids, nv)), ("bwd", lambda: ops.meanpool_bwd_n(dW, content, ids, nv, g))):
                 for _ in range(5):
                     fn()
-                ms = _time_steps(torch, lambda: [fn() for _ in range(50)]) / 50
+                torch.cuda.synchronize()
+                gr = torch.cuda.CUDAGraph()              # 20 launches per replay: the host's per-call cost (~15 us) is not the kernel's
+                with torch.cuda.graph(gr):
+                    for _ in range(20):
+                        fn()
+                gr.replay()
+                ms = _time_steps(torch, gr.replay) / 20
                 res[name] = {"us": ms * 1e3, "gbs_algorithmic": alg / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": alg / (ms * 1e-3) / 1e9 / peaks["hbm"]}
             out["meanpool"] = res
         del md, view, dh

@@ -756,8 +756,26 @@ struct PairsArgs {
                          // (ref: utils/objectives.py:59-70 weights by y_true); NULL = positives are rows [0, B)
 };
 
+// One double atomic on loss[r] per CTA instead of one per row (same-address atomics serialise: ~1.5 ns each): the warps of a
+// CTA add into a shared accumulator and the last one to arrive forwards the sum.  `active` = warps of this CTA that have a row.
+struct CtaLoss { float sum; int arrived; };
+__device__ __forceinline__ void cta_loss_init(CtaLoss* c) {
+  if (threadIdx.x == 0) { c->sum = 0.0f; c->arrived = 0; }
+  __syncthreads();
+}
+__device__ __forceinline__ void cta_loss_add(CtaLoss* c, float l, int active, double* dst) {   // lane 0 of every active warp, once
+  if (l != 0.0f) atomicAdd(&c->sum, l);
+  __threadfence_block();
+  if (atomicAdd(&c->arrived, 1) == active - 1) {
+    const float t = atomicAdd(&c->sum, 0.0f);
+    if (t != 0.0f) atomicAdd(dst, static_cast<double>(t));
+  }
+}
+
 __global__ void __launch_bounds__(256)
 pairs_score_kernel(PairsArgs a) {
+  __shared__ CtaLoss cl;
+  cta_loss_init(&cl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = (1 + a.k) * a.B;
   const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
@@ -779,12 +797,14 @@ pairs_score_kernel(PairsArgs a) {
     a.s[o] = dot * iu * iv + dotb;
     a.invu[o] = iu;
     a.invv[o] = iv;
-    if (a.u_reg != 0.0f) atomicAdd(&a.loss[r], static_cast<double>(a.u_reg * su / n));
+    if (a.u_reg != 0.0f) cta_loss_add(&cl, a.u_reg * su / n, min(8, n - static_cast<int>(blockIdx.x) * 8), &a.loss[r]);
   }
 }
 
 __global__ void __launch_bounds__(256)
 pairs_grad_kernel(PairsArgs a) {
+  __shared__ CtaLoss cl;
+  cta_loss_init(&cl);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B = a.B, k = a.k, n = (1 + k) * B;
   const int row = blockIdx.x * 8 + warp, r = blockIdx.y;
@@ -824,7 +844,7 @@ pairs_grad_kernel(PairsArgs a) {
       }
     }
   }
-  if (lane == 0 && l != 0.0f) atomicAdd(&a.loss[r], static_cast<double>(l));
+  if (lane == 0) cta_loss_add(&cl, l, min(8, n - static_cast<int>(blockIdx.x) * 8), &a.loss[r]);
   const int64_t uidx = a.uid[r * a.ids_stride + row], cidx = a.cid[r * a.ids_stride + row];
   const float* u = a.EU + uidx * a.d;
   const float* v = a.EV + cidx * a.d;
