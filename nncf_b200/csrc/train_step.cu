@@ -1292,6 +1292,17 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
     if (ensure_accum(&t->accU, &t->claimU, &t->accU_rows, tb->n_users, d, st)) return NNCF_ECUDA;
     if (ensure_accum(&t->accV, &t->claimV, &t->accV_rows, tb->n_items, d, st)) return NNCF_ECUDA;
   }
+  // the same accumulators behind the finalize pass (l2-normalised rows, pairwise losses, ...: whatever keeps the step off the
+  // plain path): the finalize kernel's sparse-SGD form adds its finished gradient rows into them (red.global.add.v4 with
+  // lr = -1) and ONE apply launch follows instead of owner / combine / apply (group_neg_shared + log-loss, R = 37: the
+  // optimizer phase was 49 of the step's 110 us).  Not under a device step clock: the claim tag is the host's step count.
+  const bool adam_fold_fin = !adam_plain && c.optimizer == NNCF_OPT_LAZY_ADAM && (d % 4 == 0) && !bias && t->n_shards <= 1 && !t->lr_dev &&
+                             [] { const char* e = getenv("NNCF_ADAM_FOLD"); return !e || atoi(e) != 0; }();
+  if (adam_fold_fin) {
+    NNCF_CHECK_ARG(tb->user_m && tb->user_v && (dense_items || (tb->item_m && tb->item_v)), "lazy Adam needs m / v tables");
+    if (ensure_accum(&t->accU, &t->claimU, &t->accU_rows, tb->n_users, d, st)) return NNCF_ECUDA;
+    if (!dense_items) if (ensure_accum(&t->accV, &t->claimV, &t->accV_rows, tb->n_items, d, st)) return NNCF_ECUDA;
+  }
   const bool drain_adds = fuse_sgd || adam_fold;     // the drain reduces into a table: no gradient staging blocks
   // t->loss is zero on entry: zeroed at creation and re-zeroed by whoever publishes the step's loss (the last finalize
   // launch, or in fused mode the last side-0 CTA of each replica inside the score kernel)
@@ -1489,6 +1500,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   fv.count_dev = group ? t->nuniq : nullptr; fv.normalize = c.norm_v; fv.need_x = (c.norm_v || pairwise) ? 1 : 0; fv.reg_scale = 0.0f;
   fv.table = dense_items ? nullptr : tb->item_table; fv.ids = item_ids; fv.ids_stride = item_stride;
   fv.grad_out = (last && io) ? io->grad_item_rows_dev : nullptr;
+  if (adam_fold_fin) {       // finished rows are ADDED into the per-table accumulators (the sparse-SGD form of the kernel with lr = -1)
+    fu.optimizer = NNCF_OPT_SGD; fu.lr = -1.0f; fu.table = t->accU; fu.write_back = 0;
+    fv.optimizer = NNCF_OPT_SGD; fv.lr = -1.0f; fv.table = dense_items ? nullptr : t->accV; fv.write_back = 0;
+  }
   if (sharded && !fuse_sgd) {
     fu.shards = gu.shards; fv.shards = gv.shards;
     // every rank has finished READING its peers' rows (gather) before anybody starts updating them
@@ -1536,9 +1551,10 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       NNCF_CHECK_ARG(tb->item_m && tb->item_v, "lazy Adam needs item_m / item_v");
       if (ensure_owner(&t->ownerV, &t->ownerV_n, tb->n_items, st)) return NNCF_ECUDA;
     }
-    if (adam_fold) {
+    if (adam_fold || adam_fold_fin) {
       AdamAccSide su{uid, B, B, nullptr, t->claimU, t->accU, tb->user_table, tb->user_m, tb->user_v};
       AdamAccSide sv{item_ids, item_stride, B, group ? t->nuniq : nullptr, t->claimV, t->accV, tb->item_table, tb->item_m, tb->item_v};
+      if (dense_items) sv = AdamAccSide{};                               // (no item table: the tower owns the item side)
       const int tag = static_cast<int>(t->adam_t & 0x7fffffff);          // (claim words start at 0, adam_t at 1)
       if (dp <= 128)
         NNCF_CUDA(launch_pdl(adam_apply_accum_kernel<1>, dim3(ceil_div(B, 32), R, 2), dim3(256), 0, st, su, sv, tag, d, lr_t,

@@ -652,3 +652,48 @@ def test_g_exchange_two_sided_matches_oracle(loss, B, d, replicas, norm, gx, mon
     dU2, dV2 = sum(r["dEU"] for r in refs2), sum(r["dEV"] for r in refs2)
     assert _rel(tU.cpu().numpy() - U1, -lr * dU2) <= 1e-2
     assert _rel(tV.cpu().numpy() - V1, -lr * dV2) <= 1e-2
+
+
+@pytest.mark.parametrize("fold", ["1", "0"])
+@pytest.mark.parametrize("scheme,loss,precision", [("group_neg_shared", "log-loss", "bf16"), ("neg_shared", "max-margin", "bf16"),
+                                                   ("neg_shared", "skip-gram", "fp32")])
+def test_lazy_adam_behind_the_finalize_pass_matches_oracle(scheme, loss, precision, fold, monkeypatch):
+    """Lazy Adam on the steps that need a finalize pass (l2-normalised rows, pairwise losses; fp32 precision): folded form (the
+    finalize kernel adds its finished rows into the per-table accumulators, one apply launch) and owner / combine / apply
+    form against the oracle over three dependent steps of R = 2 replicas with duplicate ids everywhere."""
+    from nncf_b200.ops import FusedStep, StepSpec
+    monkeypatch.setenv("NNCF_ADAM_FOLD", fold)
+    B, d, nu, ni, lr, R, steps = 256, 64, 300, 90, 0.01, 2, 3
+    norm = loss != "skip-gram"
+    lam, gamma = _params(loss)
+    EU, EV = _tables(nu, ni, d, seed=33)
+    rng = np.random.RandomState(9)
+    uid = rng.randint(0, nu, size=steps * R * B).astype(np.int32)
+    cid = rng.randint(0, ni, size=steps * R * B).astype(np.int32)
+    U, V = EU.astype(np.float64), EV.astype(np.float64)
+    mU, vU, mV, vV = np.zeros_like(U), np.zeros_like(U), np.zeros_like(V), np.zeros_like(V)
+    for t in range(steps):
+        dU = np.zeros_like(U); dV = np.zeros_like(V)
+        us, cs = [], []
+        for r in range(R):
+            sl = slice((t * R + r) * B, (t * R + r + 1) * B)
+            ref = O.step_matmul(U, V, uid[sl], cid[sl], scheme, loss, lam, gamma, u_reg=1e-3, norm_u=norm, norm_v=norm)
+            dU += ref["dEU"]; dV += ref["dEV"]; us.append(uid[sl]); cs.append(cid[sl])
+        U, mU, vU = O.lazy_adam_sparse(U, mU, vU, np.concatenate(us), dU, lr, t + 1)
+        V, mV, vV = O.lazy_adam_sparse(V, mV, vV, np.concatenate(cs), dV, lr, t + 1)
+    spec = StepSpec(scheme=scheme, loss=loss, precision=precision, batch_size_p=B, dim=d, optimizer="lazy_adam", learn_rate=lr,
+                    replicas=R, neg_loss_weight=lam, loss_gamma=gamma, u_reg=1e-3, norm_u=norm, norm_v=norm)
+    tU, tV = torch.from_numpy(EU).cuda(), torch.from_numpy(EV).cuda()
+    st = [torch.zeros_like(tU), torch.zeros_like(tU), torch.zeros_like(tV), torch.zeros_like(tV)]
+    out = FusedStep(spec).run(tU, tV, torch.from_numpy(uid).cuda(), torch.from_numpy(cid).cuda(), steps, adam_state=st)
+    torch.cuda.synchronize()
+    assert np.all(np.isfinite(out["loss"].cpu().numpy()))
+    # (Adam's first steps move every touched coordinate by ~lr whatever the gradient's size: tables compared absolutely; a
+    #  max-margin indicator or a near-zero coordinate may take one step the other way in bf16)
+    assert np.mean(np.abs(tU.cpu().numpy() - U)) <= 3e-4 and np.max(np.abs(tU.cpu().numpy() - U)) <= 2.5 * lr
+    assert np.mean(np.abs(tV.cpu().numpy() - V)) <= 3e-4 and np.max(np.abs(tV.cpu().numpy() - V)) <= 2.5 * lr
+    tol_m = 1e-3 if precision == "fp32" else 3e-2
+    assert _rel(st[0].cpu().numpy(), mU) <= tol_m and _rel(st[2].cpu().numpy(), mV) <= tol_m
+    untouched = np.setdiff1d(np.arange(nu), uid)
+    if untouched.size:
+        np.testing.assert_array_equal(tU.cpu().numpy()[untouched], EU[untouched])
