@@ -47,8 +47,10 @@ unique_kernel(const int32_t* __restrict__ ids_all, int64_t ids_stride, int n, in
   int32_t* uniq = uniq_all + (int64_t)r * out_stride;
   int32_t* inv = inv_all + (int64_t)r * out_stride;
   const int tid = threadIdx.x;
-  for (int i = tid; i < n; i += blockDim.x) s_ids[i] = ids[i];
+  pdl_launch_dependents();
+  for (int i = tid; i < n; i += blockDim.x) s_ids[i] = ids[i];     // (link ids are inputs of the step: nothing in the stream writes them)
   if (tid == 0) s_carry = 0;
+  pdl_wait();        // the previous step's kernels may still read uniq / inverse / n_unique (no-op under a plain launch)
   if (hash_slots > 0) {
     // first occurrence of every id through an open-addressing table of (id << 32 | position) entries: insert with
     // compare-and-swap into an empty slot or atomicMin into the id's slot (the smallest position wins: the result is
@@ -227,25 +229,52 @@ gather_rows_kernel(GatherArgs a0, GatherArgs a1) {
 
 // positive score per batch row:  spos[b] = <U_b, V_pos(b)>  (pos(b) = b for neg_shared, inverse[b] for group).
 // In bf16 mode the operands are rounded to bf16 first so the value matches what the tensor cores see.
+// Optionally (u_reg != 0) the same pass adds the activity regulariser's loss term u_reg * sum_d mean_b U_raw[b,d]^2 with
+// U_raw = Uf / inv (ref: utils/utilities.py:129-135): one double atomic per CTA.  Launched with programmatic dependent
+// launch behind the gather (it was two plain launches, pos_score + reg_loss: two exposed launch gaps and a second pass
+// over the user rows).
 __global__ void __launch_bounds__(256)
 pos_score_kernel(const float* __restrict__ Uf, const float* __restrict__ Vf, const int32_t* __restrict__ inverse,
-                 int rows_pad, int dp, int B, int round_bf16, float* __restrict__ spos) {
+                 int rows_pad, int dp, int B, int round_bf16, float* __restrict__ spos,
+                 const float* __restrict__ inv, float u_reg, int d_emb, double* loss) {
+  __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();                                   // the gather's staging rows must have landed
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
   const int r = blockIdx.y;
-  if (b >= B) return;
-  const int64_t base = (int64_t)r * rows_pad;
-  const int p = inverse ? inverse[base + b] : b;
-  const float* u = Uf + (base + b) * dp;
-  const float* v = Vf + (base + p) * dp;
-  float acc = 0.0f;
-  for (int c = lane; c < dp; c += 32) {
-    float a = u[c], w = v[c];
-    if (round_bf16) { a = __bfloat162float(__float2bfloat16(a)); w = __bfloat162float(__float2bfloat16(w)); }
-    acc += a * w;
+  float reg = 0.0f;
+  if (b < B) {
+    const int64_t base = (int64_t)r * rows_pad;
+    const int p = inverse ? inverse[base + b] : b;
+    const float* u = Uf + (base + b) * dp;
+    const float* v = Vf + (base + p) * dp;
+    const int ncol = d_emb > 0 ? d_emb : dp;    // the regulariser sees the embedding columns only
+    float acc = 0.0f, ss = 0.0f;
+    for (int c = lane; c < dp; c += 32) {
+      float a = u[c], w = v[c];
+      if (c < ncol) ss = fmaf(a, a, ss);
+      if (round_bf16) { a = __bfloat162float(__float2bfloat16(a)); w = __bfloat162float(__float2bfloat16(w)); }
+      acc += a * w;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) spos[base + b] = acc;
+    if (u_reg != 0.0f) {
+      ss = warp_sum(ss);
+      const float iv = inv[base + b];
+      reg = ss / (iv * iv);
+    }
   }
-  acc = warp_sum(acc);
-  if (lane == 0) spos[base + b] = acc;
+  if (u_reg != 0.0f) {                           // (uniform: every thread of the CTA reaches the barrier)
+    if (lane == 0) part[warp] = reg;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += part[w];
+      if (t != 0.0f) atomicAdd(&loss[r], static_cast<double>(u_reg) * static_cast<double>(t) / static_cast<double>(B));
+    }
+  }
 }
 
 // =================================================================================================
@@ -1320,7 +1349,7 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       const size_t sm = unique_smem_bytes(B, &slots);
       if (sm > 48 * 1024)
         NNCF_CUDA(cudaFuncSetAttribute(unique_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      unique_kernel<<<R, kUniqueThreads, sm, st>>>(cid, B, B, t->uniq, t->inverse, t->nuniq, rp, slots);
+      NNCF_CUDA(launch_pdl(unique_kernel, dim3(R), dim3(kUniqueThreads), sm, st, (const int32_t*)cid, (int64_t)B, B, t->uniq, t->inverse, t->nuniq, rp, slots));
       NNCF_LAUNCH_OK();
       item_ids = t->uniq;
       item_stride = rp;
@@ -1398,12 +1427,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
   }
   else NNCF_CUDA(launch_pdl(gather_rows_kernel, dim3(rp / 8, R, 2), dim3(256), 0, st, gu, gv));
   if (!self_gather) count_launch();
+  const bool reg_loss_here = c.u_reg != 0.0f && !drain_reg;   // (the fused step adds the regulariser's loss and gradient in the score kernel)
   if (pairwise) {
-    pos_score_kernel<<<dim3(ceil_div(B, 8), R), 256, 0, st>>>(t->Uf, t->Vf, group ? t->inverse : nullptr, rp, dp, B,
-                                                              bf16 ? 1 : 0, t->spos);
-    NNCF_LAUNCH_OK();
+    NNCF_CUDA(launch_pdl(pos_score_kernel, dim3(ceil_div(B, 8), R), dim3(256), 0, st, (const float*)t->Uf, (const float*)t->Vf,
+                         (const int32_t*)(group ? t->inverse : nullptr), rp, dp, B, bf16 ? 1 : 0, t->spos, (const float*)t->invU,
+                         reg_loss_here ? c.u_reg : 0.0f, d_emb, t->loss));
   }
-  if (c.u_reg != 0.0f && !drain_reg) {  // (the fused step adds the regulariser's loss and gradient in the score kernel)
+  if (reg_loss_here && !pairwise) {
     reg_loss_kernel<<<dim3(std::min(ceil_div(B, 8), 4 * std::max(t->resident_ctas / 2, 1)), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss, d_emb);
     NNCF_LAUNCH_OK();
   }
