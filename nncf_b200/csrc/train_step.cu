@@ -932,6 +932,8 @@ reg_loss_kernel(const float* __restrict__ Uf, const float* __restrict__ inv, int
   // Grid-stride over the rows, ONE double atomic per CTA: the first version added every row's term with its own atomic on
   // loss[r] - 16,384 same-address double atomics at C5 = 25 of the step's 530 us.
   __shared__ float part[8];
+  pdl_launch_dependents();
+  pdl_wait();                                                               // the gather's staging rows must have landed
   const int r = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ncol = d_emb > 0 ? d_emb : dp;                                  // embedding columns only
@@ -1434,8 +1436,8 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
                          reg_loss_here ? c.u_reg : 0.0f, d_emb, t->loss));
   }
   if (reg_loss_here && !pairwise) {
-    reg_loss_kernel<<<dim3(std::min(ceil_div(B, 8), 4 * std::max(t->resident_ctas / 2, 1)), R), 256, 0, st>>>(t->Uf, t->invU, rp, dp, B, c.u_reg, t->loss, d_emb);
-    NNCF_LAUNCH_OK();
+    NNCF_CUDA(launch_pdl(reg_loss_kernel, dim3(std::min(ceil_div(B, 8), 4 * std::max(t->resident_ctas / 2, 1)), R), dim3(256), 0, st,
+                         (const float*)t->Uf, (const float*)t->invU, rp, dp, B, c.u_reg, t->loss, d_emb));
   }
   NNCF_PROFILE_MARK(t, 1, st);
   // score + grad
