@@ -69,7 +69,7 @@ struct ScoreTcArgs {
   // 512 is only 8 CTAs: at R = 1 (the reference's sequential loop) the sweep is the critical path of the step.
   int split;
   int drain_vec;   // fused drain with vector reductions instead of bulk reductions (small grids), see the drain
-  int dedup;       // fused drain: rows of a warp's 32 that share an id are summed in shared memory first (crowded ids)
+  int dedup;       // fused drain, bit `side`: rows of a warp's 32 that share an id are summed in shared memory first (crowded ids)
   // fused mode has no finalize launch: the last side-0 CTA of a replica publishes the replica's loss and re-arms the
   // accumulators (loss_count[R] arrival counters, zero between steps)
   unsigned int* loss_count;
@@ -827,7 +827,7 @@ score_grad_tc_kernel(ScoreTcArgs a) {
           // one bulk reduction (TMA engine, performed at the L2) per owned row
           const int row = tid - 64;                                  // epilogue threads 0..255: the first 128 take a row each
           int64_t id = (row < 128 && ob * 128 + row < n_owner) ? ids[row] : -1;
-          if (a.dedup && row < 128) {
+          if (((a.dedup >> side) & 1) && row < 128) {
             // Crowded ids (a stratified block at N = 8 spreads 18,944 links over 62,500 item rows: its hottest row takes
             // ~10 % of them) make thousands of 512-byte reductions queue on the same L2 lines: the score kernel went from
             // 21.9 us (N = 1) to 29.6 us (N = 8).  Rows of a warp's 32 that share an id are summed in shared memory first

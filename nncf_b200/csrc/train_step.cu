@@ -1456,9 +1456,13 @@ static int step_matmul(nncf_trainer* t, const nncf_tables* tb, const int32_t* ui
       const char* e = getenv("NNCF_DRAIN_VEC");
       ta.drain_vec = e ? atoi(e) : 0;     // measured at R = 1, split 4: 8.9 us per step with bulk reductions, 10.0 with vector reductions
     }
-    {   // duplicate folding in the fused drain (one MATCH per warp: on by default; NNCF_DEDUP=0 switches it off)
+    {   // duplicate folding in the fused drain (one MATCH per warp), per side, where a step's rows crowd the table: more than
+        // one position per 20 table rows (a stratified block at N >= 2; not the 1M-row tables of one GPU, where it costs 0.3 us
+        // per step and folds next to nothing).  NNCF_DEDUP=0 / 1 switches both sides off / on.
       const char* e = getenv("NNCF_DEDUP");
-      ta.dedup = e ? atoi(e) : (drain_adds ? 1 : 0);
+      const int64_t pos = (int64_t)R * B;
+      const int crowd_u = pos * 20 > tb->n_users ? 1 : 0, crowd_v = (!dense_items && pos * 20 > tb->n_items) ? 2 : 0;
+      ta.dedup = !drain_adds ? 0 : (e ? (atoi(e) ? 3 : 0) : (crowd_u | crowd_v));
     }
     ta.split = split; ta.reg_scale = drain_reg ? 2.0f * c.u_reg / static_cast<float>(B) : 0.0f;
     ta.fuse_sgd = drain_adds ? 1 : 0; ta.d = d; ta.neg_lr = -c.learn_rate; ta.table_u = tb->user_table; ta.table_v = tb->item_table;
