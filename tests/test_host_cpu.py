@@ -348,3 +348,18 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0 and j["e2e"]["value"] == j["value"]
     assert j["config"]["workload"].startswith("C3")
+
+
+def test_gpu_runner_scripts_parse():
+    """the documented GPU runners (tools/gpu_prof_r02.sh, tools/gpu_experiments_r02.sh) are shell scripts nobody can run here:
+    at least their syntax is checked, and every experiment named in the header of the experiment runner has a case branch"""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name in ("gpu_prof_r02.sh", "gpu_experiments_r02.sh", "ablate.sh"):
+        subprocess.run(["bash", "-n", os.path.join(root, "tools", name)], check=True)
+    src = open(os.path.join(root, "tools", "gpu_experiments_r02.sh")).read()
+    named = re.findall(r"^#   (\w+)\s{2,}", src, flags=re.M)
+    assert len(named) >= 8
+    for n in named:
+        assert re.search(r"^\s+%s\)" % re.escape(n), src, flags=re.M), "no case branch for experiment %r" % n
