@@ -13,6 +13,7 @@
 #   scale8   bench.py at N = 8 / 4 / 2 / 1 the way the driver launches it (needs gpurun --gpus 8), C5 at N = 8
 #   scale4   the same at N = 4 / 2 / 1 (gpurun --gpus 4)
 #   ncu_c5   ncu --set full of the C5 step's gather and finalize kernels (B = 16,384, d = 256, l2-normalised rows, max-margin)
+#   ncu_adam   ncu --set full of the lazy-Adam apply and the finalize kernel at R = 37, launch list of the C2-like chain at R = 1
 #   ncu_score   ncu --set full + source page of the score kernel
 mkdir -p gpurun_out
 CB="python tools/config_bench.py"
@@ -126,6 +127,26 @@ for k in ['Kernel Name','gpu__time_duration.sum','launch__grid_size','launch__re
       done | tee gpurun_out/r02_c5_ncu.txt
       for sp in 0 1 2 4; do echo "== NNCF_SPLIT=$sp (0 = the host's choice)"; NNCF_SPLIT=$sp timeout 120 $CB neg_shared max-margin 16384 256 1 200 ureg norm 2>&1 | tail -1; done | tee -a gpurun_out/r02_c5_ncu.txt
       echo "== u_reg = 0"; timeout 120 $CB neg_shared max-margin 16384 256 1 200 norm 2>&1 | tail -1 ;;
+    ncu_adam)
+      for k in adam_apply_accum finalize_vec; do
+        cfg="neg_shared skip-gram 512 128 37 30 ureg adam"; [ $k = finalize_vec ] && cfg="group_neg_shared log-loss 512 128 37 30 ureg norm adam"
+        ZIPF=10,10 timeout 300 ncu --set full --clock-control none -k regex:$k -s 20 -c 1 -o gpurun_out/r02_$k $CB $cfg > /dev/null 2>&1
+        ncu -i gpurun_out/r02_$k.ncu-rep --page raw --csv 2>/dev/null | python -c "
+import csv,sys
+rows=list(csv.reader(sys.stdin)); h,u,v=rows[0],rows[1],rows[2]
+for k in ['Kernel Name','gpu__time_duration.sum','launch__grid_size','launch__registers_per_thread','dram__bytes_read.sum','dram__bytes_write.sum','gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed','lts__t_sector_hit_rate.pct','sm__warps_active.avg.pct_of_peak_sustained_active','smsp__issue_active.avg.pct_of_peak_sustained_active']:
+    if k in h: print('%-64s %s %s' % (k, v[h.index(k)][:90], u[h.index(k)]))
+"
+        rm -f gpurun_out/r02_$k.ncu-rep
+      done | tee gpurun_out/r02_adam_ncu.txt
+      ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 24 --csv --log-file gpurun_out/r02_c2_launches_after.csv $CB group_neg_shared log-loss 512 128 1 100 ureg norm adam > /dev/null 2>&1
+      python - <<PY
+import csv
+rows = [r for r in csv.reader(open("gpurun_out/r02_c2_launches_after.csv")) if len(r) > 5]
+h = rows[0]; ik, iv = h.index("Kernel Name"), h.index("Metric Value")
+for r in rows[1:17]: print("%-70s %8.2f us" % (r[ik].split("(")[0][:70], float(r[iv].replace(",", "")) / 1e3))
+PY
+      ;;
     ncu_score)
       ZIPF=10,10 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'score_grad_tc' -s 40 -c 1 -o gpurun_out/r02_score $CB neg_shared skip-gram 512 128 37 60 ureg > gpurun_out/r02_score.log 2>&1
       ncu -i gpurun_out/r02_score.ncu-rep --page source --csv > gpurun_out/r02_score_source.csv 2>/dev/null
