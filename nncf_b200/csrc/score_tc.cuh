@@ -84,6 +84,11 @@ struct ScoreTcArgs {
   float* table_u; float* table_v;             // what the fused drain adds into: the embedding tables (sparse SGD) or the
                                               // per-table gradient accumulators of the folded lazy Adam (neg_lr = 1)
   const float* pf_table_u; const float* pf_table_v;   // tables whose rows the spare warps prefetch for the next step
+  // lazy Adam (folded): the rows of THIS step's ids in the optimizer-state tables (m, v) and in the gradient accumulators are
+  // pulled into L2 by the same warps while the tile loops run, so the apply launch behind this kernel - a claim -> rows
+  // dependency chain, latency-bound - finds them there.  NULL = off.
+  const float* pf_now[2][3];                          // [side][m, v, acc]
+  int pf_now_count;                                   // ids per side (R * B)
   const int32_t* ids_u; const int32_t* ids_v; // table row of each owner row: ids_x[r * stride_x + row]
   int64_t ids_stride_u, ids_stride_v;
   ShardPtrs shards_u, shards_v;
@@ -908,6 +913,21 @@ score_grad_tc_kernel(ScoreTcArgs a) {
       int64_t id = ids[i];
       id = id < 0 ? 0 : (id >= nrows ? nrows - 1 : id);
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(table + id * a.d), "r"(row_bytes) : "memory");
+    }
+   }
+   if (a.pf_now_count > 0 && !(NNCF_ABLATE & 64)) {
+    const int cta = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int ncta = gridDim.x * gridDim.y * gridDim.z;
+    const int vside = warp == 2 + kScoreEpiWarps + 1 ? 1 : 0;
+    const int32_t* ids = vside ? a.ids_v : a.ids_u;
+    const int64_t stride = vside ? a.ids_stride_v : a.ids_stride_u;
+    const uint32_t row_bytes = static_cast<uint32_t>(a.d) * 4u;
+    for (int i = cta * 32 + lane; i < a.pf_now_count; i += ncta * 32) {
+      const int64_t id = ids[(i / a.B) * stride + i % a.B];
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        if (a.pf_now[vside][k])
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf_now[vside][k] + id * a.d), "r"(row_bytes) : "memory");
     }
    }
    if (GX && warp == 2 + kScoreEpiWarps && lane == 0) {
