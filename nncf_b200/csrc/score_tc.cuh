@@ -20,14 +20,19 @@
 // branch-free code (a first version that switched on the loss per element ran 24k cycles per tile: the unrolled
 // 4-way switch blew the instruction cache).
 //
-// Tile width TN (swept rows per tile): 64 for dp <= 128, 128 for dp = 256.  With TN = 64 a CTA needs 112 KiB of shared
-// memory and 256 TMEM columns, so TWO CTAs are resident per SM: one CTA's prologue (barrier init, TMEM alloc, X load)
-// and drain overlap the other's tile loop, and 16 epilogue warps per SM hide the MUFU / TMEM-load latencies (measured at
-// B = 512: the 1-CTA/SM version spent ~8k of its ~21k cycles per CTA outside the tile loop).  dp = 256 keeps TN = 128 and
-// one CTA per SM (its operand tiles alone are 160 KiB; an N = 64 MMA1 would read 192 B/clk of shared memory).
+// Tile width TN (swept rows per tile) = 64.  For dp <= 128 a CTA needs ~100 KiB of shared memory and 256 TMEM columns, so
+// TWO CTAs are resident per SM: one CTA's prologue (barrier init, TMEM alloc, X load) and drain overlap the other's tile
+// loop, and 16 epilogue warps per SM hide the MUFU / TMEM-load latencies (measured at B = 512: the 1-CTA/SM version spent
+// ~8k of its ~21k cycles per CTA outside the tile loop).  dp = 256: one CTA per SM, four 32 KiB stages (128-row tiles with
+// two 64 KiB stages left the next-but-one copy exposed).
 //
-// Warp roles: warp 0 = bulk-copy (TMA engine) producer, warp 1 = MMA issuer, warps 2..9 = epilogue; epilogue warp w
-// reads TMEM lanes 32*(w&3).. and the column half (w-2)>>2 (TN/2 columns) of every S tile.
+// Warp roles: warp 0 = bulk-copy (TMA engine) producer (+ the loss hand-off), warp 1 = MMA issuer, warps 2..9 = epilogue
+// (warp w reads TMEM lanes 32*(w&3).. and the column half (w-2)>>2 (TN/2 columns) of every S tile), warps 10..11 = L2
+// prefetch of the next step's rows (and of this step's Adam state) + the G' exchange's flag publisher.
+//
+// Two variants live behind compile-time switches, both measured slower and documented where they are declared (DESIGN.md
+// 8.1): NNCF_SCORE_TEAMS (four 32-column S' buffers, the two warp groups on alternate tiles) and the G' exchange
+// (template parameter GX: every block computed once by one side, the other side contracts the exchanged bf16 tiles).
 #pragma once
 #include "common.cuh"
 #include "sm100.cuh"
